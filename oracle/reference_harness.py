@@ -1,0 +1,162 @@
+"""Runs the UNMODIFIED reference (gym-roboy) on injected draws -- TEST INFRASTRUCTURE.
+
+Container-only: needs /root/reference (read-only) plus the test-only import shim under
+tests/_shim (gym / rclpy stand-ins; see tests/_shim/README.md).  It is how the oracle is
+pinned and how tests/golden/*.npz are generated (oracle/gen_golden.py).  Never imported by the
+product package, and never at run time on the GPU box (where /root/reference does not exist).
+
+The reference's random draws (gym Box.sample) are unpinned, so parity is established by
+INJECTION: a `ReplayRobot(MsjRobot)` overrides only `new_random_state()` to return the
+Philox draws the CUDA path / oracle would make for that (env id, call counter, stream).  All
+other code that runs -- RoboyEnv.step/reset/compute_reward/_did_reach_goal,
+StubSimulationClient, RoboyRobot.normalize_state, MsjRobot's spaces -- is the reference's own.
+The vec-env worker's reset-on-done (stable-baselines SubprocVecEnv, external to the reference)
+is restated in `ReferenceVecEnv.step`.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("ROBOY_REFERENCE_ROOT", "/root/reference")
+_SHIM = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "_shim")
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "gym_roboy"))
+
+
+def _import_reference():
+    if not available():
+        raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
+    for p in (REFERENCE_ROOT, _SHIM):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    sys.dont_write_bytecode = True  # /root/reference is read-only
+    with contextlib.redirect_stdout(io.StringIO()):
+        from gym_roboy.envs import RoboyEnv
+        from gym_roboy.envs.robots import MsjRobot, RobotState
+        from gym_roboy.envs.simulations import StubSimulationClient
+    return RoboyEnv, MsjRobot, RobotState, StubSimulationClient
+
+
+def _make_replay_robot(MsjRobot, RobotState, draw_fn):
+    """A fresh MsjRobot subclass whose only override is the source of random samples."""
+
+    class ReplayRobot(MsjRobot):
+        ctx = dict(gid=0, t=0, goal_real=True)
+        log = []
+
+        @classmethod
+        def new_random_state(cls):
+            caller = sys._getframe(1).f_code.co_name
+            gid, t = cls.ctx["gid"], cls.ctx["t"]
+            if caller == "get_new_goal_joint_angles":
+                cls.log.append("goal")
+                if cls.ctx["goal_real"]:
+                    g = draw_fn(gid, t, 2)
+                else:  # goal that the worker's reset() overwrites at once: never observable
+                    g = np.zeros(3, np.float32)
+                return RobotState(joint_angles=g, joint_vels=np.zeros(3, np.float32), is_feasible=True)
+            assert caller in ("forward_step_command", "__init__"), caller
+            cls.log.append("state")
+            return RobotState(joint_angles=draw_fn(gid, t, 0), joint_vels=draw_fn(gid, t, 1), is_feasible=True)
+
+    return ReplayRobot()
+
+
+class ReferenceVecEnv:
+    """N reference RoboyEnv(StubSimulationClient(ReplayRobot)) instances in lock-step."""
+
+    def __init__(self, n_envs, seed=1234, env_id_base=0, joint_vel_penalty=False, bonus=True, auto_reset=True):
+        from oracle import oracle as orc
+
+        RoboyEnv, MsjRobot, RobotState, Stub = _import_reference()
+        self.RobotState = RobotState
+        self.n = n_envs
+        self.seed = seed
+        self.auto_reset = auto_reset
+        self.t = 0
+        self.envs, self.robots = [], []
+
+        def draw_fn(gid, t, stream):
+            return orc.draw(seed, [gid], t, stream)[0]
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            for i in range(n_envs):
+                robot = _make_replay_robot(MsjRobot, RobotState, draw_fn)
+                type(robot).ctx = dict(gid=env_id_base + i, t=0, goal_real=True)
+                type(robot).log = []
+                env = RoboyEnv(Stub(robot=robot), joint_vel_penalty=joint_vel_penalty,
+                               is_agent_getting_bonus_for_reaching_goal=bonus)
+                assert type(robot).log == ["state", "goal"], type(robot).log  # SURVEY 8a a11 draw order
+                self.envs.append(env)
+                self.robots.append(robot)
+        self.gid0 = env_id_base
+        self.reward_range = self.envs[0].reward_range
+
+    # ---- injection (the batched API's set_state / set_goal / set_step_num) ----
+    def set_goal(self, i, goal_q):
+        self.envs[i]._set_new_goal(goal_joint_angle=np.asarray(goal_q, np.float32))
+
+    def set_state(self, i, q, qd, feasible=True):
+        self.envs[i]._simulation_client._state = self.RobotState(
+            joint_angles=np.asarray(q, np.float32), joint_vels=np.asarray(qd, np.float32), is_feasible=bool(feasible))
+
+    def set_step_num(self, i, k):
+        self.envs[i].step_num = int(k)
+
+    # ---- observers ----
+    def goals(self):
+        return np.stack([np.asarray(e._goal_state.joint_angles, np.float32) for e in self.envs])
+
+    def step_nums(self):
+        return np.array([e.step_num for e in self.envs], np.int64)
+
+    def _ctx(self, i, goal_real):
+        cls = type(self.robots[i])
+        cls.ctx = dict(gid=self.gid0 + i, t=self.t, goal_real=goal_real)
+        cls.log = []
+        return cls
+
+    def reset(self, mask=None):
+        self.t += 1
+        obs = np.zeros((self.n, 9), np.float64)
+        with contextlib.redirect_stdout(io.StringIO()):
+            for i, env in enumerate(self.envs):
+                if mask is not None and not mask[i]:
+                    continue
+                cls = self._ctx(i, True)
+                obs[i] = env.reset()
+                assert cls.log == ["goal"], cls.log
+        return obs
+
+    def step(self, actions):
+        """actions float32 [n,8].  Returns obs f64 [n,9], reward f64 [n], done bool [n],
+        terminal_obs f64 [n,9], raised [n] (AssertionError text or '')."""
+        self.t += 1
+        n = self.n
+        obs = np.zeros((n, 9), np.float64)
+        term = np.zeros((n, 9), np.float64)
+        rew = np.zeros(n, np.float64)
+        done = np.zeros(n, bool)
+        raised = [""] * n
+        with contextlib.redirect_stdout(io.StringIO()):
+            for i, env in enumerate(self.envs):
+                cls = self._ctx(i, not self.auto_reset)
+                try:
+                    o, r, d, _ = env.step(np.asarray(actions[i], np.float32))
+                except AssertionError as exc:  # roboy_env.py:52 / :109
+                    raised[i] = "AssertionError: %s" % (exc,)
+                    continue
+                assert isinstance(r, float) and isinstance(d, bool)
+                rew[i], done[i] = r, d
+                if d and self.auto_reset:  # SubprocVecEnv worker: reset obs replaces terminal obs
+                    term[i] = o
+                    cls.ctx["goal_real"] = True
+                    o = env.reset()
+                    assert cls.log in (["state", "goal", "goal"], ["goal", "goal"]), cls.log
+                obs[i] = o
+        return obs, rew, done, term, raised

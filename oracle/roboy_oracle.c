@@ -1,0 +1,511 @@
+/*
+ * oracle/roboy_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, CPU restatement of gym-roboy's environment hot path for the MSJ robot, used
+ * ONLY as the checker for the CUDA path (tests/, __graft_entry__.smoke(), and bench.py's
+ * cpu_baseline / --impl reference legs).  Nothing under gym_roboy_b200/ may import, link or
+ * call it.  Every function cites the reference lines it follows (paths relative to
+ * /root/reference/gym_roboy/).
+ *
+ * Parity status: PINNED.  The restatement is checked (tests/test_oracle_vs_reference.py,
+ * oracle/gen_golden.py) against the unmodified reference run in the build container through
+ * a test-only gym shim and a replay robot, and against golden vectors generated that way
+ * (tests/golden/).  Third-party arithmetic the reference leans on was pinned empirically in
+ * that container (numpy 2.3.5 + scipy-openblas 0.3.30, x86-64):
+ *   - np.linalg.norm(float32[3], ord=2) == sqrtf((float)(sum_k (double)(float)(x_k*x_k)))
+ *     (OpenBLAS sdot: float products accumulated sequentially in a double, cast to float);
+ *   - np.linalg.norm(float64[3]) == sqrt(((x0*x0)+(x1*x1))+(x2*x2))  for the float32-valued
+ *     inputs this path produces (the products are then exact, so FMA use is unobservable);
+ *   - np.exp(float32) is NOT correctly rounded (about 40 % of inputs differ from libm expf by
+ *     one ulp), so rewards are compared with a relative tolerance (1e-6), never bit-exactly.
+ *
+ * Build: make -C oracle   (gcc -O2 -ffp-contract=off; never -ffast-math).
+ *
+ * The random draws (goal / stub state) are NOT the reference's: gym's Box.sample stream is
+ * unpinned.  Draws come from Philox4x32-10 keyed by (seed) and countered by
+ * (global env id, call counter, stream); parity against the reference is established by
+ * replaying these same draws INTO the reference (oracle/reference_harness.py).
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------
+ * Configuration and state (mirrors include/roboy_b200.h field by field, written independently)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t n_envs;
+    uint64_t env_id_base;      /* global id of local env 0 (multi-GPU sharding) */
+    uint64_t seed;
+    float angle_low, angle_high;   /* msj_robot.py:9   +-pi  as float32 */
+    float vel_low, vel_high;       /* msj_robot.py:10  +-pi/6 as float32 */
+    float act_low, act_high;       /* msj_robot.py:16  +-0.3 as float32 */
+    int32_t max_episode_len;       /* roboy_env.py:28  400 */
+    int32_t joint_vel_penalty;     /* roboy_env.py:13 */
+    int32_t bonus_for_goal;        /* roboy_env.py:14 */
+    int32_t auto_reset;            /* vec-env worker semantics */
+    float penalty_boundary;        /* roboy_env.py:26  1 */
+    float bonus_goal;              /* roboy_env.py:27  1000 */
+    double reward_lo, reward_hi;   /* roboy_env.py:30,109 (use -inf/+inf to disable) */
+} orc_cfg;
+
+/* step_flags word: low 24 bits step_num, then flag bits */
+#define ORC_STEP_MASK 0x00ffffffu
+#define ORC_F_HELD_ZERO64 (1u << 24) /* held state is the reference's float64 zero state */
+#define ORC_F_HELD_INFEASIBLE (1u << 25)
+
+/* error bits (reference AssertionErrors restated as flags) */
+#define ORC_ERR_ACTION 1u       /* roboy_env.py:52 */
+#define ORC_ERR_REWARD_RANGE 2u /* roboy_env.py:109 */
+#define ORC_ERR_GOAL_BOUNDS 4u  /* roboy_robot.py:76 */
+
+enum { ST_STEPS = 0, ST_EPISODES, ST_SUCCESSES, ST_TIMEOUTS, ST_SUM_REWARD, ST_SUM_EPLEN, ST_HOLDS, ST_VIOLATIONS, ST_N };
+
+/* ------------------------------------------------------------------------------------------
+ * Philox4x32-10 (Salmon et al., SC'11, Random123) -- published algorithm restated.
+ * ---------------------------------------------------------------------------------------- */
+#define PHILOX_M0 0xD2511F53u
+#define PHILOX_M1 0xCD9E8D57u
+#define PHILOX_W0 0x9E3779B9u
+#define PHILOX_W1 0xBB67AE85u
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += PHILOX_W0; k1 += PHILOX_W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+enum { STREAM_STATE_Q = 0, STREAM_STATE_QD = 1, STREAM_GOAL = 2 };
+
+/* counter = (env id lo, env id hi, call counter lo, stream<<28 | call counter hi) */
+static void draw4(const orc_cfg *cfg, uint64_t gid, uint64_t t, uint32_t stream, uint32_t out[4]) {
+    uint32_t ctr[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t,
+                       (stream << 28) | ((uint32_t)(t >> 32) & 0x0fffffffu)};
+    uint32_t key[2] = {(uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32)};
+    orc_philox4x32_10(ctr, key, out);
+}
+
+/* u = (x>>8)*2^-24 in [0,1); v = low + (high-low)*u, float32 mul then add (no FMA).
+ * Stands in for gym Box.sample() (roboy_robot.py:37-38), whose own stream is unpinned. */
+static float uniform_in(uint32_t x, float low, float high) {
+    float u = (float)(x >> 8) * 0x1p-24f;
+    float span = high - low;
+    float m = span * u;
+    return low + m;
+}
+
+/* roboy_robot.py:35-39 new_random_state(): q ~ U[angle space]^3, and -- reference quirk --
+ * the velocities are ALSO drawn from the ANGLE space (:38). is_feasible = True. */
+void orc_draw_state(const orc_cfg *cfg, uint64_t gid, uint64_t t, float q[3], float qd[3]) {
+    uint32_t a[4], b[4];
+    draw4(cfg, gid, t, STREAM_STATE_Q, a);
+    draw4(cfg, gid, t, STREAM_STATE_QD, b);
+    for (int k = 0; k < 3; ++k) {
+        q[k] = uniform_in(a[k], cfg->angle_low, cfg->angle_high);
+        qd[k] = uniform_in(b[k], cfg->angle_low, cfg->angle_high);
+    }
+}
+
+/* simulation_client.py:46-47 get_new_goal_joint_angles(): new_random_state().joint_angles */
+void orc_draw_goal(const orc_cfg *cfg, uint64_t gid, uint64_t t, float g[3]) {
+    uint32_t a[4];
+    draw4(cfg, gid, t, STREAM_GOAL, a);
+    for (int k = 0; k < 3; ++k) g[k] = uniform_in(a[k], cfg->angle_low, cfg->angle_high);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * numpy arithmetic restated (see header for how each was pinned)
+ * ---------------------------------------------------------------------------------------- */
+/* roboy_env.py:137-140 _l2_distance on float32 operands */
+static float l2_f32(const float a[3], const float b[3]) {
+    double s = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        float d = a[k] - b[k];      /* :138 np.subtract in float32 */
+        if (isnan(d)) d = 0.0f;     /* :139 */
+        float p = d * d;            /* OpenBLAS sdot: float product ... */
+        s += (double)p;             /* ... accumulated in double */
+    }
+    return sqrtf((float)s);         /* :140 np.linalg.norm -> sqrt(float32) */
+}
+
+/* roboy_env.py:137-140 _l2_distance once either operand is float64 */
+static double l2_f64(const double a[3], const double b[3]) {
+    double s = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        double d = a[k] - b[k];
+        if (isnan(d)) d = 0.0;
+        s += d * d;
+    }
+    return sqrt(s);
+}
+
+/* roboy_robot.py:93-95  (2*val - max_val - min_val) / (max_val - min_val), in val's dtype */
+static float normalize_f32(float v, float hi, float lo) {
+    float t = 2.0f * v;
+    t = t - hi;
+    t = t - lo;
+    return t / (hi - lo);
+}
+static double normalize_f64(double v, float hi, float lo) {
+    double t = 2.0 * v;
+    t = t - (double)hi;
+    t = t - (double)lo;
+    return t / (double)(hi - lo); /* max-min is float32-float32 -> float32, then promoted */
+}
+
+/* One env's state as the reference holds it: values + the dtype numpy would carry. */
+typedef struct {
+    double q[3], qd[3]; /* float32-valued when is64 == 0 */
+    int is64;           /* 1: float64 zero state (roboy_robot.py:41-45), 0: float32 sample */
+    int feasible;
+} orc_state;
+
+/* roboy_env.py:125-134 _did_reach_goal.  goal_q is float32; goal velocities are either the
+ * float64 zeros of roboy_env.py:23 (goal_qd == NULL) or float32 values (stand-alone call). */
+static int did_reach_goal(const orc_cfg *cfg, const orc_state *s, const float goal_q[3],
+                          const float *goal_qd, float thr_angle, float thr_vel) {
+    int angles_close, vels_close;
+    if (!s->is64) {
+        float q[3] = {(float)s->q[0], (float)s->q[1], (float)s->q[2]};
+        angles_close = l2_f32(q, goal_q) < thr_angle;              /* :126-127 float32 */
+    } else {
+        double g[3] = {goal_q[0], goal_q[1], goal_q[2]};
+        angles_close = l2_f64(s->q, g) < (double)thr_angle;        /* float64 state promotes */
+    }
+    if (!s->is64 && goal_qd) {
+        float v[3] = {(float)s->qd[0], (float)s->qd[1], (float)s->qd[2]};
+        vels_close = l2_f32(v, goal_qd) < thr_vel;
+    } else {
+        double gv[3] = {0.0, 0.0, 0.0};
+        if (goal_qd) { gv[0] = goal_qd[0]; gv[1] = goal_qd[1]; gv[2] = goal_qd[2]; }
+        vels_close = l2_f64(s->qd, gv) < (double)thr_vel;          /* :129-130 float64 */
+    }
+    (void)cfg;
+    return angles_close && vels_close;                             /* :134 */
+}
+
+/* roboy_env.py:92-112 compute_reward.  Returns the python float; *violation set when the
+ * assert at :109 would fire.  `reached` is the value of the _did_reach_goal call at :105. */
+static double compute_reward(const orc_cfg *cfg, const orc_state *s, const float goal_q[3],
+                             const float *goal_qd, int reached, int *violation) {
+    const float ahi = cfg->angle_high, alo = cfg->angle_low, vhi = cfg->vel_high, vlo = cfg->vel_low;
+    double reward; /* carries float32 values exactly while the reference is in float32 */
+    int r64;       /* dtype numpy would carry */
+    float r32 = 0.0f;
+    float ng[3];
+    for (int k = 0; k < 3; ++k) ng[k] = normalize_f32(goal_q[k], ahi, alo);           /* :95 */
+    if (!s->is64) {
+        float nq[3];
+        for (int k = 0; k < 3; ++k) nq[k] = normalize_f32((float)s->q[k], ahi, alo);  /* :94 */
+        r32 = -expf(l2_f32(nq, ng));                                                  /* :96 */
+        r64 = 0;
+        reward = r32;
+    } else {
+        double nq[3], g64[3];
+        for (int k = 0; k < 3; ++k) { nq[k] = normalize_f64(s->q[k], ahi, alo); g64[k] = ng[k]; }
+        reward = -exp(l2_f64(nq, g64));
+        r64 = 1;
+    }
+    if (cfg->joint_vel_penalty) {                                                     /* :98-100 */
+        if (!s->is64 && goal_qd) { /* all-float32 stand-alone call (roboy_env.py:40-49) */
+            float nv[3], ngv[3];
+            for (int k = 0; k < 3; ++k) {
+                nv[k] = normalize_f32((float)s->qd[k], vhi, vlo);
+                ngv[k] = normalize_f32(goal_qd[k], vhi, vlo);
+            }
+            float d[3] = {nv[0] - ngv[0], nv[1] - ngv[1], nv[2] - ngv[2]};
+            double acc = 0.0;
+            for (int k = 0; k < 3; ++k) { float p = d[k] * d[k]; acc += (double)p; }
+            float v = sqrtf((float)acc);
+            float e = expf(r32);
+            float diff = r32 - e;
+            r32 = (v + 1.0f) * diff;
+            reward = r32;
+        } else {
+            double nv[3], ngv[3];
+            for (int k = 0; k < 3; ++k) {
+                nv[k] = s->is64 ? normalize_f64(s->qd[k], vhi, vlo)
+                                : (double)normalize_f32((float)s->qd[k], vhi, vlo);
+                ngv[k] = goal_qd ? (double)normalize_f32(goal_qd[k], vhi, vlo)
+                                 : normalize_f64(0.0, vhi, vlo);
+            }
+            double acc = 0.0;
+            for (int k = 0; k < 3; ++k) { double d = nv[k] - ngv[k]; acc += d * d; }
+            double v = sqrt(acc);                       /* np.linalg.norm, float64 */
+            double diff = r64 ? (reward - exp(reward)) : (double)(r32 - expf(r32));
+            reward = (v + 1.0) * diff;
+            r64 = 1;
+        }
+    }
+    if (!s->feasible) {                                                               /* :102-103 */
+        /* np.abs(int) is an int64 scalar: float32 - int64 -> float64 (NEP 50) */
+        reward = reward - (double)cfg->penalty_boundary;
+        r64 = 1;
+    }
+    if (reached && cfg->bonus_for_goal) {                                             /* :105-107 */
+        if (r64) reward = reward + (double)cfg->bonus_goal;
+        else { r32 = (float)reward + cfg->bonus_goal; reward = r32; }
+    }
+    if (!(cfg->reward_lo <= reward && reward <= cfg->reward_hi)) *violation = 1;      /* :109 */
+    return reward;                                                                    /* :112 */
+}
+
+/* roboy_env.py:24-25 + :127,:130 thresholds:  _l2_distance(low, high)/200 and /5, float32 */
+void orc_thresholds(const orc_cfg *cfg, float *thr_angle, float *thr_vel) {
+    float lo[3] = {cfg->angle_low, cfg->angle_low, cfg->angle_low};
+    float hi[3] = {cfg->angle_high, cfg->angle_high, cfg->angle_high};
+    *thr_angle = l2_f32(lo, hi) / 200.0f;
+    float vlo[3] = {cfg->vel_low, cfg->vel_low, cfg->vel_low};
+    float vhi[3] = {cfg->vel_high, cfg->vel_high, cfg->vel_high};
+    *thr_vel = l2_f32(vlo, vhi) / 5.0f;
+}
+
+/* Stand-alone GoalEnv.compute_reward(current_state, goal_state) over float32 arrays
+ * (roboy_env.py:92-112 as called from :40-49 and by the reference's tests).
+ * q,qd,goal_q,goal_qd: [n][3] row-major; feasible: [n] bytes.  goal_qd may be NULL (= the
+ * float64 zeros of roboy_env.py:23).  Outputs reward (double) and reached (byte). */
+void orc_compute_reward(const orc_cfg *cfg, uint64_t n, const float *q, const float *qd,
+                        const uint8_t *feasible, const float *goal_q, const float *goal_qd,
+                        double *reward, uint8_t *reached, uint8_t *violation) {
+    float ta, tv;
+    orc_thresholds(cfg, &ta, &tv);
+    for (uint64_t i = 0; i < n; ++i) {
+        orc_state s;
+        for (int k = 0; k < 3; ++k) { s.q[k] = q[3 * i + k]; s.qd[k] = qd[3 * i + k]; }
+        s.is64 = 0;
+        s.feasible = feasible ? feasible[i] : 1;
+        const float *gv = goal_qd ? goal_qd + 3 * i : NULL;
+        int r = did_reach_goal(cfg, &s, goal_q + 3 * i, gv, ta, tv);
+        int viol = 0;
+        reward[i] = compute_reward(cfg, &s, goal_q + 3 * i, gv, r, &viol);
+        if (reached) reached[i] = (uint8_t)r;
+        if (violation) violation[i] = (uint8_t)viol;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Batched env state.  Layout mirrors the CUDA path's structure-of-arrays:
+ *   goal[3][n] f32, step_flags[n] u32, held[6][n] f32 (q0..q2, qd0..qd2).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    orc_cfg cfg;
+    float thr_angle, thr_vel;
+    uint64_t t; /* call counter: 0 = construction, +1 per reset()/step() call */
+    float *goal;
+    uint32_t *step_flags;
+    float *held;
+    double stats[ST_N];
+    uint32_t err_flags;
+    uint64_t first_bad_env;
+} orc_env;
+
+orc_env *orc_create(const orc_cfg *cfg) {
+    orc_env *e = (orc_env *)calloc(1, sizeof(orc_env));
+    e->cfg = *cfg;
+    orc_thresholds(cfg, &e->thr_angle, &e->thr_vel);
+    uint64_t n = cfg->n_envs;
+    e->goal = (float *)calloc(3 * n + 1, sizeof(float));
+    e->step_flags = (uint32_t *)calloc(n + 1, sizeof(uint32_t));
+    e->held = (float *)calloc(6 * n + 1, sizeof(float));
+    e->first_bad_env = UINT64_MAX;
+    e->t = 0;
+    /* RoboyEnv.__init__ (roboy_env.py:12-38) over StubSimulationClient.__init__
+     * (simulation_client.py:29-31): held state := random sample, goal := random, step_num = 1 */
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t gid = cfg->env_id_base + i;
+        float q[3], qd[3], g[3];
+        orc_draw_state(cfg, gid, 0, q, qd);
+        orc_draw_goal(cfg, gid, 0, g);
+        for (int k = 0; k < 3; ++k) {
+            e->held[(size_t)k * n + i] = q[k];
+            e->held[(size_t)(3 + k) * n + i] = qd[k];
+            e->goal[(size_t)k * n + i] = g[k];
+        }
+        e->step_flags[i] = 1u;
+    }
+    return e;
+}
+
+void orc_destroy(orc_env *e) {
+    if (!e) return;
+    free(e->goal); free(e->step_flags); free(e->held); free(e);
+}
+
+float *orc_goal(orc_env *e) { return e->goal; }
+uint32_t *orc_step_flags(orc_env *e) { return e->step_flags; }
+float *orc_held(orc_env *e) { return e->held; }
+double *orc_stats(orc_env *e) { return e->stats; }
+uint64_t orc_counter(orc_env *e) { return e->t; }
+void orc_set_counter(orc_env *e, uint64_t t) { e->t = t; }
+uint32_t orc_err_flags(orc_env *e) { return e->err_flags; }
+uint64_t orc_first_bad_env(orc_env *e) { return e->first_bad_env; }
+void orc_set_reward_range(orc_env *e, double lo, double hi) { e->cfg.reward_lo = lo; e->cfg.reward_hi = hi; }
+
+static void note_error(orc_env *e, uint32_t bits, uint64_t gid) {
+    e->err_flags |= bits;
+    if (gid < e->first_bad_env) e->first_bad_env = gid;
+}
+
+/* RoboyEnv.reset() (roboy_env.py:82-87) over the Stub (simulation_client.py:42-44,33-34),
+ * for envs with mask[i] != 0 (mask == NULL: all).  obs [n][9] rows are written for reset envs
+ * only (obs may be NULL). */
+void orc_reset(orc_env *e, const uint8_t *mask, float *obs) {
+    const uint64_t n = e->cfg.n_envs;
+    e->t += 1;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (mask && !mask[i]) continue;
+        float g[3];
+        orc_draw_goal(&e->cfg, e->cfg.env_id_base + i, e->t, g);       /* :86 */
+        for (int k = 0; k < 3; ++k) e->goal[(size_t)k * n + i] = g[k];
+        e->step_flags[i] = 1u | ORC_F_HELD_ZERO64;                      /* :83-85 */
+        if (obs) {
+            for (int k = 0; k < 6; ++k) obs[9 * i + k] = 0.0f;          /* :87 */
+            for (int k = 0; k < 3; ++k) obs[9 * i + 6 + k] = g[k];
+        }
+    }
+}
+
+typedef struct {
+    orc_env *e;
+    const float *actions;
+    float *obs, *reward, *terminal_obs;
+    uint8_t *done;
+    uint64_t lo, hi;
+    double stats[ST_N];
+    uint32_t err;
+    uint64_t first_bad;
+} step_job;
+
+/* RoboyEnv.step (roboy_env.py:51-70) over StubSimulationClient.forward_step_command
+ * (simulation_client.py:36-40), then -- if cfg.auto_reset -- the vec-env worker's
+ * reset-on-done, for envs [lo, hi). */
+static void step_range(step_job *j) {
+    orc_env *e = j->e;
+    const orc_cfg *cfg = &e->cfg;
+    const uint64_t n = cfg->n_envs;
+    const uint64_t t = e->t;
+    const float in_hi = 1.0f, in_lo = -1.0f;                    /* roboy_env.py:31 */
+    const float slope = (cfg->act_high - cfg->act_low) / (in_hi - in_lo); /* :157 float32 */
+    for (uint64_t i = j->lo; i < j->hi; ++i) {
+        const uint64_t gid = cfg->env_id_base + i;
+        const float *a = j->actions + 8 * i;
+        uint32_t err = 0;
+        /* :52 assert action_space.contains(action) -- closed interval, NaN fails */
+        int ok = 1, hold = 1;
+        for (int k = 0; k < 8; ++k) {
+            if (!(a[k] >= in_lo && a[k] <= in_hi)) ok = 0;
+            float r = a[k] - in_hi;                             /* :158 float32, unfused */
+            r = slope * r;
+            r = r + cfg->act_high;
+            /* simulation_client.py:38 np.allclose(list_of_py_floats, 0): |x| <= 1e-8, NaN/inf fail */
+            if (!(fabs((double)r) <= 1e-8)) hold = 0;
+        }
+        if (!ok) err |= ORC_ERR_ACTION;
+
+        uint32_t sf = e->step_flags[i];
+        float g[3] = {e->goal[i], e->goal[n + i], e->goal[2 * n + i]};
+        orc_state s;
+        if (hold) {                                             /* simulation_client.py:38-39 */
+            if (sf & ORC_F_HELD_ZERO64) {
+                for (int k = 0; k < 3; ++k) { s.q[k] = 0.0; s.qd[k] = 0.0; }
+                s.is64 = 1; s.feasible = 1;
+            } else {
+                for (int k = 0; k < 3; ++k) {
+                    s.q[k] = e->held[(size_t)k * n + i];
+                    s.qd[k] = e->held[(size_t)(3 + k) * n + i];
+                }
+                s.is64 = 0; s.feasible = !(sf & ORC_F_HELD_INFEASIBLE);
+            }
+        } else {                                                /* :40 fresh sample, not stored */
+            float q[3], qd[3];
+            orc_draw_state(cfg, gid, t, q, qd);
+            for (int k = 0; k < 3; ++k) { s.q[k] = q[k]; s.qd[k] = qd[k]; }
+            s.is64 = 0; s.feasible = 1;
+        }
+        uint32_t step = (sf & ORC_STEP_MASK);
+        if (step < ORC_STEP_MASK) step += 1;                    /* roboy_env.py:60 (saturating) */
+
+        float o[9];                                             /* :62 -> :75-80 */
+        for (int k = 0; k < 3; ++k) { o[k] = (float)s.q[k]; o[3 + k] = (float)s.qd[k]; o[6 + k] = g[k]; }
+
+        int reached = did_reach_goal(cfg, &s, g, NULL, e->thr_angle, e->thr_vel); /* :65 / :105 */
+        int viol = 0;
+        double rew = compute_reward(cfg, &s, g, NULL, reached, &viol);           /* :64 */
+        if (viol) err |= ORC_ERR_REWARD_RANGE;
+        int timeout = (int32_t)step > cfg->max_episode_len;                       /* :72-73 */
+        int done = reached || timeout;                                           /* :65-66 */
+
+        uint32_t flags = sf & ~ORC_STEP_MASK;
+        if (done) {
+            float ng[3];
+            /* :67-68 _set_new_goal(); under auto-reset the worker's reset() (:82-87) draws
+             * again and only that second goal is observable, so one draw is materialised. */
+            orc_draw_goal(cfg, gid, t, ng);
+            for (int k = 0; k < 3; ++k) e->goal[(size_t)k * n + i] = ng[k];
+            if (cfg->auto_reset) {
+                if (j->terminal_obs) memcpy(j->terminal_obs + 9 * i, o, sizeof(o));
+                for (int k = 0; k < 6; ++k) o[k] = 0.0f;
+                for (int k = 0; k < 3; ++k) o[6 + k] = ng[k];
+                j->stats[ST_SUM_EPLEN] += (double)step - 1.0;
+                step = 1;
+                flags = ORC_F_HELD_ZERO64;
+            }
+            j->stats[ST_EPISODES] += 1.0;
+            if (reached) j->stats[ST_SUCCESSES] += 1.0;
+            else j->stats[ST_TIMEOUTS] += 1.0;
+        }
+        e->step_flags[i] = step | flags;
+        memcpy(j->obs + 9 * i, o, sizeof(o));
+        j->reward[i] = (float)rew;
+        j->done[i] = (uint8_t)done;
+        j->stats[ST_STEPS] += 1.0;
+        j->stats[ST_SUM_REWARD] += (double)(float)rew;
+        if (hold) j->stats[ST_HOLDS] += 1.0;
+        if (err) {
+            j->stats[ST_VIOLATIONS] += 1.0;
+            j->err |= err;
+            if (gid < j->first_bad) j->first_bad = gid;
+        }
+    }
+}
+
+static void *step_thread(void *p) { step_range((step_job *)p); return NULL; }
+
+/* One batched step over all envs with `threads` host threads (>=1).
+ * actions [n][8] f32; obs [n][9] f32; reward [n] f32; done [n] u8; terminal_obs [n][9] or NULL */
+void orc_step(orc_env *e, const float *actions, float *obs, float *reward, uint8_t *done,
+              float *terminal_obs, int threads) {
+    const uint64_t n = e->cfg.n_envs;
+    e->t += 1;
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > n) threads = (int)(n ? n : 1);
+    step_job *jobs = (step_job *)calloc((size_t)threads, sizeof(step_job));
+    pthread_t *tid = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    for (int k = 0; k < threads; ++k) {
+        jobs[k].e = e; jobs[k].actions = actions; jobs[k].obs = obs; jobs[k].reward = reward;
+        jobs[k].done = done; jobs[k].terminal_obs = terminal_obs;
+        jobs[k].lo = n * (uint64_t)k / (uint64_t)threads;
+        jobs[k].hi = n * (uint64_t)(k + 1) / (uint64_t)threads;
+        jobs[k].first_bad = UINT64_MAX;
+        if (threads > 1) pthread_create(&tid[k], NULL, step_thread, &jobs[k]);
+        else step_range(&jobs[k]);
+    }
+    for (int k = 0; k < threads; ++k) {
+        if (threads > 1) pthread_join(tid[k], NULL);
+        for (int s = 0; s < ST_N; ++s) e->stats[s] += jobs[k].stats[s];
+        if (jobs[k].err) note_error(e, jobs[k].err, jobs[k].first_bad);
+    }
+    free(jobs); free(tid);
+}
