@@ -1,0 +1,118 @@
+"""ctypes binding of include/roboy_b200.h -- the only door into the CUDA library.
+
+There is no CPU fallback: if libroboy_b200.so is missing this raises, and if there is no CUDA
+device `roboy_create` fails (ROBOY_E_CUDA) and `check()` raises.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+ABI_VERSION = 1
+DIM_JOINT, DIM_ACTION, DIM_OBS = 3, 8, 9
+
+STEP_MASK = 0x00FFFFFF
+F_HELD_ZERO64 = 1 << 24
+F_HELD_INFEASIBLE = 1 << 25
+ERR_ACTION, ERR_REWARD_RANGE, ERR_GOAL_BOUNDS = 1, 2, 4
+STAT_NAMES = ("steps", "episodes", "successes", "timeouts", "sum_reward", "sum_episode_len", "holds", "violations")
+(BUF_GOAL, BUF_STEP_FLAGS, BUF_HELD, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_STATS, BUF_TERMINAL_OBS) = range(8)
+
+
+class RoboyCfg(ctypes.Structure):
+    """struct roboy_cfg (include/roboy_b200.h); field order is ABI."""
+    _fields_ = [
+        ("n_envs", ctypes.c_uint64), ("env_id_base", ctypes.c_uint64), ("seed", ctypes.c_uint64),
+        ("angle_low", ctypes.c_float), ("angle_high", ctypes.c_float),
+        ("vel_low", ctypes.c_float), ("vel_high", ctypes.c_float),
+        ("act_low", ctypes.c_float), ("act_high", ctypes.c_float),
+        ("max_episode_len", ctypes.c_int32), ("joint_vel_penalty", ctypes.c_int32),
+        ("bonus_for_goal", ctypes.c_int32), ("auto_reset", ctypes.c_int32),
+        ("penalty_boundary", ctypes.c_float), ("bonus_goal", ctypes.c_float),
+        ("reward_lo", ctypes.c_double), ("reward_hi", ctypes.c_double),
+    ]
+
+
+_vp, _u64, _i32, _int = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int
+_cfgp = ctypes.POINTER(RoboyCfg)
+
+# name -> (restype, argtypes); every symbol include/roboy_b200.h declares
+SIGNATURES = {
+    "roboy_abi_version": (_int, []),
+    "roboy_last_error": (ctypes.c_char_p, []),
+    "roboy_cfg_msj": (_int, [_cfgp]),
+    "roboy_create": (_int, [_cfgp, _int, ctypes.POINTER(_vp)]),
+    "roboy_destroy": (_int, [_vp]),
+    "roboy_set_reward_range": (_int, [_vp, ctypes.c_double, ctypes.c_double]),
+    "roboy_reset": (_int, [_vp, _vp, _vp, _vp]),
+    "roboy_step": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "roboy_step_host": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "roboy_set_terminal_obs": (_int, [_vp, _vp]),
+    "roboy_compute_reward": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "roboy_set_goal": (_int, [_vp, _u64, _vp, _vp, _vp]),
+    "roboy_set_state": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "roboy_set_step_num": (_int, [_vp, _u64, _vp, _vp, _vp]),
+    "roboy_read_state": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "roboy_sim_step": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "roboy_sim_reset": (_int, [_vp, _vp, _vp]),
+    "roboy_new_goal": (_int, [_vp, _vp, _vp]),
+    "roboy_set_flags": (_int, [_vp, _int, _int, _int]),
+    "roboy_set_seed": (_int, [_vp, _u64]),
+    "roboy_buffer": (_int, [_vp, _int, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]),
+    "roboy_export_dlpack": (_vp, [_vp, _int]),
+    "roboy_get_counter": (_int, [_vp, ctypes.POINTER(_u64)]),
+    "roboy_set_counter": (_int, [_vp, _u64]),
+    "roboy_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_double), _vp]),
+    "roboy_clear_stats": (_int, [_vp, _vp]),
+    "roboy_clear_errors": (_int, [_vp, _vp]),
+    "roboy_errors": (_int, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(_u64), _vp]),
+    "roboy_launch_count": (_int, [_vp, ctypes.POINTER(_u64)]),
+    "roboy_step_geometry": (_int, [_vp, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
+}
+
+_lib = None
+
+
+class RoboyNativeError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load libroboy_b200.so (building is NOT attempted here: see gym_roboy_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RoboyNativeError(
+            "CUDA library not built: {} is missing. Build it with `python -m gym_roboy_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU fallback.".format(path))
+    L = ctypes.CDLL(path)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if L.roboy_abi_version() != ABI_VERSION:
+        raise RoboyNativeError("ABI mismatch: library {} vs binding {}".format(L.roboy_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+def check(code):
+    if code != 0:
+        msg = load().roboy_last_error()
+        raise RoboyNativeError("roboy_b200 call failed ({}): {}".format(code, (msg or b"").decode()))
+
+
+def dlpack_capsule(managed_tensor_ptr):
+    """Wrap a DLManagedTensor* in the PyCapsule torch.from_dlpack() consumes."""
+    if not managed_tensor_ptr:
+        check(-1)
+    new_capsule = ctypes.pythonapi.PyCapsule_New
+    new_capsule.restype = ctypes.py_object
+    new_capsule.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
+    return new_capsule(managed_tensor_ptr, b"dltensor", None)

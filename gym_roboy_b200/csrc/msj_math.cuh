@@ -1,0 +1,194 @@
+// Device arithmetic of the env step: normalisation, goal distance, reward, done test.
+//
+// Written against the reference's operation ORDER and numpy's dtype promotions, because the
+// done mask has to be bit-exact (paths relative to gym_roboy/ in Roboy/gym-roboy):
+//   normalisation   envs/robots/roboy_robot.py:93-95   (2*v - max - min) / (max - min)
+//   _l2_distance    envs/roboy_env.py:137-140          subtract, NaN -> 0, np.linalg.norm
+//   compute_reward  envs/roboy_env.py:92-112
+//   _did_reach_goal envs/roboy_env.py:125-134
+// np.linalg.norm(float32[3]) accumulates the float32 products in a double (OpenBLAS sdot) and
+// rounds once to float32 before the float32 sqrt; float64 operands sum sequentially.  All
+// arithmetic below uses the round-to-nearest intrinsics so nvcc never contracts a multiply and
+// an add into an FMA (numpy does not fuse).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+namespace roboy {
+
+struct RobotConsts {
+    float a_hi, a_lo, a_span;  // joint angle space (msj_robot.py:9), a_span = fl32(a_hi - a_lo)
+    float v_hi, v_lo, v_span;  // joint velocity space (msj_robot.py:10)
+    float thr_angle;           // fl32(_MAX_DISTANCE_JOINT_ANGLE / 200)  roboy_env.py:24,127
+    float thr_vel;             // fl32(_MAX_DISTANCE_JOINT_VELS / 5)     roboy_env.py:25,130
+    float penalty_boundary;    // roboy_env.py:26
+    float bonus_goal;          // roboy_env.py:27
+    double reward_lo, reward_hi;  // roboy_env.py:30,109
+};
+
+__device__ __forceinline__ float normalize32(float v, float hi, float lo, float span) {
+    float t = __fmul_rn(2.0f, v);
+    t = __fsub_rn(t, hi);
+    t = __fsub_rn(t, lo);
+    return __fdiv_rn(t, span);
+}
+
+__device__ __forceinline__ double normalize64(double v, float hi, float lo, float span) {
+    double t = __dmul_rn(2.0, v);
+    t = __dsub_rn(t, (double)hi);
+    t = __dsub_rn(t, (double)lo);
+    return __ddiv_rn(t, (double)span);
+}
+
+__device__ __forceinline__ float nan_to_zero(float d) { return (d != d) ? 0.0f : d; }
+__device__ __forceinline__ double nan_to_zero(double d) { return (d != d) ? 0.0 : d; }
+
+// ||a - b||_2 for float32 operands, exactly as numpy/OpenBLAS evaluate it.
+__device__ __forceinline__ float l2_f32(float a0, float a1, float a2, float b0, float b1, float b2) {
+    const float d0 = nan_to_zero(__fsub_rn(a0, b0));
+    const float d1 = nan_to_zero(__fsub_rn(a1, b1));
+    const float d2 = nan_to_zero(__fsub_rn(a2, b2));
+    double s = (double)__fmul_rn(d0, d0);
+    s = __dadd_rn(s, (double)__fmul_rn(d1, d1));
+    s = __dadd_rn(s, (double)__fmul_rn(d2, d2));
+    return __fsqrt_rn((float)s);
+}
+
+// ||a - b||_2 once numpy has promoted to float64.
+__device__ __forceinline__ double l2_f64(double a0, double a1, double a2, double b0, double b1, double b2) {
+    const double d0 = nan_to_zero(__dsub_rn(a0, b0));
+    const double d1 = nan_to_zero(__dsub_rn(a1, b1));
+    const double d2 = nan_to_zero(__dsub_rn(a2, b2));
+    double s = __dmul_rn(d0, d0);
+    s = __dadd_rn(s, __dmul_rn(d1, d1));
+    s = __dadd_rn(s, __dmul_rn(d2, d2));
+    return __dsqrt_rn(s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hot path: state freshly sampled (float32, feasible), goal angles float32, goal velocities
+// the float64 zeros of roboy_env.py:23.
+// ---------------------------------------------------------------------------------------------
+template <bool PENALTY, bool BONUS>
+__device__ __forceinline__ void reward_reached_sampled(const float q[3], const float qd[3], const float g[3],
+                                                       const RobotConsts &c, float &reward_out, bool &reached,
+                                                       bool &violation) {
+    // _did_reach_goal: angles in float32 (:126-127); velocities in float64 (:129-130), which
+    // only matters -- and is only evaluated -- once the angles are close.
+    reached = false;
+    if (l2_f32(q[0], q[1], q[2], g[0], g[1], g[2]) < c.thr_angle) {
+        reached = l2_f64((double)qd[0], (double)qd[1], (double)qd[2], 0.0, 0.0, 0.0) < (double)c.thr_vel;
+    }
+    // compute_reward :94-96
+    float nq[3], ng[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        nq[k] = normalize32(q[k], c.a_hi, c.a_lo, c.a_span);
+        ng[k] = normalize32(g[k], c.a_hi, c.a_lo, c.a_span);
+    }
+    float r32 = -expf(l2_f32(nq[0], nq[1], nq[2], ng[0], ng[1], ng[2]));
+    double r64 = 0.0;
+    if (PENALTY) {  // :98-100, float64 because the goal velocities are
+        const double gz = normalize64(0.0, c.v_hi, c.v_lo, c.v_span);
+        const double v = l2_f64((double)normalize32(qd[0], c.v_hi, c.v_lo, c.v_span),
+                                (double)normalize32(qd[1], c.v_hi, c.v_lo, c.v_span),
+                                (double)normalize32(qd[2], c.v_hi, c.v_lo, c.v_span), gz, gz, gz);
+        r64 = __dmul_rn(__dadd_rn(v, 1.0), (double)__fsub_rn(r32, expf(r32)));
+        if (BONUS && reached) r64 = __dadd_rn(r64, (double)c.bonus_goal);  // :105-107
+        reward_out = (float)r64;
+    } else {
+        if (BONUS && reached) r32 = __fadd_rn(r32, c.bonus_goal);
+        r64 = (double)r32;
+        reward_out = r32;
+    }
+    violation = !(c.reward_lo <= r64 && r64 <= c.reward_hi);  // :109
+}
+
+// ---------------------------------------------------------------------------------------------
+// General path: any state dtype the reference can hold (float32 sample / injected state, or the
+// float64 zero state), feasibility flag, optional float32 goal velocities.  Used by the hold
+// branch of the step, and by the stand-alone compute_reward kernel.
+// ---------------------------------------------------------------------------------------------
+struct HeldState {
+    double q[3], qd[3];  // float32-valued unless is64
+    bool is64;           // numpy dtype of the arrays: float64 zero state vs float32
+    bool feasible;
+};
+
+static __device__ __noinline__ void reward_reached_general(const HeldState &s, const float g[3], bool has_goal_qd,
+                                                    const float gqd[3], bool penalty, bool bonus,
+                                                    const RobotConsts &c, double &reward_out, bool &reached,
+                                                    bool &violation) {
+    bool angles_close, vels_close;
+    if (!s.is64) {
+        angles_close = l2_f32((float)s.q[0], (float)s.q[1], (float)s.q[2], g[0], g[1], g[2]) < c.thr_angle;
+    } else {
+        angles_close = l2_f64(s.q[0], s.q[1], s.q[2], (double)g[0], (double)g[1], (double)g[2]) < (double)c.thr_angle;
+    }
+    if (!s.is64 && has_goal_qd) {
+        vels_close = l2_f32((float)s.qd[0], (float)s.qd[1], (float)s.qd[2], gqd[0], gqd[1], gqd[2]) < c.thr_vel;
+    } else {
+        const double v0 = has_goal_qd ? (double)gqd[0] : 0.0, v1 = has_goal_qd ? (double)gqd[1] : 0.0,
+                     v2 = has_goal_qd ? (double)gqd[2] : 0.0;
+        vels_close = l2_f64(s.qd[0], s.qd[1], s.qd[2], v0, v1, v2) < (double)c.thr_vel;
+    }
+    reached = angles_close && vels_close;
+
+    float ng[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ng[k] = normalize32(g[k], c.a_hi, c.a_lo, c.a_span);
+    float r32 = 0.0f;
+    double r = 0.0;
+    bool r_is64;
+    if (!s.is64) {
+        const float n0 = normalize32((float)s.q[0], c.a_hi, c.a_lo, c.a_span);
+        const float n1 = normalize32((float)s.q[1], c.a_hi, c.a_lo, c.a_span);
+        const float n2 = normalize32((float)s.q[2], c.a_hi, c.a_lo, c.a_span);
+        r32 = -expf(l2_f32(n0, n1, n2, ng[0], ng[1], ng[2]));
+        r = (double)r32;
+        r_is64 = false;
+    } else {
+        const double n0 = normalize64(s.q[0], c.a_hi, c.a_lo, c.a_span);
+        const double n1 = normalize64(s.q[1], c.a_hi, c.a_lo, c.a_span);
+        const double n2 = normalize64(s.q[2], c.a_hi, c.a_lo, c.a_span);
+        r = -exp(l2_f64(n0, n1, n2, (double)ng[0], (double)ng[1], (double)ng[2]));
+        r_is64 = true;
+    }
+    if (penalty) {
+        if (!s.is64 && has_goal_qd) {  // everything float32 (roboy_env.py:40-49 path)
+            const float v = l2_f32(normalize32((float)s.qd[0], c.v_hi, c.v_lo, c.v_span),
+                                   normalize32((float)s.qd[1], c.v_hi, c.v_lo, c.v_span),
+                                   normalize32((float)s.qd[2], c.v_hi, c.v_lo, c.v_span),
+                                   normalize32(gqd[0], c.v_hi, c.v_lo, c.v_span),
+                                   normalize32(gqd[1], c.v_hi, c.v_lo, c.v_span),
+                                   normalize32(gqd[2], c.v_hi, c.v_lo, c.v_span));
+            r32 = __fmul_rn(__fadd_rn(v, 1.0f), __fsub_rn(r32, expf(r32)));
+            r = (double)r32;
+        } else {
+            double nv[3], ngv[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                nv[k] = s.is64 ? normalize64(s.qd[k], c.v_hi, c.v_lo, c.v_span)
+                               : (double)normalize32((float)s.qd[k], c.v_hi, c.v_lo, c.v_span);
+                ngv[k] = has_goal_qd ? (double)normalize32(gqd[k], c.v_hi, c.v_lo, c.v_span)
+                                     : normalize64(0.0, c.v_hi, c.v_lo, c.v_span);
+            }
+            const double v = l2_f64(nv[0], nv[1], nv[2], ngv[0], ngv[1], ngv[2]);
+            const double diff = r_is64 ? __dsub_rn(r, exp(r)) : (double)__fsub_rn(r32, expf(r32));
+            r = __dmul_rn(__dadd_rn(v, 1.0), diff);
+            r_is64 = true;
+        }
+    }
+    if (!s.feasible) {  // :102-103  float32 - int64 scalar promotes to float64
+        r = __dsub_rn(r, (double)c.penalty_boundary);
+        r_is64 = true;
+    }
+    if (reached && bonus) {  // :105-107
+        if (r_is64) r = __dadd_rn(r, (double)c.bonus_goal);
+        else r = (double)__fadd_rn((float)r, c.bonus_goal);
+    }
+    violation = !(c.reward_lo <= r && r <= c.reward_hi);
+    reward_out = r;
+}
+
+}  // namespace roboy

@@ -1,0 +1,677 @@
+// C-ABI of the B200-native batched MSJ env step (see include/roboy_b200.h for the contract and
+// the reference lines each entry point replaces).  Host side only: handle, HBM allocation,
+// launch bookkeeping, the pinned/pipelined host-buffer path and DLPack export.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+
+#include "../../include/roboy_b200.h"
+#include "dlpack_min.h"
+#include "roboy_kernels.cuh"
+
+using namespace roboy;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(ROBOY_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kHostStreams = 4;            // ring of streams for the host-buffer pipeline
+constexpr uint64_t kHostChunkEnvs = 1u << 18;  // 262,144 envs per pipeline stage (8 MiB in, 10.25 MiB out)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// roboy_env.py:24-25 _l2_distance(space.low, space.high) in float32, numpy evaluation order
+// (float32 products accumulated in double, rounded to float32, float32 sqrt).
+float box_diagonal_f32(float lo, float hi, int dim) {
+    volatile float d = lo - hi;
+    volatile float p = d * d;
+    double s = 0.0;
+    for (int k = 0; k < dim; ++k) s += (double)p;
+    return sqrtf((float)s);
+}
+
+}  // namespace
+
+struct roboy_env {
+    roboy_cfg cfg;
+    int device = 0;
+    int sm_count = 148;
+    std::atomic<int> refs{1};
+    uint64_t t = 0;         // Philox call counter
+    uint32_t goal_sub = 0;  // goal draws already made at this call counter (un-fused API)
+    uint64_t launches = 0;  // kernels launched through this handle
+    PhiloxKeys keys;
+    RobotConsts consts;
+    float act_slope = 0.f;
+    // HBM
+    float *goal = nullptr;
+    uint32_t *step_flags = nullptr;
+    float *held = nullptr;
+    float *obs = nullptr;
+    float *reward = nullptr;
+    uint8_t *done = nullptr;
+    double *stats = nullptr;
+    uint32_t *err_flags = nullptr;
+    unsigned long long *first_bad = nullptr;
+    float *terminal_obs = nullptr;  // caller-owned
+    // host-buffer pipeline (lazily created)
+    float *actions_stage = nullptr;  // device copy of the host actions
+    cudaStream_t hs[kHostStreams] = {};
+    bool host_ready = false;
+};
+
+namespace {
+
+void free_env(roboy_env *e) {
+    DeviceGuard g(e->device);
+    cudaFree(e->goal);
+    cudaFree(e->step_flags);
+    cudaFree(e->held);
+    cudaFree(e->obs);
+    cudaFree(e->reward);
+    cudaFree(e->done);
+    cudaFree(e->stats);
+    cudaFree(e->err_flags);
+    cudaFree(e->first_bad);
+    cudaFree(e->actions_stage);
+    if (e->host_ready)
+        for (int i = 0; i < kHostStreams; ++i) cudaStreamDestroy(e->hs[i]);
+    delete e;
+}
+
+void unref(roboy_env *e) {
+    if (e->refs.fetch_sub(1) == 1) free_env(e);
+}
+
+void fill_step_params(roboy_env *e, StepParams &p, const float *actions, float *obs, float *reward, uint8_t *done) {
+    p.n = e->cfg.n_envs;
+    p.e_begin = 0;
+    p.e_end = e->cfg.n_envs;
+    p.gid_base = e->cfg.env_id_base;
+    p.t = e->t;
+    p.keys = e->keys;
+    p.c = e->consts;
+    p.act_in_hi = 1.0f;   // roboy_env.py:31
+    p.act_in_lo = -1.0f;
+    p.act_hi = e->cfg.act_high;
+    p.act_slope = e->act_slope;
+    p.max_len = e->cfg.max_episode_len;
+    p.actions = actions;
+    p.goal = e->goal;
+    p.step_flags = e->step_flags;
+    p.held = e->held;
+    p.obs = obs ? obs : e->obs;
+    p.reward = reward ? reward : e->reward;
+    p.done = done ? done : e->done;
+    p.terminal_obs = e->terminal_obs;
+    p.stats = e->stats;
+    p.err_flags = e->err_flags;
+    p.first_bad = e->first_bad;
+}
+
+void advance_counter(roboy_env *env) {
+    env->t += 1;
+    env->goal_sub = 0;
+}
+
+int check_env(roboy_env *e) {
+    if (!e) return fail(ROBOY_E_ARG, "NULL handle");
+    return ROBOY_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int roboy_abi_version(void) { return ROBOY_B200_ABI_VERSION; }
+const char *roboy_last_error(void) { return g_err; }
+
+int roboy_cfg_msj(roboy_cfg *cfg) {
+    if (!cfg) return fail(ROBOY_E_ARG, "NULL cfg");
+    memset(cfg, 0, sizeof(*cfg));
+    const double pi = 3.14159265358979323846;
+    cfg->n_envs = 1;
+    cfg->angle_high = (float)pi;  // msj_robot.py:9  Box(low=-np.pi, high=np.pi, dtype float32)
+    cfg->angle_low = (float)(-pi);
+    cfg->vel_high = (float)(pi / 6);  // msj_robot.py:10
+    cfg->vel_low = (float)(-pi / 6);
+    cfg->act_high = (float)0.3;  // msj_robot.py:15-16
+    cfg->act_low = (float)(-0.3);
+    cfg->max_episode_len = 400;      // roboy_env.py:28
+    cfg->joint_vel_penalty = 0;      // roboy_env.py:13
+    cfg->bonus_for_goal = 1;         // roboy_env.py:14
+    cfg->auto_reset = 1;
+    cfg->penalty_boundary = 1.0f;    // roboy_env.py:26
+    cfg->bonus_goal = 1000.0f;       // roboy_env.py:27
+    cfg->reward_lo = -INFINITY;
+    cfg->reward_hi = INFINITY;
+    return ROBOY_OK;
+}
+
+int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
+    if (!cfg || !out) return fail(ROBOY_E_ARG, "NULL argument");
+    *out = nullptr;
+    if (cfg->n_envs == 0) return fail(ROBOY_E_ARG, "n_envs must be > 0");
+    if (!(cfg->angle_high > cfg->angle_low) || !(cfg->vel_high > cfg->vel_low) || !(cfg->act_high > cfg->act_low))
+        return fail(ROBOY_E_ARG, "empty robot space");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(ROBOY_E_CUDA, "no CUDA device: roboy_b200 has no CPU path");
+    }
+    if (device < 0 || device >= n_dev) return fail(ROBOY_E_ARG, "device %d out of range (%d devices)", device, n_dev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ROBOY_E_CUDA, "cudaSetDevice(%d) failed", device);
+
+    roboy_env *e = new (std::nothrow) roboy_env();
+    if (!e) return fail(ROBOY_E_ALLOC, "out of host memory");
+    e->cfg = *cfg;
+    e->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+    e->keys = make_philox_keys(cfg->seed);
+    RobotConsts &c = e->consts;
+    c.a_hi = cfg->angle_high;
+    c.a_lo = cfg->angle_low;
+    c.a_span = cfg->angle_high - cfg->angle_low;
+    c.v_hi = cfg->vel_high;
+    c.v_lo = cfg->vel_low;
+    c.v_span = cfg->vel_high - cfg->vel_low;
+    c.thr_angle = box_diagonal_f32(cfg->angle_low, cfg->angle_high, ROBOY_DIM_JOINT) / 200.0f;  // roboy_env.py:127
+    c.thr_vel = box_diagonal_f32(cfg->vel_low, cfg->vel_high, ROBOY_DIM_JOINT) / 5.0f;          // roboy_env.py:130
+    c.penalty_boundary = fabsf(cfg->penalty_boundary);
+    c.bonus_goal = cfg->bonus_goal;
+    c.reward_lo = cfg->reward_lo;
+    c.reward_hi = cfg->reward_hi;
+    e->act_slope = (cfg->act_high - cfg->act_low) / (1.0f - (-1.0f));  // roboy_env.py:157, float32
+
+    const uint64_t n = cfg->n_envs;
+    cudaError_t err = cudaSuccess;
+    auto alloc = [&](void **p, size_t bytes) {
+        if (err == cudaSuccess) err = cudaMalloc(p, bytes);
+    };
+    alloc((void **)&e->goal, sizeof(float) * 3 * n);
+    alloc((void **)&e->step_flags, sizeof(uint32_t) * n);
+    alloc((void **)&e->held, sizeof(float) * 6 * n);
+    alloc((void **)&e->obs, sizeof(float) * ROBOY_DIM_OBS * n);
+    alloc((void **)&e->reward, sizeof(float) * n);
+    alloc((void **)&e->done, n);
+    alloc((void **)&e->stats, sizeof(double) * ROBOY_STAT_COUNT);
+    alloc((void **)&e->err_flags, sizeof(uint32_t));
+    alloc((void **)&e->first_bad, sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMemset(e->stats, 0, sizeof(double) * ROBOY_STAT_COUNT);
+    if (err == cudaSuccess) err = cudaMemset(e->err_flags, 0, sizeof(uint32_t));
+    if (err == cudaSuccess) err = cudaMemset(e->first_bad, 0xff, sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMemset(e->done, 0, n);
+    if (err == cudaSuccess) {
+        InitParams ip{};
+        ip.n = n;
+        ip.gid_base = cfg->env_id_base;
+        ip.t = 0;
+        ip.keys = e->keys;
+        ip.a_lo = c.a_lo;
+        ip.a_span = c.a_span;
+        ip.goal = e->goal;
+        ip.step_flags = e->step_flags;
+        ip.held = e->held;
+        ip.mask = nullptr;
+        ip.obs = nullptr;
+        err = launch_init_or_reset(ip, 0);
+        e->launches++;
+        e->goal_sub = 1;  // construction consumed goal draw 0 of counter 0
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(0);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        int code = err == cudaErrorMemoryAllocation ? ROBOY_E_ALLOC : ROBOY_E_CUDA;
+        fail(code, "roboy_create(n_envs=%llu): %s", (unsigned long long)n, cudaGetErrorString(err));
+        free_env(e);
+        return code;
+    }
+    *out = e;
+    return ROBOY_OK;
+}
+
+int roboy_destroy(roboy_env *env) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    {
+        DeviceGuard g(env->device);
+        cudaDeviceSynchronize();
+    }
+    unref(env);
+    return ROBOY_OK;
+}
+
+int roboy_set_reward_range(roboy_env *env, double lo, double hi) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    env->cfg.reward_lo = env->consts.reward_lo = lo;
+    env->cfg.reward_hi = env->consts.reward_hi = hi;
+    return ROBOY_OK;
+}
+
+int roboy_reset(roboy_env *env, const uint8_t *mask_dev, float *obs_dev, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    DeviceGuard g(env->device);
+    advance_counter(env);
+    env->goal_sub = 1;  // the reset itself consumed goal draw 0 of this counter value
+    InitParams ip{};
+    ip.n = env->cfg.n_envs;
+    ip.gid_base = env->cfg.env_id_base;
+    ip.t = env->t;
+    ip.keys = env->keys;
+    ip.a_lo = env->consts.a_lo;
+    ip.a_span = env->consts.a_span;
+    ip.goal = env->goal;
+    ip.step_flags = env->step_flags;
+    ip.held = nullptr;
+    ip.mask = mask_dev;
+    ip.obs = obs_dev ? obs_dev : env->obs;
+    CUDA_TRY(launch_init_or_reset(ip, (cudaStream_t)stream));
+    env->launches++;
+    return ROBOY_OK;
+}
+
+int roboy_step(roboy_env *env, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
+               void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!actions_dev) return fail(ROBOY_E_ARG, "actions_dev is NULL");
+    if (((uintptr_t)actions_dev & 15) || ((uintptr_t)(obs_dev ? obs_dev : env->obs) & 15))
+        return fail(ROBOY_E_ARG, "actions and obs must be 16-byte aligned");
+    DeviceGuard g(env->device);
+    advance_counter(env);
+    env->goal_sub = 1;  // done envs consume goal draw 0 of this counter value
+    StepParams p;
+    fill_step_params(env, p, actions_dev, obs_dev, reward_dev, done_dev);
+    CUDA_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset, env->sm_count,
+                         (cudaStream_t)stream));
+    env->launches++;
+    return ROBOY_OK;
+}
+
+int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, float *reward_host,
+                    uint8_t *done_host) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!actions_host || !obs_host || !reward_host || !done_host) return fail(ROBOY_E_ARG, "NULL host buffer");
+    DeviceGuard g(env->device);
+    const uint64_t n = env->cfg.n_envs;
+    if (!env->host_ready) {
+        CUDA_TRY(cudaMalloc((void **)&env->actions_stage, sizeof(float) * ROBOY_DIM_ACTION * n));
+        for (int i = 0; i < kHostStreams; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&env->hs[i], cudaStreamNonBlocking));
+        env->host_ready = true;
+    }
+    advance_counter(env);
+    env->goal_sub = 1;
+    StepParams p;
+    fill_step_params(env, p, env->actions_stage, nullptr, nullptr, nullptr);
+    // Pipeline: per stage H2D(actions) -> step kernel -> D2H(obs, reward, done) on one stream of a
+    // ring, so the copy engines of both directions and the SMs overlap across stages.
+    int stage = 0;
+    for (uint64_t b = 0; b < n; b += kHostChunkEnvs, ++stage) {
+        const uint64_t eend = b + kHostChunkEnvs < n ? b + kHostChunkEnvs : n;
+        const uint64_t cnt = eend - b;
+        cudaStream_t s = env->hs[stage % kHostStreams];
+        CUDA_TRY(cudaMemcpyAsync(env->actions_stage + b * ROBOY_DIM_ACTION, actions_host + b * ROBOY_DIM_ACTION,
+                                 sizeof(float) * ROBOY_DIM_ACTION * cnt, cudaMemcpyHostToDevice, s));
+        p.e_begin = b;
+        p.e_end = eend;
+        CUDA_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
+                             env->sm_count, s));
+        env->launches++;
+        CUDA_TRY(cudaMemcpyAsync(obs_host + b * ROBOY_DIM_OBS, env->obs + b * ROBOY_DIM_OBS,
+                                 sizeof(float) * ROBOY_DIM_OBS * cnt, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(reward_host + b, env->reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(done_host + b, env->done + b, cnt, cudaMemcpyDeviceToHost, s));
+    }
+    const int used = stage < kHostStreams ? stage : kHostStreams;
+    for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamSynchronize(env->hs[i]));
+    return ROBOY_OK;
+}
+
+int roboy_set_terminal_obs(roboy_env *env, float *terminal_obs_dev) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    env->terminal_obs = terminal_obs_dev;
+    return ROBOY_OK;
+}
+
+int roboy_compute_reward(roboy_env *env, uint64_t k, const float *q_dev, const float *qd_dev,
+                         const uint8_t *feasible_dev, const float *goal_q_dev, const float *goal_qd_dev,
+                         double *reward_dev, uint8_t *reached_dev, int check_range, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!q_dev || !qd_dev || !goal_q_dev || !reward_dev) return fail(ROBOY_E_ARG, "NULL device pointer");
+    DeviceGuard g(env->device);
+    RewardParams p{};
+    p.k = k;
+    p.c = env->consts;
+    p.penalty = env->cfg.joint_vel_penalty != 0;
+    p.bonus = env->cfg.bonus_for_goal != 0;
+    p.check_range = check_range != 0;
+    p.gid_base = env->cfg.env_id_base;
+    p.q = q_dev;
+    p.qd = qd_dev;
+    p.goal_q = goal_q_dev;
+    p.goal_qd = goal_qd_dev;
+    p.feasible = feasible_dev;
+    p.reward = reward_dev;
+    p.reached = reached_dev;
+    p.stats = env->stats;
+    p.err_flags = env->err_flags;
+    p.first_bad = env->first_bad;
+    CUDA_TRY(launch_compute_reward(p, (cudaStream_t)stream));
+    env->launches++;
+    return ROBOY_OK;
+}
+
+static int scatter_common(roboy_env *env, ScatterParams &p, uint64_t k, const int64_t *idx, void *stream) {
+    DeviceGuard g(env->device);
+    p.k = k;
+    p.n = env->cfg.n_envs;
+    p.idx = idx;
+    p.a_lo = env->consts.a_lo;
+    p.a_hi = env->consts.a_hi;
+    p.gid_base = env->cfg.env_id_base;
+    p.goal = env->goal;
+    p.held = env->held;
+    p.step_flags = env->step_flags;
+    p.err_flags = env->err_flags;
+    p.first_bad = env->first_bad;
+    CUDA_TRY(launch_scatter(p, (cudaStream_t)stream));
+    env->launches++;
+    return ROBOY_OK;
+}
+
+int roboy_set_goal(roboy_env *env, uint64_t k, const int64_t *idx_dev, const float *goal_q_dev, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!goal_q_dev) return fail(ROBOY_E_ARG, "goal_q_dev is NULL");
+    ScatterParams p{};
+    p.goal_q = goal_q_dev;
+    return scatter_common(env, p, k, idx_dev, stream);
+}
+
+int roboy_set_state(roboy_env *env, uint64_t k, const int64_t *idx_dev, const float *q_dev, const float *qd_dev,
+                    const uint8_t *feasible_dev, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!q_dev || !qd_dev) return fail(ROBOY_E_ARG, "q_dev/qd_dev is NULL");
+    ScatterParams p{};
+    p.q = q_dev;
+    p.qd = qd_dev;
+    p.feasible = feasible_dev;
+    return scatter_common(env, p, k, idx_dev, stream);
+}
+
+int roboy_set_step_num(roboy_env *env, uint64_t k, const int64_t *idx_dev, const int32_t *step_dev, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!step_dev) return fail(ROBOY_E_ARG, "step_dev is NULL");
+    ScatterParams p{};
+    p.step = step_dev;
+    return scatter_common(env, p, k, idx_dev, stream);
+}
+
+int roboy_read_state(roboy_env *env, uint64_t k, const int64_t *idx_dev, float *q_dev, float *qd_dev,
+                     uint8_t *feasible_dev, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!q_dev || !qd_dev) return fail(ROBOY_E_ARG, "q_dev/qd_dev is NULL");
+    ScatterParams p{};
+    p.out_q = q_dev;
+    p.out_qd = qd_dev;
+    p.out_feasible = feasible_dev;
+    return scatter_common(env, p, k, idx_dev, stream);
+}
+
+static void fill_sim_params(roboy_env *env, SimParams &p, int mode) {
+    p.mode = mode;
+    p.n = env->cfg.n_envs;
+    p.gid_base = env->cfg.env_id_base;
+    p.t = env->t;
+    p.sub = env->goal_sub;
+    p.keys = env->keys;
+    p.a_lo = env->consts.a_lo;
+    p.a_span = env->consts.a_span;
+    p.step_flags = env->step_flags;
+    p.held = env->held;
+    p.stats = env->stats;
+}
+
+int roboy_sim_step(roboy_env *env, const float *actions_dev, float *q_dev, float *qd_dev, uint8_t *feasible_dev,
+                   void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!actions_dev || !q_dev || !qd_dev) return fail(ROBOY_E_ARG, "NULL device pointer");
+    if ((uintptr_t)actions_dev & 15) return fail(ROBOY_E_ARG, "actions must be 16-byte aligned");
+    DeviceGuard g(env->device);
+    advance_counter(env);
+    SimParams p{};
+    fill_sim_params(env, p, 0);
+    p.actions = actions_dev;
+    p.out_q = q_dev;
+    p.out_qd = qd_dev;
+    p.out_feasible = feasible_dev;
+    CUDA_TRY(launch_sim(p, (cudaStream_t)stream));
+    env->launches++;
+    return ROBOY_OK;
+}
+
+int roboy_sim_reset(roboy_env *env, const uint8_t *mask_dev, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    DeviceGuard g(env->device);
+    advance_counter(env);
+    SimParams p{};
+    fill_sim_params(env, p, 1);
+    p.mask = mask_dev;
+    CUDA_TRY(launch_sim(p, (cudaStream_t)stream));
+    env->launches++;
+    return ROBOY_OK;
+}
+
+int roboy_new_goal(roboy_env *env, float *goal_q_dev, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!goal_q_dev) return fail(ROBOY_E_ARG, "goal_q_dev is NULL");
+    DeviceGuard g(env->device);
+    if (env->goal_sub >= 255) advance_counter(env);
+    SimParams p{};
+    fill_sim_params(env, p, 2);
+    p.out_q = goal_q_dev;
+    CUDA_TRY(launch_sim(p, (cudaStream_t)stream));
+    env->goal_sub += 1;
+    env->launches++;
+    return ROBOY_OK;
+}
+
+int roboy_set_flags(roboy_env *env, int joint_vel_penalty, int bonus_for_goal, int auto_reset) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    env->cfg.joint_vel_penalty = joint_vel_penalty != 0;
+    env->cfg.bonus_for_goal = bonus_for_goal != 0;
+    env->cfg.auto_reset = auto_reset != 0;
+    return ROBOY_OK;
+}
+
+int roboy_set_seed(roboy_env *env, uint64_t seed) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    env->cfg.seed = seed;
+    env->keys = make_philox_keys(seed);
+    return ROBOY_OK;
+}
+
+int roboy_buffer(roboy_env *env, int which, void **dev_ptr, uint64_t *nbytes) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    const uint64_t n = env->cfg.n_envs;
+    void *p = nullptr;
+    uint64_t b = 0;
+    switch (which) {
+        case ROBOY_BUF_GOAL: p = env->goal; b = 12 * n; break;
+        case ROBOY_BUF_STEP_FLAGS: p = env->step_flags; b = 4 * n; break;
+        case ROBOY_BUF_HELD: p = env->held; b = 24 * n; break;
+        case ROBOY_BUF_OBS: p = env->obs; b = 36 * n; break;
+        case ROBOY_BUF_REWARD: p = env->reward; b = 4 * n; break;
+        case ROBOY_BUF_DONE: p = env->done; b = n; break;
+        case ROBOY_BUF_STATS: p = env->stats; b = 8 * ROBOY_STAT_COUNT; break;
+        case ROBOY_BUF_TERMINAL_OBS: p = env->terminal_obs; b = env->terminal_obs ? 36 * n : 0; break;
+        default: return fail(ROBOY_E_ARG, "unknown buffer id %d", which);
+    }
+    if (dev_ptr) *dev_ptr = p;
+    if (nbytes) *nbytes = b;
+    return ROBOY_OK;
+}
+
+struct DlCtx {
+    roboy_env *env;
+    int64_t shape[2];
+};
+
+static void dl_deleter(DLManagedTensor *self) {
+    DlCtx *ctx = (DlCtx *)self->manager_ctx;
+    unref(ctx->env);
+    delete ctx;
+    delete self;
+}
+
+void *roboy_export_dlpack(roboy_env *env, int which) {
+    if (check_env(env)) return nullptr;
+    const int64_t n = (int64_t)env->cfg.n_envs;
+    DLManagedTensor *m = new (std::nothrow) DLManagedTensor();
+    DlCtx *ctx = new (std::nothrow) DlCtx();
+    if (!m || !ctx) {
+        delete m;
+        delete ctx;
+        fail(ROBOY_E_ALLOC, "out of host memory");
+        return nullptr;
+    }
+    DLTensor &t = m->dl_tensor;
+    t.device.device_type = kDLCUDA;
+    t.device.device_id = env->device;
+    t.strides = nullptr;
+    t.byte_offset = 0;
+    t.shape = ctx->shape;
+    t.dtype.lanes = 1;
+    t.dtype.code = kDLFloat;
+    t.dtype.bits = 32;
+    t.ndim = 2;
+    switch (which) {
+        case ROBOY_BUF_GOAL: t.data = env->goal; ctx->shape[0] = 3; ctx->shape[1] = n; break;
+        case ROBOY_BUF_HELD: t.data = env->held; ctx->shape[0] = 6; ctx->shape[1] = n; break;
+        case ROBOY_BUF_OBS: t.data = env->obs; ctx->shape[0] = n; ctx->shape[1] = ROBOY_DIM_OBS; break;
+        case ROBOY_BUF_REWARD: t.data = env->reward; t.ndim = 1; ctx->shape[0] = n; break;
+        case ROBOY_BUF_STEP_FLAGS:
+            t.data = env->step_flags; t.ndim = 1; ctx->shape[0] = n;
+            t.dtype.code = kDLInt;  // torch has no uint32 arithmetic; the top bits used stay below 2^31
+            break;
+        case ROBOY_BUF_DONE:
+            t.data = env->done; t.ndim = 1; ctx->shape[0] = n;
+            t.dtype.code = kDLUInt; t.dtype.bits = 8;
+            break;
+        case ROBOY_BUF_STATS:
+            t.data = env->stats; t.ndim = 1; ctx->shape[0] = ROBOY_STAT_COUNT;
+            t.dtype.bits = 64;
+            break;
+        default:
+            delete m;
+            delete ctx;
+            fail(ROBOY_E_ARG, "buffer %d cannot be exported", which);
+            return nullptr;
+    }
+    env->refs.fetch_add(1);
+    ctx->env = env;
+    m->manager_ctx = ctx;
+    m->deleter = dl_deleter;
+    return m;
+}
+
+int roboy_get_counter(roboy_env *env, uint64_t *t) {
+    if (check_env(env) || !t) return fail(ROBOY_E_ARG, "NULL argument");
+    *t = env->t;
+    return ROBOY_OK;
+}
+
+int roboy_set_counter(roboy_env *env, uint64_t t) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    env->t = t;
+    env->goal_sub = 1;
+    return ROBOY_OK;
+}
+
+int roboy_stats(roboy_env *env, double out_host[ROBOY_STAT_COUNT], void *stream) {
+    if (check_env(env) || !out_host) return fail(ROBOY_E_ARG, "NULL argument");
+    DeviceGuard g(env->device);
+    CUDA_TRY(cudaMemcpyAsync(out_host, env->stats, sizeof(double) * ROBOY_STAT_COUNT, cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return ROBOY_OK;
+}
+
+int roboy_clear_stats(roboy_env *env, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    DeviceGuard g(env->device);
+    CUDA_TRY(cudaMemsetAsync(env->stats, 0, sizeof(double) * ROBOY_STAT_COUNT, (cudaStream_t)stream));
+    CUDA_TRY(cudaMemsetAsync(env->err_flags, 0, sizeof(uint32_t), (cudaStream_t)stream));
+    CUDA_TRY(cudaMemsetAsync(env->first_bad, 0xff, sizeof(unsigned long long), (cudaStream_t)stream));
+    return ROBOY_OK;
+}
+
+int roboy_clear_errors(roboy_env *env, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    DeviceGuard g(env->device);
+    CUDA_TRY(cudaMemsetAsync(env->err_flags, 0, sizeof(uint32_t), (cudaStream_t)stream));
+    CUDA_TRY(cudaMemsetAsync(env->first_bad, 0xff, sizeof(unsigned long long), (cudaStream_t)stream));
+    return ROBOY_OK;
+}
+
+int roboy_errors(roboy_env *env, uint32_t *err_flags, uint64_t *first_bad_env, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    DeviceGuard g(env->device);
+    uint32_t f = 0;
+    unsigned long long b = 0;
+    CUDA_TRY(cudaMemcpyAsync(&f, env->err_flags, sizeof(f), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpyAsync(&b, env->first_bad, sizeof(b), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (err_flags) *err_flags = f;
+    if (first_bad_env) *first_bad_env = (uint64_t)b;
+    return ROBOY_OK;
+}
+
+int roboy_launch_count(roboy_env *env, uint64_t *launches) {
+    if (check_env(env) || !launches) return fail(ROBOY_E_ARG, "NULL argument");
+    *launches = env->launches;
+    return ROBOY_OK;
+}
+
+int roboy_step_geometry(roboy_env *env, int *grid, int *block, int *smem_bytes) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    DeviceGuard g(env->device);
+    const LaunchGeom geo = step_geometry(env->cfg.n_envs, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal,
+                                         env->cfg.auto_reset, env->sm_count);
+    if (grid) *grid = geo.grid;
+    if (block) *block = geo.block;
+    if (smem_bytes) *smem_bytes = geo.smem;
+    return ROBOY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// Kernel parameter blocks and launcher prototypes shared by roboy_kernels.cu and roboy_capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "msj_math.cuh"
+#include "philox.cuh"
+
+namespace roboy {
+
+constexpr int kStepBlock = 256;            // threads per CTA of the step kernel
+constexpr int kWarpsPerBlock = kStepBlock / 32;
+constexpr int kObsDim = 9, kActDim = 8;
+
+struct StepParams {
+    uint64_t n;         // envs in this shard (= leading dimension of the SoA arrays)
+    uint64_t e_begin;   // this launch covers local envs [e_begin, e_end); e_begin % 32 == 0
+    uint64_t e_end;
+    uint64_t gid_base;  // global id of local env 0
+    uint64_t t;         // Philox call counter of this launch
+    PhiloxKeys keys;
+    RobotConsts c;
+    float act_in_hi, act_in_lo;  // RoboyEnv.action_space bounds, roboy_env.py:31
+    float act_hi, act_slope;     // robot action space high and fl32((hi-lo)/(in_hi-in_lo)), roboy_env.py:157
+    int32_t max_len;             // roboy_env.py:28
+    // inputs / state / outputs (device pointers)
+    const float *__restrict__ actions;  // [n][8]
+    float *__restrict__ goal;           // [3][n]
+    uint32_t *__restrict__ step_flags;  // [n]
+    const float *__restrict__ held;     // [6][n]
+    float *__restrict__ obs;            // [n][9]
+    float *__restrict__ reward;         // [n]
+    uint8_t *__restrict__ done;         // [n]
+    float *__restrict__ terminal_obs;   // [n][9] or nullptr
+    double *__restrict__ stats;         // [ROBOY_STAT_COUNT]
+    uint32_t *__restrict__ err_flags;
+    unsigned long long *__restrict__ first_bad;
+};
+
+struct LaunchGeom {
+    int grid, block, smem;
+};
+
+LaunchGeom step_geometry(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, int sm_count);
+cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto_reset, int sm_count,
+                        cudaStream_t stream);
+
+struct InitParams {
+    uint64_t n, gid_base, t;
+    PhiloxKeys keys;
+    float a_lo, a_span;
+    float *goal;
+    uint32_t *step_flags;
+    float *held;             // nullptr for reset (held state becomes the zero state via the flag)
+    const uint8_t *mask;     // nullptr: all envs
+    float *obs;              // nullptr: do not write observations
+};
+// init (held != nullptr): RoboyEnv.__init__ / Stub.__init__;  reset (held == nullptr): RoboyEnv.reset
+cudaError_t launch_init_or_reset(const InitParams &p, cudaStream_t stream);
+
+struct RewardParams {
+    uint64_t k;
+    RobotConsts c;
+    bool penalty, bonus, check_range;
+    uint64_t gid_base;
+    const float *q, *qd, *goal_q, *goal_qd;  // [k][3]; goal_qd may be nullptr
+    const uint8_t *feasible;                 // [k] or nullptr
+    double *reward;                          // [k]
+    uint8_t *reached;                        // [k] or nullptr
+    double *stats;
+    uint32_t *err_flags;
+    unsigned long long *first_bad;
+};
+cudaError_t launch_compute_reward(const RewardParams &p, cudaStream_t stream);
+
+struct ScatterParams {
+    uint64_t k, n;
+    const int64_t *idx;
+    float a_lo, a_hi;
+    uint64_t gid_base;
+    // any of the following groups may be null
+    const float *goal_q;  // -> goal
+    const float *q, *qd;  // -> held (+ flags)
+    const uint8_t *feasible;
+    const int32_t *step;  // -> step_num
+    float *goal;
+    float *held;
+    uint32_t *step_flags;
+    uint32_t *err_flags;
+    unsigned long long *first_bad;
+    // gather (read_state): outputs
+    float *out_q, *out_qd;
+    uint8_t *out_feasible;
+};
+cudaError_t launch_scatter(const ScatterParams &p, cudaStream_t stream);
+
+// The un-fused plug-in calls of SimulationClient (simulation_client.py:11-23), batched:
+//   mode 0  forward_step_command(action in robot units)  -> state      (:36-40)
+//   mode 1  forward_reset_command()                      -> zero state (:42-44), masked
+//   mode 2  get_new_goal_joint_angles()                  -> goal draw  (:46-47), does not touch env state
+struct SimParams {
+    int mode;
+    uint64_t n, gid_base, t;
+    uint32_t sub;
+    PhiloxKeys keys;
+    float a_lo, a_span;
+    const float *actions;  // mode 0: [n][8] robot units
+    const uint8_t *mask;   // mode 1
+    uint32_t *step_flags;
+    const float *held;
+    float *out_q, *out_qd;  // [n][3]; mode 2 writes the goal to out_q
+    uint8_t *out_feasible;  // [n] or nullptr
+    double *stats;
+};
+cudaError_t launch_sim(const SimParams &p, cudaStream_t stream);
+
+}  // namespace roboy

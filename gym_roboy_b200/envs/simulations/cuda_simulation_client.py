@@ -1,0 +1,280 @@
+"""`CudaSimulationClient`: the in-process simulation client, batched on one B200.
+
+It plays the role `StubSimulationClient` plays in the reference
+(envs/simulations/simulation_client.py:26-47) -- the ROS-free, in-process client the unit tests
+use -- for `num_envs` environments at once, with all state resident in HBM:
+
+* the four `SimulationClient` calls (`read_state`, `forward_step_command`,
+  `forward_reset_command`, `get_new_goal_joint_angles`) run as (un-fused) kernels, so the
+  *reference's own* `RoboyEnv` can sit on top of this client unchanged (`num_envs=1`);
+* `step_fused` / `reset_fused` run the whole `RoboyEnv.step` / `reset` in one kernel; the
+  batched `RoboyEnv` of this package drives those.
+
+Everything goes through the C-ABI in include/roboy_b200.h; there is no CPU path.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from ... import _native
+from ..robots import MsjRobot, RobotState, RoboyRobot
+from .simulation_client import SimulationClient
+
+
+def _scalar_bound(space_side, what):
+    v = np.unique(np.asarray(space_side))
+    if v.size != 1:
+        raise ValueError("per-component {} bounds are not supported by the CUDA path".format(what))
+    return float(v[0])
+
+
+class CudaSimulationClient(SimulationClient):
+
+    def __init__(self, robot: RoboyRobot = None, num_envs: int = 1, device=None, seed: int = None,
+                 env_id_base: int = 0):
+        self.robot = robot if robot is not None else MsjRobot()
+        if self.robot.get_joint_angles_space().shape != (_native.DIM_JOINT,) or \
+                self.robot.get_action_space().shape != (_native.DIM_ACTION,):
+            raise ValueError("the CUDA path is built for 3 joint angles and 8 tendons (MSJ)")
+        self.num_envs = int(num_envs)
+        if self.num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        self._lib = _native.load()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cuda:0"
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _native.RoboyNativeError("CudaSimulationClient needs a CUDA device; there is no CPU fallback")
+        self.seed_value = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & (2 ** 64 - 1)
+        self.env_id_base = int(env_id_base)
+
+        cfg = _native.RoboyCfg()
+        _native.check(self._lib.roboy_cfg_msj(ctypes.byref(cfg)))
+        cfg.n_envs, cfg.env_id_base, cfg.seed = self.num_envs, self.env_id_base, self.seed_value
+        angles, vels, acts = (self.robot.get_joint_angles_space(), self.robot.get_joint_vels_space(),
+                              self.robot.get_action_space())
+        cfg.angle_low, cfg.angle_high = _scalar_bound(angles.low, "angle"), _scalar_bound(angles.high, "angle")
+        cfg.vel_low, cfg.vel_high = _scalar_bound(vels.low, "velocity"), _scalar_bound(vels.high, "velocity")
+        cfg.act_low, cfg.act_high = _scalar_bound(acts.low, "action"), _scalar_bound(acts.high, "action")
+        self._cfg = cfg
+        handle = ctypes.c_void_p()
+        _native.check(self._lib.roboy_create(ctypes.byref(cfg), self.device.index or 0, ctypes.byref(handle)))
+        self._h = handle
+
+        # zero-copy torch views of the HBM buffers the handle owns (DLPack)
+        self.goal = self._view(_native.BUF_GOAL)                # float32 [3, N]
+        self.step_flags = self._view(_native.BUF_STEP_FLAGS)    # int32   [N]
+        self.held = self._view(_native.BUF_HELD)                # float32 [6, N]
+        self.obs = self._view(_native.BUF_OBS)                  # float32 [N, 9]
+        self.reward = self._view(_native.BUF_REWARD)            # float32 [N]
+        self.done_u8 = self._view(_native.BUF_DONE)             # uint8   [N]
+        self.done = self.done_u8.view(torch.bool)
+        self.stats_tensor = self._view(_native.BUF_STATS)       # float64 [8]
+        self.terminal_obs = None
+        self._all_idx = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _view(self, which):
+        ptr = self._lib.roboy_export_dlpack(self._h, which)
+        return torch.from_dlpack(_native.dlpack_capsule(ptr))
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.roboy_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, x, dtype, shape=None):
+        t = torch.as_tensor(x, dtype=dtype, device=self.device).contiguous()
+        if shape is not None:
+            t = t.reshape(shape)
+        return t
+
+    def _idx(self, idx):
+        if idx is None:
+            if self._all_idx is None:
+                self._all_idx = torch.arange(self.num_envs, dtype=torch.int64, device=self.device)
+            return self._all_idx
+        return self._dev(idx, torch.int64).reshape(-1)
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def _state_out(self, q, qd, feasible):
+        if self.num_envs == 1:
+            return RobotState(q[0].cpu().numpy(), qd[0].cpu().numpy(), bool(feasible[0].item()))
+        return RobotState(q, qd, feasible.view(torch.bool))
+
+    # ------------------------------------------------------------------ SimulationClient API
+    def read_state(self) -> RobotState:
+        """simulation_client.py:33-34"""
+        n = self.num_envs
+        q = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        qd = torch.empty_like(q)
+        f = torch.empty(n, dtype=torch.uint8, device=self.device)
+        _native.check(self._lib.roboy_read_state(self._h, n, self._p(self._idx(None)), self._p(q), self._p(qd),
+                                                 self._p(f), self._stream()))
+        return self._state_out(q, qd, f)
+
+    def forward_step_command(self, action) -> RobotState:
+        """simulation_client.py:36-40.  `action`: 8 floats in robot units (or a `[N,8]` tensor)."""
+        if not torch.is_tensor(action):
+            assert self.robot.get_action_space().shape[0] == len(action)
+        a = self._dev(action, torch.float32, (self.num_envs, _native.DIM_ACTION))
+        n = self.num_envs
+        q = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        qd = torch.empty_like(q)
+        f = torch.empty(n, dtype=torch.uint8, device=self.device)
+        _native.check(self._lib.roboy_sim_step(self._h, self._p(a), self._p(q), self._p(qd), self._p(f), self._stream()))
+        return self._state_out(q, qd, f)
+
+    def forward_reset_command(self, mask=None) -> RobotState:
+        """simulation_client.py:42-44 (optionally only the envs selected by a `[N]` mask)."""
+        m = None if mask is None else self._dev(mask, torch.uint8, (self.num_envs,))
+        _native.check(self._lib.roboy_sim_reset(self._h, self._p(m), self._stream()))
+        return self.read_state()
+
+    def get_new_goal_joint_angles(self):
+        """simulation_client.py:46-47: `(3,)` numpy array for one env, `[N,3]` tensor otherwise."""
+        g = torch.empty((self.num_envs, 3), dtype=torch.float32, device=self.device)
+        _native.check(self._lib.roboy_new_goal(self._h, self._p(g), self._stream()))
+        return g[0].cpu().numpy() if self.num_envs == 1 else g
+
+    # ------------------------------------------------------------------ fused path (RoboyEnv drives these)
+    def configure_env(self, joint_vel_penalty, bonus_for_goal, auto_reset):
+        _native.check(self._lib.roboy_set_flags(self._h, int(joint_vel_penalty), int(bonus_for_goal), int(auto_reset)))
+
+    def set_reward_range(self, lo, hi):
+        _native.check(self._lib.roboy_set_reward_range(self._h, float(lo), float(hi)))
+
+    def set_seed(self, seed):
+        self.seed_value = int(seed) & (2 ** 64 - 1)
+        _native.check(self._lib.roboy_set_seed(self._h, self.seed_value))
+
+    def enable_terminal_obs(self, enable=True):
+        if enable and self.terminal_obs is None:
+            self.terminal_obs = torch.zeros((self.num_envs, _native.DIM_OBS), dtype=torch.float32, device=self.device)
+        if not enable:
+            self.terminal_obs = None
+        _native.check(self._lib.roboy_set_terminal_obs(self._h, self._p(self.terminal_obs)))
+
+    def step_fused(self, actions, obs=None, reward=None, done=None):
+        """One launch: RoboyEnv.step for all envs.  `actions` float32 CUDA `[N,8]`, contiguous.
+        Results land in the handle's obs/reward/done buffers unless output tensors are given."""
+        if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous() \
+                or actions.numel() != self.num_envs * _native.DIM_ACTION:
+            raise ValueError("actions must be a contiguous float32 CUDA tensor of shape [N, 8]")
+        _native.check(self._lib.roboy_step(self._h, self._p(actions), self._p(obs), self._p(reward), self._p(done),
+                                           self._stream()))
+
+    def reset_fused(self, mask=None, obs=None):
+        m = None if mask is None else self._dev(mask, torch.uint8, (self.num_envs,))
+        _native.check(self._lib.roboy_reset(self._h, self._p(m), self._p(obs), self._stream()))
+
+    def step_host(self, actions, obs, reward, done):
+        """The fused step through HOST numpy buffers (pinned for full speed); synchronous."""
+        for a, dt, k in ((actions, np.float32, 8), (obs, np.float32, 9), (reward, np.float32, 1), (done, np.uint8, 1)):
+            if a.dtype != dt or not a.flags["C_CONTIGUOUS"] or a.size != self.num_envs * k:
+                raise ValueError("host buffers must be C-contiguous float32 [N,8], float32 [N,9], float32 [N], uint8 [N]")
+        _native.check(self._lib.roboy_step_host(self._h, actions.ctypes.data, obs.ctypes.data, reward.ctypes.data,
+                                                done.ctypes.data))
+
+    def compute_reward(self, q, qd, feasible, goal_q, goal_qd=None, check_range=False):
+        """Batched compute_reward + _did_reach_goal: returns (reward float64 [k], reached bool [k])."""
+        q = self._dev(q, torch.float32).reshape(-1, 3)
+        k = q.shape[0]
+        qd = self._dev(qd, torch.float32, (k, 3))
+        goal_q = self._dev(goal_q, torch.float32, (k, 3))
+        gqd = None if goal_qd is None else self._dev(goal_qd, torch.float32, (k, 3))
+        f = None if feasible is None else self._dev(feasible, torch.uint8, (k,))
+        reward = torch.empty(k, dtype=torch.float64, device=self.device)
+        reached = torch.empty(k, dtype=torch.uint8, device=self.device)
+        _native.check(self._lib.roboy_compute_reward(self._h, k, self._p(q), self._p(qd), self._p(f), self._p(goal_q),
+                                                     self._p(gqd), self._p(reward), self._p(reached), int(check_range),
+                                                     self._stream()))
+        return reward, reached.view(torch.bool)
+
+    # ------------------------------------------------------------------ injection / introspection
+    def set_goal(self, goal_q, idx=None):
+        i = self._idx(idx)
+        g = self._dev(goal_q, torch.float32, (i.numel(), 3))
+        _native.check(self._lib.roboy_set_goal(self._h, i.numel(), self._p(i), self._p(g), self._stream()))
+
+    def set_state(self, q, qd, feasible=None, idx=None):
+        i = self._idx(idx)
+        q = self._dev(q, torch.float32, (i.numel(), 3))
+        qd = self._dev(qd, torch.float32, (i.numel(), 3))
+        f = None if feasible is None else self._dev(feasible, torch.uint8, (i.numel(),))
+        _native.check(self._lib.roboy_set_state(self._h, i.numel(), self._p(i), self._p(q), self._p(qd), self._p(f),
+                                                self._stream()))
+
+    def set_step_num(self, step_num, idx=None):
+        i = self._idx(idx)
+        s = self._dev(step_num, torch.int32).reshape(-1).expand(i.numel()).contiguous()
+        _native.check(self._lib.roboy_set_step_num(self._h, i.numel(), self._p(i), self._p(s), self._stream()))
+
+    @property
+    def step_num(self):
+        return self.step_flags & _native.STEP_MASK
+
+    @property
+    def counter(self):
+        t = ctypes.c_uint64()
+        _native.check(self._lib.roboy_get_counter(self._h, ctypes.byref(t)))
+        return t.value
+
+    @counter.setter
+    def counter(self, t):
+        _native.check(self._lib.roboy_set_counter(self._h, int(t)))
+
+    def stats(self):
+        out = (ctypes.c_double * len(_native.STAT_NAMES))()
+        _native.check(self._lib.roboy_stats(self._h, out, self._stream()))
+        return dict(zip(_native.STAT_NAMES, list(out)))
+
+    def clear_stats(self):
+        _native.check(self._lib.roboy_clear_stats(self._h, self._stream()))
+
+    def clear_errors(self):
+        _native.check(self._lib.roboy_clear_errors(self._h, self._stream()))
+
+    def errors(self):
+        """(error word, first offending global env id or None); synchronises the stream."""
+        flags, first = ctypes.c_uint32(), ctypes.c_uint64()
+        _native.check(self._lib.roboy_errors(self._h, ctypes.byref(flags), ctypes.byref(first), self._stream()))
+        return flags.value, (None if first.value == 2 ** 64 - 1 else first.value)
+
+    def launch_count(self):
+        n = ctypes.c_uint64()
+        _native.check(self._lib.roboy_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def step_geometry(self):
+        g, b, s = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _native.check(self._lib.roboy_step_geometry(self._h, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
+        return dict(grid=g.value, block=b.value, smem_bytes=s.value)
+
+    # ------------------------------------------------------------------ checkpoint
+    def state_dict(self):
+        return dict(goal=self.goal.clone(), step_flags=self.step_flags.clone(), held=self.held.clone(),
+                    counter=self.counter, seed=self.seed_value, env_id_base=self.env_id_base,
+                    stats=self.stats_tensor.clone())
+
+    def load_state_dict(self, sd):
+        self.goal.copy_(sd["goal"])
+        self.step_flags.copy_(sd["step_flags"])
+        self.held.copy_(sd["held"])
+        self.stats_tensor.copy_(sd["stats"])
+        self.set_seed(sd["seed"])
+        self.counter = sd["counter"]

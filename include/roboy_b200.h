@@ -1,0 +1,209 @@
+/*
+ * roboy_b200.h -- C-ABI of the B200-native batched MSJ environment step.
+ *
+ * This is the drop-in boundary for gym-roboy's environment hot path.  Every entry point names
+ * the reference interface it replaces (paths relative to gym_roboy/ in Roboy/gym-roboy).
+ * The reference is pure Python, so the binding a maintainer adds is a ctypes stub
+ * (INTEGRATION.md shows it); gym_roboy_b200/_native.py is that stub for this repo's host side.
+ *
+ * Conventions
+ *   - plain C types only; `stream` is a cudaStream_t passed as void* (NULL = legacy default).
+ *   - pointers suffixed _dev are device pointers (e.g. torch tensor .data_ptr()); suffixed
+ *     _host are host pointers.  Device entry points are asynchronous on `stream`.
+ *   - every call returns 0 on success, a negative ROBOY_E_* code on failure;
+ *     roboy_last_error() returns a thread-local message for the last failure.
+ *   - the reference reports contract violations by raising AssertionError; a batched device
+ *     path cannot raise per env, so violations are recorded in an error word + the first
+ *     offending global env id (roboy_errors) and counted in the statistics.
+ *   - there is no CPU fallback: without a CUDA device roboy_create fails with ROBOY_E_CUDA.
+ *
+ * Memory layout in HBM (structure of arrays, n = n_envs of this shard):
+ *   goal        float32 [3][n]   desired joint angles            (RoboyEnv._goal_state)
+ *   step_flags  uint32  [n]      bits 0..23 step_num, bit 24 HELD_ZERO64, bit 25 HELD_INFEASIBLE
+ *   held        float32 [6][n]   StubSimulationClient._state: q0..q2, qd0..qd2 (cold; read only
+ *                                on the hold branch when HELD_ZERO64 is clear)
+ *   obs         float32 [n][9]   row-major, what the policy consumes (roboy_env.py:75-80)
+ *   reward      float32 [n]
+ *   done        uint8   [n]
+ *   stats       float64 [8]      ROBOY_STAT_*
+ */
+#ifndef ROBOY_B200_H_
+#define ROBOY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROBOY_B200_ABI_VERSION 1
+
+#define ROBOY_DIM_JOINT 3  /* msj_robot.py:8  */
+#define ROBOY_DIM_ACTION 8 /* msj_robot.py:12 */
+#define ROBOY_DIM_OBS 9    /* roboy_env.py:32-36 */
+
+/* error codes */
+#define ROBOY_OK 0
+#define ROBOY_E_ARG (-1)   /* bad argument (NULL handle, n == 0, misaligned pointer ...) */
+#define ROBOY_E_CUDA (-2)  /* CUDA runtime failure, or no CUDA device: there is no CPU path */
+#define ROBOY_E_ALLOC (-3)
+
+/* step_flags bits */
+#define ROBOY_STEP_MASK 0x00ffffffu
+#define ROBOY_F_HELD_ZERO64 (1u << 24)     /* held state is the float64 zero state of roboy_robot.py:41-45 */
+#define ROBOY_F_HELD_INFEASIBLE (1u << 25) /* held state has is_feasible == False */
+
+/* bits of the device error word (the reference's AssertionErrors) */
+#define ROBOY_ERR_ACTION 1u       /* roboy_env.py:52   action outside [-1,1]^8 or NaN */
+#define ROBOY_ERR_REWARD_RANGE 2u /* roboy_env.py:109  reward outside reward_range */
+#define ROBOY_ERR_GOAL_BOUNDS 4u  /* roboy_robot.py:76 injected goal outside the angle space */
+
+/* indices into the statistics vector */
+enum {
+    ROBOY_STAT_STEPS = 0,       /* env-steps executed */
+    ROBOY_STAT_EPISODES = 1,    /* done flags raised */
+    ROBOY_STAT_SUCCESSES = 2,   /* ... because _did_reach_goal (roboy_env.py:125-134) */
+    ROBOY_STAT_TIMEOUTS = 3,    /* ... because step_num > 400 only (roboy_env.py:72-73) */
+    ROBOY_STAT_SUM_REWARD = 4,  /* sum of all step rewards */
+    ROBOY_STAT_SUM_EPLEN = 5,   /* sum of lengths of auto-reset episodes */
+    ROBOY_STAT_HOLDS = 6,       /* steps that took the Stub's hold branch (simulation_client.py:38-39) */
+    ROBOY_STAT_VIOLATIONS = 7,  /* env-steps with a non-zero error word */
+    ROBOY_STAT_COUNT = 8
+};
+
+/* buffers owned by a handle, for roboy_buffer / roboy_export_dlpack */
+enum {
+    ROBOY_BUF_GOAL = 0, ROBOY_BUF_STEP_FLAGS = 1, ROBOY_BUF_HELD = 2, ROBOY_BUF_OBS = 3,
+    ROBOY_BUF_REWARD = 4, ROBOY_BUF_DONE = 5, ROBOY_BUF_STATS = 6, ROBOY_BUF_TERMINAL_OBS = 7,
+    ROBOY_BUF_COUNT = 8
+};
+
+/* Constructor arguments of RoboyEnv (roboy_env.py:12-14) + the robot's bounds
+ * (MsjRobot, msj_robot.py:8-16) + sharding.  Field order is ABI. */
+typedef struct roboy_cfg {
+    uint64_t n_envs;       /* envs in this shard (one shard per GPU) */
+    uint64_t env_id_base;  /* global id of local env 0; Philox counters use the global id */
+    uint64_t seed;         /* Philox key (RoboyEnv(seed=...), roboy_env.py:12,15) */
+    float angle_low, angle_high; /* msj_robot.py:9 */
+    float vel_low, vel_high;     /* msj_robot.py:10 */
+    float act_low, act_high;     /* msj_robot.py:16 */
+    int32_t max_episode_len;     /* roboy_env.py:28 */
+    int32_t joint_vel_penalty;   /* roboy_env.py:13 */
+    int32_t bonus_for_goal;      /* roboy_env.py:14 is_agent_getting_bonus_for_reaching_goal */
+    int32_t auto_reset;          /* 1: reset-on-done inside the step (vec-env worker semantics) */
+    float penalty_boundary;      /* roboy_env.py:26 */
+    float bonus_goal;            /* roboy_env.py:27 */
+    double reward_lo, reward_hi; /* roboy_env.py:30,109; +-inf disables the check */
+} roboy_cfg;
+
+typedef struct roboy_env roboy_env; /* opaque */
+
+int roboy_abi_version(void);
+const char *roboy_last_error(void);
+
+/* Fill `cfg` with the MSJ robot constants (msj_robot.py:8-16), RoboyEnv's defaults
+ * (roboy_env.py:12-14,26-28), auto_reset = 1 and an unbounded reward range. */
+int roboy_cfg_msj(roboy_cfg *cfg);
+
+/* RoboyEnv.__init__ over StubSimulationClient.__init__ (roboy_env.py:12-38,
+ * simulation_client.py:29-31) for n_envs envs on CUDA device `device`: allocates the SoA state
+ * in HBM and runs the init kernel (held state := random sample, goal := random, step_num := 1). */
+int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out);
+int roboy_destroy(roboy_env *env);
+
+/* roboy_env.py:30,109 -- (re)set the reward range checked inside the step kernel. */
+int roboy_set_reward_range(roboy_env *env, double lo, double hi);
+
+/* RoboyEnv.reset (roboy_env.py:82-87) over Stub.forward_reset_command / read_state
+ * (simulation_client.py:42-44,33-34) for every env with mask_dev[i] != 0 (NULL: all envs).
+ * Writes obs rows of the reset envs into obs_dev (NULL: the handle's obs buffer). */
+int roboy_reset(roboy_env *env, const uint8_t *mask_dev, float *obs_dev, void *stream);
+
+/* RoboyEnv.step (roboy_env.py:51-70) fused with StubSimulationClient.forward_step_command
+ * (simulation_client.py:36-40), RoboyRobot.normalize_state (roboy_robot.py:80-95),
+ * compute_reward (roboy_env.py:92-112), _did_reach_goal (:125-134), _set_new_goal (:117-123)
+ * and, when cfg.auto_reset, the vec-env worker's reset-on-done.  One launch over all envs.
+ *   actions_dev float32 [n][8] in [-1,1];  outputs: NULL selects the handle's own buffer. */
+int roboy_step(roboy_env *env, const float *actions_dev, float *obs_dev, float *reward_dev,
+               uint8_t *done_dev, void *stream);
+
+/* The same step through HOST buffers: pinned staging, chunked H2D -> kernel -> D2H pipelined
+ * over internal streams; returns when the outputs are in host memory.  This is the call a
+ * host-side (CPU policy) trainer makes, and what bench.py's e2e number times. */
+int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, float *reward_host,
+                    uint8_t *done_host);
+
+/* Optional side buffer float32 [n][9] receiving the pre-reset observation of envs that
+ * finish an episode (the vec-env `terminal_observation`).  NULL disables. */
+int roboy_set_terminal_obs(roboy_env *env, float *terminal_obs_dev);
+
+/* Stand-alone GoalEnv.compute_reward(current_state, goal_state) (roboy_env.py:92-112) and
+ * _did_reach_goal (:125-134) over float32 device arrays [k][3]; feasible_dev uint8 [k] or NULL
+ * (all feasible); goal_qd_dev NULL = the float64 zero velocities of roboy_env.py:23.
+ * reward_dev float64 [k] (the reference returns a python float), reached_dev uint8 [k] or NULL.
+ * check_range != 0 applies the handle's reward range (violations go to the error word). */
+int roboy_compute_reward(roboy_env *env, uint64_t k, const float *q_dev, const float *qd_dev,
+                         const uint8_t *feasible_dev, const float *goal_q_dev, const float *goal_qd_dev,
+                         double *reward_dev, uint8_t *reached_dev, int check_range, void *stream);
+
+/* State injection (parity tests, RoboyEnv._set_new_goal(goal_joint_angle=...) roboy_env.py:117-123,
+ * and tests that poke StubSimulationClient._state / RoboyEnv.step_num).  idx_dev: int64 [k]
+ * local env indices; values are [k][3] float32 / [k] uint8 / [k] int32 device arrays. */
+int roboy_set_goal(roboy_env *env, uint64_t k, const int64_t *idx_dev, const float *goal_q_dev, void *stream);
+int roboy_set_state(roboy_env *env, uint64_t k, const int64_t *idx_dev, const float *q_dev,
+                    const float *qd_dev, const uint8_t *feasible_dev, void *stream);
+int roboy_set_step_num(roboy_env *env, uint64_t k, const int64_t *idx_dev, const int32_t *step_dev, void *stream);
+
+/* SimulationClient.read_state (simulation_client.py:33-34) for k envs: the held state as
+ * float32 [k][3] q, [k][3] qd, uint8 [k] feasible. */
+int roboy_read_state(roboy_env *env, uint64_t k, const int64_t *idx_dev, float *q_dev, float *qd_dev,
+                     uint8_t *feasible_dev, void *stream);
+
+/* The un-fused plug-in calls of SimulationClient (simulation_client.py:11-23), batched over the
+ * shard, for callers that keep the reference's own RoboyEnv on top:
+ *   roboy_sim_step   forward_step_command(action) -- simulation_client.py:36-40.  actions_dev is
+ *                    float32 [n][8] in ROBOT units (after roboy_env.py:54-57); advances the call
+ *                    counter; writes the returned state (q, qd [n][3], feasible [n] or NULL).
+ *   roboy_sim_reset  forward_reset_command()      -- simulation_client.py:42-44, envs with
+ *                    mask_dev[i] != 0 (NULL: all); advances the call counter.
+ *   roboy_new_goal   get_new_goal_joint_angles()  -- simulation_client.py:46-47; writes [n][3]
+ *                    draws to goal_q_dev and does NOT change the env's goal (RoboyEnv._set_new_goal
+ *                    does that, via roboy_set_goal).  Repeated calls give fresh draws. */
+int roboy_sim_step(roboy_env *env, const float *actions_dev, float *q_dev, float *qd_dev, uint8_t *feasible_dev,
+                   void *stream);
+int roboy_sim_reset(roboy_env *env, const uint8_t *mask_dev, void *stream);
+int roboy_new_goal(roboy_env *env, float *goal_q_dev, void *stream);
+
+/* RoboyEnv constructor flags (roboy_env.py:13-14) and reset-on-done, changeable after create. */
+int roboy_set_flags(roboy_env *env, int joint_vel_penalty, int bonus_for_goal, int auto_reset);
+/* RoboyEnv.seed (roboy_env.py:114-115): re-key the Philox generator; state is left as is. */
+int roboy_set_seed(roboy_env *env, uint64_t seed);
+
+/* Zero-copy access to the handle's buffers (ROBOY_BUF_*): raw device pointer + byte size, or
+ * a DLPack DLManagedTensor* (consume with PyCapsule "dltensor" -> torch.from_dlpack). */
+int roboy_buffer(roboy_env *env, int which, void **dev_ptr, uint64_t *nbytes);
+void *roboy_export_dlpack(roboy_env *env, int which);
+
+/* Philox call counter (0 after create, +1 per reset/step call) -- with the state buffers and
+ * the seed this is the complete checkpoint of the env shard. */
+int roboy_get_counter(roboy_env *env, uint64_t *t);
+int roboy_set_counter(roboy_env *env, uint64_t t);
+
+/* Episode statistics (ROBOY_STAT_*) accumulated on the device by the step kernel.
+ * roboy_stats copies them to the host (synchronises `stream`); the device vector itself is
+ * ROBOY_BUF_STATS, which is what the multi-GPU NCCL all-reduce operates on. */
+int roboy_stats(roboy_env *env, double out_host[ROBOY_STAT_COUNT], void *stream);
+int roboy_clear_stats(roboy_env *env, void *stream);   /* statistics and error word */
+int roboy_clear_errors(roboy_env *env, void *stream);  /* error word only */
+/* Device error word and first offending global env id (UINT64_MAX if none); synchronises. */
+int roboy_errors(roboy_env *env, uint32_t *err_flags, uint64_t *first_bad_env, void *stream);
+
+/* Introspection for bench.py / tests: kernels launched by this handle so far, and the
+ * launch geometry the step kernel uses for this n_envs. */
+int roboy_launch_count(roboy_env *env, uint64_t *launches);
+int roboy_step_geometry(roboy_env *env, int *grid, int *block, int *smem_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROBOY_B200_H_ */

@@ -231,10 +231,10 @@ def _uniform(x, low, high):
     return (low + (span * u).astype(np.float32)).astype(np.float32)
 
 
-def draw(seed, gids, t, stream, low=MSJ["angle_low"], high=MSJ["angle_high"]):
+def draw(seed, gids, t, stream, low=MSJ["angle_low"], high=MSJ["angle_high"], sub=0):
     """float32 [n,3] draws for global env ids `gids` at call counter `t` on `stream`."""
     gids = np.asarray(gids, np.uint64)
-    c3 = (int(stream) << 28) | ((int(t) >> 32) & 0x0FFFFFFF)
+    c3 = (int(stream) << 28) | ((int(sub) & 0xFF) << 20) | ((int(t) >> 32) & 0x000FFFFF)
     x = philox4x32_10(gids & np.uint64(0xFFFFFFFF), gids >> np.uint64(32), int(t) & 0xFFFFFFFF, c3,
                       int(seed) & 0xFFFFFFFF, int(seed) >> 32)
     return np.stack([_uniform(x[k], low, high) for k in range(3)], axis=-1)

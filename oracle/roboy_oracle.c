@@ -89,12 +89,16 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 enum { STREAM_STATE_Q = 0, STREAM_STATE_QD = 1, STREAM_GOAL = 2 };
 
-/* counter = (env id lo, env id hi, call counter lo, stream<<28 | call counter hi) */
-static void draw4(const orc_cfg *cfg, uint64_t gid, uint64_t t, uint32_t stream, uint32_t out[4]) {
+/* counter = (env id lo, env id hi, call counter lo, stream<<28 | sub<<20 | call counter hi);
+ * sub numbers repeated goal draws at one call counter (un-fused plug-in API); 0 in the step. */
+static void draw4s(const orc_cfg *cfg, uint64_t gid, uint64_t t, uint32_t stream, uint32_t sub, uint32_t out[4]) {
     uint32_t ctr[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t,
-                       (stream << 28) | ((uint32_t)(t >> 32) & 0x0fffffffu)};
+                       (stream << 28) | ((sub & 0xffu) << 20) | ((uint32_t)(t >> 32) & 0x000fffffu)};
     uint32_t key[2] = {(uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32)};
     orc_philox4x32_10(ctr, key, out);
+}
+static void draw4(const orc_cfg *cfg, uint64_t gid, uint64_t t, uint32_t stream, uint32_t out[4]) {
+    draw4s(cfg, gid, t, stream, 0, out);
 }
 
 /* u = (x>>8)*2^-24 in [0,1); v = low + (high-low)*u, float32 mul then add (no FMA).
@@ -119,6 +123,11 @@ void orc_draw_state(const orc_cfg *cfg, uint64_t gid, uint64_t t, float q[3], fl
 }
 
 /* simulation_client.py:46-47 get_new_goal_joint_angles(): new_random_state().joint_angles */
+void orc_draw_goal_sub(const orc_cfg *cfg, uint64_t gid, uint64_t t, uint32_t sub, float g[3]) {
+    uint32_t a[4];
+    draw4s(cfg, gid, t, STREAM_GOAL, sub, a);
+    for (int k = 0; k < 3; ++k) g[k] = uniform_in(a[k], cfg->angle_low, cfg->angle_high);
+}
 void orc_draw_goal(const orc_cfg *cfg, uint64_t gid, uint64_t t, float g[3]) {
     uint32_t a[4];
     draw4(cfg, gid, t, STREAM_GOAL, a);

@@ -1,0 +1,301 @@
+"""CUDA path vs the CPU oracle on identical seeded inputs (bit-exact done/obs/state, rewards to
+1e-6 relative), at sizes the oracle finishes in seconds, plus size-independent properties at
+BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6  # north_star tolerance for fp32 rewards
+
+
+def make_pair(n, seed, **flags):
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    base = flags.pop("env_id_base", 0)
+    client = CudaSimulationClient(num_envs=n, seed=seed, env_id_base=base, device="cuda:0")
+    env = RoboyEnv(client, joint_vel_penalty=flags.get("penalty", False),
+                   is_agent_getting_bonus_for_reaching_goal=flags.get("bonus", True),
+                   auto_reset=flags.get("auto_reset", True), strict=False)
+    ora = orc.OracleEnv(n, seed=seed, env_id_base=base, joint_vel_penalty=flags.get("penalty", False),
+                        bonus=flags.get("bonus", True), auto_reset=flags.get("auto_reset", True), threads=8)
+    return env, client, ora
+
+
+def actions_for(rng, n, hold_frac=0.01):
+    a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+    a[rng.random(n) < hold_frac] = 0.0
+    up, dn = np.float32(2.0 ** -25), np.float32(-(2.0 ** -24))
+    k = min(n, 8)
+    rows = [np.full(8, up), np.full(8, np.nextafter(up, np.float32(1))), np.full(8, dn),
+            np.full(8, np.nextafter(dn, np.float32(-1))), np.array([0, 0, 0, 0, 0, 0, 0, 1e-7]),
+            np.full(8, 1.0), np.full(8, -1.0), np.array([up, dn, 0, 0, dn, up, 0, 0])]
+    idx = rng.choice(n, size=k, replace=False)
+    for i, r in zip(idx, rows):
+        a[i] = r.astype(np.float32)
+    return a
+
+
+def compare_step(env, client, ora, a, t):
+    obs, rew, done, _ = env.step(torch.as_tensor(a, device="cuda:0"))
+    o_obs, o_rew, o_done = ora.step(a)
+    assert np.array_equal(done.cpu().numpy(), o_done), "done mask differs at step %d" % t
+    assert np.array_equal(obs.cpu().numpy(), o_obs), "obs differ at step %d" % t
+    r = rew.cpu().numpy().astype(np.float64)
+    rel = np.abs(r - o_rew) / np.maximum(np.abs(o_rew.astype(np.float64)), 1e-30)
+    assert rel.max() <= RTOL, "reward rel err %g at step %d" % (rel.max(), t)
+    return float(rel.max())
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 4096])
+def test_construction_and_reset_match_oracle(n):
+    env, client, ora = make_pair(n, seed=99)
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+    assert np.array_equal(client.held.cpu().numpy(), ora.held)
+    assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
+    obs = env.reset()
+    assert np.array_equal(obs.cpu().numpy().reshape(n, 9), ora.reset())
+    assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
+    mask = (np.arange(n) % 3 == 0).astype(np.uint8)
+    obs = env.reset(mask=torch.as_tensor(mask)).cpu().numpy().reshape(n, 9)
+    o = ora.reset(mask)
+    assert np.array_equal(obs[mask.astype(bool)], o[mask.astype(bool)])
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+
+
+@pytest.mark.parametrize("flags", [dict(), dict(penalty=True), dict(bonus=False), dict(auto_reset=False),
+                                   dict(penalty=True, bonus=False, auto_reset=False)],
+                         ids=["default", "penalty", "nobonus", "manual_reset", "penalty_nobonus_manual"])
+def test_rollout_4096_envs_matches_oracle(flags):
+    """configs[1]: 4,096 envs, T > 2 x 400 so the timeout reset fires twice per env."""
+    n, T = 4096, 1001
+    env, client, ora = make_pair(n, seed=1234, **flags)
+    rng = np.random.default_rng(7)
+    env.reset(); ora.reset()
+    # de-synchronise episode phases and plant goals the sampled state will hit
+    steps = rng.integers(1, 400, n).astype(np.int32)
+    client.set_step_num(steps)
+    ora.step_flags[:] = (ora.step_flags & ~np.uint32(orc.STEP_MASK)) | steps.astype(np.uint32)
+    worst = 0.0
+    for t in range(T):
+        if t % 50 == 10:   # goals next to the state the Philox draw will produce -> goal reached on the sampled branch
+            c = ora.counter + 1
+            q = orc.draw(1234, np.arange(n), c, orc.STREAM_STATE_Q)
+            g = np.clip(q + np.float32(0.005), -orc.PI32, orc.PI32).astype(np.float32)
+            client.set_goal(g); ora.goal[:] = g.T
+        worst = max(worst, compare_step(env, client, ora, actions_for(rng, n), t))
+        if not flags.get("auto_reset", True):
+            d = client.done.cpu().numpy()
+            if d.any():
+                env.reset(mask=torch.as_tensor(d.astype(np.uint8))); ora.reset(d.astype(np.uint8))
+        if t % 100 == 0:
+            assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+            assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+    assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
+    s, so = client.stats(), ora.stats()
+    for k in ("steps", "episodes", "successes", "timeouts", "sum_episode_len", "holds", "violations"):
+        assert s[k] == so[k], (k, s[k], so[k])
+    assert abs(s["sum_reward"] - so["sum_reward"]) <= 1e-6 * abs(so["sum_reward"])
+    assert s["successes"] > 0 and s["timeouts"] > 2 * n * 0.9 and s["holds"] > 0
+    assert client.errors()[0] == ora.errors()[0]
+    if client.errors()[0]:
+        assert client.errors()[1] == ora.errors()[1]
+
+
+def test_held_state_injection_and_thresholds():
+    """Near-threshold goal distances on the hold branch, float32 and float64 held states,
+    infeasible penalty -- compared env by env with the oracle."""
+    n = 2048
+    env, client, ora = make_pair(n, seed=5)
+    env.reset(); ora.reset()
+    rng = np.random.default_rng(3)
+    thr_a, thr_v = orc.thresholds(ora.cfg)
+    q = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    scale = (1 + rng.uniform(-4e-7, 4e-7, n)).astype(np.float32)
+    direction = rng.normal(size=(n, 3)); direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+    goal = np.clip(q + (direction * thr_a * scale[:, None]).astype(np.float32), -orc.PI32, orc.PI32).astype(np.float32)
+    vdir = rng.normal(size=(n, 3)); vdir /= np.linalg.norm(vdir, axis=1, keepdims=True)
+    vscale = np.where(rng.random(n) < 0.5, 1 + rng.uniform(-4e-7, 4e-7, n), rng.uniform(0, 0.9, n))
+    qd = (vdir * thr_v * vscale[:, None]).astype(np.float32)
+    feasible = (rng.random(n) > 0.2)
+    half = n // 2   # first half: float32 held states; second half keeps the float64 zero state
+    idx = np.arange(half)
+    client.set_state(q[:half], qd[:half], feasible[:half].astype(np.uint8), idx=idx)
+    ora.held[0:3, :half] = q[:half].T; ora.held[3:6, :half] = qd[:half].T
+    ora.step_flags[:half] = (ora.step_flags[:half] & np.uint32(orc.STEP_MASK)) | \
+        np.where(feasible[:half], 0, orc.F_HELD_INFEASIBLE).astype(np.uint32)
+    goal[half:] = (direction[half:] * thr_a * scale[half:, None]).astype(np.float32)  # around the zero state
+    client.set_goal(goal); ora.goal[:] = goal.T
+    a = np.zeros((n, 8), np.float32)
+    compare_step(env, client, ora, a, 0)
+    d = client.done.cpu().numpy()
+    assert 0.2 < d[:half].mean() < 0.8 and 0.2 < d[half:].mean() < 0.8   # the threshold really was straddled
+    assert client.stats()["holds"] == n
+
+
+def test_compute_reward_kats():
+    """SURVEY.md 8a KAT table (values produced by the reference itself) + oracle on random states."""
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.robots import RobotState
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    kats = [  # q, qd, goal, feasible, reward(pen=False), reward(pen=True), reached
+        ((0.5, -1.0, 2.0), (0.1, -0.2, 0.3), (0.25, -0.75, 1.5), True, -1.2152187824249268, -2.5922478480921027, False),
+        ((0.26, -0.74, 1.51), (0.05, 0, -0.05), (0.25, -0.75, 1.5), True, 998.9944458007812, 998.4434189188644, True),
+        ((0.26, -0.74, 1.51), (0.3, 0.3, 0.3), (0.25, -0.75, 1.5), True, -1.0055285692214966, -2.7323260694901483, False),
+        ((3, -3, 3), (0.5, -0.5, 0.5), (-3, 3, -3), False, -28.329681396484375, -73.53261015329933, False),
+        ((1, 1, 1), (0, 0, 0), (1, 1, 1), True, 999.0, 998.6321206092834, True),
+    ]
+    for pen in (False, True):
+        env = RoboyEnv(CudaSimulationClient(num_envs=1, seed=0, device="cuda:0"), joint_vel_penalty=pen)
+        for q, qd, g, feas, r0, r1, reached in kats:
+            cur = RobotState(np.array(q, np.float32), np.array(qd, np.float32), feas)
+            goal = RobotState(np.array(g, np.float32), np.zeros(3), True)   # float64 zero goal velocities
+            want = r1 if pen else r0
+            got = env.compute_reward(cur, goal)
+            assert isinstance(got, float)
+            assert abs(got - want) <= RTOL * abs(want), (q, pen, got, want)
+            assert env._did_reach_goal(cur, goal) is reached
+    # reward_range pins (SURVEY.md 8a a9 / test_roboy_env.py:82-89)
+    env = RoboyEnv(CudaSimulationClient(num_envs=1, seed=0, device="cuda:0"))
+    assert env.reward_range == (-32.947744369506836, 999.0)
+    envp = RoboyEnv(CudaSimulationClient(num_envs=1, seed=0, device="cuda:0"), joint_vel_penalty=True)
+    assert np.allclose(envp.reward_range, (-143.61798095703125, 998.6321411132812), rtol=RTOL, atol=0)
+    envn = RoboyEnv(CudaSimulationClient(num_envs=1, seed=0, device="cuda:0"),
+                    is_agent_getting_bonus_for_reaching_goal=False)
+    assert envn.reward_range == (-32.947744369506836, -1.0)
+    # random batch vs the oracle, float32 goal velocities (all-float32 numpy path) and float64-zero ones
+    rng = np.random.default_rng(0)
+    k = 20000
+    q = rng.uniform(-np.pi, np.pi, (k, 3)).astype(np.float32)
+    g = np.where(rng.random((k, 1)) < 0.3, q + rng.uniform(-0.04, 0.04, (k, 3)), rng.uniform(-3.1, 3.1, (k, 3))).astype(np.float32)
+    qd = (rng.uniform(-0.5, 0.5, (k, 3)) * rng.random((k, 1))).astype(np.float32)
+    gqd = rng.uniform(-0.1, 0.1, (k, 3)).astype(np.float32)
+    feas = rng.random(k) > 0.1
+    for pen in (False, True):
+        client = CudaSimulationClient(num_envs=1, seed=0, device="cuda:0")
+        client.configure_env(pen, True, True)
+        cfg = orc.make_cfg(1, joint_vel_penalty=pen)
+        for goal_qd in (None, gqd):
+            r, reached = client.compute_reward(q, qd, feas.astype(np.uint8), g, goal_qd)
+            ro, reached_o, _ = orc.compute_reward(cfg, q, qd, feas, g, goal_qd)
+            assert np.array_equal(reached.cpu().numpy(), reached_o)
+            assert reached_o.sum() > 100
+            rel = np.abs(r.cpu().numpy() - ro) / np.abs(ro)
+            assert rel.max() <= RTOL
+
+
+def test_sharding_invariance_and_determinism():
+    """Philox counters use the global env id: two half-shards == one full shard, bit for bit;
+    and the same seed replays the same rollout."""
+    n, T = 8192, 60
+    rng = np.random.default_rng(11)
+    acts = [actions_for(rng, n) for _ in range(T)]
+    outs = {}
+    for label, shards in (("full", [(0, n)]), ("halves", [(0, n // 2), (n // 2, n)]), ("again", [(0, n)])):
+        pieces = []
+        for b, e in shards:
+            env, client, _ = make_pair(e - b, seed=77, env_id_base=b)
+            env.reset()
+            client.set_step_num(np.full(e - b, 380, np.int32))
+            rec = []
+            for t in range(T):
+                obs, rew, done, _ = env.step(torch.as_tensor(acts[t][b:e], device="cuda:0"))
+                rec.append((obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), done.cpu().numpy().copy()))
+            pieces.append((rec, client.stats()))
+        outs[label] = pieces
+    for t in range(T):
+        for k in range(3):
+            full = outs["full"][0][0][t][k]
+            assert np.array_equal(full, np.concatenate([p[0][t][k] for p in outs["halves"]]))
+            assert np.array_equal(full, outs["again"][0][0][t][k])
+    for key in ("steps", "episodes", "successes", "timeouts", "holds"):
+        assert outs["full"][0][1][key] == sum(p[1][key] for p in outs["halves"])
+    assert outs["full"][0][1]["episodes"] >= n
+
+
+def test_host_buffer_step_equals_device_step():
+    n = 300_000   # more than one pipeline stage (262,144 envs), ragged tail
+    env_a, client_a, _ = make_pair(n, seed=3)
+    env_b, client_b, _ = make_pair(n, seed=3)
+    env_a.reset(); env_b.reset()
+    rng = np.random.default_rng(1)
+    for t in range(3):
+        a = actions_for(rng, n)
+        obs = np.empty((n, 9), np.float32); rew = np.empty(n, np.float32); done = np.empty(n, np.uint8)
+        client_a.step_host(a, obs, rew, done)
+        o2, r2, d2, _ = env_b.step(torch.as_tensor(a, device="cuda:0"))
+        assert np.array_equal(obs, o2.cpu().numpy()) and np.array_equal(rew, r2.cpu().numpy())
+        assert np.array_equal(done.astype(bool), d2.cpu().numpy())
+    assert client_a.stats() == client_b.stats()
+
+
+def test_outputs_are_zero_copy_views_of_the_library_buffers():
+    import ctypes
+    from gym_roboy_b200 import _native
+    env, client, _ = make_pair(1024, seed=1)
+    for which, t in ((_native.BUF_OBS, client.obs), (_native.BUF_REWARD, client.reward), (_native.BUF_DONE, client.done_u8),
+                     (_native.BUF_GOAL, client.goal), (_native.BUF_STEP_FLAGS, client.step_flags)):
+        ptr, nbytes = ctypes.c_void_p(), ctypes.c_uint64()
+        _native.check(client._lib.roboy_buffer(client._h, which, ctypes.byref(ptr), ctypes.byref(nbytes)))
+        assert t.data_ptr() == ptr.value and t.numel() * t.element_size() == nbytes.value and t.is_cuda
+    obs, rew, done, _ = env.step(torch.zeros((1024, 8), device="cuda:0"))
+    assert obs.data_ptr() == client.obs.data_ptr() and done.dtype == torch.bool
+
+
+def test_checkpoint_resume_is_exact():
+    n = 5000
+    env, client, _ = make_pair(n, seed=21)
+    env.reset()
+    rng = np.random.default_rng(2)
+    acts = [torch.as_tensor(actions_for(rng, n), device="cuda:0") for _ in range(20)]
+    for a in acts[:10]:
+        env.step(a)
+    sd = client.state_dict()
+    tail = []
+    for a in acts[10:]:
+        o, r, d, _ = env.step(a)
+        tail.append((o.clone(), r.clone(), d.clone()))
+    env2, client2, _ = make_pair(n, seed=999)   # different seed: everything must come from the checkpoint
+    client2.load_state_dict(sd)
+    for a, (o, r, d) in zip(acts[10:], tail):
+        o2, r2, d2, _ = env2.step(a)
+        assert torch.equal(o, o2) and torch.equal(r, r2) and torch.equal(d, d2)
+
+
+@pytest.mark.parametrize("n", [262_144, 4_194_304])
+def test_full_size_properties(n):
+    """configs[2]/[3] sizes: properties that need no oracle."""
+    env, client, _ = make_pair(4, seed=0)  # noqa: F841 (warm the library)
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    client = CudaSimulationClient(num_envs=n, seed=42, device="cuda:0")
+    env = RoboyEnv(client)
+    env.reset()
+    client.set_step_num(torch.randint(1, 400, (n,), dtype=torch.int32, device="cuda:0"))
+    gen = torch.Generator(device="cuda:0"); gen.manual_seed(0)
+    pi = float(orc.PI32)
+    total_done = 0
+    for t in range(5):
+        goal_before = client.goal.clone()
+        steps_before = client.step_num.clone()
+        a = torch.rand((n, 8), device="cuda:0", generator=gen) * 2 - 1
+        obs, rew, done, _ = env.step(a)
+        assert obs.shape == (n, 9) and rew.shape == (n,) and done.shape == (n,)
+        nd = ~done
+        assert torch.equal(obs[nd][:, 6:9], goal_before.t()[nd])          # obs carries the goal in force
+        assert torch.equal(obs[done][:, 6:9], client.goal.t()[done])      # reset obs carries the NEW goal
+        assert (obs[done][:, 0:6] == 0).all()                             # reset obs: zero state
+        assert (obs[:, 0:6].abs() <= pi).all() and (obs[:, 6:9].abs() <= pi).all()
+        assert torch.equal(client.step_num[nd], steps_before[nd] + 1)
+        assert (client.step_num[done] == 1).all()
+        lo, hi = env.reward_range
+        assert (rew >= lo).all() and (rew <= hi).all()
+        assert (rew[nd] <= -1.0).all()                                    # -exp(d) <= -1 without the bonus
+        total_done += int(done.sum())
+    s = client.stats()
+    assert s["steps"] == 5 * n and s["episodes"] == total_done and s["violations"] == 0
+    assert s["episodes"] == s["successes"] + s["timeouts"] and total_done > 0
+    assert client.errors() == (0, None)

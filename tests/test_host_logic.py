@@ -1,0 +1,97 @@
+"""Host-side pieces that need no GPU: spaces, robots (reference test_robot_state.py:7-60
+restated), registration, sharding arithmetic."""
+import numpy as np
+import pytest
+
+import gym_roboy_b200
+from gym_roboy_b200.envs.robots import MsjRobot, RobotState, RoboyRobot
+from gym_roboy_b200.sharding import shard_range, summarize
+from gym_roboy_b200.spaces import Box
+
+MSJ = MsjRobot()
+
+
+def test_box_old_gym_semantics():
+    b = Box(-1, 1, (8,), "float32")
+    assert b.contains(np.zeros(8)) and b.contains(np.ones(8, np.float32)) and b.contains(-np.ones(8))
+    assert not b.contains(np.full(8, 1.0000001)) and not b.contains(np.full(8, np.nan)) and not b.contains(np.zeros(7))
+    assert b.low.dtype == np.float32 and b.sample().dtype == np.float32 and b.contains(b.sample())
+    c = Box(low=-np.random.uniform(size=3), high=np.random.uniform(size=3), dtype="float32")
+    assert c.shape == (3,)
+
+
+def test_msj_spaces_are_the_reference_float32_constants():       # msj_robot.py:8-16
+    assert float(MSJ.get_joint_angles_space().high[0]).hex() == "0x1.921fb60000000p+1"
+    assert float(MSJ.get_joint_vels_space().high[0]).hex() == "0x1.0c15240000000p-1"
+    assert float(MSJ.get_action_space().high[0]).hex() == "0x1.3333340000000p-2"
+    assert MSJ.get_action_space().shape == (8,) and MSJ.get_joint_angles_space().shape == (3,)
+    with pytest.raises(NotImplementedError):
+        RoboyRobot.get_action_space()
+
+
+def test_robot_state_interpolate():                              # test_robot_state.py:7-13
+    s1, s2 = MsjRobot.new_random_state(), MsjRobot.new_random_state()
+    mid = RobotState.interpolate(s1, s2)
+    assert np.allclose(mid.joint_angles, (s1.joint_angles + s2.joint_angles) / 2)
+    assert np.allclose(mid.joint_vels, (s1.joint_vels + s2.joint_vels) / 2)
+    assert mid.is_feasible is True
+
+
+def test_state_factories():                                      # test_robot_state.py:16-38
+    za = MsjRobot.new_random_zero_angles_state()
+    assert np.allclose(za.joint_angles, 0) and not np.allclose(za.joint_vels, 0)
+    zv = MsjRobot.new_random_zero_vels_state()
+    assert np.allclose(zv.joint_vels, 0) and not np.allclose(zv.joint_angles, 0)
+    assert MsjRobot.new_zero_state().joint_angles.dtype == np.float64          # roboy_robot.py:43-44
+    mx, mn = MSJ.new_max_state(), MSJ.new_min_state()
+    assert np.allclose(mx.joint_angles, MSJ.get_joint_angles_space().high) and mx.is_feasible is False
+    assert np.allclose(mn.joint_vels, MSJ.get_joint_vels_space().low)
+    rs = MsjRobot.new_random_state()
+    assert np.abs(rs.joint_vels).max() <= np.pi    # quirk: velocities come from the ANGLE space (roboy_robot.py:38)
+
+
+def test_normalize():                                            # test_robot_state.py:41-60
+    one = np.ones(3)
+    n = MSJ.normalize_state(MSJ.new_max_state())
+    assert np.allclose(n.joint_angles, one) and np.allclose(n.joint_vels, one)
+    n = MSJ.normalize_state(MSJ.new_min_state())
+    assert np.allclose(n.joint_angles, -one) and np.allclose(n.joint_vels, -one)
+    hi = np.random.random(); lo = hi - abs(np.random.random())
+    assert np.isclose(1, MSJ._normalize_between_minus1_and1(hi, max_val=hi, min_val=lo))
+    assert np.isclose(-1, MsjRobot._normalize_between_minus1_and1(lo, max_val=hi, min_val=lo))
+
+
+def test_new_state_checks_angles_and_feasible_type():            # roboy_robot.py:71-78
+    MsjRobot.new_state([0, 0, 0], [9, 9, 9], True)               # velocities are NOT checked (:77)
+    with pytest.raises(AssertionError):
+        MsjRobot.new_state([4, 0, 0], [0, 0, 0], True)
+    with pytest.raises(TypeError):
+        MsjRobot.new_state([0, 0, 0], [0, 0, 0], 1)
+    with pytest.raises(TypeError):
+        RobotState([0, 0, 0], [0, 0, 0], "yes")
+
+
+def test_registration():
+    entry, kwargs = gym_roboy_b200.spec("msj-control-v1")
+    assert entry == "gym_roboy_b200.envs:RoboyEnv" and kwargs == {}
+    with pytest.raises(KeyError):
+        gym_roboy_b200.make("msj-control-v0")                    # the reference's id never worked; not provided
+    gym_roboy_b200.register("unit-test-env-v0", entry_point=lambda **kw: ("made", kw), kwargs=dict(a=1))
+    assert gym_roboy_b200.make("unit-test-env-v0", b=2) == ("made", dict(a=1, b=2))
+
+
+@pytest.mark.parametrize("total,world", [(1 << 20, 8), (1000, 3), (7, 8), (4096, 1), (134_217_728, 8)])
+def test_shard_range_partitions_the_population(total, world):
+    blocks = [shard_range(total, world, r) for r in range(world)]
+    assert blocks[0][0] == 0 and blocks[-1][1] == total
+    assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+    sizes = [e - b for b, e in blocks]
+    assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(total, world, world)
+
+
+def test_summarize():
+    import torch
+    s = summarize(torch.tensor([1000.0, 10, 4, 6, -2500.0, 900, 3, 0], dtype=torch.float64))
+    assert s["success_rate"] == 0.4 and s["mean_step_reward"] == -2.5 and s["mean_episode_len"] == 90

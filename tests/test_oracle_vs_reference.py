@@ -1,0 +1,55 @@
+"""Oracle vs the UNMODIFIED reference, live (build container only: skipped where
+/root/reference does not exist).  Also re-runs the reference's own unit tests through the
+test-only gym shim, so the shim itself is pinned."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import oracle as orc
+from oracle import reference_harness as rh
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not rh.available(), reason="reference checkout not present")]
+
+
+def test_reference_own_suite_passes_through_the_shim(tmp_path):
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests", "_shim"), rh.REFERENCE_ROOT]),
+               PYTHONDONTWRITEBYTECODE="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(rh.REFERENCE_ROOT, "gym_roboy", "envs", "tests"),
+                          "-q", "-p", "no:cacheprovider"], cwd=tmp_path, env=env, capture_output=True, text=True)
+    assert "21 passed, 12 skipped" in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("penalty,bonus,auto", [(False, True, True), (True, True, True), (False, False, False)])
+def test_random_rollout_matches_reference(penalty, bonus, auto):
+    N, T = 12, 150
+    ref = rh.ReferenceVecEnv(N, seed=5, joint_vel_penalty=penalty, bonus=bonus, auto_reset=auto)
+    o = orc.OracleEnv(N, seed=5, joint_vel_penalty=penalty, bonus=bonus, auto_reset=auto)
+    assert ref.reward_range == o.reward_range
+    assert np.array_equal(ref.goals().T, o.goal)
+    assert np.array_equal(ref.reset().astype(np.float32), o.reset())
+    steps = np.array([1 + (53 * i) % 400 for i in range(N)])
+    for i in range(N):
+        ref.set_step_num(i, steps[i])
+    o.step_flags[:] = (o.step_flags & ~np.uint32(orc.STEP_MASK)) | steps.astype(np.uint32)
+    rng = np.random.default_rng(0)
+    alive = np.ones(N, bool)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, 8)).astype(np.float32)
+        a[rng.random(N) < 0.1] = 0
+        ro, rr, rd, rt, raised = ref.step(a)
+        oo, orw, od, ot = o.step(a, want_terminal_obs=True)
+        alive &= np.array([m == "" for m in raised])
+        assert np.array_equal(ro.astype(np.float32)[alive], oo[alive])
+        assert np.array_equal(rd[alive], od[alive])
+        assert np.allclose(orw[alive], rr[alive], rtol=1e-6, atol=0)
+        if not auto and rd.any():
+            ref.reset(mask=rd); o.reset(rd.astype(np.uint8))
+        assert np.array_equal(ref.goals()[alive], o.goal.T[alive])
+        assert np.array_equal(ref.step_nums()[alive], o.step_num[alive])
+    if not alive.all():   # the reference raised roboy_env.py:109 -> the oracle flagged the same env first
+        assert o.errors()[0] & orc.ERR_REWARD_RANGE

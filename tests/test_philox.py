@@ -1,0 +1,39 @@
+"""Philox4x32-10 known-answer vectors (Random123 kat_vectors) for both oracle implementations,
+and the draw -> float32 mapping."""
+import numpy as np
+
+from oracle import oracle as orc
+
+KATS = [
+    ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]
+
+
+def test_known_answers_c_and_numpy():
+    L = orc.lib()
+    for ctr, key, want in KATS:
+        c, k, o = np.array(ctr, np.uint32), np.array(key, np.uint32), np.zeros(4, np.uint32)
+        L.orc_philox4x32_10(c.ctypes.data, k.ctypes.data, o.ctypes.data)
+        assert tuple(int(x) for x in o) == want
+        got = orc.philox4x32_10(*ctr, *key)
+        assert tuple(int(x) for x in got) == want
+
+
+def test_draws_stay_inside_the_angle_space_and_match_between_implementations():
+    n = 100000
+    gids = np.arange(5, 5 + n)
+    for stream in (orc.STREAM_STATE_Q, orc.STREAM_STATE_QD, orc.STREAM_GOAL):
+        d = orc.draw(987654321, gids, 123, stream)
+        assert d.dtype == np.float32 and (np.abs(d) <= orc.PI32).all()
+        assert abs(d.mean()) < 0.02 and abs(d.std() - 2 * np.pi / np.sqrt(12)) < 0.02
+    env = orc.OracleEnv(n, seed=987654321, env_id_base=5)
+    assert np.array_equal(env.goal.T, orc.draw(987654321, gids, 0, orc.STREAM_GOAL))
+    assert np.array_equal(env.held[0:3].T, orc.draw(987654321, gids, 0, orc.STREAM_STATE_Q))
+    assert np.array_equal(env.held[3:6].T, orc.draw(987654321, gids, 0, orc.STREAM_STATE_QD))
+    # 64-bit env ids and call counters reach the upper counter words
+    big = orc.draw(1, np.array([2 ** 40 + 3], np.uint64), 2 ** 33 + 1, orc.STREAM_GOAL)
+    small = orc.draw(1, np.array([3], np.uint64), 1, orc.STREAM_GOAL)
+    assert not np.array_equal(big, small)
