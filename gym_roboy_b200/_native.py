@@ -41,6 +41,7 @@ SIGNATURES = {
     "roboy_abi_version": (_int, []),
     "roboy_last_error": (ctypes.c_char_p, []),
     "roboy_cfg_msj": (_int, [_cfgp]),
+    "roboy_hold_interval": (_int, [_cfgp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "roboy_create": (_int, [_cfgp, _int, ctypes.POINTER(_vp)]),
     "roboy_destroy": (_int, [_vp]),
     "roboy_set_reward_range": (_int, [_vp, ctypes.c_double, ctypes.c_double]),
@@ -78,7 +79,8 @@ class RoboyNativeError(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB_PATH
+    # ROBOY_B200_LIB: point at another build of the same library (kernel experiments only)
+    return os.environ.get("ROBOY_B200_LIB") or _build.LIB_PATH
 
 
 def load():

@@ -66,42 +66,86 @@ __device__ __forceinline__ double l2_f64(double a0, double a1, double a2, double
 }
 
 // ---------------------------------------------------------------------------------------------
-// Hot path: state freshly sampled (float32, feasible), goal angles float32, goal velocities
-// the float64 zeros of roboy_env.py:23.
+// Hot path: state freshly sampled (float32, feasible, finite), goal angles float32 inside the
+// angle space, goal velocities the float64 zeros of roboy_env.py:23.
+//
+// Three exactness-preserving shortcuts keep this path short (it is issue-bound otherwise):
+//  * FASTDIV: x / c as  q0 = x*rc; r = fma(-q0, c, x); q = fma(r, rc, q0)  -- bit-identical to the
+//    IEEE division for every numerator this path can produce with the MSJ constants (proved by
+//    exhaustion: oracle/verify_fastdiv.c, tests/test_fastdiv_proof.py); other robots take
+//    __fdiv_rn.
+//  * the done test's angle distance is first bounded with a 3-instruction float32 estimate
+//    against a threshold widened by 1e-5 (the estimate is within 4e-7 of the exact sum); the
+//    exact numpy-order evaluation runs only when that cannot exclude "close".
+//  * NaN -> 0 of _l2_distance (roboy_env.py:139) cannot trigger: all operands are finite.
 // ---------------------------------------------------------------------------------------------
-template <bool PENALTY, bool BONUS>
-__device__ __forceinline__ void reward_reached_sampled(const float q[3], const float qd[3], const float g[3],
-                                                       const RobotConsts &c, float &reward_out, bool &reached,
+struct FastConsts {
+    float a_rc, v_rc;        // RN(1 / a_span), RN(1 / v_span)
+    float thr_angle_sq_hi;   // (thr_angle^2) * (1 + 1e-5), rounded up
+    float a_span24;          // a_span * 2^-24 (exact): uniform_in's span*u == a_span24 * float(x >> 8)
+    float reward_lo_f, reward_hi_f;  // reward range rounded INWARD to float32: for a float32 reward
+                                     // r,  lo <= r <= hi  <=>  reward_lo_f <= r <= reward_hi_f
+};
+
+template <bool FASTDIV>
+__device__ __forceinline__ float div_span(float t, float span, float rc) {
+    if (FASTDIV) {
+        const float q0 = __fmul_rn(t, rc);
+        const float r = fmaf(-q0, span, t);
+        return fmaf(r, rc, q0);
+    }
+    return __fdiv_rn(t, span);
+}
+
+template <bool FASTDIV>
+__device__ __forceinline__ float normalize32_hot(float v, float hi, float lo, float span, float rc) {
+    return div_span<FASTDIV>(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, v), hi), lo), span, rc);
+}
+
+template <bool PENALTY, bool BONUS, bool FASTDIV>
+__device__ __forceinline__ void reward_reached_sampled(float q0, float q1, float q2, float qd0, float qd1, float qd2,
+                                                       float g0, float g1, float g2, const RobotConsts &c,
+                                                       const FastConsts &f, float &reward_out, bool &reached,
                                                        bool &violation) {
-    // _did_reach_goal: angles in float32 (:126-127); velocities in float64 (:129-130), which
-    // only matters -- and is only evaluated -- once the angles are close.
+    // _did_reach_goal (:125-134): angles in float32, velocities in float64 -- evaluated exactly
+    // only when the cheap bound cannot rule "close" out.
     reached = false;
-    if (l2_f32(q[0], q[1], q[2], g[0], g[1], g[2]) < c.thr_angle) {
-        reached = l2_f64((double)qd[0], (double)qd[1], (double)qd[2], 0.0, 0.0, 0.0) < (double)c.thr_vel;
+    {
+        const float e0 = __fsub_rn(q0, g0), e1 = __fsub_rn(q1, g1), e2 = __fsub_rn(q2, g2);
+        const float est = fmaf(e2, e2, fmaf(e1, e1, __fmul_rn(e0, e0)));
+        if (est <= f.thr_angle_sq_hi) {
+            double s = (double)__fmul_rn(e0, e0);
+            s = __dadd_rn(s, (double)__fmul_rn(e1, e1));
+            s = __dadd_rn(s, (double)__fmul_rn(e2, e2));
+            if (__fsqrt_rn((float)s) < c.thr_angle)
+                reached = l2_f64((double)qd0, (double)qd1, (double)qd2, 0.0, 0.0, 0.0) < (double)c.thr_vel;
+        }
     }
     // compute_reward :94-96
-    float nq[3], ng[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        nq[k] = normalize32(q[k], c.a_hi, c.a_lo, c.a_span);
-        ng[k] = normalize32(g[k], c.a_hi, c.a_lo, c.a_span);
-    }
-    float r32 = -expf(l2_f32(nq[0], nq[1], nq[2], ng[0], ng[1], ng[2]));
-    double r64 = 0.0;
+    const float d0 = __fsub_rn(normalize32_hot<FASTDIV>(q0, c.a_hi, c.a_lo, c.a_span, f.a_rc),
+                               normalize32_hot<FASTDIV>(g0, c.a_hi, c.a_lo, c.a_span, f.a_rc));
+    const float d1 = __fsub_rn(normalize32_hot<FASTDIV>(q1, c.a_hi, c.a_lo, c.a_span, f.a_rc),
+                               normalize32_hot<FASTDIV>(g1, c.a_hi, c.a_lo, c.a_span, f.a_rc));
+    const float d2 = __fsub_rn(normalize32_hot<FASTDIV>(q2, c.a_hi, c.a_lo, c.a_span, f.a_rc),
+                               normalize32_hot<FASTDIV>(g2, c.a_hi, c.a_lo, c.a_span, f.a_rc));
+    double s = (double)__fmul_rn(d0, d0);                    // OpenBLAS sdot: float products, double sum
+    s = __dadd_rn(s, (double)__fmul_rn(d1, d1));
+    s = __dadd_rn(s, (double)__fmul_rn(d2, d2));
+    float r32 = -expf(__fsqrt_rn((float)s));
     if (PENALTY) {  // :98-100, float64 because the goal velocities are
         const double gz = normalize64(0.0, c.v_hi, c.v_lo, c.v_span);
-        const double v = l2_f64((double)normalize32(qd[0], c.v_hi, c.v_lo, c.v_span),
-                                (double)normalize32(qd[1], c.v_hi, c.v_lo, c.v_span),
-                                (double)normalize32(qd[2], c.v_hi, c.v_lo, c.v_span), gz, gz, gz);
-        r64 = __dmul_rn(__dadd_rn(v, 1.0), (double)__fsub_rn(r32, expf(r32)));
+        const double v = l2_f64((double)normalize32_hot<FASTDIV>(qd0, c.v_hi, c.v_lo, c.v_span, f.v_rc),
+                                (double)normalize32_hot<FASTDIV>(qd1, c.v_hi, c.v_lo, c.v_span, f.v_rc),
+                                (double)normalize32_hot<FASTDIV>(qd2, c.v_hi, c.v_lo, c.v_span, f.v_rc), gz, gz, gz);
+        double r64 = __dmul_rn(__dadd_rn(v, 1.0), (double)__fsub_rn(r32, expf(r32)));
         if (BONUS && reached) r64 = __dadd_rn(r64, (double)c.bonus_goal);  // :105-107
         reward_out = (float)r64;
+        violation = !(c.reward_lo <= r64 && r64 <= c.reward_hi);  // :109
     } else {
         if (BONUS && reached) r32 = __fadd_rn(r32, c.bonus_goal);
-        r64 = (double)r32;
         reward_out = r32;
+        violation = !(r32 >= f.reward_lo_f && r32 <= f.reward_hi_f);  // :109
     }
-    violation = !(c.reward_lo <= r64 && r64 <= c.reward_hi);  // :109
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -66,4 +66,10 @@ __device__ __forceinline__ float uniform_in(uint32_t x, float low, float span) {
     return __fadd_rn(low, __fmul_rn(span, u));
 }
 
+// Same value as uniform_in: (x>>8) * 2^-24 is exact and so is span * 2^-24, hence
+// RN(span * RN((x>>8) * 2^-24)) == RN(span24 * float(x>>8)) with span24 = span * 2^-24.
+__device__ __forceinline__ float uniform_in24(uint32_t x, float low, float span24) {
+    return __fadd_rn(low, __fmul_rn(span24, __uint2float_rn(x >> 8)));
+}
+
 }  // namespace roboy

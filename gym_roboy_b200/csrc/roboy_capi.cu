@@ -61,6 +61,66 @@ float box_diagonal_f32(float lo, float hi, int dim) {
     return sqrtf((float)s);
 }
 
+// ---- host-side derivation of the hot path's constants (config time, not the data path) ----
+uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+// order-preserving map float32 -> uint32 (for bisection over floats)
+uint32_t fkey(float f) { const uint32_t u = f2u(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+float fkey_inv(uint32_t k) { return u2f((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+// roboy_env.py:157-158 in float32, unfused: slope*(a - in_hi) + out_hi
+float rescale_f32(float a, float in_hi, float slope, float act_hi) {
+    volatile float r = a - in_hi;
+    r = slope * r;
+    r = r + act_hi;
+    return r;
+}
+
+// The set of action components a in [in_lo, in_hi] whose rescaled value passes numpy's
+// allclose(., 0) (|x| <= 1e-8, simulation_client.py:38).  rescale is monotone non-decreasing in a,
+// so the set is an interval of floats; both ends by bisection.  Empty -> lo > hi.
+void hold_interval(float in_lo, float in_hi, float slope, float act_hi, float *lo, float *hi) {
+    const double tol = 1e-8;
+    uint32_t a = fkey(in_lo), b = fkey(in_hi);
+    // smallest a with rescale(a) >= -tol
+    uint32_t l = a, r = b;
+    if ((double)rescale_f32(in_hi, in_hi, slope, act_hi) < -tol) { *lo = 1.f; *hi = -1.f; return; }
+    while (l < r) {
+        const uint32_t m = l + (r - l) / 2;
+        if ((double)rescale_f32(fkey_inv(m), in_hi, slope, act_hi) >= -tol) r = m; else l = m + 1;
+    }
+    const float first = fkey_inv(l);
+    // largest a with rescale(a) <= tol
+    l = a; r = b;
+    if ((double)rescale_f32(in_lo, in_hi, slope, act_hi) > tol) { *lo = 1.f; *hi = -1.f; return; }
+    while (l < r) {
+        const uint32_t m = l + (r - l + 1) / 2;
+        if ((double)rescale_f32(fkey_inv(m), in_hi, slope, act_hi) <= tol) l = m; else r = m - 1;
+    }
+    const float last = fkey_inv(l);
+    if (first > last) { *lo = 1.f; *hi = -1.f; return; }
+    *lo = first;
+    *hi = last;
+}
+
+float round_up_f32(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = nextafterf(f, INFINITY);
+    return f;
+}
+float round_down_f32(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = nextafterf(f, -INFINITY);
+    return f;
+}
+
+// The 3-instruction division of the sampled-state path is proved bit-exact (oracle/verify_fastdiv.c)
+// for the MSJ spans only: 2*pi_f32 (0x40c90fdb) and (pi/3)_f32 (0x3f860a92).
+bool spans_are_proved(const roboy_cfg &c) {
+    return f2u(c.angle_high - c.angle_low) == 0x40c90fdbu && c.angle_low == -c.angle_high &&
+           f2u(c.vel_high - c.vel_low) == 0x3f860a92u && c.vel_low == -c.vel_high;
+}
+
 }  // namespace
 
 struct roboy_env {
@@ -73,7 +133,10 @@ struct roboy_env {
     uint64_t launches = 0;  // kernels launched through this handle
     PhiloxKeys keys;
     RobotConsts consts;
+    FastConsts fast;
     float act_slope = 0.f;
+    float hold_lo = 1.f, hold_hi = -1.f;
+    bool fastdiv = false;
     // HBM
     float *goal = nullptr;
     uint32_t *step_flags = nullptr;
@@ -122,6 +185,11 @@ void fill_step_params(roboy_env *e, StepParams &p, const float *actions, float *
     p.t = e->t;
     p.keys = e->keys;
     p.c = e->consts;
+    p.f = e->fast;
+    p.f.reward_lo_f = round_up_f32(e->consts.reward_lo);
+    p.f.reward_hi_f = round_down_f32(e->consts.reward_hi);
+    p.hold_lo = e->hold_lo;
+    p.hold_hi = e->hold_hi;
     p.act_in_hi = 1.0f;   // roboy_env.py:31
     p.act_in_lo = -1.0f;
     p.act_hi = e->cfg.act_high;
@@ -179,6 +247,13 @@ int roboy_cfg_msj(roboy_cfg *cfg) {
     return ROBOY_OK;
 }
 
+int roboy_hold_interval(const roboy_cfg *cfg, float *lo, float *hi) {
+    if (!cfg || !lo || !hi) return fail(ROBOY_E_ARG, "NULL argument");
+    const float slope = (cfg->act_high - cfg->act_low) / (1.0f - (-1.0f));
+    hold_interval(-1.0f, 1.0f, slope, cfg->act_high, lo, hi);
+    return ROBOY_OK;
+}
+
 int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
     if (!cfg || !out) return fail(ROBOY_E_ARG, "NULL argument");
     *out = nullptr;
@@ -215,6 +290,14 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
     c.reward_lo = cfg->reward_lo;
     c.reward_hi = cfg->reward_hi;
     e->act_slope = (cfg->act_high - cfg->act_low) / (1.0f - (-1.0f));  // roboy_env.py:157, float32
+    hold_interval(-1.0f, 1.0f, e->act_slope, cfg->act_high, &e->hold_lo, &e->hold_hi);
+    e->fast.a_rc = (float)(1.0 / (double)c.a_span);
+    e->fast.v_rc = (float)(1.0 / (double)c.v_span);
+    e->fast.thr_angle_sq_hi = round_up_f32((double)c.thr_angle * (double)c.thr_angle * (1.0 + 1e-5));
+    e->fast.a_span24 = c.a_span * 0x1p-24f;
+    e->fast.reward_lo_f = -INFINITY;
+    e->fast.reward_hi_f = INFINITY;
+    e->fastdiv = spans_are_proved(*cfg);
 
     const uint64_t n = cfg->n_envs;
     cudaError_t err = cudaSuccess;
@@ -313,8 +396,8 @@ int roboy_step(roboy_env *env, const float *actions_dev, float *obs_dev, float *
     env->goal_sub = 1;  // done envs consume goal draw 0 of this counter value
     StepParams p;
     fill_step_params(env, p, actions_dev, obs_dev, reward_dev, done_dev);
-    CUDA_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset, env->sm_count,
-                         (cudaStream_t)stream));
+    CUDA_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset, env->fastdiv,
+                         env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -345,7 +428,7 @@ int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, 
                                  sizeof(float) * ROBOY_DIM_ACTION * cnt, cudaMemcpyHostToDevice, s));
         p.e_begin = b;
         p.e_end = eend;
-        CUDA_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
+        CUDA_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset, env->fastdiv,
                              env->sm_count, s));
         env->launches++;
         CUDA_TRY(cudaMemcpyAsync(obs_host + b * ROBOY_DIM_OBS, env->obs + b * ROBOY_DIM_OBS,
@@ -667,7 +750,7 @@ int roboy_step_geometry(roboy_env *env, int *grid, int *block, int *smem_bytes) 
     if (check_env(env)) return ROBOY_E_ARG;
     DeviceGuard g(env->device);
     const LaunchGeom geo = step_geometry(env->cfg.n_envs, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal,
-                                         env->cfg.auto_reset, env->sm_count);
+                                         env->cfg.auto_reset, env->fastdiv, env->sm_count);
     if (grid) *grid = geo.grid;
     if (block) *block = geo.block;
     if (smem_bytes) *smem_bytes = geo.smem;

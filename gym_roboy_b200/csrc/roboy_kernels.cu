@@ -25,27 +25,72 @@
 
 namespace roboy {
 
+#ifndef ROBOY_PREFETCH
+#define ROBOY_PREFETCH 1  // 0: none, 1: next chunk into registers, 2: next chunk into L2
+#endif
+
 namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
 
-__device__ __forceinline__ float4 ld_stream4(const float4 *p) { return __ldcs(p); }
-
-// |fl(fl(slope*fl(a - in_hi)) + act_hi)| <= hold_tol  <=> np.allclose(rescaled, 0) for this
-// component (roboy_env.py:157-158 then simulation_client.py:38; hold_tol is the largest float32
-// not above numpy's atol 1e-8, so the float32 compare equals numpy's float64 one).
-struct ActionTest {
-    float in_hi, in_lo, slope, act_hi, hold_tol;
-    __device__ __forceinline__ bool ok(float a) const { return a >= in_lo && a <= in_hi; }  // NaN -> false
-    __device__ __forceinline__ bool hold(float a) const {
-        const float r = __fadd_rn(__fmul_rn(slope, __fsub_rn(a, in_hi)), act_hi);
-        return fabsf(r) <= hold_tol;  // NaN -> false
-    }
-    __device__ __forceinline__ bool ok4(const float4 &v) const { return ok(v.x) && ok(v.y) && ok(v.z) && ok(v.w); }
-    __device__ __forceinline__ bool hold4(const float4 &v) const {
-        return hold(v.x) && hold(v.y) && hold(v.z) && hold(v.w);
-    }
+// One chunk's inputs: 32 envs = 1 KiB of actions (2 x float4 per lane), goal, step word.
+struct ChunkIn {
+    float4 a0, a1;
+    float g0, g1, g2;
+    uint32_t sf;
 };
+
+__device__ __forceinline__ ChunkIn load_chunk(const StepParams &p, uint64_t base, int lane) {
+    ChunkIn in;
+    const uint64_t n_end = p.e_end;
+    const float4 *a4 = reinterpret_cast<const float4 *>(p.actions) + base * 2;
+    if (base + 32 <= n_end) {
+        in.a0 = __ldcs(a4 + lane);  // streamed once: evict-first
+        in.a1 = __ldcs(a4 + 32 + lane);
+        const uint64_t e = base + lane;
+        in.g0 = p.goal[e];
+        in.g1 = p.goal[p.n + e];
+        in.g2 = p.goal[2 * p.n + e];
+        in.sf = p.step_flags[e];
+    } else {  // ragged tail: out-of-range slots read as neutral values
+        const float4 z = make_float4(0.5f, 0.5f, 0.5f, 0.5f);  // in range, not "close to zero"
+        in.a0 = (base * 2 + lane < n_end * 2) ? __ldcs(a4 + lane) : z;
+        in.a1 = (base * 2 + 32 + lane < n_end * 2) ? __ldcs(a4 + 32 + lane) : z;
+        const uint64_t e = base + lane;
+        const bool live = e < n_end;
+        in.g0 = live ? p.goal[e] : 0.f;
+        in.g1 = live ? p.goal[p.n + e] : 0.f;
+        in.g2 = live ? p.goal[2 * p.n + e] : 0.f;
+        in.sf = live ? p.step_flags[e] : 1u;
+    }
+    return in;
+}
+
+// Next-chunk prefetch into L2 (no registers held across the compute phase): lanes 0..7 touch the
+// chunk's eight 128 B action lines, lanes 8..10 its three goal lines, lane 11 the step-word line.
+__device__ __forceinline__ void prefetch_chunk_l2(const StepParams &p, uint64_t base, int lane) {
+    const char *addr;
+    if (lane < 8) addr = reinterpret_cast<const char *>(p.actions) + base * 32 + lane * 128;
+    else if (lane < 11) addr = reinterpret_cast<const char *>(p.goal + (uint64_t)(lane - 8) * p.n + base);
+    else addr = reinterpret_cast<const char *>(p.step_flags + base);
+    if (lane < 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+}
+
+// roboy_env.py:52: every component inside [-1, 1] (closed; NaN fails).
+__device__ __forceinline__ bool action_ok4(const float4 &v, float hi) {
+    return fabsf(v.x) <= hi && fabsf(v.y) <= hi && fabsf(v.z) <= hi && fabsf(v.w) <= hi;
+}
+
+// simulation_client.py:38 on the rescaled action (roboy_env.py:157-158): all four components
+// inside [hold_lo, hold_hi] -- the exact pre-image of numpy's allclose(rescaled, 0), found on
+// the host by bisection over the monotone float32 map a -> rescaled(a).  A max-magnitude
+// filter keeps the eight compares off the common path (NaN passes the filter and then fails
+// the compares, as it must).
+__device__ __forceinline__ bool action_hold4(const float4 &v, float lo, float hi, float mag) {
+    const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    if (m > mag) return false;
+    return v.x >= lo && v.x <= hi && v.y >= lo && v.y <= hi && v.z >= lo && v.z <= hi && v.w >= lo && v.w <= hi;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -53,11 +98,15 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+struct HoldOut {
+    float q0, q1, q2, qd0, qd1, qd2, reward;
+    uint32_t flags;  // bit 0 reached, bit 1 violation
+};
+
 // Hold branch of the Stub (simulation_client.py:38-39): the stored state is returned.  Rare and
 // divergent, so it is kept out of line and out of the hot path's register budget.
-__device__ __noinline__ void hold_branch(const StepParams &p, uint64_t e, uint32_t sf, const float g[3],
-                                         bool penalty, bool bonus, float q[3], float qd[3], float &reward,
-                                         bool &reached, bool &violation) {
+__device__ __noinline__ HoldOut hold_branch(const StepParams &p, uint64_t e, uint32_t sf, float g0, float g1, float g2,
+                                            bool penalty, bool bonus) {
     HeldState s;
     if (sf & ROBOY_F_HELD_ZERO64) {
 #pragma unroll
@@ -74,91 +123,100 @@ __device__ __noinline__ void hold_branch(const StepParams &p, uint64_t e, uint32
         s.feasible = !(sf & ROBOY_F_HELD_INFEASIBLE);
     }
     double r;
+    bool reached, violation;
+    const float g[3] = {g0, g1, g2};
     const float no_gqd[3] = {0.f, 0.f, 0.f};
     reward_reached_general(s, g, false, no_gqd, penalty, bonus, p.c, r, reached, violation);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        q[k] = (float)s.q[k];
-        qd[k] = (float)s.qd[k];
-    }
-    reward = (float)r;
+    HoldOut o;
+    o.q0 = (float)s.q[0]; o.q1 = (float)s.q[1]; o.q2 = (float)s.q[2];
+    o.qd0 = (float)s.qd[0]; o.qd1 = (float)s.qd[1]; o.qd2 = (float)s.qd[2];
+    o.reward = (float)r;
+    o.flags = (reached ? 1u : 0u) | (violation ? 2u : 0u);
+    return o;
 }
 
 }  // namespace
 
-template <bool PENALTY, bool BONUS, bool AUTO_RESET>
-__global__ void __launch_bounds__(kStepBlock) step_kernel(const __grid_constant__ StepParams p) {
+template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV>
+__global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const __grid_constant__ StepParams p) {
     __shared__ __align__(16) float s_obs[kWarpsPerBlock][32 * kObsDim];
-    __shared__ double s_red[kWarpsPerBlock][ROBOY_STAT_COUNT];
+    __shared__ double s_red[kWarpsPerBlock];
+    // rare events (done ~1/400 of env-steps, holds, violations) are counted with shared-memory
+    // atomics where they happen instead of tying up registers in the hot loop
+    __shared__ unsigned int s_cnt[5];  // done, success, hold, violation, sum of episode lengths
+    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const uint64_t n = p.n;
     const uint64_t n_end = p.e_end;
-    const uint64_t chunk0 = p.e_begin >> 5;
     const uint64_t n_chunks = (n_end + 31) >> 5;
     const uint64_t warp_stride = (uint64_t)gridDim.x * kWarpsPerBlock;
-    const float hold_tol = (double)1e-8f > 1e-8 ? __uint_as_float(__float_as_uint(1e-8f) - 1u) : 1e-8f;
-    const ActionTest at{p.act_in_hi, p.act_in_lo, p.act_slope, p.act_hi, hold_tol};
+    const float hold_mag = fmaxf(fabsf(p.hold_lo), fabsf(p.hold_hi));
+    float *so = s_obs[warp];
 
-    uint32_t n_steps = 0, n_done = 0, n_succ = 0, n_hold = 0, n_viol = 0, sum_eplen = 0;
+    uint32_t n_steps = 0;
     double sum_reward = 0.0;
 
-    for (uint64_t chunk = chunk0 + (uint64_t)blockIdx.x * kWarpsPerBlock + warp; chunk < n_chunks; chunk += warp_stride) {
+    uint64_t chunk = (p.e_begin >> 5) + (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
+#if ROBOY_PREFETCH == 1
+    ChunkIn in;
+    if (chunk < n_chunks) in = load_chunk(p, chunk << 5, lane);
+#endif
+
+    while (chunk < n_chunks) {
         const uint64_t base = chunk << 5;
         const uint64_t e = base + lane;
         const bool full = base + 32 <= n_end;
         const bool live = e < n_end;
-
-        // ---- loads: 2 x 16 B of actions, 3 x 4 B goal, 4 B step word, all issued up front ----
-        const float4 *a4 = reinterpret_cast<const float4 *>(p.actions) + base * 2;
-        float4 A0, A1;
-        bool v0 = true, v1 = true;
-        if (full) {
-            A0 = ld_stream4(a4 + lane);
-            A1 = ld_stream4(a4 + 32 + lane);
-        } else {
-            v0 = base * 2 + lane < n_end * 2;
-            v1 = base * 2 + 32 + lane < n_end * 2;
-            A0 = v0 ? ld_stream4(a4 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-            A1 = v1 ? ld_stream4(a4 + 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float g[3] = {0.f, 0.f, 0.f};
-        uint32_t sf = 1u;
-        if (live) {
-            g[0] = p.goal[e];
-            g[1] = p.goal[n + e];
-            g[2] = p.goal[2 * n + e];
-            sf = p.step_flags[e];
-        }
+        const uint64_t next = chunk + warp_stride;
+#if ROBOY_PREFETCH == 1
+        // software prefetch into registers: the next chunk's loads are in flight during this compute
+        const ChunkIn cur = in;
+        if (next < n_chunks) in = load_chunk(p, next << 5, lane);
+#else
+        const ChunkIn cur = load_chunk(p, base, lane);
+#if ROBOY_PREFETCH == 2
+        if (next < n_chunks) prefetch_chunk_l2(p, next << 5, lane);
+#endif
+#endif
 
         // ---- roboy_env.py:52 assert + simulation_client.py:38 allclose, as warp ballots ----
-        const uint32_t okm0 = __ballot_sync(kFull, at.ok4(A0) || !v0);
-        const uint32_t okm1 = __ballot_sync(kFull, at.ok4(A1) || !v1);
-        const uint32_t hdm0 = __ballot_sync(kFull, at.hold4(A0) && v0);
-        const uint32_t hdm1 = __ballot_sync(kFull, at.hold4(A1) && v1);
-        const uint32_t sh = (lane & 15) << 1;  // env `lane` owns float4 2*lane and 2*lane+1 of the chunk
+        // env `lane` owns float4 2*lane and 2*lane+1 of the chunk's 64
+        const uint32_t okm0 = __ballot_sync(kFull, action_ok4(cur.a0, p.act_in_hi));
+        const uint32_t okm1 = __ballot_sync(kFull, action_ok4(cur.a1, p.act_in_hi));
+        const uint32_t hdm0 = __ballot_sync(kFull, action_hold4(cur.a0, p.hold_lo, p.hold_hi, hold_mag));
+        const uint32_t hdm1 = __ballot_sync(kFull, action_hold4(cur.a1, p.hold_lo, p.hold_hi, hold_mag));
+        const uint32_t sh = (lane & 15) << 1;
         const bool act_ok = (((lane < 16 ? okm0 : okm1) >> sh) & 3u) == 3u;
         const bool hold = live && (((lane < 16 ? hdm0 : hdm1) >> sh) & 3u) == 3u;
 
         const uint64_t gid = p.gid_base + e;
-        float q[3], qd[3], reward;
+        const float g0 = cur.g0, g1 = cur.g1, g2 = cur.g2;
+        const uint32_t sf = cur.sf;
+        float q0, q1, q2, qd0, qd1, qd2, reward;
         bool reached, violation;
         if (!hold) {
             // simulation_client.py:40 -> roboy_robot.py:35-39: fresh sample; velocities are drawn
             // from the ANGLE space too (reference quirk, :38)
             const uint4 ra = philox_draw(gid, p.t, kStreamStateQ, p.keys);
             const uint4 rb = philox_draw(gid, p.t, kStreamStateQd, p.keys);
-            q[0] = uniform_in(ra.x, p.c.a_lo, p.c.a_span);
-            q[1] = uniform_in(ra.y, p.c.a_lo, p.c.a_span);
-            q[2] = uniform_in(ra.z, p.c.a_lo, p.c.a_span);
-            qd[0] = uniform_in(rb.x, p.c.a_lo, p.c.a_span);
-            qd[1] = uniform_in(rb.y, p.c.a_lo, p.c.a_span);
-            qd[2] = uniform_in(rb.z, p.c.a_lo, p.c.a_span);
-            reward_reached_sampled<PENALTY, BONUS>(q, qd, g, p.c, reward, reached, violation);
+            q0 = uniform_in24(ra.x, p.c.a_lo, p.f.a_span24);
+            q1 = uniform_in24(ra.y, p.c.a_lo, p.f.a_span24);
+            q2 = uniform_in24(ra.z, p.c.a_lo, p.f.a_span24);
+            qd0 = uniform_in24(rb.x, p.c.a_lo, p.f.a_span24);
+            qd1 = uniform_in24(rb.y, p.c.a_lo, p.f.a_span24);
+            qd2 = uniform_in24(rb.z, p.c.a_lo, p.f.a_span24);
+            reward_reached_sampled<PENALTY, BONUS, FASTDIV>(q0, q1, q2, qd0, qd1, qd2, g0, g1, g2, p.c, p.f, reward,
+                                                            reached, violation);
         } else {
-            hold_branch(p, e, sf, g, PENALTY, BONUS, q, qd, reward, reached, violation);
-            ++n_hold;
+            const HoldOut h = hold_branch(p, e, sf, g0, g1, g2, PENALTY, BONUS);
+            q0 = h.q0; q1 = h.q1; q2 = h.q2; qd0 = h.qd0; qd1 = h.qd1; qd2 = h.qd2;
+            reward = h.reward;
+            reached = h.flags & 1u;
+            violation = h.flags & 2u;
+            atomicAdd(&s_cnt[2], 1u);
         }
 
         uint32_t step = sf & ROBOY_STEP_MASK;
@@ -167,46 +225,43 @@ __global__ void __launch_bounds__(kStepBlock) step_kernel(const __grid_constant_
         const bool done = reached || timeout;                 // :65-66
         uint32_t flags = sf & ~ROBOY_STEP_MASK;
 
-        float o[kObsDim] = {q[0], q[1], q[2], qd[0], qd[1], qd[2], g[0], g[1], g[2]};  // :75-80
+        // obs = [q, qd, goal] (:75-80), staged in shared memory; stride 9 is bank-conflict-free
+        float *row = so + lane * kObsDim;
+        row[0] = q0; row[1] = q1; row[2] = q2; row[3] = qd0; row[4] = qd1; row[5] = qd2;
+        row[6] = g0; row[7] = g1; row[8] = g2;
 
         if (done && live) {
             // :67-68 new goal.  Under auto-reset the worker's reset() (:82-87) draws once more and
             // only that goal is ever observable, so a single draw is materialised.
             const uint4 rg = philox_draw(gid, p.t, kStreamGoal, p.keys);
-            const float ng0 = uniform_in(rg.x, p.c.a_lo, p.c.a_span);
-            const float ng1 = uniform_in(rg.y, p.c.a_lo, p.c.a_span);
-            const float ng2 = uniform_in(rg.z, p.c.a_lo, p.c.a_span);
+            const float ng0 = uniform_in24(rg.x, p.c.a_lo, p.f.a_span24);
+            const float ng1 = uniform_in24(rg.y, p.c.a_lo, p.f.a_span24);
+            const float ng2 = uniform_in24(rg.z, p.c.a_lo, p.f.a_span24);
             p.goal[e] = ng0;
             p.goal[n + e] = ng1;
             p.goal[2 * n + e] = ng2;
             if (AUTO_RESET) {
                 if (p.terminal_obs) {
 #pragma unroll
-                    for (int k = 0; k < kObsDim; ++k) p.terminal_obs[e * kObsDim + k] = o[k];
+                    for (int k = 0; k < kObsDim; ++k) p.terminal_obs[e * kObsDim + k] = row[k];
                 }
-                o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.0f;  // reset(): zero state, :83-84,87
-                o[6] = ng0;
-                o[7] = ng1;
-                o[8] = ng2;
-                sum_eplen += step - 1;
+                row[0] = row[1] = row[2] = row[3] = row[4] = row[5] = 0.0f;  // reset(): zero state, :83-84,87
+                row[6] = ng0; row[7] = ng1; row[8] = ng2;
+                atomicAdd(&s_cnt[4], step - 1);
                 step = 1;                                        // :85
                 flags = ROBOY_F_HELD_ZERO64;
             }
-            ++n_done;
-            n_succ += reached;
+            atomicAdd(&s_cnt[0], 1u);
+            if (reached) atomicAdd(&s_cnt[1], 1u);
         }
 
-        bool bad = live && (violation || !act_ok);
-        if (bad) {
+        if (live && (violation || !act_ok)) {
             atomicOr(p.err_flags, (violation ? ROBOY_ERR_REWARD_RANGE : 0u) | (!act_ok ? ROBOY_ERR_ACTION : 0u));
             atomicMin(p.first_bad, (unsigned long long)gid);
-            ++n_viol;
+            atomicAdd(&s_cnt[3], 1u);
         }
 
         // ---- stores ----
-        float *so = s_obs[warp];
-#pragma unroll
-        for (int k = 0; k < kObsDim; ++k) so[lane * kObsDim + k] = o[k];  // stride 9: conflict-free
         if (live) {
             p.step_flags[e] = step | flags;
             __stcs(p.reward + e, reward);
@@ -226,24 +281,28 @@ __global__ void __launch_bounds__(kStepBlock) step_kernel(const __grid_constant_
             for (uint32_t i = lane; i < n_valid; i += 32) p.obs[base * kObsDim + i] = so[i];
         }
         __syncwarp();
+        chunk = next;
     }
 
     // ---- K3: episode statistics, one set of atomics per CTA ----
-    const double vals[ROBOY_STAT_COUNT] = {
-        (double)__reduce_add_sync(kFull, n_steps), (double)__reduce_add_sync(kFull, n_done),
-        (double)__reduce_add_sync(kFull, n_succ),  (double)__reduce_add_sync(kFull, n_done - n_succ),
-        warp_sum(sum_reward),                      (double)__reduce_add_sync(kFull, sum_eplen),
-        (double)__reduce_add_sync(kFull, n_hold),  (double)__reduce_add_sync(kFull, n_viol)};
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < ROBOY_STAT_COUNT; ++k) s_red[warp][k] = vals[k];
-    }
+    const uint32_t w_steps = __reduce_add_sync(kFull, n_steps);
+    const double w_reward = warp_sum(sum_reward);
+    if (lane == 0) s_red[warp] = w_reward;
+    __shared__ unsigned int s_steps;
+    if (threadIdx.x == 0) s_steps = 0;
     __syncthreads();
-    if (threadIdx.x < ROBOY_STAT_COUNT) {
-        double acc = 0.0;
+    if (lane == 0) atomicAdd(&s_steps, w_steps);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0;
 #pragma unroll
-        for (int w = 0; w < kWarpsPerBlock; ++w) acc += s_red[w][threadIdx.x];
-        if (acc != 0.0) atomicAdd(p.stats + threadIdx.x, acc);
+        for (int w = 0; w < kWarpsPerBlock; ++w) r += s_red[w];
+        const double done = (double)s_cnt[0], succ = (double)s_cnt[1];
+        const double v[ROBOY_STAT_COUNT] = {(double)s_steps, done, succ, done - succ, r, (double)s_cnt[4],
+                                            (double)s_cnt[2], (double)s_cnt[3]};
+#pragma unroll
+        for (int k = 0; k < ROBOY_STAT_COUNT; ++k)
+            if (v[k] != 0.0) atomicAdd(p.stats + k, v[k]);
     }
 }
 
@@ -252,16 +311,39 @@ __global__ void __launch_bounds__(kStepBlock) step_kernel(const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-template <bool P, bool B, bool A>
-int blocks_per_sm() {
-    static int cached = 0;
-    if (!cached) {
-        int b = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, step_kernel<P, B, A>, kStepBlock, 0) != cudaSuccess || b < 1)
-            b = 1;
-        cached = b;
+using StepKernelFn = void (*)(const StepParams);
+
+template <int SEL>
+StepKernelFn kernel_for() {
+    return step_kernel<(SEL & 8) != 0, (SEL & 4) != 0, (SEL & 2) != 0, (SEL & 1) != 0>;
+}
+
+StepKernelFn select_kernel(int sel) {
+    switch (sel & 15) {
+        case 0: return kernel_for<0>();   case 1: return kernel_for<1>();
+        case 2: return kernel_for<2>();   case 3: return kernel_for<3>();
+        case 4: return kernel_for<4>();   case 5: return kernel_for<5>();
+        case 6: return kernel_for<6>();   case 7: return kernel_for<7>();
+        case 8: return kernel_for<8>();   case 9: return kernel_for<9>();
+        case 10: return kernel_for<10>(); case 11: return kernel_for<11>();
+        case 12: return kernel_for<12>(); case 13: return kernel_for<13>();
+        case 14: return kernel_for<14>(); default: return kernel_for<15>();
     }
-    return cached;
+}
+
+int selector(bool penalty, bool bonus, bool auto_reset, bool fastdiv) {
+    return (penalty ? 8 : 0) | (bonus ? 4 : 0) | (auto_reset ? 2 : 0) | (fastdiv ? 1 : 0);
+}
+
+int blocks_per_sm(int sel) {
+    static int cached[16] = {0};
+    if (!cached[sel]) {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, select_kernel(sel), kStepBlock, 0) != cudaSuccess || b < 1)
+            b = 1;
+        cached[sel] = b;
+    }
+    return cached[sel];
 }
 
 int grid_for(uint64_t n_range, int per_sm, int sm_count) {
@@ -271,48 +353,21 @@ int grid_for(uint64_t n_range, int per_sm, int sm_count) {
     return (int)(want < cap ? want : cap);
 }
 
-template <bool P, bool B, bool A>
-cudaError_t launch_step_t(const StepParams &p, int sm_count, cudaStream_t stream) {
-    const int grid = grid_for(p.e_end - p.e_begin, blocks_per_sm<P, B, A>(), sm_count);
-    step_kernel<P, B, A><<<grid, kStepBlock, 0, stream>>>(p);
-    return cudaGetLastError();
-}
-
-int blocks_per_sm_sel(int sel) {
-    switch (sel) {
-        case 0: return blocks_per_sm<false, false, false>();
-        case 1: return blocks_per_sm<false, false, true>();
-        case 2: return blocks_per_sm<false, true, false>();
-        case 3: return blocks_per_sm<false, true, true>();
-        case 4: return blocks_per_sm<true, false, false>();
-        case 5: return blocks_per_sm<true, false, true>();
-        case 6: return blocks_per_sm<true, true, false>();
-        default: return blocks_per_sm<true, true, true>();
-    }
-}
-
 }  // namespace
 
-LaunchGeom step_geometry(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, int sm_count) {
-    const int sel = (penalty ? 4 : 0) | (bonus ? 2 : 0) | (auto_reset ? 1 : 0);
-    return LaunchGeom{grid_for(n_range, blocks_per_sm_sel(sel), sm_count), kStepBlock,
+LaunchGeom step_geometry(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count) {
+    const int sel = selector(penalty, bonus, auto_reset, fastdiv);
+    return LaunchGeom{grid_for(n_range, blocks_per_sm(sel), sm_count), kStepBlock,
                       (int)(sizeof(float) * kWarpsPerBlock * 32 * kObsDim + sizeof(double) * kWarpsPerBlock * ROBOY_STAT_COUNT)};
 }
 
-cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto_reset, int sm_count,
+cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count,
                         cudaStream_t stream) {
     if (p.e_end <= p.e_begin) return cudaSuccess;
-    const int sel = (penalty ? 4 : 0) | (bonus ? 2 : 0) | (auto_reset ? 1 : 0);
-    switch (sel) {
-        case 0: return launch_step_t<false, false, false>(p, sm_count, stream);
-        case 1: return launch_step_t<false, false, true>(p, sm_count, stream);
-        case 2: return launch_step_t<false, true, false>(p, sm_count, stream);
-        case 3: return launch_step_t<false, true, true>(p, sm_count, stream);
-        case 4: return launch_step_t<true, false, false>(p, sm_count, stream);
-        case 5: return launch_step_t<true, false, true>(p, sm_count, stream);
-        case 6: return launch_step_t<true, true, false>(p, sm_count, stream);
-        default: return launch_step_t<true, true, true>(p, sm_count, stream);
-    }
+    const int sel = selector(penalty, bonus, auto_reset, fastdiv);
+    const int grid = grid_for(p.e_end - p.e_begin, blocks_per_sm(sel), sm_count);
+    select_kernel(sel)<<<grid, kStepBlock, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

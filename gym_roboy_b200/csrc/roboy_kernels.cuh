@@ -10,6 +10,10 @@ namespace roboy {
 
 constexpr int kStepBlock = 256;            // threads per CTA of the step kernel
 constexpr int kWarpsPerBlock = kStepBlock / 32;
+#ifndef ROBOY_STEP_MIN_BLOCKS
+#define ROBOY_STEP_MIN_BLOCKS 3
+#endif
+constexpr int kStepMinBlocks = ROBOY_STEP_MIN_BLOCKS;  // __launch_bounds__ min CTAs/SM (register cap)
 constexpr int kObsDim = 9, kActDim = 8;
 
 struct StepParams {
@@ -20,6 +24,10 @@ struct StepParams {
     uint64_t t;         // Philox call counter of this launch
     PhiloxKeys keys;
     RobotConsts c;
+    FastConsts f;
+    float hold_lo, hold_hi;      // the float32 interval of action components a for which
+                                 // |fl(fl(slope*fl(a - in_hi)) + act_hi)| <= 1e-8, i.e. numpy's
+                                 // allclose(rescaled, 0) (roboy_env.py:157-158, simulation_client.py:38)
     float act_in_hi, act_in_lo;  // RoboyEnv.action_space bounds, roboy_env.py:31
     float act_hi, act_slope;     // robot action space high and fl32((hi-lo)/(in_hi-in_lo)), roboy_env.py:157
     int32_t max_len;             // roboy_env.py:28
@@ -41,8 +49,8 @@ struct LaunchGeom {
     int grid, block, smem;
 };
 
-LaunchGeom step_geometry(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, int sm_count);
-cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto_reset, int sm_count,
+LaunchGeom step_geometry(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count);
+cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count,
                         cudaStream_t stream);
 
 struct InitParams {

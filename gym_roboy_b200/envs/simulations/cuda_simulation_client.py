@@ -82,8 +82,9 @@ class CudaSimulationClient(SimulationClient):
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            self._lib.roboy_destroy(h)
+        destroy = getattr(getattr(self, "_lib", None), "roboy_destroy", None)
+        if h and destroy is not None:   # (None during interpreter shutdown)
+            destroy(h)
 
     def __del__(self):
         try:

@@ -105,6 +105,12 @@ const char *roboy_last_error(void);
  * (roboy_env.py:12-14,26-28), auto_reset = 1 and an unbounded reward range. */
 int roboy_cfg_msj(roboy_cfg *cfg);
 
+/* Host-only helper (no GPU needed): the closed float32 interval [lo, hi] of action components
+ * for which the Stub holds its state -- the pre-image of numpy's allclose(rescaled, 0)
+ * (simulation_client.py:38) under the float32 rescale of roboy_env.py:157-158.  For MSJ this is
+ * [-2^-24, 2^-25].  lo > hi means the interval is empty.  The step kernel compares against it. */
+int roboy_hold_interval(const roboy_cfg *cfg, float *lo, float *hi);
+
 /* RoboyEnv.__init__ over StubSimulationClient.__init__ (roboy_env.py:12-38,
  * simulation_client.py:29-31) for n_envs envs on CUDA device `device`: allocates the SoA state
  * in HBM and runs the init kernel (held state := random sample, goal := random, step_num := 1). */
