@@ -82,7 +82,8 @@ __device__ __forceinline__ double l2_f64(double a0, double a1, double a2, double
 struct FastConsts {
     float a_rc, v_rc;        // RN(1 / a_span), RN(1 / v_span)
     float thr_angle_sq_hi;   // (thr_angle^2) * (1 + 1e-5), rounded up
-    float a_span24;          // a_span * 2^-24 (exact): uniform_in's span*u == a_span24 * float(x >> 8)
+    float a_span24;          // a_span * 2^-24 (exact): goal draws,  v = low + a_span24 * float(x >> 8)
+    float a_span21;          // a_span * 2^-21 (exact): state draws, v = low + a_span21 * float(k), k < 2^21
     float reward_lo_f, reward_hi_f;  // reward range rounded INWARD to float32: for a float32 reward
                                      // r,  lo <= r <= hi  <=>  reward_lo_f <= r <= reward_hi_f
 };

@@ -16,7 +16,7 @@
 
 namespace roboy {
 
-enum : uint32_t { kStreamStateQ = 0, kStreamStateQd = 1, kStreamGoal = 2 };
+enum : uint32_t { kStreamState = 0, kStreamGoal = 2 };
 
 struct PhiloxKeys {
     // the ten round keys, k + r*W, precomputed on the host (uniform across the grid)
@@ -70,6 +70,29 @@ __device__ __forceinline__ float uniform_in(uint32_t x, float low, float span) {
 // RN(span * RN((x>>8) * 2^-24)) == RN(span24 * float(x>>8)) with span24 = span * 2^-24.
 __device__ __forceinline__ float uniform_in24(uint32_t x, float low, float span24) {
     return __fadd_rn(low, __fmul_rn(span24, __uint2float_rn(x >> 8)));
+}
+
+// A state draw (RoboyRobot.new_random_state: 3 angles + 3 velocities, roboy_robot.py:35-39) takes
+// ONE Philox block: its 128 bits are cut into six 21-bit integers k0..k5 (bits 127..2, the last
+// two unused), v_i = low + (span * 2^-21) * float(k_i).  21 bits put the samples on a grid of
+// 3e-6 rad; a second block per draw would cost a quarter of the step kernel's instructions.
+struct Draw6 {
+    uint32_t k[6];
+};
+
+__device__ __forceinline__ Draw6 split6x21(const uint4 r) {
+    Draw6 d;
+    d.k[0] = r.x >> 11;
+    d.k[1] = __funnelshift_r(r.y, r.x, 22) & 0x1fffffu;  // low 11 bits of x, high 10 bits of y
+    d.k[2] = (r.y >> 1) & 0x1fffffu;
+    d.k[3] = r.z >> 11;
+    d.k[4] = __funnelshift_r(r.w, r.z, 22) & 0x1fffffu;
+    d.k[5] = (r.w >> 1) & 0x1fffffu;
+    return d;
+}
+
+__device__ __forceinline__ float uniform_in21(uint32_t k, float low, float span21) {
+    return __fadd_rn(low, __fmul_rn(span21, __uint2float_rn(k)));
 }
 
 }  // namespace roboy

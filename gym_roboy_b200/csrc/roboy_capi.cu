@@ -190,6 +190,7 @@ void fill_step_params(roboy_env *e, StepParams &p, const float *actions, float *
     p.f.reward_hi_f = round_down_f32(e->consts.reward_hi);
     p.hold_lo = e->hold_lo;
     p.hold_hi = e->hold_hi;
+    p.hold_mag = fmaxf(fabsf(e->hold_lo), fabsf(e->hold_hi));
     p.act_in_hi = 1.0f;   // roboy_env.py:31
     p.act_in_lo = -1.0f;
     p.act_hi = e->cfg.act_high;
@@ -197,6 +198,8 @@ void fill_step_params(roboy_env *e, StepParams &p, const float *actions, float *
     p.max_len = e->cfg.max_episode_len;
     p.actions = actions;
     p.goal = e->goal;
+    p.goal1 = e->goal + e->cfg.n_envs;
+    p.goal2 = e->goal + 2 * e->cfg.n_envs;
     p.step_flags = e->step_flags;
     p.held = e->held;
     p.obs = obs ? obs : e->obs;
@@ -258,6 +261,7 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
     if (!cfg || !out) return fail(ROBOY_E_ARG, "NULL argument");
     *out = nullptr;
     if (cfg->n_envs == 0) return fail(ROBOY_E_ARG, "n_envs must be > 0");
+    if (cfg->n_envs > 0xfffffff0ull) return fail(ROBOY_E_ARG, "a shard holds fewer than 2^32 envs");
     if (!(cfg->angle_high > cfg->angle_low) || !(cfg->vel_high > cfg->vel_low) || !(cfg->act_high > cfg->act_low))
         return fail(ROBOY_E_ARG, "empty robot space");
     int n_dev = 0;
@@ -295,6 +299,7 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
     e->fast.v_rc = (float)(1.0 / (double)c.v_span);
     e->fast.thr_angle_sq_hi = round_up_f32((double)c.thr_angle * (double)c.thr_angle * (1.0 + 1e-5));
     e->fast.a_span24 = c.a_span * 0x1p-24f;
+    e->fast.a_span21 = c.a_span * 0x1p-21f;
     e->fast.reward_lo_f = -INFINITY;
     e->fast.reward_hi_f = INFINITY;
     e->fastdiv = spans_are_proved(*cfg);

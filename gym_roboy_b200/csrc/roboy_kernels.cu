@@ -26,7 +26,7 @@
 namespace roboy {
 
 #ifndef ROBOY_PREFETCH
-#define ROBOY_PREFETCH 1  // 0: none, 1: next chunk into registers, 2: next chunk into L2
+#define ROBOY_PREFETCH 2  // 0: none, 1: next chunk into registers, 2: next chunk into L2 (measured best)
 #endif
 
 namespace {
@@ -40,27 +40,29 @@ struct ChunkIn {
     uint32_t sf;
 };
 
-__device__ __forceinline__ ChunkIn load_chunk(const StepParams &p, uint64_t base, int lane) {
+// Local env indices are 32-bit (a shard holds < 2^32 envs: 4 Gi envs would need 400 GB of HBM);
+// only the Philox counter uses the 64-bit global id.
+template <bool TAIL>
+__device__ __forceinline__ ChunkIn load_chunk(const StepParams &p, uint32_t base, int lane) {
     ChunkIn in;
-    const uint64_t n_end = p.e_end;
-    const float4 *a4 = reinterpret_cast<const float4 *>(p.actions) + base * 2;
-    if (base + 32 <= n_end) {
+    const float4 *a4 = reinterpret_cast<const float4 *>(p.actions) + (size_t)base * 2;
+    const uint32_t e = base + lane;
+    if (!TAIL) {
         in.a0 = __ldcs(a4 + lane);  // streamed once: evict-first
         in.a1 = __ldcs(a4 + 32 + lane);
-        const uint64_t e = base + lane;
         in.g0 = p.goal[e];
-        in.g1 = p.goal[p.n + e];
-        in.g2 = p.goal[2 * p.n + e];
+        in.g1 = p.goal1[e];
+        in.g2 = p.goal2[e];
         in.sf = p.step_flags[e];
     } else {  // ragged tail: out-of-range slots read as neutral values
+        const uint32_t n_end = (uint32_t)p.e_end;
         const float4 z = make_float4(0.5f, 0.5f, 0.5f, 0.5f);  // in range, not "close to zero"
         in.a0 = (base * 2 + lane < n_end * 2) ? __ldcs(a4 + lane) : z;
         in.a1 = (base * 2 + 32 + lane < n_end * 2) ? __ldcs(a4 + 32 + lane) : z;
-        const uint64_t e = base + lane;
         const bool live = e < n_end;
         in.g0 = live ? p.goal[e] : 0.f;
-        in.g1 = live ? p.goal[p.n + e] : 0.f;
-        in.g2 = live ? p.goal[2 * p.n + e] : 0.f;
+        in.g1 = live ? p.goal1[e] : 0.f;
+        in.g2 = live ? p.goal2[e] : 0.f;
         in.sf = live ? p.step_flags[e] : 1u;
     }
     return in;
@@ -68,13 +70,27 @@ __device__ __forceinline__ ChunkIn load_chunk(const StepParams &p, uint64_t base
 
 // Next-chunk prefetch into L2 (no registers held across the compute phase): lanes 0..7 touch the
 // chunk's eight 128 B action lines, lanes 8..10 its three goal lines, lane 11 the step-word line.
-__device__ __forceinline__ void prefetch_chunk_l2(const StepParams &p, uint64_t base, int lane) {
-    const char *addr;
-    if (lane < 8) addr = reinterpret_cast<const char *>(p.actions) + base * 32 + lane * 128;
-    else if (lane < 11) addr = reinterpret_cast<const char *>(p.goal + (uint64_t)(lane - 8) * p.n + base);
-    else addr = reinterpret_cast<const char *>(p.step_flags + base);
-    if (lane < 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
-}
+// The per-lane pointer and its per-iteration increment are set up once, outside the loop.
+struct L2Prefetch {
+    const char *ptr;   // address this lane touches for the warp's NEXT chunk (lanes >= 12: unused)
+    uint32_t inc;      // bytes per loop iteration
+    __device__ __forceinline__ void init(const StepParams &p, uint32_t first_chunk, uint32_t warp_stride, int lane) {
+        const size_t base = (size_t)(first_chunk + warp_stride) << 5;
+        if (lane < 8) {
+            ptr = reinterpret_cast<const char *>(p.actions) + base * 32 + lane * 128;
+            inc = warp_stride * 32u * 32u;
+        } else {
+            const float *row = lane == 8 ? p.goal : lane == 9 ? p.goal1 : lane == 10 ? p.goal2
+                                                                     : reinterpret_cast<const float *>(p.step_flags);
+            ptr = reinterpret_cast<const char *>(row + base);
+            inc = warp_stride * 32u * 4u;
+        }
+    }
+    __device__ __forceinline__ void issue_and_advance(bool valid, int lane) {
+        if (valid && lane < 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        ptr += inc;
+    }
+};
 
 // roboy_env.py:52: every component inside [-1, 1] (closed; NaN fails).
 __device__ __forceinline__ bool action_ok4(const float4 &v, float hi) {
@@ -105,7 +121,7 @@ struct HoldOut {
 
 // Hold branch of the Stub (simulation_client.py:38-39): the stored state is returned.  Rare and
 // divergent, so it is kept out of line and out of the hot path's register budget.
-__device__ __noinline__ HoldOut hold_branch(const StepParams &p, uint64_t e, uint32_t sf, float g0, float g1, float g2,
+__device__ __noinline__ HoldOut hold_branch(const StepParams &p, uint32_t e, uint32_t sf, float g0, float g1, float g2,
                                             bool penalty, bool bonus) {
     HeldState s;
     if (sf & ROBOY_F_HELD_ZERO64) {
@@ -116,8 +132,8 @@ __device__ __noinline__ HoldOut hold_branch(const StepParams &p, uint64_t e, uin
     } else {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            s.q[k] = (double)p.held[(uint64_t)k * p.n + e];
-            s.qd[k] = (double)p.held[(uint64_t)(3 + k) * p.n + e];
+            s.q[k] = (double)p.held[(size_t)k * p.n + e];
+            s.qd[k] = (double)p.held[(size_t)(3 + k) * p.n + e];
         }
         s.is64 = false;
         s.feasible = !(sf & ROBOY_F_HELD_INFEASIBLE);
@@ -135,6 +151,116 @@ __device__ __noinline__ HoldOut hold_branch(const StepParams &p, uint64_t e, uin
     return o;
 }
 
+// Rare: an env finished its episode (:65-68) -- new goal, and under auto-reset the worker's
+// reset() (:82-87).  Out of line: ~1/400 of env-steps.
+__device__ __noinline__ uint32_t finish_episode(const StepParams &p, uint32_t e, uint32_t step, bool reached,
+                                                bool auto_reset, float *row, unsigned int *s_cnt) {
+    const uint64_t gid = p.gid_base + e;
+    // Under auto-reset the reference draws twice (:68 then :86) and only the second goal is ever
+    // observable, so a single draw is materialised.
+    const uint4 rg = philox_draw(gid, p.t, kStreamGoal, p.keys);
+    const float ng0 = uniform_in24(rg.x, p.c.a_lo, p.f.a_span24);
+    const float ng1 = uniform_in24(rg.y, p.c.a_lo, p.f.a_span24);
+    const float ng2 = uniform_in24(rg.z, p.c.a_lo, p.f.a_span24);
+    p.goal[e] = ng0;
+    p.goal1[e] = ng1;
+    p.goal2[e] = ng2;
+    atomicAdd(&s_cnt[0], 1u);
+    if (reached) atomicAdd(&s_cnt[1], 1u);
+    if (!auto_reset) return step | 0x80000000u;  // top bit: keep the flag bits
+    if (p.terminal_obs) {
+#pragma unroll
+        for (int k = 0; k < kObsDim; ++k) p.terminal_obs[(size_t)e * kObsDim + k] = row[k];
+    }
+    row[0] = row[1] = row[2] = row[3] = row[4] = row[5] = 0.0f;  // reset(): zero state, :83-84,87
+    row[6] = ng0; row[7] = ng1; row[8] = ng2;
+    atomicAdd(&s_cnt[4], step - 1);
+    return 1u;                                                   // :85, with the flags replaced
+}
+
+template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV, bool TAIL>
+__device__ __forceinline__ void process_chunk(const StepParams &p, const ChunkIn &cur, uint32_t base, int lane,
+                                              float *so, unsigned int *s_cnt, float &sum_reward) {
+    const uint32_t e = base + lane;
+    const bool live = TAIL ? (e < (uint32_t)p.e_end) : true;
+
+    // ---- roboy_env.py:52 assert + simulation_client.py:38 allclose, as warp ballots ----
+    // env `lane` owns float4 2*lane and 2*lane+1 of the chunk's 64
+    const float hold_mag = p.hold_mag;
+    const uint32_t okm0 = __ballot_sync(kFull, action_ok4(cur.a0, p.act_in_hi));
+    const uint32_t okm1 = __ballot_sync(kFull, action_ok4(cur.a1, p.act_in_hi));
+    const uint32_t hdm0 = __ballot_sync(kFull, action_hold4(cur.a0, p.hold_lo, p.hold_hi, hold_mag));
+    const uint32_t hdm1 = __ballot_sync(kFull, action_hold4(cur.a1, p.hold_lo, p.hold_hi, hold_mag));
+    const uint32_t sh = (lane & 15) << 1;
+    const bool act_ok = (((lane < 16 ? okm0 : okm1) >> sh) & 3u) == 3u;
+    const bool hold = live && (((lane < 16 ? hdm0 : hdm1) >> sh) & 3u) == 3u;
+
+    const float g0 = cur.g0, g1 = cur.g1, g2 = cur.g2;
+    const uint32_t sf = cur.sf;
+    float q0, q1, q2, qd0, qd1, qd2, reward;
+    bool reached, violation;
+    if (!hold) {
+        // simulation_client.py:40 -> roboy_robot.py:35-39: fresh sample; velocities are drawn
+        // from the ANGLE space too (reference quirk, :38)
+        const Draw6 d = split6x21(philox_draw(p.gid_base + e, p.t, kStreamState, p.keys));
+        q0 = uniform_in21(d.k[0], p.c.a_lo, p.f.a_span21);
+        q1 = uniform_in21(d.k[1], p.c.a_lo, p.f.a_span21);
+        q2 = uniform_in21(d.k[2], p.c.a_lo, p.f.a_span21);
+        qd0 = uniform_in21(d.k[3], p.c.a_lo, p.f.a_span21);
+        qd1 = uniform_in21(d.k[4], p.c.a_lo, p.f.a_span21);
+        qd2 = uniform_in21(d.k[5], p.c.a_lo, p.f.a_span21);
+        reward_reached_sampled<PENALTY, BONUS, FASTDIV>(q0, q1, q2, qd0, qd1, qd2, g0, g1, g2, p.c, p.f, reward,
+                                                        reached, violation);
+    } else {
+        const HoldOut h = hold_branch(p, e, sf, g0, g1, g2, PENALTY, BONUS);
+        q0 = h.q0; q1 = h.q1; q2 = h.q2; qd0 = h.qd0; qd1 = h.qd1; qd2 = h.qd2;
+        reward = h.reward;
+        reached = h.flags & 1u;
+        violation = h.flags & 2u;
+        atomicAdd(&s_cnt[2], 1u);
+    }
+
+    uint32_t step = sf & ROBOY_STEP_MASK;
+    step += step < ROBOY_STEP_MASK;                       // roboy_env.py:60
+    const bool done = reached || (int32_t)step > p.max_len;  // :65-66, :72-73
+    uint32_t word = step | (sf & ~ROBOY_STEP_MASK);
+
+    // obs = [q, qd, goal] (:75-80), staged in shared memory; stride 9 is bank-conflict-free
+    float *row = so + lane * kObsDim;
+    row[0] = q0; row[1] = q1; row[2] = q2; row[3] = qd0; row[4] = qd1; row[5] = qd2;
+    row[6] = g0; row[7] = g1; row[8] = g2;
+
+    if (done && live) {
+        const uint32_t r = finish_episode(p, e, step, reached, AUTO_RESET, row, s_cnt);
+        word = (r & 0x80000000u) ? word : (r | ROBOY_F_HELD_ZERO64);
+    }
+    if (live && (violation || !act_ok)) {
+        atomicOr(p.err_flags, (violation ? ROBOY_ERR_REWARD_RANGE : 0u) | (!act_ok ? ROBOY_ERR_ACTION : 0u));
+        atomicMin(p.first_bad, (unsigned long long)(p.gid_base + e));
+        atomicAdd(&s_cnt[3], 1u);
+    }
+
+    // ---- stores ----
+    if (live) {
+        p.step_flags[e] = word;
+        __stcs(p.reward + e, reward);
+        p.done[e] = (uint8_t)done;
+        sum_reward += reward;
+    }
+    __syncwarp();
+    if (!TAIL) {
+        float4 *dst = reinterpret_cast<float4 *>(p.obs + (size_t)base * kObsDim);  // 1152 B per chunk: 16 B aligned
+        const float4 *src = reinterpret_cast<const float4 *>(so);
+        __stcs(dst + lane, src[lane]);
+        __stcs(dst + 32 + lane, src[32 + lane]);
+        if (lane < 8) __stcs(dst + 64 + lane, src[64 + lane]);
+    } else {
+        const uint32_t n_valid = ((uint32_t)p.e_end - base) * kObsDim;
+        for (uint32_t i = lane; i < n_valid; i += 32) p.obs[(size_t)base * kObsDim + i] = so[i];
+    }
+    __syncwarp();
+}
+
 }  // namespace
 
 template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV>
@@ -149,156 +275,52 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const uint64_t n = p.n;
-    const uint64_t n_end = p.e_end;
-    const uint64_t n_chunks = (n_end + 31) >> 5;
-    const uint64_t warp_stride = (uint64_t)gridDim.x * kWarpsPerBlock;
-    const float hold_mag = fmaxf(fabsf(p.hold_lo), fabsf(p.hold_hi));
+    const uint32_t n_full = (uint32_t)(p.e_end >> 5);  // chunks [chunk0, n_full) are complete
+    const uint32_t warp_stride = gridDim.x * kWarpsPerBlock;
     float *so = s_obs[warp];
+    // per-thread reward sum: a thread adds at most a few hundred float32 rewards per launch, the
+    // cross-thread reduction below is in double
+    float sum_reward = 0.0f;
 
-    uint32_t n_steps = 0;
-    double sum_reward = 0.0;
-
-    uint64_t chunk = (p.e_begin >> 5) + (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
+    uint32_t chunk = (uint32_t)(p.e_begin >> 5) + blockIdx.x * kWarpsPerBlock + warp;
 #if ROBOY_PREFETCH == 1
     ChunkIn in;
-    if (chunk < n_chunks) in = load_chunk(p, chunk << 5, lane);
+    if (chunk < n_full) in = load_chunk<false>(p, chunk << 5, lane);
+#elif ROBOY_PREFETCH == 2
+    L2Prefetch pf;
+    pf.init(p, chunk, warp_stride, lane);
 #endif
-
-    while (chunk < n_chunks) {
-        const uint64_t base = chunk << 5;
-        const uint64_t e = base + lane;
-        const bool full = base + 32 <= n_end;
-        const bool live = e < n_end;
-        const uint64_t next = chunk + warp_stride;
+    while (chunk < n_full) {
+        const uint32_t next = chunk + warp_stride;
 #if ROBOY_PREFETCH == 1
         // software prefetch into registers: the next chunk's loads are in flight during this compute
         const ChunkIn cur = in;
-        if (next < n_chunks) in = load_chunk(p, next << 5, lane);
+        if (next < n_full) in = load_chunk<false>(p, next << 5, lane);
 #else
-        const ChunkIn cur = load_chunk(p, base, lane);
+        const ChunkIn cur = load_chunk<false>(p, chunk << 5, lane);
 #if ROBOY_PREFETCH == 2
-        if (next < n_chunks) prefetch_chunk_l2(p, next << 5, lane);
+        pf.issue_and_advance(next < n_full, lane);
 #endif
 #endif
-
-        // ---- roboy_env.py:52 assert + simulation_client.py:38 allclose, as warp ballots ----
-        // env `lane` owns float4 2*lane and 2*lane+1 of the chunk's 64
-        const uint32_t okm0 = __ballot_sync(kFull, action_ok4(cur.a0, p.act_in_hi));
-        const uint32_t okm1 = __ballot_sync(kFull, action_ok4(cur.a1, p.act_in_hi));
-        const uint32_t hdm0 = __ballot_sync(kFull, action_hold4(cur.a0, p.hold_lo, p.hold_hi, hold_mag));
-        const uint32_t hdm1 = __ballot_sync(kFull, action_hold4(cur.a1, p.hold_lo, p.hold_hi, hold_mag));
-        const uint32_t sh = (lane & 15) << 1;
-        const bool act_ok = (((lane < 16 ? okm0 : okm1) >> sh) & 3u) == 3u;
-        const bool hold = live && (((lane < 16 ? hdm0 : hdm1) >> sh) & 3u) == 3u;
-
-        const uint64_t gid = p.gid_base + e;
-        const float g0 = cur.g0, g1 = cur.g1, g2 = cur.g2;
-        const uint32_t sf = cur.sf;
-        float q0, q1, q2, qd0, qd1, qd2, reward;
-        bool reached, violation;
-        if (!hold) {
-            // simulation_client.py:40 -> roboy_robot.py:35-39: fresh sample; velocities are drawn
-            // from the ANGLE space too (reference quirk, :38)
-            const uint4 ra = philox_draw(gid, p.t, kStreamStateQ, p.keys);
-            const uint4 rb = philox_draw(gid, p.t, kStreamStateQd, p.keys);
-            q0 = uniform_in24(ra.x, p.c.a_lo, p.f.a_span24);
-            q1 = uniform_in24(ra.y, p.c.a_lo, p.f.a_span24);
-            q2 = uniform_in24(ra.z, p.c.a_lo, p.f.a_span24);
-            qd0 = uniform_in24(rb.x, p.c.a_lo, p.f.a_span24);
-            qd1 = uniform_in24(rb.y, p.c.a_lo, p.f.a_span24);
-            qd2 = uniform_in24(rb.z, p.c.a_lo, p.f.a_span24);
-            reward_reached_sampled<PENALTY, BONUS, FASTDIV>(q0, q1, q2, qd0, qd1, qd2, g0, g1, g2, p.c, p.f, reward,
-                                                            reached, violation);
-        } else {
-            const HoldOut h = hold_branch(p, e, sf, g0, g1, g2, PENALTY, BONUS);
-            q0 = h.q0; q1 = h.q1; q2 = h.q2; qd0 = h.qd0; qd1 = h.qd1; qd2 = h.qd2;
-            reward = h.reward;
-            reached = h.flags & 1u;
-            violation = h.flags & 2u;
-            atomicAdd(&s_cnt[2], 1u);
-        }
-
-        uint32_t step = sf & ROBOY_STEP_MASK;
-        step += step < ROBOY_STEP_MASK;                       // roboy_env.py:60
-        const bool timeout = (int32_t)step > p.max_len;       // :72-73
-        const bool done = reached || timeout;                 // :65-66
-        uint32_t flags = sf & ~ROBOY_STEP_MASK;
-
-        // obs = [q, qd, goal] (:75-80), staged in shared memory; stride 9 is bank-conflict-free
-        float *row = so + lane * kObsDim;
-        row[0] = q0; row[1] = q1; row[2] = q2; row[3] = qd0; row[4] = qd1; row[5] = qd2;
-        row[6] = g0; row[7] = g1; row[8] = g2;
-
-        if (done && live) {
-            // :67-68 new goal.  Under auto-reset the worker's reset() (:82-87) draws once more and
-            // only that goal is ever observable, so a single draw is materialised.
-            const uint4 rg = philox_draw(gid, p.t, kStreamGoal, p.keys);
-            const float ng0 = uniform_in24(rg.x, p.c.a_lo, p.f.a_span24);
-            const float ng1 = uniform_in24(rg.y, p.c.a_lo, p.f.a_span24);
-            const float ng2 = uniform_in24(rg.z, p.c.a_lo, p.f.a_span24);
-            p.goal[e] = ng0;
-            p.goal[n + e] = ng1;
-            p.goal[2 * n + e] = ng2;
-            if (AUTO_RESET) {
-                if (p.terminal_obs) {
-#pragma unroll
-                    for (int k = 0; k < kObsDim; ++k) p.terminal_obs[e * kObsDim + k] = row[k];
-                }
-                row[0] = row[1] = row[2] = row[3] = row[4] = row[5] = 0.0f;  // reset(): zero state, :83-84,87
-                row[6] = ng0; row[7] = ng1; row[8] = ng2;
-                atomicAdd(&s_cnt[4], step - 1);
-                step = 1;                                        // :85
-                flags = ROBOY_F_HELD_ZERO64;
-            }
-            atomicAdd(&s_cnt[0], 1u);
-            if (reached) atomicAdd(&s_cnt[1], 1u);
-        }
-
-        if (live && (violation || !act_ok)) {
-            atomicOr(p.err_flags, (violation ? ROBOY_ERR_REWARD_RANGE : 0u) | (!act_ok ? ROBOY_ERR_ACTION : 0u));
-            atomicMin(p.first_bad, (unsigned long long)gid);
-            atomicAdd(&s_cnt[3], 1u);
-        }
-
-        // ---- stores ----
-        if (live) {
-            p.step_flags[e] = step | flags;
-            __stcs(p.reward + e, reward);
-            p.done[e] = (uint8_t)done;
-            ++n_steps;
-            sum_reward += (double)reward;
-        }
-        __syncwarp();
-        if (full) {
-            float4 *dst = reinterpret_cast<float4 *>(p.obs + base * kObsDim);  // 1152 B per chunk: 16 B aligned
-            const float4 *src = reinterpret_cast<const float4 *>(so);
-            __stcs(dst + lane, src[lane]);
-            __stcs(dst + 32 + lane, src[32 + lane]);
-            if (lane < 8) __stcs(dst + 64 + lane, src[64 + lane]);
-        } else {
-            const uint32_t n_valid = (uint32_t)(n_end - base) * kObsDim;
-            for (uint32_t i = lane; i < n_valid; i += 32) p.obs[base * kObsDim + i] = so[i];
-        }
-        __syncwarp();
+        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false>(p, cur, chunk << 5, lane, so, s_cnt, sum_reward);
         chunk = next;
+    }
+    if (chunk == n_full && (p.e_end & 31)) {  // the ragged last chunk belongs to exactly one warp
+        const ChunkIn cur = load_chunk<true>(p, chunk << 5, lane);
+        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true>(p, cur, chunk << 5, lane, so, s_cnt, sum_reward);
     }
 
     // ---- K3: episode statistics, one set of atomics per CTA ----
-    const uint32_t w_steps = __reduce_add_sync(kFull, n_steps);
-    const double w_reward = warp_sum(sum_reward);
+    const double w_reward = warp_sum((double)sum_reward);
     if (lane == 0) s_red[warp] = w_reward;
-    __shared__ unsigned int s_steps;
-    if (threadIdx.x == 0) s_steps = 0;
-    __syncthreads();
-    if (lane == 0) atomicAdd(&s_steps, w_steps);
     __syncthreads();
     if (threadIdx.x == 0) {
         double r = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; ++w) r += s_red[w];
         const double done = (double)s_cnt[0], succ = (double)s_cnt[1];
-        const double v[ROBOY_STAT_COUNT] = {(double)s_steps, done, succ, done - succ, r, (double)s_cnt[4],
+        const double steps = blockIdx.x == 0 ? (double)(p.e_end - p.e_begin) : 0.0;
+        const double v[ROBOY_STAT_COUNT] = {steps, done, succ, done - succ, r, (double)s_cnt[4],
                                             (double)s_cnt[2], (double)s_cnt[3]};
 #pragma unroll
         for (int k = 0; k < ROBOY_STAT_COUNT; ++k)
@@ -387,14 +409,9 @@ __global__ void __launch_bounds__(256) init_or_reset_kernel(const __grid_constan
         p.goal[2 * p.n + e] = g2;
         if (p.held) {
             // StubSimulationClient.__init__ (simulation_client.py:31): _state = new_random_state()
-            const uint4 ra = philox_draw(gid, p.t, kStreamStateQ, p.keys);
-            const uint4 rb = philox_draw(gid, p.t, kStreamStateQd, p.keys);
-            p.held[e] = uniform_in(ra.x, p.a_lo, p.a_span);
-            p.held[p.n + e] = uniform_in(ra.y, p.a_lo, p.a_span);
-            p.held[2 * p.n + e] = uniform_in(ra.z, p.a_lo, p.a_span);
-            p.held[3 * p.n + e] = uniform_in(rb.x, p.a_lo, p.a_span);
-            p.held[4 * p.n + e] = uniform_in(rb.y, p.a_lo, p.a_span);
-            p.held[5 * p.n + e] = uniform_in(rb.z, p.a_lo, p.a_span);
+            const Draw6 d = split6x21(philox_draw(gid, p.t, kStreamState, p.keys));
+#pragma unroll
+            for (int k = 0; k < 6; ++k) p.held[(size_t)k * p.n + e] = uniform_in21(d.k[k], p.a_lo, p.a_span * 0x1p-21f);
             p.step_flags[e] = 1u;  // roboy_env.py:38
         } else {
             // forward_reset_command (simulation_client.py:42-44): _state = float64 zero state
@@ -550,14 +567,12 @@ __global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ SimPar
             feasible = z || !(sf & ROBOY_F_HELD_INFEASIBLE);
             if (p.mode == 0) atomicAdd(p.stats + ROBOY_STAT_HOLDS, 1.0);
         } else {
-            const uint4 ra = philox_draw(gid, p.t, kStreamStateQ, p.keys);
-            const uint4 rb = philox_draw(gid, p.t, kStreamStateQd, p.keys);
-            q[0] = uniform_in(ra.x, p.a_lo, p.a_span);
-            q[1] = uniform_in(ra.y, p.a_lo, p.a_span);
-            q[2] = uniform_in(ra.z, p.a_lo, p.a_span);
-            qd[0] = uniform_in(rb.x, p.a_lo, p.a_span);
-            qd[1] = uniform_in(rb.y, p.a_lo, p.a_span);
-            qd[2] = uniform_in(rb.z, p.a_lo, p.a_span);
+            const Draw6 d = split6x21(philox_draw(gid, p.t, kStreamState, p.keys));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                q[k] = uniform_in21(d.k[k], p.a_lo, p.a_span * 0x1p-21f);
+                qd[k] = uniform_in21(d.k[3 + k], p.a_lo, p.a_span * 0x1p-21f);
+            }
         }
         if (p.out_q) {
 #pragma unroll

@@ -25,6 +25,7 @@ struct StepParams {
     PhiloxKeys keys;
     RobotConsts c;
     FastConsts f;
+    float hold_mag;              // max(|hold_lo|, |hold_hi|): cheap pre-filter for the hold test
     float hold_lo, hold_hi;      // the float32 interval of action components a for which
                                  // |fl(fl(slope*fl(a - in_hi)) + act_hi)| <= 1e-8, i.e. numpy's
                                  // allclose(rescaled, 0) (roboy_env.py:157-158, simulation_client.py:38)
@@ -34,6 +35,8 @@ struct StepParams {
     // inputs / state / outputs (device pointers)
     const float *__restrict__ actions;  // [n][8]
     float *__restrict__ goal;           // [3][n]
+    float *__restrict__ goal1;          // goal + n, goal + 2n (row pointers, so an address is one IMAD.WIDE)
+    float *__restrict__ goal2;
     uint32_t *__restrict__ step_flags;  // [n]
     const float *__restrict__ held;     // [6][n]
     float *__restrict__ obs;            // [n][9]

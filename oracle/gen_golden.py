@@ -100,12 +100,13 @@ def sampled_branch_goals(seed, N, T, thr_v, counter_of_step, taken):
     ev = []
     for t in range(40, T):
         c = counter_of_step(t)
-        qd = orc.draw(seed, np.arange(N), c, orc.STREAM_STATE_QD).astype(np.float64)
+        q_all, qd = orc.draw_state(seed, np.arange(N), c)
+        qd = qd.astype(np.float64)
         slow = np.flatnonzero(np.sqrt((qd * qd).sum(1)) < 0.9 * float(thr_v))
         for e in slow:
             if (t, int(e)) in taken:
                 continue
-            q = orc.draw(seed, [int(e)], c, orc.STREAM_STATE_Q)[0]
+            q = q_all[int(e)]
             g = np.clip(q + np.float32(0.01), -orc.PI32, orc.PI32)
             ev.append((t, int(e), EV_SET_GOAL, list(g) + [0, 0, 0, 0]))
     return ev
@@ -173,7 +174,7 @@ def run_fixture(name, N, T, seed, joint_vel_penalty, bonus, auto_reset=True):
 FIXTURES = [
     # name, N, T, seed, joint_vel_penalty, bonus, auto_reset
     ("rollout_default", 48, 450, 20240901, False, True, True),
-    ("rollout_penalty", 48, 450, 20240902, True, True, True),
+    ("rollout_penalty", 48, 450, 20240912, True, True, True),
     ("rollout_nobonus", 32, 420, 20240903, False, False, True),
     ("rollout_manual_reset", 32, 420, 20240904, False, True, False),
 ]

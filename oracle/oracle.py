@@ -19,7 +19,7 @@ F_HELD_ZERO64 = 1 << 24
 F_HELD_INFEASIBLE = 1 << 25
 ERR_ACTION, ERR_REWARD_RANGE, ERR_GOAL_BOUNDS = 1, 2, 4
 STAT_NAMES = ("steps", "episodes", "successes", "timeouts", "sum_reward", "sum_episode_len", "holds", "violations")
-STREAM_STATE_Q, STREAM_STATE_QD, STREAM_GOAL = 0, 1, 2
+STREAM_STATE, STREAM_GOAL = 0, 2
 
 # float32 MSJ bounds, msj_robot.py:9,10,16
 PI32 = np.float32(np.pi)
@@ -158,8 +158,8 @@ class OracleEnv:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            lib().orc_destroy(h)
+        if h and _lib is not None and lib is not None:   # (module globals are None at interpreter shutdown)
+            _lib.orc_destroy(h)
 
     @property
     def counter(self):
@@ -231,10 +231,28 @@ def _uniform(x, low, high):
     return (low + (span * u).astype(np.float32)).astype(np.float32)
 
 
-def draw(seed, gids, t, stream, low=MSJ["angle_low"], high=MSJ["angle_high"], sub=0):
-    """float32 [n,3] draws for global env ids `gids` at call counter `t` on `stream`."""
+def _block(seed, gids, t, stream, sub=0):
     gids = np.asarray(gids, np.uint64)
     c3 = (int(stream) << 28) | ((int(sub) & 0xFF) << 20) | ((int(t) >> 32) & 0x000FFFFF)
-    x = philox4x32_10(gids & np.uint64(0xFFFFFFFF), gids >> np.uint64(32), int(t) & 0xFFFFFFFF, c3,
-                      int(seed) & 0xFFFFFFFF, int(seed) >> 32)
+    return philox4x32_10(gids & np.uint64(0xFFFFFFFF), gids >> np.uint64(32), int(t) & 0xFFFFFFFF, c3,
+                         int(seed) & 0xFFFFFFFF, int(seed) >> 32)
+
+
+def draw_goal(seed, gids, t, low=MSJ["angle_low"], high=MSJ["angle_high"], sub=0):
+    """float32 [n,3] goal draws: v = low + span * ((x >> 8) * 2^-24) from words x, y, z of the block."""
+    x = _block(seed, gids, t, STREAM_GOAL, sub)
     return np.stack([_uniform(x[k], low, high) for k in range(3)], axis=-1)
+
+
+def draw_state(seed, gids, t, low=MSJ["angle_low"], high=MSJ["angle_high"]):
+    """(q, qd) float32 [n,3] each: six 21-bit integers from ONE block, v = low + (span*2^-21)*k."""
+    r = [w.astype(np.uint64) for w in _block(seed, gids, t, STREAM_STATE)]
+    m21 = np.uint64(0x1FFFFF)
+    k = [r[0] >> np.uint64(11), (((r[0] & np.uint64(0x7FF)) << np.uint64(10)) | (r[1] >> np.uint64(22))) & m21,
+         (r[1] >> np.uint64(1)) & m21,
+         r[2] >> np.uint64(11), (((r[2] & np.uint64(0x7FF)) << np.uint64(10)) | (r[3] >> np.uint64(22))) & m21,
+         (r[3] >> np.uint64(1)) & m21]
+    low = np.float32(low)
+    span21 = np.float32(np.float32(np.float32(high) - low) * np.float32(2.0 ** -21))
+    v = [(low + (span21 * ki.astype(np.float32)).astype(np.float32)).astype(np.float32) for ki in k]
+    return np.stack(v[0:3], axis=-1), np.stack(v[3:6], axis=-1)

@@ -42,7 +42,7 @@ def _import_reference():
     return RoboyEnv, MsjRobot, RobotState, StubSimulationClient
 
 
-def _make_replay_robot(MsjRobot, RobotState, draw_fn):
+def _make_replay_robot(MsjRobot, RobotState, state_fn, goal_fn):
     """A fresh MsjRobot subclass whose only override is the source of random samples."""
 
     class ReplayRobot(MsjRobot):
@@ -56,13 +56,14 @@ def _make_replay_robot(MsjRobot, RobotState, draw_fn):
             if caller == "get_new_goal_joint_angles":
                 cls.log.append("goal")
                 if cls.ctx["goal_real"]:
-                    g = draw_fn(gid, t, 2)
+                    g = goal_fn(gid, t)
                 else:  # goal that the worker's reset() overwrites at once: never observable
                     g = np.zeros(3, np.float32)
                 return RobotState(joint_angles=g, joint_vels=np.zeros(3, np.float32), is_feasible=True)
             assert caller in ("forward_step_command", "__init__"), caller
             cls.log.append("state")
-            return RobotState(joint_angles=draw_fn(gid, t, 0), joint_vels=draw_fn(gid, t, 1), is_feasible=True)
+            q, qd = state_fn(gid, t)
+            return RobotState(joint_angles=q, joint_vels=qd, is_feasible=True)
 
     return ReplayRobot()
 
@@ -81,12 +82,16 @@ class ReferenceVecEnv:
         self.t = 0
         self.envs, self.robots = [], []
 
-        def draw_fn(gid, t, stream):
-            return orc.draw(seed, [gid], t, stream)[0]
+        def state_fn(gid, t):
+            q, qd = orc.draw_state(seed, [gid], t)
+            return q[0], qd[0]
+
+        def goal_fn(gid, t):
+            return orc.draw_goal(seed, [gid], t)[0]
 
         with contextlib.redirect_stdout(io.StringIO()):
             for i in range(n_envs):
-                robot = _make_replay_robot(MsjRobot, RobotState, draw_fn)
+                robot = _make_replay_robot(MsjRobot, RobotState, state_fn, goal_fn)
                 type(robot).ctx = dict(gid=env_id_base + i, t=0, goal_real=True)
                 type(robot).log = []
                 env = RoboyEnv(Stub(robot=robot), joint_vel_penalty=joint_vel_penalty,

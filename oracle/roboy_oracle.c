@@ -87,7 +87,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-enum { STREAM_STATE_Q = 0, STREAM_STATE_QD = 1, STREAM_GOAL = 2 };
+enum { STREAM_STATE = 0, STREAM_GOAL = 2 };
 
 /* counter = (env id lo, env id hi, call counter lo, stream<<28 | sub<<20 | call counter hi);
  * sub numbers repeated goal draws at one call counter (un-fused plug-in API); 0 in the step. */
@@ -111,14 +111,24 @@ static float uniform_in(uint32_t x, float low, float high) {
 }
 
 /* roboy_robot.py:35-39 new_random_state(): q ~ U[angle space]^3, and -- reference quirk --
- * the velocities are ALSO drawn from the ANGLE space (:38). is_feasible = True. */
+ * the velocities are ALSO drawn from the ANGLE space (:38). is_feasible = True.
+ * One Philox block per state: its 128 bits are cut into six 21-bit integers k0..k5 (bits 127..2),
+ * v_i = low + (span * 2^-21) * (float)k_i  (float32 multiply then add). */
 void orc_draw_state(const orc_cfg *cfg, uint64_t gid, uint64_t t, float q[3], float qd[3]) {
-    uint32_t a[4], b[4];
-    draw4(cfg, gid, t, STREAM_STATE_Q, a);
-    draw4(cfg, gid, t, STREAM_STATE_QD, b);
-    for (int k = 0; k < 3; ++k) {
-        q[k] = uniform_in(a[k], cfg->angle_low, cfg->angle_high);
-        qd[k] = uniform_in(b[k], cfg->angle_low, cfg->angle_high);
+    uint32_t r[4], k[6];
+    draw4(cfg, gid, t, STREAM_STATE, r);
+    k[0] = r[0] >> 11;
+    k[1] = ((r[0] & 0x7ffu) << 10) | (r[1] >> 22);
+    k[2] = (r[1] >> 1) & 0x1fffffu;
+    k[3] = r[2] >> 11;
+    k[4] = ((r[2] & 0x7ffu) << 10) | (r[3] >> 22);
+    k[5] = (r[3] >> 1) & 0x1fffffu;
+    const float span21 = (cfg->angle_high - cfg->angle_low) * 0x1p-21f;
+    for (int i = 0; i < 3; ++i) {
+        float m = span21 * (float)k[i];
+        q[i] = cfg->angle_low + m;
+        m = span21 * (float)k[3 + i];
+        qd[i] = cfg->angle_low + m;
     }
 }
 

@@ -16,8 +16,9 @@ def test_plugin_calls_match_the_stub_semantics():
     gids = np.arange(7, 7 + n)
     # __init__: random held state (simulation_client.py:31)
     s = c.read_state()
-    assert np.array_equal(s.joint_angles.cpu().numpy(), orc.draw(seed, gids, 0, orc.STREAM_STATE_Q))
-    assert np.array_equal(s.joint_vels.cpu().numpy(), orc.draw(seed, gids, 0, orc.STREAM_STATE_QD))
+    q0, qd0 = orc.draw_state(seed, gids, 0)
+    assert np.array_equal(s.joint_angles.cpu().numpy(), q0)
+    assert np.array_equal(s.joint_vels.cpu().numpy(), qd0)
     assert s.is_feasible.all()
     # zero action -> the held state, unchanged and not advanced (:38-39)
     h = c.forward_step_command(torch.zeros((n, 8)))
@@ -29,7 +30,7 @@ def test_plugin_calls_match_the_stub_semantics():
     a[1::4] = 0.0      # these hold
     r = c.forward_step_command(a)
     t = c.counter
-    fresh_q = orc.draw(seed, gids, t, orc.STREAM_STATE_Q)
+    fresh_q, _ = orc.draw_state(seed, gids, t)
     hold = np.zeros(n, bool); hold[1::4] = True
     got = r.joint_angles.cpu().numpy()
     assert np.array_equal(got[~hold], fresh_q[~hold]) and np.array_equal(got[hold], s.joint_angles.cpu().numpy()[hold])
@@ -41,8 +42,8 @@ def test_plugin_calls_match_the_stub_semantics():
     g1, g2 = c.get_new_goal_joint_angles(), c.get_new_goal_joint_angles()
     assert not torch.equal(g1, g2)
     assert (g1.abs() <= float(orc.PI32)).all() and (g2.abs() <= float(orc.PI32)).all()
-    assert np.array_equal(g1.cpu().numpy(), orc.draw(seed, gids, c.counter, orc.STREAM_GOAL, sub=0))
-    assert np.array_equal(g2.cpu().numpy(), orc.draw(seed, gids, c.counter, orc.STREAM_GOAL, sub=1))
+    assert np.array_equal(g1.cpu().numpy(), orc.draw_goal(seed, gids, c.counter, sub=0))
+    assert np.array_equal(g2.cpu().numpy(), orc.draw_goal(seed, gids, c.counter, sub=1))
 
 
 def test_single_env_view_returns_reference_types():

@@ -86,7 +86,7 @@ def test_rollout_4096_envs_matches_oracle(flags):
     for t in range(T):
         if t % 50 == 10:   # goals next to the state the Philox draw will produce -> goal reached on the sampled branch
             c = ora.counter + 1
-            q = orc.draw(1234, np.arange(n), c, orc.STREAM_STATE_Q)
+            q, _ = orc.draw_state(1234, np.arange(n), c)
             g = np.clip(q + np.float32(0.005), -orc.PI32, orc.PI32).astype(np.float32)
             client.set_goal(g); ora.goal[:] = g.T
         worst = max(worst, compare_step(env, client, ora, actions_for(rng, n), t))
@@ -234,7 +234,9 @@ def test_host_buffer_step_equals_device_step():
         o2, r2, d2, _ = env_b.step(torch.as_tensor(a, device="cuda:0"))
         assert np.array_equal(obs, o2.cpu().numpy()) and np.array_equal(rew, r2.cpu().numpy())
         assert np.array_equal(done.astype(bool), d2.cpu().numpy())
-    assert client_a.stats() == client_b.stats()
+    sa, sb = client_a.stats(), client_b.stats()
+    for k in sa:   # counters are exact; the reward sum is reduced in a different order per launch shape
+        assert sa[k] == sb[k] if k != "sum_reward" else abs(sa[k] - sb[k]) <= 1e-6 * abs(sb[k]), k
 
 
 def test_outputs_are_zero_copy_views_of_the_library_buffers():

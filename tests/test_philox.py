@@ -25,15 +25,17 @@ def test_known_answers_c_and_numpy():
 def test_draws_stay_inside_the_angle_space_and_match_between_implementations():
     n = 100000
     gids = np.arange(5, 5 + n)
-    for stream in (orc.STREAM_STATE_Q, orc.STREAM_STATE_QD, orc.STREAM_GOAL):
-        d = orc.draw(987654321, gids, 123, stream)
+    q, qd = orc.draw_state(987654321, gids, 123)
+    for d in (q, qd, orc.draw_goal(987654321, gids, 123)):
         assert d.dtype == np.float32 and (np.abs(d) <= orc.PI32).all()
         assert abs(d.mean()) < 0.02 and abs(d.std() - 2 * np.pi / np.sqrt(12)) < 0.02
+    six = np.concatenate([q, qd], axis=1)           # the six 21-bit fields of one block are independent
+    assert np.abs(np.corrcoef(six.T) - np.eye(6)).max() < 0.02
     env = orc.OracleEnv(n, seed=987654321, env_id_base=5)
-    assert np.array_equal(env.goal.T, orc.draw(987654321, gids, 0, orc.STREAM_GOAL))
-    assert np.array_equal(env.held[0:3].T, orc.draw(987654321, gids, 0, orc.STREAM_STATE_Q))
-    assert np.array_equal(env.held[3:6].T, orc.draw(987654321, gids, 0, orc.STREAM_STATE_QD))
+    q0, qd0 = orc.draw_state(987654321, gids, 0)
+    assert np.array_equal(env.goal.T, orc.draw_goal(987654321, gids, 0))
+    assert np.array_equal(env.held[0:3].T, q0) and np.array_equal(env.held[3:6].T, qd0)
     # 64-bit env ids and call counters reach the upper counter words
-    big = orc.draw(1, np.array([2 ** 40 + 3], np.uint64), 2 ** 33 + 1, orc.STREAM_GOAL)
-    small = orc.draw(1, np.array([3], np.uint64), 1, orc.STREAM_GOAL)
+    big = orc.draw_goal(1, np.array([2 ** 40 + 3], np.uint64), 2 ** 33 + 1)
+    small = orc.draw_goal(1, np.array([3], np.uint64), 1)
     assert not np.array_equal(big, small)
