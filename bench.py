@@ -63,6 +63,20 @@ def workload_config(envs, n_gpus):
     }
 
 
+class stdout_to_stderr:
+    """Temporarily point file descriptor 1 at stderr (for native libraries that print to stdout)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """Samples SM clock and throttle reasons via NVML while the timed region runs."""
@@ -210,7 +224,10 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with stdout_to_stderr():   # NCCL prints its version banner on stdout; rank 0 must print ONE JSON line
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
     from gym_roboy_b200.envs import RoboyEnv
     from gym_roboy_b200.envs.simulations import CudaSimulationClient
     from gym_roboy_b200.sharding import all_reduce_stats, shard_range, summarize

@@ -28,6 +28,9 @@ namespace roboy {
 #ifndef ROBOY_PREFETCH
 #define ROBOY_PREFETCH 2  // 0: none, 1: next chunk into registers, 2: next chunk into L2 (measured best)
 #endif
+#ifndef ROBOY_PREFETCH_DIST
+#define ROBOY_PREFETCH_DIST 1  // how many of this warp's chunks ahead the L2 prefetch runs
+#endif
 
 namespace {
 
@@ -75,7 +78,7 @@ struct L2Prefetch {
     const char *ptr;   // address this lane touches for the warp's NEXT chunk (lanes >= 12: unused)
     uint32_t inc;      // bytes per loop iteration
     __device__ __forceinline__ void init(const StepParams &p, uint32_t first_chunk, uint32_t warp_stride, int lane) {
-        const size_t base = (size_t)(first_chunk + warp_stride) << 5;
+        const size_t base = (size_t)(first_chunk + ROBOY_PREFETCH_DIST * warp_stride) << 5;
         if (lane < 8) {
             ptr = reinterpret_cast<const char *>(p.actions) + base * 32 + lane * 128;
             inc = warp_stride * 32u * 32u;
@@ -199,6 +202,12 @@ __device__ __forceinline__ void process_chunk(const StepParams &p, const ChunkIn
     const uint32_t sf = cur.sf;
     float q0, q1, q2, qd0, qd1, qd2, reward;
     bool reached, violation;
+#ifdef ROBOY_EXPERIMENT_MEMONLY  // traffic-pattern ceiling experiment: same loads/stores, no arithmetic
+    if (!hold) {
+        q0 = cur.a0.x; q1 = cur.a0.y; q2 = cur.a0.z; qd0 = cur.a1.x; qd1 = cur.a1.y; qd2 = cur.a1.z;
+        reward = g0 + g1; reached = false; violation = false;
+    } else
+#endif
     if (!hold) {
         // simulation_client.py:40 -> roboy_robot.py:35-39: fresh sample; velocities are drawn
         // from the ANGLE space too (reference quirk, :38)
@@ -299,7 +308,7 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
 #else
         const ChunkIn cur = load_chunk<false>(p, chunk << 5, lane);
 #if ROBOY_PREFETCH == 2
-        pf.issue_and_advance(next < n_full, lane);
+        pf.issue_and_advance(chunk + ROBOY_PREFETCH_DIST * warp_stride < n_full, lane);
 #endif
 #endif
         process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false>(p, cur, chunk << 5, lane, so, s_cnt, sum_reward);
