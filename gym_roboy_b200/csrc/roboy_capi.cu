@@ -128,7 +128,10 @@ struct roboy_env {
     int device = 0;
     int sm_count = 148;
     std::atomic<int> refs{1};
-    uint64_t t = 0;         // Philox call counter
+    // The Philox call counter is DEVICE state (t_dev): kernels read it and the last CTA of an
+    // advancing launch bumps it, so launches carry no host state and are CUDA-graph capturable.
+    unsigned long long *t_dev = nullptr;
+    unsigned int *cta_done = nullptr;
     uint32_t goal_sub = 0;  // goal draws already made at this call counter (un-fused API)
     uint64_t launches = 0;  // kernels launched through this handle
     PhiloxKeys keys;
@@ -167,6 +170,8 @@ void free_env(roboy_env *e) {
     cudaFree(e->stats);
     cudaFree(e->err_flags);
     cudaFree(e->first_bad);
+    cudaFree(e->t_dev);
+    cudaFree(e->cta_done);
     cudaFree(e->actions_stage);
     if (e->host_ready)
         for (int i = 0; i < kHostStreams; ++i) cudaStreamDestroy(e->hs[i]);
@@ -177,12 +182,21 @@ void unref(roboy_env *e) {
     if (e->refs.fetch_sub(1) == 1) free_env(e);
 }
 
+CallCounter counter(roboy_env *e, CallCounter::Mode mode, unsigned long long t_fixed = 0) {
+    CallCounter c;
+    c.t_dev = e->t_dev;
+    c.cta_done = e->cta_done;
+    c.t_fixed = t_fixed;
+    c.mode = mode;
+    return c;
+}
+
 void fill_step_params(roboy_env *e, StepParams &p, const float *actions, float *obs, float *reward, uint8_t *done) {
     p.n = e->cfg.n_envs;
     p.e_begin = 0;
     p.e_end = e->cfg.n_envs;
     p.gid_base = e->cfg.env_id_base;
-    p.t = e->t;
+    p.cc = counter(e, CallCounter::kAdvance);
     p.keys = e->keys;
     p.c = e->consts;
     p.f = e->fast;
@@ -209,11 +223,6 @@ void fill_step_params(roboy_env *e, StepParams &p, const float *actions, float *
     p.stats = e->stats;
     p.err_flags = e->err_flags;
     p.first_bad = e->first_bad;
-}
-
-void advance_counter(roboy_env *env) {
-    env->t += 1;
-    env->goal_sub = 0;
 }
 
 int check_env(roboy_env *e) {
@@ -318,6 +327,10 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
     alloc((void **)&e->stats, sizeof(double) * ROBOY_STAT_COUNT);
     alloc((void **)&e->err_flags, sizeof(uint32_t));
     alloc((void **)&e->first_bad, sizeof(unsigned long long));
+    alloc((void **)&e->t_dev, sizeof(unsigned long long));
+    alloc((void **)&e->cta_done, sizeof(unsigned int));
+    if (err == cudaSuccess) err = cudaMemset(e->t_dev, 0, sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMemset(e->cta_done, 0, sizeof(unsigned int));
     if (err == cudaSuccess) err = cudaMemset(e->stats, 0, sizeof(double) * ROBOY_STAT_COUNT);
     if (err == cudaSuccess) err = cudaMemset(e->err_flags, 0, sizeof(uint32_t));
     if (err == cudaSuccess) err = cudaMemset(e->first_bad, 0xff, sizeof(unsigned long long));
@@ -326,7 +339,7 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
         InitParams ip{};
         ip.n = n;
         ip.gid_base = cfg->env_id_base;
-        ip.t = 0;
+        ip.cc = counter(e, CallCounter::kFixed, 0);
         ip.keys = e->keys;
         ip.a_lo = c.a_lo;
         ip.a_span = c.a_span;
@@ -371,12 +384,11 @@ int roboy_set_reward_range(roboy_env *env, double lo, double hi) {
 int roboy_reset(roboy_env *env, const uint8_t *mask_dev, float *obs_dev, void *stream) {
     if (check_env(env)) return ROBOY_E_ARG;
     DeviceGuard g(env->device);
-    advance_counter(env);
-    env->goal_sub = 1;  // the reset itself consumed goal draw 0 of this counter value
+    env->goal_sub = 1;  // the reset itself consumes goal draw 0 of the new counter value
     InitParams ip{};
     ip.n = env->cfg.n_envs;
     ip.gid_base = env->cfg.env_id_base;
-    ip.t = env->t;
+    ip.cc = counter(env, CallCounter::kAdvance);
     ip.keys = env->keys;
     ip.a_lo = env->consts.a_lo;
     ip.a_span = env->consts.a_span;
@@ -397,8 +409,7 @@ int roboy_step(roboy_env *env, const float *actions_dev, float *obs_dev, float *
     if (((uintptr_t)actions_dev & 15) || ((uintptr_t)(obs_dev ? obs_dev : env->obs) & 15))
         return fail(ROBOY_E_ARG, "actions and obs must be 16-byte aligned");
     DeviceGuard g(env->device);
-    advance_counter(env);
-    env->goal_sub = 1;  // done envs consume goal draw 0 of this counter value
+    env->goal_sub = 1;  // done envs consume goal draw 0 of the new counter value
     StepParams p;
     fill_step_params(env, p, actions_dev, obs_dev, reward_dev, done_dev);
     CUDA_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset, env->fastdiv,
@@ -418,10 +429,15 @@ int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, 
         for (int i = 0; i < kHostStreams; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&env->hs[i], cudaStreamNonBlocking));
         env->host_ready = true;
     }
-    advance_counter(env);
     env->goal_sub = 1;
+    // The stages run on several streams at once, so they all get the new counter value from the
+    // host (this call is synchronous anyway) and the device copy is updated when they are done.
+    unsigned long long t_now = 0;
+    CUDA_TRY(cudaMemcpy(&t_now, env->t_dev, sizeof(t_now), cudaMemcpyDeviceToHost));
+    t_now += 1;
     StepParams p;
     fill_step_params(env, p, env->actions_stage, nullptr, nullptr, nullptr);
+    p.cc = counter(env, CallCounter::kFixed, t_now);
     // Pipeline: per stage H2D(actions) -> step kernel -> D2H(obs, reward, done) on one stream of a
     // ring, so the copy engines of both directions and the SMs overlap across stages.
     int stage = 0;
@@ -443,6 +459,7 @@ int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, 
     }
     const int used = stage < kHostStreams ? stage : kHostStreams;
     for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamSynchronize(env->hs[i]));
+    CUDA_TRY(cudaMemcpy(env->t_dev, &t_now, sizeof(t_now), cudaMemcpyHostToDevice));
     return ROBOY_OK;
 }
 
@@ -540,7 +557,7 @@ static void fill_sim_params(roboy_env *env, SimParams &p, int mode) {
     p.mode = mode;
     p.n = env->cfg.n_envs;
     p.gid_base = env->cfg.env_id_base;
-    p.t = env->t;
+    p.cc = counter(env, mode == 2 ? CallCounter::kPeek : CallCounter::kAdvance);
     p.sub = env->goal_sub;
     p.keys = env->keys;
     p.a_lo = env->consts.a_lo;
@@ -556,7 +573,7 @@ int roboy_sim_step(roboy_env *env, const float *actions_dev, float *q_dev, float
     if (!actions_dev || !q_dev || !qd_dev) return fail(ROBOY_E_ARG, "NULL device pointer");
     if ((uintptr_t)actions_dev & 15) return fail(ROBOY_E_ARG, "actions must be 16-byte aligned");
     DeviceGuard g(env->device);
-    advance_counter(env);
+    env->goal_sub = 0;
     SimParams p{};
     fill_sim_params(env, p, 0);
     p.actions = actions_dev;
@@ -571,7 +588,7 @@ int roboy_sim_step(roboy_env *env, const float *actions_dev, float *q_dev, float
 int roboy_sim_reset(roboy_env *env, const uint8_t *mask_dev, void *stream) {
     if (check_env(env)) return ROBOY_E_ARG;
     DeviceGuard g(env->device);
-    advance_counter(env);
+    env->goal_sub = 0;
     SimParams p{};
     fill_sim_params(env, p, 1);
     p.mask = mask_dev;
@@ -584,7 +601,7 @@ int roboy_new_goal(roboy_env *env, float *goal_q_dev, void *stream) {
     if (check_env(env)) return ROBOY_E_ARG;
     if (!goal_q_dev) return fail(ROBOY_E_ARG, "goal_q_dev is NULL");
     DeviceGuard g(env->device);
-    if (env->goal_sub >= 255) advance_counter(env);
+    if (env->goal_sub >= 255) return fail(ROBOY_E_ARG, "more than 255 goal draws without a step or reset in between");
     SimParams p{};
     fill_sim_params(env, p, 2);
     p.out_q = goal_q_dev;
@@ -695,13 +712,20 @@ void *roboy_export_dlpack(roboy_env *env, int which) {
 
 int roboy_get_counter(roboy_env *env, uint64_t *t) {
     if (check_env(env) || !t) return fail(ROBOY_E_ARG, "NULL argument");
-    *t = env->t;
+    DeviceGuard g(env->device);
+    unsigned long long v = 0;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(&v, env->t_dev, sizeof(v), cudaMemcpyDeviceToHost));
+    *t = v;
     return ROBOY_OK;
 }
 
 int roboy_set_counter(roboy_env *env, uint64_t t) {
     if (check_env(env)) return ROBOY_E_ARG;
-    env->t = t;
+    DeviceGuard g(env->device);
+    const unsigned long long v = t;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(env->t_dev, &v, sizeof(v), cudaMemcpyHostToDevice));
     env->goal_sub = 1;
     return ROBOY_OK;
 }

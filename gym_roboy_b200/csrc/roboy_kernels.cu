@@ -156,12 +156,12 @@ __device__ __noinline__ HoldOut hold_branch(const StepParams &p, uint32_t e, uin
 
 // Rare: an env finished its episode (:65-68) -- new goal, and under auto-reset the worker's
 // reset() (:82-87).  Out of line: ~1/400 of env-steps.
-__device__ __noinline__ uint32_t finish_episode(const StepParams &p, uint32_t e, uint32_t step, bool reached,
-                                                bool auto_reset, float *row, unsigned int *s_cnt) {
+__device__ __noinline__ uint32_t finish_episode(const StepParams &p, uint64_t t, uint32_t e, uint32_t step,
+                                                bool reached, bool auto_reset, float *row, unsigned int *s_cnt) {
     const uint64_t gid = p.gid_base + e;
     // Under auto-reset the reference draws twice (:68 then :86) and only the second goal is ever
     // observable, so a single draw is materialised.
-    const uint4 rg = philox_draw(gid, p.t, kStreamGoal, p.keys);
+    const uint4 rg = philox_draw(gid, t, kStreamGoal, p.keys);
     const float ng0 = uniform_in24(rg.x, p.c.a_lo, p.f.a_span24);
     const float ng1 = uniform_in24(rg.y, p.c.a_lo, p.f.a_span24);
     const float ng2 = uniform_in24(rg.z, p.c.a_lo, p.f.a_span24);
@@ -182,8 +182,8 @@ __device__ __noinline__ uint32_t finish_episode(const StepParams &p, uint32_t e,
 }
 
 template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV, bool TAIL>
-__device__ __forceinline__ void process_chunk(const StepParams &p, const ChunkIn &cur, uint32_t base, int lane,
-                                              float *so, unsigned int *s_cnt, float &sum_reward) {
+__device__ __forceinline__ void process_chunk(const StepParams &p, uint64_t t, const ChunkIn &cur, uint32_t base,
+                                              int lane, float *so, unsigned int *s_cnt, float &sum_reward) {
     const uint32_t e = base + lane;
     const bool live = TAIL ? (e < (uint32_t)p.e_end) : true;
 
@@ -211,7 +211,7 @@ __device__ __forceinline__ void process_chunk(const StepParams &p, const ChunkIn
     if (!hold) {
         // simulation_client.py:40 -> roboy_robot.py:35-39: fresh sample; velocities are drawn
         // from the ANGLE space too (reference quirk, :38)
-        const Draw6 d = split6x21(philox_draw(p.gid_base + e, p.t, kStreamState, p.keys));
+        const Draw6 d = split6x21(philox_draw(p.gid_base + e, t, kStreamState, p.keys));
         q0 = uniform_in21(d.k[0], p.c.a_lo, p.f.a_span21);
         q1 = uniform_in21(d.k[1], p.c.a_lo, p.f.a_span21);
         q2 = uniform_in21(d.k[2], p.c.a_lo, p.f.a_span21);
@@ -240,7 +240,7 @@ __device__ __forceinline__ void process_chunk(const StepParams &p, const ChunkIn
     row[6] = g0; row[7] = g1; row[8] = g2;
 
     if (done && live) {
-        const uint32_t r = finish_episode(p, e, step, reached, AUTO_RESET, row, s_cnt);
+        const uint32_t r = finish_episode(p, t, e, step, reached, AUTO_RESET, row, s_cnt);
         word = (r & 0x80000000u) ? word : (r | ROBOY_F_HELD_ZERO64);
     }
     if (live && (violation || !act_ok)) {
@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const uint64_t t = counter_begin(p.cc);
     const uint32_t n_full = (uint32_t)(p.e_end >> 5);  // chunks [chunk0, n_full) are complete
     const uint32_t warp_stride = gridDim.x * kWarpsPerBlock;
     float *so = s_obs[warp];
@@ -311,12 +312,12 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
         pf.issue_and_advance(chunk + ROBOY_PREFETCH_DIST * warp_stride < n_full, lane);
 #endif
 #endif
-        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false>(p, cur, chunk << 5, lane, so, s_cnt, sum_reward);
+        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false>(p, t, cur, chunk << 5, lane, so, s_cnt, sum_reward);
         chunk = next;
     }
     if (chunk == n_full && (p.e_end & 31)) {  // the ragged last chunk belongs to exactly one warp
         const ChunkIn cur = load_chunk<true>(p, chunk << 5, lane);
-        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true>(p, cur, chunk << 5, lane, so, s_cnt, sum_reward);
+        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true>(p, t, cur, chunk << 5, lane, so, s_cnt, sum_reward);
     }
 
     // ---- K3: episode statistics, one set of atomics per CTA ----
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
 #pragma unroll
         for (int k = 0; k < ROBOY_STAT_COUNT; ++k)
             if (v[k] != 0.0) atomicAdd(p.stats + k, v[k]);
+        counter_end(p.cc, t);
     }
 }
 
@@ -405,11 +407,12 @@ cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto
 // K2: construction and reset
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) init_or_reset_kernel(const __grid_constant__ InitParams p) {
+    const uint64_t t = counter_begin(p.cc);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += stride) {
         if (p.mask && !p.mask[e]) continue;
         const uint64_t gid = p.gid_base + e;
-        const uint4 rg = philox_draw(gid, p.t, kStreamGoal, p.keys);
+        const uint4 rg = philox_draw(gid, t, kStreamGoal, p.keys);
         const float g0 = uniform_in(rg.x, p.a_lo, p.a_span);
         const float g1 = uniform_in(rg.y, p.a_lo, p.a_span);
         const float g2 = uniform_in(rg.z, p.a_lo, p.a_span);
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(256) init_or_reset_kernel(const __grid_constan
         p.goal[2 * p.n + e] = g2;
         if (p.held) {
             // StubSimulationClient.__init__ (simulation_client.py:31): _state = new_random_state()
-            const Draw6 d = split6x21(philox_draw(gid, p.t, kStreamState, p.keys));
+            const Draw6 d = split6x21(philox_draw(gid, t, kStreamState, p.keys));
 #pragma unroll
             for (int k = 0; k < 6; ++k) p.held[(size_t)k * p.n + e] = uniform_in21(d.k[k], p.a_lo, p.a_span * 0x1p-21f);
             p.step_flags[e] = 1u;  // roboy_env.py:38
@@ -434,6 +437,8 @@ __global__ void __launch_bounds__(256) init_or_reset_kernel(const __grid_constan
             o[8] = g2;
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) counter_end(p.cc, t);
 }
 
 cudaError_t launch_init_or_reset(const InitParams &p, cudaStream_t stream) {
@@ -540,11 +545,12 @@ __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ Sc
 // Un-fused SimulationClient calls (the plug-in API the reference's own RoboyEnv drives)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ SimParams p) {
+    const uint64_t t = counter_begin(p.cc);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += stride) {
         const uint64_t gid = p.gid_base + e;
         if (p.mode == 2) {
-            const uint4 rg = philox_draw(gid, p.t, kStreamGoal, p.keys, p.sub);
+            const uint4 rg = philox_draw(gid, t, kStreamGoal, p.keys, p.sub);
             p.out_q[e * 3 + 0] = uniform_in(rg.x, p.a_lo, p.a_span);
             p.out_q[e * 3 + 1] = uniform_in(rg.y, p.a_lo, p.a_span);
             p.out_q[e * 3 + 2] = uniform_in(rg.z, p.a_lo, p.a_span);
@@ -576,7 +582,7 @@ __global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ SimPar
             feasible = z || !(sf & ROBOY_F_HELD_INFEASIBLE);
             if (p.mode == 0) atomicAdd(p.stats + ROBOY_STAT_HOLDS, 1.0);
         } else {
-            const Draw6 d = split6x21(philox_draw(gid, p.t, kStreamState, p.keys));
+            const Draw6 d = split6x21(philox_draw(gid, t, kStreamState, p.keys));
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 q[k] = uniform_in21(d.k[k], p.a_lo, p.a_span * 0x1p-21f);
@@ -592,6 +598,8 @@ __global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ SimPar
             if (p.out_feasible) p.out_feasible[e] = (uint8_t)feasible;
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) counter_end(p.cc, t);
 }
 
 cudaError_t launch_sim(const SimParams &p, cudaStream_t stream) {

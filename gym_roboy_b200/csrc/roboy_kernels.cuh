@@ -16,12 +16,42 @@ constexpr int kWarpsPerBlock = kStepBlock / 32;
 constexpr int kStepMinBlocks = ROBOY_STEP_MIN_BLOCKS;  // __launch_bounds__ min CTAs/SM (register cap)
 constexpr int kObsDim = 9, kActDim = 8;
 
+// The Philox call counter lives in device memory so that launches carry no host state and can be
+// captured in CUDA graphs (closed-loop rollouts: policy + step, replayed many times).
+//   kFixed    t = t_fixed (host supplied; the multi-stream host-buffer path, construction)
+//   kAdvance  t = *t_dev + 1, and the LAST CTA of the launch to finish stores it back
+//   kPeek     t = *t_dev (get_new_goal_joint_angles between steps)
+struct CallCounter {
+    enum Mode : int { kFixed = 0, kAdvance = 1, kPeek = 2 };
+    unsigned long long *t_dev;
+    unsigned int *cta_done;  // CTAs of the current launch that have finished
+    unsigned long long t_fixed;
+    int mode;
+};
+
+__device__ __forceinline__ uint64_t counter_begin(const CallCounter &c) {
+    if (c.mode == CallCounter::kFixed) return c.t_fixed;
+    const unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(c.t_dev);
+    return c.mode == CallCounter::kAdvance ? t + 1 : t;
+}
+
+// Call once per CTA, by one thread, after the CTA's last use of the counter value.  Every CTA read
+// *t_dev before it got here, and the store happens only after ALL CTAs got here.
+__device__ __forceinline__ void counter_end(const CallCounter &c, uint64_t t) {
+    if (c.mode != CallCounter::kAdvance) return;
+    __threadfence();
+    if (atomicAdd(c.cta_done, 1u) == gridDim.x - 1) {
+        *c.cta_done = 0;
+        *c.t_dev = t;
+    }
+}
+
 struct StepParams {
     uint64_t n;         // envs in this shard (= leading dimension of the SoA arrays)
     uint64_t e_begin;   // this launch covers local envs [e_begin, e_end); e_begin % 32 == 0
     uint64_t e_end;
     uint64_t gid_base;  // global id of local env 0
-    uint64_t t;         // Philox call counter of this launch
+    CallCounter cc;     // Philox call counter of this launch
     PhiloxKeys keys;
     RobotConsts c;
     FastConsts f;
@@ -57,7 +87,8 @@ cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto
                         cudaStream_t stream);
 
 struct InitParams {
-    uint64_t n, gid_base, t;
+    uint64_t n, gid_base;
+    CallCounter cc;
     PhiloxKeys keys;
     float a_lo, a_span;
     float *goal;
@@ -111,7 +142,8 @@ cudaError_t launch_scatter(const ScatterParams &p, cudaStream_t stream);
 //   mode 2  get_new_goal_joint_angles()                  -> goal draw  (:46-47), does not touch env state
 struct SimParams {
     int mode;
-    uint64_t n, gid_base, t;
+    uint64_t n, gid_base;
+    CallCounter cc;
     uint32_t sub;
     PhiloxKeys keys;
     float a_lo, a_span;

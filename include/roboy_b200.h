@@ -191,7 +191,10 @@ int roboy_buffer(roboy_env *env, int which, void **dev_ptr, uint64_t *nbytes);
 void *roboy_export_dlpack(roboy_env *env, int which);
 
 /* Philox call counter (0 after create, +1 per reset/step call) -- with the state buffers and
- * the seed this is the complete checkpoint of the env shard. */
+ * the seed this is the complete checkpoint of the env shard.  The counter is DEVICE state: every
+ * counter-advancing kernel reads it and its last CTA stores the new value, so roboy_step /
+ * roboy_reset / roboy_sim_* launches carry no host state and can be captured in a CUDA graph and
+ * replayed (each replay advances the counter).  Both calls below synchronise the device. */
 int roboy_get_counter(roboy_env *env, uint64_t *t);
 int roboy_set_counter(roboy_env *env, uint64_t t);
 

@@ -306,3 +306,39 @@ def test_full_size_properties(n):
     assert s["steps"] == 5 * n and s["episodes"] == total_done and s["violations"] == 0
     assert s["episodes"] == s["successes"] + s["timeouts"] and total_done > 0
     assert client.errors() == (0, None)
+
+
+def test_steps_captured_in_a_cuda_graph_replay_like_eager_steps():
+    """The call counter is device state, so a captured sequence of steps can be replayed and each
+    replay continues the trajectory exactly as eager stepping would."""
+    n, k, rounds = 20000, 8, 3
+    rng = np.random.default_rng(5)
+    acts = [torch.as_tensor(actions_for(rng, n), device="cuda:0") for _ in range(k)]
+    env_a, client_a, _ = make_pair(n, seed=8)
+    env_b, client_b, _ = make_pair(n, seed=8)
+    for env, client in ((env_a, client_a), (env_b, client_b)):
+        env.reset()
+        client.set_step_num(np.full(n, 390, np.int32))     # timeouts (goal draws) inside the captured region
+    obs_buf = torch.zeros((k, n, 9), device="cuda:0")
+    rew_buf = torch.zeros((k, n), device="cuda:0")
+    done_buf = torch.zeros((k, n), dtype=torch.uint8, device="cuda:0")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        client_b.step_fused(acts[0])                        # warm-up outside capture (occupancy query etc.)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    client_b.load_state_dict(client_a.state_dict())         # undo the warm-up step exactly
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for t in range(k):
+            client_b.step_fused(acts[t], obs=obs_buf[t], reward=rew_buf[t], done=done_buf[t])
+    client_b.load_state_dict(client_a.state_dict())         # capture does not execute; be explicit anyway
+    for r in range(rounds):
+        graph.replay()
+        torch.cuda.synchronize()
+        for t in range(k):
+            o, rw, d, _ = env_a.step(acts[t])
+            assert torch.equal(o, obs_buf[t]) and torch.equal(rw, rew_buf[t]) and torch.equal(d, done_buf[t].bool()), (r, t)
+    assert client_a.counter == client_b.counter == 1 + rounds * k
+    assert client_a.stats()["episodes"] == client_b.stats()["episodes"] > 0
