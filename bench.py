@@ -337,6 +337,35 @@ def run_b200_arm(args):
             del e, c, acts
         del flush
 
+    # ---- closed-loop policy rollouts (BASELINE configs[1] size and configs[4] shape; N = 1 only) ----
+    rollout = None
+    if world == 1 and not args.no_sweep:
+        from gym_roboy_b200.rollout import MlpPolicy, RolloutCollector
+        rollout = []
+        for n in (4096, 262144):
+            for graph in (False, True):
+                torch.manual_seed(0)
+                e, c = make(n)
+                col = RolloutCollector(e, MlpPolicy().to(dev), n_steps=128)
+                if graph:
+                    col.capture()
+                for _ in range(2):
+                    col.collect()
+                torch.cuda.synchronize()
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 5
+                s_.record()
+                for _ in range(reps):
+                    col.collect()
+                e_.record()
+                torch.cuda.synchronize()
+                ms = s_.elapsed_time(e_) / reps
+                rollout.append({"envs": n, "n_steps": 128, "cuda_graph": graph, "ms_per_rollout": ms,
+                                "env_steps_per_s": n * 128 / (ms * 1e-3),
+                                "what": "MlpPolicy 9-64-64-8 (+value net) forward, Gaussian sample, device clip, fused env "
+                                        "step writing into [T,N] buffers, GAE kernel"})
+                del col, e, c
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
@@ -354,7 +383,7 @@ def run_b200_arm(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(envs, world), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
-            "episode_stats": stats, "sweep": sweep, "impl": "b200",
+            "episode_stats": stats, "sweep": sweep, "rollout": rollout, "impl": "b200",
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -769,6 +769,25 @@ int roboy_errors(roboy_env *env, uint32_t *err_flags, uint64_t *first_bad_env, v
     return ROBOY_OK;
 }
 
+int roboy_gae(uint64_t T, uint64_t n, const float *reward_dev, const float *value_dev, const uint8_t *done_dev,
+              const float *last_value_dev, float gamma, float lam, float *adv_dev, float *ret_dev, void *stream) {
+    if (!reward_dev || !value_dev || !done_dev || !last_value_dev || !adv_dev || !ret_dev)
+        return fail(ROBOY_E_ARG, "NULL device pointer");
+    GaeParams p{};
+    p.T = T;
+    p.n = n;
+    p.reward = reward_dev;
+    p.value = value_dev;
+    p.done = done_dev;
+    p.last_value = last_value_dev;
+    p.gamma = gamma;
+    p.lam = lam;
+    p.adv = adv_dev;
+    p.ret = ret_dev;
+    CUDA_TRY(launch_gae(p, (cudaStream_t)stream));
+    return ROBOY_OK;
+}
+
 int roboy_launch_count(roboy_env *env, uint64_t *launches) {
     if (check_env(env) || !launches) return fail(ROBOY_E_ARG, "NULL argument");
     *launches = env->launches;

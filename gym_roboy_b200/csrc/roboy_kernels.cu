@@ -618,4 +618,35 @@ cudaError_t launch_scatter(const ScatterParams &p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rollout consumer: GAE(lambda) over [T][n] buffers, one thread per env walking t backwards
+// (all accesses coalesced across envs).  delta_t = r_t + gamma*V_{t+1}*(1-done_t) - V_t;
+// A_t = delta_t + gamma*lam*(1-done_t)*A_{t+1};  R_t = A_t + V_t.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gae_kernel(const __grid_constant__ GaeParams p) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += stride) {
+        float next_v = p.last_value[e];
+        float gae = 0.0f;
+        for (uint64_t t = p.T; t-- > 0;) {
+            const size_t i = (size_t)t * p.n + e;
+            const float nonterminal = p.done[i] ? 0.0f : 1.0f;
+            const float v = p.value[i];
+            const float delta = p.reward[i] + p.gamma * next_v * nonterminal - v;
+            gae = delta + p.gamma * p.lam * nonterminal * gae;
+            p.adv[i] = gae;
+            p.ret[i] = gae + v;
+            next_v = v;
+        }
+    }
+}
+
+cudaError_t launch_gae(const GaeParams &p, cudaStream_t stream) {
+    if (p.n == 0 || p.T == 0) return cudaSuccess;
+    const uint64_t want = (p.n + 255) / 256;
+    const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    gae_kernel<<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 }  // namespace roboy

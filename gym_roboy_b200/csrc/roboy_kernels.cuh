@@ -157,4 +157,16 @@ struct SimParams {
 };
 cudaError_t launch_sim(const SimParams &p, cudaStream_t stream);
 
+// Generalised advantage estimation over rollout buffers [T][n] that the step kernel filled in place
+// (the PPO2 runner of train_parallel.py:31-34 does this on the host; stable-baselines is external).
+struct GaeParams {
+    uint64_t T, n;
+    const float *reward, *value;   // [T][n]
+    const uint8_t *done;           // [T][n]  done[t] = episode ended AT step t
+    const float *last_value;       // [n]     V(obs after the last step)
+    float gamma, lam;
+    float *adv, *ret;              // [T][n]
+};
+cudaError_t launch_gae(const GaeParams &p, cudaStream_t stream);
+
 }  // namespace roboy

@@ -207,6 +207,13 @@ int roboy_clear_errors(roboy_env *env, void *stream);  /* error word only */
 /* Device error word and first offending global env id (UINT64_MAX if none); synchronises. */
 int roboy_errors(roboy_env *env, uint32_t *err_flags, uint64_t *first_bad_env, void *stream);
 
+/* Rollout consumer: GAE(lambda) advantages and returns over rollout buffers
+ * [T][n] that roboy_step filled in place -- what the PPO2 runner behind train_parallel.py:31-34
+ * computes on the host.  done[t] = the episode ended AT step t (no bootstrap across it);
+ * last_value [n] = V(observation after the last step).  Runs on the current device, async. */
+int roboy_gae(uint64_t T, uint64_t n, const float *reward_dev, const float *value_dev, const uint8_t *done_dev,
+              const float *last_value_dev, float gamma, float lam, float *adv_dev, float *ret_dev, void *stream);
+
 /* Introspection for bench.py / tests: kernels launched by this handle so far, and the
  * launch geometry the step kernel uses for this n_envs. */
 int roboy_launch_count(roboy_env *env, uint64_t *launches);
