@@ -302,7 +302,7 @@ def run_b200_arm(args):
         e2e = {"value": envs * world * k2 / dt, "unit": UNIT, "h2d_bytes_per_step": H2D_BYTES * n,
                "d2h_bytes_per_step": D2H_BYTES * n, "steps": k2, "ms_per_step": 1e3 * dt / k2,
                "api": "roboy_step_host (C-ABI): pinned host actions -> H2D -> step kernel -> D2H obs+reward+done, "
-                      "pipelined over 4 streams in 262,144-env stages", "gpu_launches": client.launch_count() - l0,
+                      "pipelined over 2 streams in 524,288-env stages", "gpu_launches": client.launch_count() - l0,
                "checksum": float(rew_h[:1024].double().sum())}
         del a_host, obs_h, rew_h, done_h, bufs
     del env, client, actions
@@ -322,6 +322,26 @@ def run_b200_arm(args):
                    "GBps_algorithmic": BYTES_PER_ENV_STEP * n / (mean_ms * 1e-3) / 1e9,
                    "frac_of_peak": BYTES_PER_ENV_STEP * n / (mean_ms * 1e-3) / 1e9 / peak,
                    "regime": "launch-bound" if n <= 32768 else ("L2-resident" if BYTES_PER_ENV_STEP * n < 126e6 else "HBM-bound")}
+            if n <= 4194304:   # launch/host-bound sizes: the same steps captured in one CUDA graph and replayed
+                kg = 100
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for i in range(kg):
+                        c.step_fused(acts[i & 1])
+                for _ in range(2):
+                    g.replay()
+                torch.cuda.synchronize()
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record()
+                for _ in range(3):
+                    g.replay()
+                e_.record()
+                torch.cuda.synchronize()
+                gms = s_.elapsed_time(e_) / (3 * kg)
+                row["cuda_graph_ms_per_step"] = gms
+                row["cuda_graph_env_steps_per_s"] = n / (gms * 1e-3)
+                row["cuda_graph_GBps_algorithmic"] = BYTES_PER_ENV_STEP * n / (gms * 1e-3) / 1e9
+                del g
             if BYTES_PER_ENV_STEP * n < 2 * 126e6:     # fits (mostly) in L2: also time with an explicit L2 flush per step
                 times = []
                 for i in range(12):

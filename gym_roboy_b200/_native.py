@@ -48,6 +48,7 @@ SIGNATURES = {
     "roboy_reset": (_int, [_vp, _vp, _vp, _vp]),
     "roboy_step": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "roboy_step_host": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "roboy_set_host_pipeline": (_int, [_vp, _u64, _int]),
     "roboy_set_terminal_obs": (_int, [_vp, _vp]),
     "roboy_compute_reward": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "roboy_set_goal": (_int, [_vp, _u64, _vp, _vp, _vp]),

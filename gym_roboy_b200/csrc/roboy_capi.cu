@@ -35,8 +35,9 @@ int fail(int code, const char *fmt, ...) {
             return fail(ROBOY_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int kHostStreams = 4;            // ring of streams for the host-buffer pipeline
-constexpr uint64_t kHostChunkEnvs = 1u << 18;  // 262,144 envs per pipeline stage (8 MiB in, 10.25 MiB out)
+constexpr int kHostStreamsMax = 8;         // ring of streams for the host-buffer pipeline
+constexpr int kHostStreamsDefault = 2;                // measured best on PCIe Gen5 (tools/e2e_sweep.py)
+constexpr uint64_t kHostStageEnvsDefault = 1u << 19;  // 524,288 envs per pipeline stage (16 MiB in, 20.5 MiB out)
 
 struct DeviceGuard {
     int prev = -1;
@@ -153,7 +154,9 @@ struct roboy_env {
     float *terminal_obs = nullptr;  // caller-owned
     // host-buffer pipeline (lazily created)
     float *actions_stage = nullptr;  // device copy of the host actions
-    cudaStream_t hs[kHostStreams] = {};
+    cudaStream_t hs[kHostStreamsMax] = {};
+    int host_streams = kHostStreamsDefault;
+    uint64_t host_stage_envs = kHostStageEnvsDefault;
     bool host_ready = false;
 };
 
@@ -174,7 +177,7 @@ void free_env(roboy_env *e) {
     cudaFree(e->cta_done);
     cudaFree(e->actions_stage);
     if (e->host_ready)
-        for (int i = 0; i < kHostStreams; ++i) cudaStreamDestroy(e->hs[i]);
+        for (int i = 0; i < kHostStreamsMax; ++i) cudaStreamDestroy(e->hs[i]);
     delete e;
 }
 
@@ -426,7 +429,7 @@ int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, 
     const uint64_t n = env->cfg.n_envs;
     if (!env->host_ready) {
         CUDA_TRY(cudaMalloc((void **)&env->actions_stage, sizeof(float) * ROBOY_DIM_ACTION * n));
-        for (int i = 0; i < kHostStreams; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&env->hs[i], cudaStreamNonBlocking));
+        for (int i = 0; i < kHostStreamsMax; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&env->hs[i], cudaStreamNonBlocking));
         env->host_ready = true;
     }
     env->goal_sub = 1;
@@ -441,10 +444,11 @@ int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, 
     // Pipeline: per stage H2D(actions) -> step kernel -> D2H(obs, reward, done) on one stream of a
     // ring, so the copy engines of both directions and the SMs overlap across stages.
     int stage = 0;
-    for (uint64_t b = 0; b < n; b += kHostChunkEnvs, ++stage) {
-        const uint64_t eend = b + kHostChunkEnvs < n ? b + kHostChunkEnvs : n;
+    const uint64_t stage_envs = env->host_stage_envs;
+    for (uint64_t b = 0; b < n; b += stage_envs, ++stage) {
+        const uint64_t eend = b + stage_envs < n ? b + stage_envs : n;
         const uint64_t cnt = eend - b;
-        cudaStream_t s = env->hs[stage % kHostStreams];
+        cudaStream_t s = env->hs[stage % env->host_streams];
         CUDA_TRY(cudaMemcpyAsync(env->actions_stage + b * ROBOY_DIM_ACTION, actions_host + b * ROBOY_DIM_ACTION,
                                  sizeof(float) * ROBOY_DIM_ACTION * cnt, cudaMemcpyHostToDevice, s));
         p.e_begin = b;
@@ -457,9 +461,18 @@ int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, 
         CUDA_TRY(cudaMemcpyAsync(reward_host + b, env->reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(done_host + b, env->done + b, cnt, cudaMemcpyDeviceToHost, s));
     }
-    const int used = stage < kHostStreams ? stage : kHostStreams;
+    const int used = stage < env->host_streams ? stage : env->host_streams;
     for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamSynchronize(env->hs[i]));
     CUDA_TRY(cudaMemcpy(env->t_dev, &t_now, sizeof(t_now), cudaMemcpyHostToDevice));
+    return ROBOY_OK;
+}
+
+int roboy_set_host_pipeline(roboy_env *env, uint64_t stage_envs, int n_streams) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (stage_envs == 0 || (stage_envs & 31) || n_streams < 1 || n_streams > kHostStreamsMax)
+        return fail(ROBOY_E_ARG, "stage_envs must be a positive multiple of 32 and 1 <= n_streams <= %d", kHostStreamsMax);
+    env->host_stage_envs = stage_envs;
+    env->host_streams = n_streams;
     return ROBOY_OK;
 }
 

@@ -72,6 +72,10 @@ class RoboyEnv(_GoalEnvBase):
         self.reward_range = self._create_reward_range()
         client.set_reward_range(*self.reward_range)
         self._last_obs = None
+        self._info = {}                      # batched: {'terminal_observation': tensor} once enabled on the client
+        client.info_sink = self._info
+        if client.terminal_obs is not None:
+            self._info["terminal_observation"] = client.terminal_obs
 
     # ------------------------------------------------------------------ reference surface
     def _create_reward_range(self):
@@ -86,6 +90,11 @@ class RoboyEnv(_GoalEnvBase):
 
     def step(self, action):
         client = self._simulation_client
+        if not self._single and not self._strict and torch.is_tensor(action) and action.is_cuda \
+                and action.dtype == torch.float32 and action.is_contiguous():
+            client.step_fused(action)   # hot path of a batched trainer: no conversions, no sync
+            self._last_obs = client.obs
+            return client.obs, client.reward, client.done, self._info
         if self._single and not torch.is_tensor(action):
             a = np.asarray(action)
             assert self.action_space.contains(a)                                              # roboy_env.py:52
@@ -99,10 +108,7 @@ class RoboyEnv(_GoalEnvBase):
             self.check_errors()
         if self._single:
             return (client.obs[0].cpu().numpy(), float(client.reward[0].item()), bool(client.done[0].item()), {})
-        info = {}
-        if client.terminal_obs is not None:
-            info["terminal_observation"] = client.terminal_obs
-        return client.obs, client.reward, client.done, info
+        return client.obs, client.reward, client.done, self._info
 
     def reset(self, mask=None):
         """roboy_env.py:82-87.  Batched envs may reset only the envs selected by a `[N]` mask."""

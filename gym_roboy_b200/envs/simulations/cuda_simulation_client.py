@@ -73,6 +73,7 @@ class CudaSimulationClient(SimulationClient):
         self.done = self.done_u8.view(torch.bool)
         self.stats_tensor = self._view(_native.BUF_STATS)       # float64 [8]
         self.terminal_obs = None
+        self.info_sink = None
         self._all_idx = None
 
     # ------------------------------------------------------------------ plumbing
@@ -168,6 +169,10 @@ class CudaSimulationClient(SimulationClient):
             self.terminal_obs = torch.zeros((self.num_envs, _native.DIM_OBS), dtype=torch.float32, device=self.device)
         if not enable:
             self.terminal_obs = None
+        if self.info_sink is not None:   # RoboyEnv's info dict: carries the side buffer when enabled
+            self.info_sink.pop("terminal_observation", None)
+            if self.terminal_obs is not None:
+                self.info_sink["terminal_observation"] = self.terminal_obs
         _native.check(self._lib.roboy_set_terminal_obs(self._h, self._p(self.terminal_obs)))
 
     def step_fused(self, actions, obs=None, reward=None, done=None):
@@ -182,6 +187,9 @@ class CudaSimulationClient(SimulationClient):
     def reset_fused(self, mask=None, obs=None):
         m = None if mask is None else self._dev(mask, torch.uint8, (self.num_envs,))
         _native.check(self._lib.roboy_reset(self._h, self._p(m), self._p(obs), self._stream()))
+
+    def set_host_pipeline(self, stage_envs=1 << 19, n_streams=2):
+        _native.check(self._lib.roboy_set_host_pipeline(self._h, int(stage_envs), int(n_streams)))
 
     def step_host(self, actions, obs, reward, done):
         """The fused step through HOST numpy buffers (pinned for full speed); synchronous."""

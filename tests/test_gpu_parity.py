@@ -222,9 +222,10 @@ def test_sharding_invariance_and_determinism():
 
 
 def test_host_buffer_step_equals_device_step():
-    n = 300_000   # more than one pipeline stage (262,144 envs), ragged tail
+    n = 300_000   # more than one pipeline stage, ragged tail
     env_a, client_a, _ = make_pair(n, seed=3)
     env_b, client_b, _ = make_pair(n, seed=3)
+    client_a.set_host_pipeline(stage_envs=1 << 16, n_streams=3)
     env_a.reset(); env_b.reset()
     rng = np.random.default_rng(1)
     for t in range(3):
