@@ -68,6 +68,8 @@ SIGNATURES = {
     "roboy_clear_stats": (_int, [_vp, _vp]),
     "roboy_clear_errors": (_int, [_vp, _vp]),
     "roboy_errors": (_int, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(_u64), _vp]),
+    "roboy_step_external": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "roboy_reset_external": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "roboy_gae": (_int, [_u64, _u64, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]),
     "roboy_launch_count": (_int, [_vp, ctypes.POINTER(_u64)]),
     "roboy_step_geometry": (_int, [_vp, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),

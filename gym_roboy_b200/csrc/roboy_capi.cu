@@ -782,6 +782,50 @@ int roboy_errors(roboy_env *env, uint32_t *err_flags, uint64_t *first_bad_env, v
     return ROBOY_OK;
 }
 
+static int external_common(roboy_env *env, int reset, const uint8_t *mask, const float *q, const float *qd,
+                           const uint8_t *feasible, float *obs, float *reward, uint8_t *done, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!q || !qd) return fail(ROBOY_E_ARG, "q_dev/qd_dev is NULL");
+    DeviceGuard g(env->device);
+    env->goal_sub = 1;
+    ExternalParams p{};
+    p.reset = reset;
+    p.n = env->cfg.n_envs;
+    p.gid_base = env->cfg.env_id_base;
+    p.cc = counter(env, CallCounter::kAdvance);
+    p.keys = env->keys;
+    p.c = env->consts;
+    p.a_span24 = env->fast.a_span24;
+    p.penalty = env->cfg.joint_vel_penalty != 0;
+    p.bonus = env->cfg.bonus_for_goal != 0;
+    p.max_len = env->cfg.max_episode_len;
+    p.q = q;
+    p.qd = qd;
+    p.feasible = feasible;
+    p.mask = mask;
+    p.goal = env->goal;
+    p.step_flags = env->step_flags;
+    p.obs = obs ? obs : env->obs;
+    p.reward = reward ? reward : env->reward;
+    p.done = done ? done : env->done;
+    p.stats = env->stats;
+    p.err_flags = env->err_flags;
+    p.first_bad = env->first_bad;
+    CUDA_TRY(launch_external(p, (cudaStream_t)stream));
+    env->launches++;
+    return ROBOY_OK;
+}
+
+int roboy_step_external(roboy_env *env, const float *q_dev, const float *qd_dev, const uint8_t *feasible_dev,
+                        float *obs_dev, float *reward_dev, uint8_t *done_dev, void *stream) {
+    return external_common(env, 0, nullptr, q_dev, qd_dev, feasible_dev, obs_dev, reward_dev, done_dev, stream);
+}
+
+int roboy_reset_external(roboy_env *env, const uint8_t *mask_dev, const float *q_dev, const float *qd_dev,
+                         float *obs_dev, void *stream) {
+    return external_common(env, 1, mask_dev, q_dev, qd_dev, nullptr, obs_dev, nullptr, nullptr, stream);
+}
+
 int roboy_gae(uint64_t T, uint64_t n, const float *reward_dev, const float *value_dev, const uint8_t *done_dev,
               const float *last_value_dev, float gamma, float lam, float *adv_dev, float *ret_dev, void *stream) {
     if (!reward_dev || !value_dev || !done_dev || !last_value_dev || !adv_dev || !ret_dev)

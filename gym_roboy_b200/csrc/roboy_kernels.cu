@@ -659,6 +659,86 @@ cudaError_t launch_scatter(const ScatterParams &p, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Env step / reset fed by an external simulator.  The wire values are float64 in the reference
+// (python floats -> np.array), so the float64 branches of compute_reward / _did_reach_goal apply.
+// One thread per env; this path is bound by the external simulator, not by this kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) external_kernel(const __grid_constant__ ExternalParams p) {
+    const uint64_t t = counter_begin(p.cc);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += stride) {
+        if (p.reset && p.mask && !p.mask[e]) continue;
+        const uint64_t gid = p.gid_base + e;
+        HeldState s;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            s.q[k] = (double)p.q[e * 3 + k];
+            s.qd[k] = (double)p.qd[e * 3 + k];
+        }
+        s.is64 = true;
+        s.feasible = p.feasible ? p.feasible[e] != 0 : true;
+        float g[3] = {p.goal[e], p.goal[p.n + e], p.goal[2 * p.n + e]};
+        uint32_t sf = p.step_flags[e];
+        bool new_goal = p.reset != 0;
+        if (!p.reset) {
+            double r;
+            bool reached, violation;
+            const float no_gqd[3] = {0.f, 0.f, 0.f};
+            reward_reached_general(s, g, false, no_gqd, p.penalty, p.bonus, p.c, r, reached, violation);
+            uint32_t step = sf & ROBOY_STEP_MASK;
+            step += step < ROBOY_STEP_MASK;                                   // roboy_env.py:60
+            const bool done = reached || (int32_t)step > p.max_len;           // :65-66
+            sf = step | (sf & ~ROBOY_STEP_MASK);
+            p.reward[e] = (float)r;
+            p.done[e] = (uint8_t)done;
+            new_goal = done;                                                  // :67-68
+            atomicAdd(p.stats + ROBOY_STAT_STEPS, 1.0);
+            atomicAdd(p.stats + ROBOY_STAT_SUM_REWARD, (double)(float)r);
+            if (done) {
+                atomicAdd(p.stats + ROBOY_STAT_EPISODES, 1.0);
+                atomicAdd(p.stats + (reached ? ROBOY_STAT_SUCCESSES : ROBOY_STAT_TIMEOUTS), 1.0);
+            }
+            if (violation) {
+                atomicOr(p.err_flags, ROBOY_ERR_REWARD_RANGE);
+                atomicMin(p.first_bad, (unsigned long long)gid);
+                atomicAdd(p.stats + ROBOY_STAT_VIOLATIONS, 1.0);
+            }
+        } else {
+            sf = 1u | (sf & ~ROBOY_STEP_MASK);                                // :85
+        }
+        float *o = p.obs + e * kObsDim;
+        if (!p.reset) {                                                       // :62 obs carries the goal in force
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { o[k] = (float)s.q[k]; o[3 + k] = (float)s.qd[k]; o[6 + k] = g[k]; }
+        }
+        if (new_goal) {
+            const uint4 rg = philox_draw(gid, t, kStreamGoal, p.keys);
+            g[0] = uniform_in24(rg.x, p.c.a_lo, p.a_span24);
+            g[1] = uniform_in24(rg.y, p.c.a_lo, p.a_span24);
+            g[2] = uniform_in24(rg.z, p.c.a_lo, p.a_span24);
+            p.goal[e] = g[0];
+            p.goal[p.n + e] = g[1];
+            p.goal[2 * p.n + e] = g[2];
+        }
+        if (p.reset) {                                                        // :86-87 obs carries the NEW goal
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { o[k] = (float)s.q[k]; o[3 + k] = (float)s.qd[k]; o[6 + k] = g[k]; }
+        }
+        p.step_flags[e] = sf;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) counter_end(p.cc, t);
+}
+
+cudaError_t launch_external(const ExternalParams &p, cudaStream_t stream) {
+    if (p.n == 0) return cudaSuccess;
+    const uint64_t want = (p.n + 255) / 256;
+    const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    external_kernel<<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Rollout consumer: GAE(lambda) over [T][n] buffers, one thread per env walking t backwards
 // (all accesses coalesced across envs).  delta_t = r_t + gamma*V_{t+1}*(1-done_t) - V_t;
 // A_t = delta_t + gamma*lam*(1-done_t)*A_{t+1};  R_t = A_t + V_t.

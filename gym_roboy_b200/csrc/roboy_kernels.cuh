@@ -157,6 +157,31 @@ struct SimParams {
 };
 cudaError_t launch_sim(const SimParams &p, cudaStream_t stream);
 
+// RoboyEnv.step / reset when the states come from an EXTERNAL simulator (the role of
+// RosSimulationClient, ros_simulation_client.py:40-60: q, qdot, feasible arrive over the wire and
+// are held as float64 arrays) instead of the in-process Stub.
+struct ExternalParams {
+    int reset;                 // 0: step (roboy_env.py:51-70), 1: reset (roboy_env.py:82-87)
+    uint64_t n, gid_base;
+    CallCounter cc;
+    PhiloxKeys keys;
+    RobotConsts c;
+    float a_span24;
+    bool penalty, bonus;
+    int32_t max_len;
+    const float *q, *qd;       // [n][3]
+    const uint8_t *feasible;   // [n] or nullptr
+    const uint8_t *mask;       // reset only; nullptr = all
+    float *goal;               // [3][n]
+    uint32_t *step_flags;
+    float *obs, *reward;
+    uint8_t *done;
+    double *stats;
+    uint32_t *err_flags;
+    unsigned long long *first_bad;
+};
+cudaError_t launch_external(const ExternalParams &p, cudaStream_t stream);
+
 // Generalised advantage estimation over rollout buffers [T][n] that the step kernel filled in place
 // (the PPO2 runner of train_parallel.py:31-34 does this on the host; stable-baselines is external).
 struct GaeParams {

@@ -110,6 +110,23 @@ class RoboyEnv(_GoalEnvBase):
             return (client.obs[0].cpu().numpy(), float(client.reward[0].item()), bool(client.done[0].item()), {})
         return client.obs, client.reward, client.done, self._info
 
+    def step_from_states(self, joint_angles, joint_vels, is_feasible=None):
+        """`step` for envs whose simulator runs elsewhere: the caller has already
+        forwarded its actions; this computes obs / reward / done / goal resample for the returned
+        states (`[N,3]`, `[N,3]`, `[N]`).  No auto-reset -- see `reset_from_states`."""
+        client = self._simulation_client
+        client.step_external(joint_angles, joint_vels, is_feasible)
+        self._last_obs = client.obs
+        if self._strict:
+            self.check_errors()
+        return client.obs, client.reward, client.done, {}
+
+    def reset_from_states(self, joint_angles, joint_vels, mask=None):
+        client = self._simulation_client
+        client.reset_external(joint_angles, joint_vels, mask)
+        self._last_obs = client.obs
+        return client.obs
+
     def reset(self, mask=None):
         """roboy_env.py:82-87.  Batched envs may reset only the envs selected by a `[N]` mask."""
         client = self._simulation_client

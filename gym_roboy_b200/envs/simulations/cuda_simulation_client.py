@@ -188,6 +188,21 @@ class CudaSimulationClient(SimulationClient):
         m = None if mask is None else self._dev(mask, torch.uint8, (self.num_envs,))
         _native.check(self._lib.roboy_reset(self._h, self._p(m), self._p(obs), self._stream()))
 
+    def step_external(self, q, qd, feasible=None, obs=None, reward=None, done=None):
+        """RoboyEnv.step on states produced by an external simulator (float32 CUDA `[N,3]`, uint8 `[N]`)."""
+        n = self.num_envs
+        q, qd = self._dev(q, torch.float32, (n, 3)), self._dev(qd, torch.float32, (n, 3))
+        f = None if feasible is None else self._dev(feasible, torch.uint8, (n,))
+        _native.check(self._lib.roboy_step_external(self._h, self._p(q), self._p(qd), self._p(f), self._p(obs),
+                                                    self._p(reward), self._p(done), self._stream()))
+
+    def reset_external(self, q, qd, mask=None, obs=None):
+        n = self.num_envs
+        q, qd = self._dev(q, torch.float32, (n, 3)), self._dev(qd, torch.float32, (n, 3))
+        m = None if mask is None else self._dev(mask, torch.uint8, (n,))
+        _native.check(self._lib.roboy_reset_external(self._h, self._p(m), self._p(q), self._p(qd), self._p(obs),
+                                                     self._stream()))
+
     def set_host_pipeline(self, stage_envs=1 << 19, n_streams=2):
         _native.check(self._lib.roboy_set_host_pipeline(self._h, int(stage_envs), int(n_streams)))
 

@@ -211,6 +211,19 @@ int roboy_clear_errors(roboy_env *env, void *stream);  /* error word only */
 /* Device error word and first offending global env id (UINT64_MAX if none); synchronises. */
 int roboy_errors(roboy_env *env, uint32_t *err_flags, uint64_t *first_bad_env, void *stream);
 
+/* External-simulator feed.  RoboyEnv.step / reset (roboy_env.py:51-70, :82-87)
+ * when the robot states come from an external simulator -- the role RosSimulationClient plays
+ * (ros_simulation_client.py:40-60: q, qdot, feasible arrive over the wire) -- instead of the
+ * in-process Stub: the caller forwards the actions to its simulator itself and hands the resulting
+ * batch [n][3] q, [n][3] qd, [n] feasible (NULL = all feasible) to the same reward / done / goal
+ * kernel.  The reference holds wire values as float64 arrays, so its float64 arithmetic applies.
+ * No auto-reset: on done the goal is re-drawn (:67-68); the caller resets its simulator and calls
+ * roboy_reset_external (mask NULL = all) with the post-reset states. */
+int roboy_step_external(roboy_env *env, const float *q_dev, const float *qd_dev, const uint8_t *feasible_dev,
+                        float *obs_dev, float *reward_dev, uint8_t *done_dev, void *stream);
+int roboy_reset_external(roboy_env *env, const uint8_t *mask_dev, const float *q_dev, const float *qd_dev,
+                         float *obs_dev, void *stream);
+
 /* Rollout consumer: GAE(lambda) advantages and returns over rollout buffers
  * [T][n] that roboy_step filled in place -- what the PPO2 runner behind train_parallel.py:31-34
  * computes on the host.  done[t] = the episode ended AT step t (no bootstrap across it);

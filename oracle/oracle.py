@@ -77,6 +77,7 @@ def lib():
         L.orc_set_reward_range.argtypes = [vp, ctypes.c_double, ctypes.c_double]
         L.orc_reset.argtypes = [vp, vp, vp]
         L.orc_step.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int]
+        L.orc_external.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
         L.orc_compute_reward.argtypes = [ctypes.POINTER(OrcCfg), u64, vp, vp, vp, vp, vp, vp, vp, vp]
         L.orc_thresholds.argtypes = [ctypes.POINTER(OrcCfg), f32p, f32p]
         L.orc_philox4x32_10.argtypes = [vp, vp, vp]
@@ -183,6 +184,20 @@ class OracleEnv:
         obs = np.zeros((self.n, 9), np.float32)
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         lib().orc_reset(self._h, _ptr(m), _ptr(obs))
+        return obs
+
+    def step_external(self, q, qd, feasible=None):
+        q, qd = np.ascontiguousarray(q, np.float32), np.ascontiguousarray(qd, np.float32)
+        f = None if feasible is None else np.ascontiguousarray(feasible, np.uint8)
+        obs, rew, done = np.zeros((self.n, 9), np.float32), np.zeros(self.n, np.float32), np.zeros(self.n, np.uint8)
+        lib().orc_external(self._h, 0, None, _ptr(q), _ptr(qd), _ptr(f), _ptr(obs), _ptr(rew), _ptr(done))
+        return obs, rew, done.astype(bool)
+
+    def reset_external(self, q, qd, mask=None):
+        q, qd = np.ascontiguousarray(q, np.float32), np.ascontiguousarray(qd, np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        obs = np.zeros((self.n, 9), np.float32)
+        lib().orc_external(self._h, 1, _ptr(m), _ptr(q), _ptr(qd), None, _ptr(obs), None, None)
         return obs
 
     def step(self, actions, want_terminal_obs=False):

@@ -165,3 +165,71 @@ class ReferenceVecEnv:
                     assert cls.log in (["state", "goal", "goal"], ["goal", "goal"]), cls.log
                 obs[i] = o
         return obs, rew, done, term, raised
+
+
+class ReferenceFeedEnv:
+    """N reference RoboyEnv instances over a test-double SimulationClient that is FED its states,
+    the way RosSimulationClient receives them from the external simulator
+    (ros_simulation_client.py:40-60): python-float lists -> robot.new_state(...) -> float64 arrays.
+    Pins the oracle's / kernel's external-simulator path (roboy_step_external)."""
+
+    def __init__(self, n_envs, seed=1234, env_id_base=0, joint_vel_penalty=False, bonus=True):
+        from oracle import oracle as orc
+
+        RoboyEnv, MsjRobot, RobotState, _ = _import_reference()
+        from gym_roboy.envs.simulations import SimulationClient
+        outer = self
+        self.n, self.seed, self.gid0, self.t = n_envs, seed, env_id_base, 0
+
+        class FeedClient(SimulationClient):
+            def __init__(self, robot, gid):
+                self.robot, self.gid, self.next_state = robot, gid, None
+
+            def read_state(self):
+                return self.next_state
+
+            def forward_step_command(self, action):
+                return self.next_state
+
+            def forward_reset_command(self):
+                return self.next_state
+
+            def get_new_goal_joint_angles(self):
+                return orc.draw_goal(outer.seed, [self.gid], outer.t)[0]
+
+        self.robot = MsjRobot()
+        with contextlib.redirect_stdout(io.StringIO()):
+            self.clients = [FeedClient(self.robot, env_id_base + i) for i in range(n_envs)]
+            self.envs = [RoboyEnv(c, joint_vel_penalty=joint_vel_penalty,
+                                  is_agent_getting_bonus_for_reaching_goal=bonus) for c in self.clients]
+
+    def _feed(self, i, q, qd, feasible):
+        # exactly RosSimulationClient._make_robot_state: lists of python floats
+        self.clients[i].next_state = self.robot.new_state(
+            joint_angle=[float(x) for x in q], joint_vel=[float(x) for x in qd], is_feasible=bool(feasible))
+
+    def goals(self):
+        return np.stack([np.asarray(e._goal_state.joint_angles, np.float32) for e in self.envs])
+
+    def set_step_num(self, i, k):
+        self.envs[i].step_num = int(k)
+
+    def reset(self, q, qd, mask=None):
+        self.t += 1
+        obs = np.zeros((self.n, 9))
+        with contextlib.redirect_stdout(io.StringIO()):
+            for i, env in enumerate(self.envs):
+                if mask is not None and not mask[i]:
+                    continue
+                self._feed(i, q[i], qd[i], True)
+                obs[i] = env.reset()
+        return obs
+
+    def step(self, q, qd, feasible):
+        self.t += 1
+        obs, rew, done = np.zeros((self.n, 9)), np.zeros(self.n), np.zeros(self.n, bool)
+        with contextlib.redirect_stdout(io.StringIO()):
+            for i, env in enumerate(self.envs):
+                self._feed(i, q[i], qd[i], feasible[i])
+                obs[i], rew[i], done[i], _ = env.step(np.zeros(8, np.float32))
+        return obs, rew, done

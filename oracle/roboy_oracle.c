@@ -396,6 +396,53 @@ void orc_reset(orc_env *e, const uint8_t *mask, float *obs) {
     }
 }
 
+/* RoboyEnv.step (roboy_env.py:51-70) / reset (:82-87) on states handed in by an external simulator
+ * (RosSimulationClient's role, ros_simulation_client.py:40-60; wire values are float64 arrays).
+ * q, qd [n][3] float32 values; feasible [n] or NULL; reset != 0: masked reset, obs carries the NEW goal. */
+void orc_external(orc_env *e, int reset, const uint8_t *mask, const float *q, const float *qd,
+                  const uint8_t *feasible, float *obs, float *reward, uint8_t *done) {
+    const orc_cfg *cfg = &e->cfg;
+    const uint64_t n = cfg->n_envs;
+    e->t += 1;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (reset && mask && !mask[i]) continue;
+        const uint64_t gid = cfg->env_id_base + i;
+        orc_state s;
+        for (int k = 0; k < 3; ++k) { s.q[k] = q[3 * i + k]; s.qd[k] = qd[3 * i + k]; }
+        s.is64 = 1;
+        s.feasible = feasible ? feasible[i] != 0 : 1;
+        float g[3] = {e->goal[i], e->goal[n + i], e->goal[2 * n + i]};
+        uint32_t sf = e->step_flags[i];
+        int new_goal = reset;
+        if (!reset) {
+            int reached = did_reach_goal(cfg, &s, g, NULL, e->thr_angle, e->thr_vel);
+            int viol = 0;
+            double r = compute_reward(cfg, &s, g, NULL, reached, &viol);
+            uint32_t step = sf & ORC_STEP_MASK;
+            if (step < ORC_STEP_MASK) step += 1;
+            int dn = reached || (int32_t)step > cfg->max_episode_len;
+            sf = step | (sf & ~ORC_STEP_MASK);
+            reward[i] = (float)r;
+            done[i] = (uint8_t)dn;
+            new_goal = dn;
+            e->stats[ST_STEPS] += 1.0;
+            e->stats[ST_SUM_REWARD] += (double)(float)r;
+            if (dn) { e->stats[ST_EPISODES] += 1.0; e->stats[reached ? ST_SUCCESSES : ST_TIMEOUTS] += 1.0; }
+            if (viol) { e->stats[ST_VIOLATIONS] += 1.0; note_error(e, ORC_ERR_REWARD_RANGE, gid); }
+            for (int k = 0; k < 3; ++k) { obs[9 * i + k] = (float)s.q[k]; obs[9 * i + 3 + k] = (float)s.qd[k]; obs[9 * i + 6 + k] = g[k]; }
+        } else {
+            sf = 1u | (sf & ~ORC_STEP_MASK);
+        }
+        if (new_goal) {
+            orc_draw_goal(cfg, gid, e->t, g);
+            for (int k = 0; k < 3; ++k) e->goal[(size_t)k * n + i] = g[k];
+        }
+        if (reset)
+            for (int k = 0; k < 3; ++k) { obs[9 * i + k] = (float)s.q[k]; obs[9 * i + 3 + k] = (float)s.qd[k]; obs[9 * i + 6 + k] = g[k]; }
+        e->step_flags[i] = sf;
+    }
+}
+
 typedef struct {
     orc_env *e;
     const float *actions;

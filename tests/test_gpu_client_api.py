@@ -57,3 +57,45 @@ def test_single_env_view_returns_reference_types():
     assert isinstance(g, np.ndarray) and g.shape == (3,) and g.dtype == np.float32
     with pytest.raises(AssertionError):
         c.forward_step_command([0.0] * 7)            # simulation_client.py:37
+
+
+def test_external_simulator_feed_matches_oracle():
+    """roboy_step_external / roboy_reset_external vs the oracle (itself pinned against the reference
+    in tests/test_oracle_vs_reference.py::test_external_simulator_feed_matches_reference)."""
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    n, T = 3000, 40
+    rng = np.random.default_rng(4)
+    for penalty in (False, True):
+        client = CudaSimulationClient(num_envs=n, seed=9, device="cuda:0")
+        env = RoboyEnv(client, joint_vel_penalty=penalty, auto_reset=False, strict=False)
+        o = orc.OracleEnv(n, seed=9, joint_vel_penalty=penalty, auto_reset=False)
+        q0 = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+        qd0 = rng.uniform(-0.5, 0.5, (n, 3)).astype(np.float32)
+        assert np.array_equal(env.reset_from_states(q0, qd0).cpu().numpy(), o.reset_external(q0, qd0))
+        steps = rng.integers(370, 400, n).astype(np.int32)
+        client.set_step_num(steps)
+        o.step_flags[:] = (o.step_flags & ~np.uint32(orc.STEP_MASK)) | steps.astype(np.uint32)
+        reached = 0
+        for t in range(T):
+            q = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+            qd = rng.uniform(-0.5, 0.5, (n, 3)).astype(np.float32)
+            near = rng.random(n) < 0.3
+            q[near] = np.clip(o.goal.T[near] + rng.uniform(-0.04, 0.04, (near.sum(), 3)), -3.1, 3.1).astype(np.float32)
+            qd[near] = rng.uniform(-0.25, 0.25, (near.sum(), 3)).astype(np.float32)
+            feas = (rng.random(n) > 0.2).astype(np.uint8)
+            obs, rew, done, _ = env.step_from_states(q, qd, feas)
+            oo, orw, od = o.step_external(q, qd, feas)
+            assert np.array_equal(done.cpu().numpy(), od) and np.array_equal(obs.cpu().numpy(), oo)
+            rel = np.abs(rew.cpu().numpy() - orw) / np.abs(orw)
+            assert rel.max() <= 1e-6
+            reached += int((od & (orw > 500)).sum())
+            if od.any():
+                ro = env.reset_from_states(q, qd, mask=od.astype(np.uint8)).cpu().numpy()
+                assert np.array_equal(ro[od], o.reset_external(q, qd, od)[od])
+            assert np.array_equal(client.goal.cpu().numpy(), o.goal)
+            assert np.array_equal(client.step_num.cpu().numpy(), o.step_num)
+        assert reached > 100
+        s, so = client.stats(), o.stats()
+        for k in ("steps", "episodes", "successes", "timeouts", "violations"):
+            assert s[k] == so[k], k

@@ -53,3 +53,36 @@ def test_random_rollout_matches_reference(penalty, bonus, auto):
         assert np.array_equal(ref.step_nums()[alive], o.step_num[alive])
     if not alive.all():   # the reference raised roboy_env.py:109 -> the oracle flagged the same env first
         assert o.errors()[0] & orc.ERR_REWARD_RANGE
+
+
+def test_external_simulator_feed_matches_reference():
+    """states fed in from outside (float64 wire values, as RosSimulationClient holds
+    them) through the reference's own RoboyEnv vs the oracle's external path."""
+    N, T = 10, 60
+    rng = np.random.default_rng(3)
+    ref = rh.ReferenceFeedEnv(N, seed=9)
+    o = orc.OracleEnv(N, seed=9, auto_reset=False)
+    assert np.array_equal(ref.goals().T, o.goal)
+    q0 = rng.uniform(-3, 3, (N, 3)).astype(np.float32)
+    qd0 = rng.uniform(-0.5, 0.5, (N, 3)).astype(np.float32)
+    assert np.array_equal(ref.reset(q0, qd0).astype(np.float32), o.reset_external(q0, qd0))
+    for i in range(N):
+        ref.set_step_num(i, 380 + 3 * i)
+    o.step_flags[:] = (o.step_flags & ~np.uint32(orc.STEP_MASK)) | (380 + 3 * np.arange(N)).astype(np.uint32)
+    n_done = n_reached = 0
+    for t in range(T):
+        q = rng.uniform(-3, 3, (N, 3)).astype(np.float32)
+        qd = rng.uniform(-0.5, 0.5, (N, 3)).astype(np.float32)
+        near = rng.random(N) < 0.3                       # some states land next to the goal, slowly
+        q[near] = np.clip(o.goal.T[near] + rng.uniform(-0.04, 0.04, (near.sum(), 3)), -3.1, 3.1).astype(np.float32)
+        qd[near] = rng.uniform(-0.25, 0.25, (near.sum(), 3)).astype(np.float32)
+        feas = rng.random(N) > 0.2
+        ro, rr, rd = ref.step(q, qd, feas)
+        oo, orw, od = o.step_external(q, qd, feas)
+        assert np.array_equal(rd, od) and np.array_equal(ro.astype(np.float32), oo)
+        assert np.allclose(orw, rr, rtol=1e-6, atol=0)
+        n_done += rd.sum(); n_reached += (rd & (rr > 500)).sum()
+        if rd.any():
+            assert np.array_equal(ref.reset(q, qd, mask=rd).astype(np.float32)[rd], o.reset_external(q, qd, rd)[rd])
+        assert np.array_equal(ref.goals().T, o.goal)
+    assert n_reached >= 5 and n_done > n_reached
