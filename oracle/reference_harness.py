@@ -42,6 +42,31 @@ def _import_reference():
     return RoboyEnv, MsjRobot, RobotState, StubSimulationClient
 
 
+def _custom_reference_robot(bounds):
+    """A robot plug-in written against the REFERENCE's RoboyRobot base (3 joints, 8 tendons, other spaces)."""
+    from gym import spaces
+    from gym_roboy.envs.robots import RoboyRobot
+
+    class CustomRobot(RoboyRobot):
+        _A = spaces.Box(low=bounds["angle_low"], high=bounds["angle_high"], shape=(3,), dtype="float32")
+        _V = spaces.Box(low=bounds["vel_low"], high=bounds["vel_high"], shape=(3,), dtype="float32")
+        _T = spaces.Box(low=bounds["act_low"], high=bounds["act_high"], shape=(8,), dtype="float32")
+
+        @classmethod
+        def get_action_space(cls):
+            return cls._T
+
+        @classmethod
+        def get_joint_angles_space(cls):
+            return cls._A
+
+        @classmethod
+        def get_joint_vels_space(cls):
+            return cls._V
+
+    return CustomRobot
+
+
 def _make_replay_robot(MsjRobot, RobotState, state_fn, goal_fn):
     """A fresh MsjRobot subclass whose only override is the source of random samples."""
 
@@ -71,10 +96,15 @@ def _make_replay_robot(MsjRobot, RobotState, state_fn, goal_fn):
 class ReferenceVecEnv:
     """N reference RoboyEnv(StubSimulationClient(ReplayRobot)) instances in lock-step."""
 
-    def __init__(self, n_envs, seed=1234, env_id_base=0, joint_vel_penalty=False, bonus=True, auto_reset=True):
+    def __init__(self, n_envs, seed=1234, env_id_base=0, joint_vel_penalty=False, bonus=True, auto_reset=True,
+                 bounds=None):
         from oracle import oracle as orc
 
         RoboyEnv, MsjRobot, RobotState, Stub = _import_reference()
+        low, high = orc.MSJ["angle_low"], orc.MSJ["angle_high"]
+        if bounds is not None:   # another robot: same dims, other spaces (a RoboyRobot subclass of the reference)
+            MsjRobot = _custom_reference_robot(bounds)
+            low, high = bounds["angle_low"], bounds["angle_high"]
         self.RobotState = RobotState
         self.n = n_envs
         self.seed = seed
@@ -83,11 +113,11 @@ class ReferenceVecEnv:
         self.envs, self.robots = [], []
 
         def state_fn(gid, t):
-            q, qd = orc.draw_state(seed, [gid], t)
+            q, qd = orc.draw_state(seed, [gid], t, low, high)
             return q[0], qd[0]
 
         def goal_fn(gid, t):
-            return orc.draw_goal(seed, [gid], t)[0]
+            return orc.draw_goal(seed, [gid], t, low, high)[0]
 
         with contextlib.redirect_stdout(io.StringIO()):
             for i in range(n_envs):

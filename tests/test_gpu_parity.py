@@ -343,3 +343,60 @@ def test_steps_captured_in_a_cuda_graph_replay_like_eager_steps():
             assert torch.equal(o, obs_buf[t]) and torch.equal(rw, rew_buf[t]) and torch.equal(d, done_buf[t].bool()), (r, t)
     assert client_a.counter == client_b.counter == 1 + rounds * k
     assert client_a.stats()["episodes"] == client_b.stats()["episodes"] > 0
+
+
+OTHER_ROBOTS = {
+    "symmetric": dict(angle_low=-2.0, angle_high=2.0, vel_low=-0.7, vel_high=0.7, act_low=-0.5, act_high=0.5),
+    "asymmetric": dict(angle_low=-1.0, angle_high=2.5, vel_low=-0.25, vel_high=0.75, act_low=-0.1, act_high=0.4),
+}
+
+
+@pytest.mark.parametrize("name", sorted(OTHER_ROBOTS))
+@pytest.mark.parametrize("penalty", [False, True])
+def test_other_robot_bounds_match_oracle(name, penalty):
+    """a RoboyRobot plug-in with other spaces.  The kernel takes the generic
+    IEEE-division path (the 3-instruction division is only proved for the MSJ spans) and a different
+    hold interval; the oracle for these robots is pinned against the reference in
+    tests/test_oracle_vs_reference.py::test_other_robot_bounds_match_reference."""
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.robots import RoboyRobot
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    from gym_roboy_b200.spaces import Box
+    b = OTHER_ROBOTS[name]
+
+    class OtherRobot(RoboyRobot):
+        _A = Box(b["angle_low"], b["angle_high"], (3,), "float32")
+        _V = Box(b["vel_low"], b["vel_high"], (3,), "float32")
+        _T = Box(b["act_low"], b["act_high"], (8,), "float32")
+        get_action_space = classmethod(lambda cls: cls._T)
+        get_joint_angles_space = classmethod(lambda cls: cls._A)
+        get_joint_vels_space = classmethod(lambda cls: cls._V)
+
+    n, T = 4096, 450
+    client = CudaSimulationClient(robot=OtherRobot(), num_envs=n, seed=6, device="cuda:0")
+    env = RoboyEnv(client, joint_vel_penalty=penalty, strict=False)
+    ora = orc.OracleEnv(n, seed=6, joint_vel_penalty=penalty, threads=8, **b)
+    assert np.allclose(env.reward_range, ora.reward_range, rtol=RTOL, atol=0)
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal) and np.array_equal(client.held.cpu().numpy(), ora.held)
+    env.reset(); ora.reset()
+    rng = np.random.default_rng(2)
+    zero_action = np.float32(1 - 2 * b["act_high"] / (b["act_high"] - b["act_low"]))
+    steps = rng.integers(1, 400, n).astype(np.int32)
+    client.set_step_num(steps)
+    ora.step_flags[:] = (ora.step_flags & ~np.uint32(orc.STEP_MASK)) | steps.astype(np.uint32)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        hold_rows = rng.random(n) < 0.02
+        a[hold_rows] = zero_action
+        a[rng.random(n) < 0.01] = np.nextafter(zero_action, np.float32(1))   # right next to the hold interval
+        if t % 40 == 5:
+            q, _ = orc.draw_state(6, np.arange(n), ora.counter + 1, b["angle_low"], b["angle_high"])
+            g = np.clip(q + np.float32(0.004), b["angle_low"], b["angle_high"]).astype(np.float32)
+            client.set_goal(g); ora.goal[:] = g.T
+        compare_step(env, client, ora, a, t)
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+    assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
+    s, so = client.stats(), ora.stats()
+    for k in ("steps", "episodes", "successes", "timeouts", "holds", "violations"):
+        assert s[k] == so[k], k
+    assert s["holds"] > 0 and s["timeouts"] > 0

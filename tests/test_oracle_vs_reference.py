@@ -86,3 +86,40 @@ def test_external_simulator_feed_matches_reference():
             assert np.array_equal(ref.reset(q, qd, mask=rd).astype(np.float32)[rd], o.reset_external(q, qd, rd)[rd])
         assert np.array_equal(ref.goals().T, o.goal)
     assert n_reached >= 5 and n_done > n_reached
+
+
+CUSTOM_ROBOTS = {
+    "symmetric": dict(angle_low=-2.0, angle_high=2.0, vel_low=-0.7, vel_high=0.7, act_low=-0.5, act_high=0.5),
+    # asymmetric spaces: normalisation no longer cancels, the hold interval is not centred
+    "asymmetric": dict(angle_low=-1.0, angle_high=2.5, vel_low=-0.25, vel_high=0.75, act_low=-0.1, act_high=0.4),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CUSTOM_ROBOTS))
+def test_other_robot_bounds_match_reference(name):
+    """a RoboyRobot plug-in with other spaces (same dims) through the reference."""
+    b = CUSTOM_ROBOTS[name]
+    N, T = 8, 120
+    ref = rh.ReferenceVecEnv(N, seed=2, bounds=b)
+    o = orc.OracleEnv(N, seed=2, **b)
+    assert np.allclose(ref.reward_range, o.reward_range, rtol=1e-6, atol=0)
+    assert np.array_equal(ref.goals().T, o.goal)
+    assert np.array_equal(ref.reset().astype(np.float32), o.reset())
+    for i in range(N):
+        ref.set_step_num(i, 330 + 9 * i)
+    o.step_flags[:] = (o.step_flags & ~np.uint32(orc.STEP_MASK)) | (330 + 9 * np.arange(N)).astype(np.uint32)
+    rng = np.random.default_rng(1)
+    alive = np.ones(N, bool)
+    # the action that rescales to exactly 0 in the robot's space is where the Stub holds
+    zero_action = np.float32(1 - 2 * b["act_high"] / (b["act_high"] - b["act_low"]))
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, 8)).astype(np.float32)
+        a[rng.random(N) < 0.15] = zero_action
+        ro, rr, rd, rt, raised = ref.step(a)
+        oo, orw, od, ot = o.step(a, want_terminal_obs=True)
+        alive &= np.array([m == "" for m in raised])
+        assert np.array_equal(ro.astype(np.float32)[alive], oo[alive]), t
+        assert np.array_equal(rd[alive], od[alive]), t
+        assert np.allclose(orw[alive], rr[alive], rtol=1e-6, atol=0)
+        assert np.array_equal(ref.goals()[alive], o.goal.T[alive])
+    assert o.stats()["episodes"] >= N and o.stats()["holds"] > 0
