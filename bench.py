@@ -222,6 +222,10 @@ def run_b200_arm(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
                          "(use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
+    numa_cpus = None
+    if world > 1 and not os.environ.get("ROBOY_BENCH_NO_NUMA_BIND"):
+        from gym_roboy_b200.sharding import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local)   # pinned host buffers on the GPU's NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         with stdout_to_stderr():   # NCCL prints its version banner on stdout; rank 0 must print ONE JSON line
@@ -303,7 +307,8 @@ def run_b200_arm(args):
                "d2h_bytes_per_step": D2H_BYTES * n, "steps": k2, "ms_per_step": 1e3 * dt / k2,
                "api": "roboy_step_host (C-ABI): pinned host actions -> H2D -> step kernel -> D2H obs+reward+done, "
                       "pipelined over 2 streams in 524,288-env stages", "gpu_launches": client.launch_count() - l0,
-               "checksum": float(rew_h[:1024].double().sum())}
+               "checksum": float(rew_h[:1024].double().sum()),
+               "numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
         del a_host, obs_h, rew_h, done_h, bufs
     del env, client, actions
     torch.cuda.empty_cache()

@@ -7,6 +7,8 @@ collective.  Philox counters use the GLOBAL env id, which makes every env's traj
 of the number of ranks.  The only communication is the all-reduce (sum) of the 8 episode
 statistics the step kernel accumulates -- 64 bytes, NCCL over NVLink on GPUs, gloo in CPU tests.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -19,6 +21,26 @@ def shard_range(total_envs: int, world_size: int, rank: int):
     base, extra = divmod(int(total_envs), int(world_size))
     begin = rank * base + min(rank, extra)
     return begin, begin + base + (1 if rank < extra else 0)
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Restrict this process to the CPUs NVML reports as local to GPU `device_index`, so that pinned
+    host buffers (first touch) and the copy-issuing thread sit on the GPU's NUMA node.  Matters for the
+    host-buffer path with several ranks per box; a no-op when NVML or the affinity call is unavailable.
+    Returns the CPU set chosen (or None)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        local = {w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = local & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return sorted(allowed)
+    except Exception:
+        pass
+    return None
 
 
 def all_reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:

@@ -400,3 +400,38 @@ def test_other_robot_bounds_match_oracle(name, penalty):
     for k in ("steps", "episodes", "successes", "timeouts", "holds", "violations"):
         assert s[k] == so[k], k
     assert s["holds"] > 0 and s["timeouts"] > 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 95, 255, 257, 1000, 4097])
+def test_ragged_sizes_with_guarded_output_buffers(n):
+    """compute-sanitizer is not available on the GPU pool, so out-of-bounds stores are hunted with
+    canaries: the step writes into caller tensors that sit inside larger, pre-filled buffers."""
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    client = CudaSimulationClient(num_envs=n, seed=13, device="cuda:0")
+    env = RoboyEnv(client, strict=False, auto_reset=True)
+    env._single = False
+    ora = orc.OracleEnv(n, seed=13)
+    env.reset(); ora.reset()
+    steps = (np.arange(n) % 5 + 397).astype(np.int32)
+    client.set_step_num(steps)
+    ora.step_flags[:] = (ora.step_flags & ~np.uint32(orc.STEP_MASK)) | steps.astype(np.uint32)
+    pad, canary = 64, 7777.0
+    obs_big = torch.full((n + 2 * pad, 9), canary, device="cuda:0")
+    rew_big = torch.full((n + 2 * pad,), canary, device="cuda:0")
+    done_big = torch.full((n + 2 * pad,), 77, dtype=torch.uint8, device="cuda:0")
+    # 16-byte aligned views (pad * 36 B and pad * 4 B are multiples of 16)
+    obs, rew, done = obs_big[pad:pad + n], rew_big[pad:pad + n], done_big[pad:pad + n]
+    rng = np.random.default_rng(n)
+    for t in range(6):
+        a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        a[rng.random(n) < 0.2] = 0
+        client.step_fused(torch.as_tensor(a, device="cuda:0"), obs=obs, reward=rew, done=done)
+        o, r, d = ora.step(a)
+        assert np.array_equal(obs.cpu().numpy(), o) and np.array_equal(done.cpu().numpy().astype(bool), d)
+        assert np.allclose(rew.cpu().numpy(), r, rtol=RTOL, atol=0)
+        for big, val in ((obs_big, canary), (rew_big, canary), (done_big, 77)):
+            assert (big[:pad] == val).all() and (big[pad + n:] == val).all(), "store outside the output range"
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+    assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
+    assert client.stats()["steps"] == 6 * n and client.stats()["episodes"] == ora.stats()["episodes"] > 0
