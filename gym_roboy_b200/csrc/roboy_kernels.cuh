@@ -8,7 +8,10 @@
 
 namespace roboy {
 
-constexpr int kStepBlock = 256;            // threads per CTA of the step kernel
+#ifndef ROBOY_STEP_BLOCK
+#define ROBOY_STEP_BLOCK 256
+#endif
+constexpr int kStepBlock = ROBOY_STEP_BLOCK;  // threads per CTA of the step kernel
 constexpr int kWarpsPerBlock = kStepBlock / 32;
 #ifndef ROBOY_STEP_MIN_BLOCKS
 #define ROBOY_STEP_MIN_BLOCKS 3
