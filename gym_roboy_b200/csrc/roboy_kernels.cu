@@ -32,6 +32,9 @@ namespace roboy {
 #define ROBOY_PREFETCH_DIST 1  // how many of this warp's chunks ahead the L2 prefetch runs
 #endif
 
+#ifndef ROBOY_OBS_BULK_STORE
+#define ROBOY_OBS_BULK_STORE 1  // 1 (measured +1%): drain the staged observations with cp.async.bulk (TMA bulk copy smem -> global)
+#endif
 #ifndef ROBOY_LD_HINT
 #define ROBOY_LD_HINT 0  // streamed inputs:  0 default (measured best: +3% over .cs), 1 ld.global.cs, 2 ld.global.nc.L1::no_allocate
 #endif
@@ -296,6 +299,24 @@ __device__ __forceinline__ void process_chunk(const StepParams &p, uint64_t t, c
         sum_reward += reward;
     }
 #endif
+#if ROBOY_OBS_BULK_STORE
+    if (!TAIL) {
+        // every lane publishes its shared-memory writes to the async proxy, then one lane hands the
+        // warp's 1152 contiguous bytes to the bulk-copy engine (SASS: UBLKCP); the staging buffer is
+        // double-buffered by the caller, so the copy drains while the next chunk is computed
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t src = (uint32_t)__cvta_generic_to_shared(so);
+            float *dst = p.obs + (size_t)base * kObsDim;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                         "n"(32 * kObsDim * 4)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        return;
+    }
+#endif
     __syncwarp();
     if (!TAIL) {
         float4 *dst = reinterpret_cast<float4 *>(p.obs + (size_t)base * kObsDim);  // 1152 B per chunk: 16 B aligned
@@ -314,7 +335,11 @@ __device__ __forceinline__ void process_chunk(const StepParams &p, uint64_t t, c
 
 template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV>
 __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const __grid_constant__ StepParams p) {
+#if ROBOY_OBS_BULK_STORE
+    __shared__ __align__(128) float s_obs[2][kWarpsPerBlock][32 * kObsDim];
+#else
     __shared__ __align__(16) float s_obs[kWarpsPerBlock][32 * kObsDim];
+#endif
     __shared__ double s_red[kWarpsPerBlock];
     // rare events (done ~1/400 of env-steps, holds, violations) are counted with shared-memory
     // atomics where they happen instead of tying up registers in the hot loop
@@ -327,7 +352,12 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
     const uint64_t t = counter_begin(p.cc);
     const uint32_t n_full = (uint32_t)(p.e_end >> 5);  // chunks [chunk0, n_full) are complete
     const uint32_t warp_stride = gridDim.x * kWarpsPerBlock;
+#if ROBOY_OBS_BULK_STORE
+    float *so = s_obs[0][warp];
+    uint32_t parity = 0;
+#else
     float *so = s_obs[warp];
+#endif
     // per-thread reward sum: a thread adds at most a few hundred float32 rewards per launch, the
     // cross-thread reduction below is in double
     float sum_reward = 0.0f;
@@ -352,9 +382,21 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
         pf.issue_and_advance(chunk + ROBOY_PREFETCH_DIST * warp_stride < n_full, lane);
 #endif
 #endif
+#if ROBOY_OBS_BULK_STORE
+        // the bulk copy issued two chunks ago read this buffer: wait until at most one is still reading
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        so = s_obs[parity][warp];
+        parity ^= 1;
+#endif
         process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false>(p, t, cur, chunk << 5, lane, so, s_cnt, sum_reward);
         chunk = next;
     }
+#if ROBOY_OBS_BULK_STORE
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    so = s_obs[0][warp];
+#endif
     if (chunk == n_full && (p.e_end & 31)) {  // the ragged last chunk belongs to exactly one warp
         const ChunkIn cur = load_chunk<true>(p, chunk << 5, lane);
         process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true>(p, t, cur, chunk << 5, lane, so, s_cnt, sum_reward);
