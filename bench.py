@@ -144,6 +144,19 @@ def cpu_port_rate(envs, steps, warmup, threads):
     return envs * steps / dt, dt
 
 
+def reference_python_context():
+    """The unmodified Python reference timed in the build container (oracle/time_reference.py); context
+    only -- it is not measured on this box and is not the `value` of any baseline object."""
+    path = os.path.join(ROOT, "profiles", "r1_reference_python_cpu.json")
+    if not os.path.exists(path):
+        return None
+    j = json.load(open(path))
+    return {"where": j["where"], "cores": j["cores"],
+            "single_env_steps_per_s": j["single_env_steps_per_s"]["median"],
+            "vec_env_restated_steps_per_s": j["vec_env_restated_steps_per_s"]["value"],
+            "independent_processes_steps_per_s": j["independent_processes_steps_per_s"]["value"]}
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -167,7 +180,8 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "{:,} envs x {} steps per timed run, oracle/roboy_oracle.c (C port of the "
                                    "reference algorithm; the Python reference itself cannot travel to this box), "
-                                   "pthreads over all host cores".format(sample, args.steps)},
+                                   "pthreads over all host cores".format(sample, args.steps),
+                         "reference_python": reference_python_context()},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -400,7 +414,8 @@ def run_b200_arm(args):
         rate, dt = cpu_port_rate(sample, k, 1, threads)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": "{:,} envs x {} steps ({:.1f} s wall on {} threads), oracle/roboy_oracle.c".format(
-                            sample, k, dt, threads)}
+                            sample, k, dt, threads),
+                        "reference_python": reference_python_context()}
 
     if rank == 0:
         line = {
