@@ -220,6 +220,7 @@ void fill_step_params(roboy_env *e, StepParams &p, const float *actions, float *
     p.step_flags = e->step_flags;
     p.held = e->held;
     p.obs = obs ? obs : e->obs;
+    p.obs_aligned = ((uintptr_t)p.obs & 15) == 0;
     p.reward = reward ? reward : e->reward;
     p.done = done ? done : e->done;
     p.terminal_obs = e->terminal_obs;
@@ -273,7 +274,7 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
     if (!cfg || !out) return fail(ROBOY_E_ARG, "NULL argument");
     *out = nullptr;
     if (cfg->n_envs == 0) return fail(ROBOY_E_ARG, "n_envs must be > 0");
-    if (cfg->n_envs > 0xfffffff0ull) return fail(ROBOY_E_ARG, "a shard holds fewer than 2^32 envs");
+    if (cfg->n_envs > 0x7fffff00ull) return fail(ROBOY_E_ARG, "a shard holds fewer than 2^31 envs");
     if (!(cfg->angle_high > cfg->angle_low) || !(cfg->vel_high > cfg->vel_low) || !(cfg->act_high > cfg->act_low))
         return fail(ROBOY_E_ARG, "empty robot space");
     int n_dev = 0;
@@ -409,8 +410,8 @@ int roboy_step(roboy_env *env, const float *actions_dev, float *obs_dev, float *
                void *stream) {
     if (check_env(env)) return ROBOY_E_ARG;
     if (!actions_dev) return fail(ROBOY_E_ARG, "actions_dev is NULL");
-    if (((uintptr_t)actions_dev & 15) || ((uintptr_t)(obs_dev ? obs_dev : env->obs) & 15))
-        return fail(ROBOY_E_ARG, "actions and obs must be 16-byte aligned");
+    if ((uintptr_t)actions_dev & 15) return fail(ROBOY_E_ARG, "actions must be 16-byte aligned");
+    if (obs_dev && ((uintptr_t)obs_dev & 3)) return fail(ROBOY_E_ARG, "obs must be 4-byte aligned");
     DeviceGuard g(env->device);
     env->goal_sub = 1;  // done envs consume goal draw 0 of the new counter value
     StepParams p;

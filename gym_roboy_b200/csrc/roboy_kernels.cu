@@ -300,7 +300,7 @@ __device__ __forceinline__ void process_chunk(const StepParams &p, uint64_t t, c
     }
 #endif
 #if ROBOY_OBS_BULK_STORE
-    if (!TAIL) {
+    if (!TAIL && p.obs_aligned) {
         // every lane publishes its shared-memory writes to the async proxy, then one lane hands the
         // warp's 1152 contiguous bytes to the bulk-copy engine (SASS: UBLKCP); the staging buffer is
         // double-buffered by the caller, so the copy drains while the next chunk is computed
@@ -318,14 +318,15 @@ __device__ __forceinline__ void process_chunk(const StepParams &p, uint64_t t, c
     }
 #endif
     __syncwarp();
-    if (!TAIL) {
+    if (!TAIL && p.obs_aligned) {
         float4 *dst = reinterpret_cast<float4 *>(p.obs + (size_t)base * kObsDim);  // 1152 B per chunk: 16 B aligned
         const float4 *src = reinterpret_cast<const float4 *>(so);
         st_stream(dst + lane, src[lane]);
         st_stream(dst + 32 + lane, src[32 + lane]);
         if (lane < 8) st_stream(dst + 64 + lane, src[64 + lane]);
-    } else {
-        const uint32_t n_valid = ((uint32_t)p.e_end - base) * kObsDim;
+    } else {  // ragged tail, or a caller-supplied obs pointer that is only 4-byte aligned: scalar stores
+        const uint32_t rows = TAIL ? (uint32_t)p.e_end - base : 32u;
+        const uint32_t n_valid = rows * kObsDim;
         for (uint32_t i = lane; i < n_valid; i += 32) p.obs[(size_t)base * kObsDim + i] = so[i];
     }
     __syncwarp();

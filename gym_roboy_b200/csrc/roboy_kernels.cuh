@@ -65,6 +65,7 @@ struct StepParams {
     float act_in_hi, act_in_lo;  // RoboyEnv.action_space bounds, roboy_env.py:31
     float act_hi, act_slope;     // robot action space high and fl32((hi-lo)/(in_hi-in_lo)), roboy_env.py:157
     int32_t max_len;             // roboy_env.py:28
+    int32_t obs_aligned;         // obs pointer is 16-byte aligned: vector / bulk stores allowed
     // inputs / state / outputs (device pointers)
     const float *__restrict__ actions;  // [n][8]
     float *__restrict__ goal;           // [3][n]

@@ -420,8 +420,11 @@ def test_ragged_sizes_with_guarded_output_buffers(n):
     obs_big = torch.full((n + 2 * pad, 9), canary, device="cuda:0")
     rew_big = torch.full((n + 2 * pad,), canary, device="cuda:0")
     done_big = torch.full((n + 2 * pad,), 77, dtype=torch.uint8, device="cuda:0")
-    # 16-byte aligned views (pad * 36 B and pad * 4 B are multiples of 16)
-    obs, rew, done = obs_big[pad:pad + n], rew_big[pad:pad + n], done_big[pad:pad + n]
+    # the obs view is 16-byte aligned for even n and only 4-byte aligned for odd n (offset (pad+n%2)*36 B):
+    # both the bulk-store path and the scalar fallback get exercised
+    off = pad + (n % 2)
+    obs, rew, done = obs_big[off:off + n], rew_big[pad:pad + n], done_big[pad:pad + n]
+    assert (obs.data_ptr() % 16 == 0) == (n % 2 == 0)
     rng = np.random.default_rng(n)
     for t in range(6):
         a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
@@ -430,7 +433,8 @@ def test_ragged_sizes_with_guarded_output_buffers(n):
         o, r, d = ora.step(a)
         assert np.array_equal(obs.cpu().numpy(), o) and np.array_equal(done.cpu().numpy().astype(bool), d)
         assert np.allclose(rew.cpu().numpy(), r, rtol=RTOL, atol=0)
-        for big, val in ((obs_big, canary), (rew_big, canary), (done_big, 77)):
+        assert (obs_big[:off] == canary).all() and (obs_big[off + n:] == canary).all(), "obs store outside its range"
+        for big, val in ((rew_big, canary), (done_big, 77)):
             assert (big[:pad] == val).all() and (big[pad + n:] == val).all(), "store outside the output range"
     assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
     assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
