@@ -99,3 +99,50 @@ def test_external_simulator_feed_matches_oracle():
         s, so = client.stats(), o.stats()
         for k in ("steps", "episodes", "successes", "timeouts", "violations"):
             assert s[k] == so[k], k
+
+
+def test_unfused_plugin_protocol_reproduces_the_fused_env():
+    """INTEGRATION.md level 1: the four SimulationClient calls, issued in the order the reference's
+    RoboyEnv issues them (step: forward_step_command, then on done _set_new_goal ->
+    get_new_goal_joint_angles; reset: forward_reset_command, read_state, get_new_goal_joint_angles),
+    walk exactly the trajectory the fused step kernel walks from the same seed."""
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    n, T, seed = 2000, 30, 77
+    fused_client = CudaSimulationClient(num_envs=n, seed=seed, device="cuda:0")
+    fused = RoboyEnv(fused_client, auto_reset=False, strict=False)
+    plug = CudaSimulationClient(num_envs=n, seed=seed, device="cuda:0")     # driven call by call
+    act_space = plug.robot.get_action_space()
+    lo, hi = np.float32(act_space.low[0]), np.float32(act_space.high[0])
+    slope = np.float32((hi - lo) / np.float32(2.0))
+
+    def plug_reset(mask=None):
+        state = plug.forward_reset_command(mask)                              # roboy_env.py:83-84
+        goal = plug.get_new_goal_joint_angles()                               # :86 -> _set_new_goal
+        idx = None if mask is None else torch.nonzero(torch.as_tensor(mask)).flatten()
+        plug.set_goal(goal if idx is None else goal[idx.to(goal.device)], idx=idx)
+        return state
+
+    assert torch.equal(fused_client.goal, plug.goal) and torch.equal(fused_client.held, plug.held)
+    fused.reset(); plug_reset()
+    assert torch.equal(fused_client.goal, plug.goal)
+    fused_client.set_step_num(np.full(n, 395, np.int32))
+    rng = np.random.default_rng(0)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        a[rng.random(n) < 0.1] = 0.0
+        obs, _, done, _ = fused.step(torch.as_tensor(a, device="cuda:0"))
+        rescaled = slope * (a - np.float32(1.0)) + hi                          # roboy_env.py:54-57,157-158
+        state = plug.forward_step_command(torch.as_tensor(rescaled))          # :59
+        assert torch.equal(state.joint_angles, obs[:, 0:3]) and torch.equal(state.joint_vels, obs[:, 3:6])
+        assert torch.equal(obs[:, 6:9], plug.goal.t())                        # obs carries the goal in force
+        d = done.cpu().numpy()
+        if d.any():
+            idx = torch.nonzero(done).flatten()
+            plug.set_goal(plug.get_new_goal_joint_angles()[idx], idx=idx)     # :67-68 _set_new_goal()
+            assert torch.equal(fused_client.goal, plug.goal)
+            fused.reset(mask=done.to(torch.uint8))                            # the caller's reset()
+            plug_reset(d.astype(np.uint8))
+            assert torch.equal(fused_client.goal, plug.goal)
+    assert fused_client.counter == plug.counter
+    assert fused_client.stats()["holds"] == plug.stats()["holds"] > 0

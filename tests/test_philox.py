@@ -39,3 +39,27 @@ def test_draws_stay_inside_the_angle_space_and_match_between_implementations():
     big = orc.draw_goal(1, np.array([2 ** 40 + 3], np.uint64), 2 ** 33 + 1)
     small = orc.draw_goal(1, np.array([3], np.uint64), 1)
     assert not np.array_equal(big, small)
+
+
+def test_draw_fields_are_uniform_and_uncorrelated():
+    """Statistical sanity of the draw mapping: each of the six 21-bit state fields and the three
+    goal words is uniform (chi-square over 64 bins), and draws are uncorrelated across neighbouring
+    env ids and consecutive call counters."""
+    n = 400_000
+    gids = np.arange(n)
+    q, qd = orc.draw_state(42, gids, 7)
+    g = orc.draw_goal(42, gids, 7)
+    cols = [q[:, k] for k in range(3)] + [qd[:, k] for k in range(3)] + [g[:, k] for k in range(3)]
+    for c in cols:
+        hist, _ = np.histogram(c, bins=64, range=(-float(orc.PI32), float(orc.PI32)))
+        chi2 = ((hist - n / 64) ** 2 / (n / 64)).sum()
+        assert chi2 < 130, chi2            # 63 dof: mean 63, p(>130) ~ 1e-6
+    q_next_env = orc.draw_state(42, gids + 1, 7)[0]
+    q_next_call = orc.draw_state(42, gids, 8)[0]
+    for other in (q_next_env, q_next_call, qd, g):
+        r = np.corrcoef(q[:, 0], other[:, 0])[0, 1]
+        assert abs(r) < 0.01, r
+    # the 21-bit grid: values are low + k * span * 2^-21
+    span21 = np.float32(np.float32(2 * orc.PI32) * np.float32(2.0 ** -21))
+    k = np.round((q[:1000, 0].astype(np.float64) + float(orc.PI32)) / float(span21))
+    assert np.abs(k * float(span21) - float(orc.PI32) - q[:1000, 0]).max() < 1e-6 and k.max() < 2 ** 21
