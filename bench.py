@@ -376,6 +376,33 @@ def run_b200_arm(args):
             del e, c, acts
         del flush
 
+    # ---- open-loop fused T-step variant (73 B per env-step, state stays in registers) ----
+    open_loop = None
+    if world == 1 and not args.no_sweep:
+        n, T = 1 << 22, 16     # 4,194,304 envs x 16 pre-recorded steps: 4.9 GB per launch
+        e, c = make(n)
+        gen = torch.Generator(device=dev); gen.manual_seed(1)
+        a = torch.rand((T, n, 8), device=dev, generator=gen) * 2 - 1
+        obs = torch.empty((T, n, 9), device=dev); rew = torch.empty((T, n), device=dev)
+        dn = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            c.step_many(a, obs, rew, dn)
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        s_.record()
+        for _ in range(reps):
+            c.step_many(a, obs, rew, dn)
+        e_.record()
+        torch.cuda.synchronize()
+        ms = s_.elapsed_time(e_) / reps
+        open_loop = {"envs": n, "T": T, "ms_per_launch": ms, "env_steps_per_s": n * T / (ms * 1e-3),
+                     "algorithmic_bytes_per_env_step": 73, "GBps_algorithmic": 73 * n * T / (ms * 1e-3) / 1e9,
+                     "frac_of_peak": 73 * n * T / (ms * 1e-3) / 1e9 / peak,
+                     "api": "roboy_step_many: pre-recorded actions [T,N,8], one launch, bit-identical to T roboy_step calls"}
+        del e, c, a, obs, rew, dn
+        torch.cuda.empty_cache()
+
     # ---- closed-loop policy rollouts (BASELINE configs[1] size and configs[4] shape; N = 1 only) ----
     rollout = None
     if world == 1 and not args.no_sweep:
@@ -423,7 +450,7 @@ def run_b200_arm(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(envs, world), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
-            "episode_stats": stats, "sweep": sweep, "rollout": rollout, "impl": "b200",
+            "episode_stats": stats, "sweep": sweep, "open_loop": open_loop, "rollout": rollout, "impl": "b200",
         }
         print(json.dumps(line), flush=True)
     if world > 1:

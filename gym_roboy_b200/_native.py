@@ -47,6 +47,7 @@ SIGNATURES = {
     "roboy_set_reward_range": (_int, [_vp, ctypes.c_double, ctypes.c_double]),
     "roboy_reset": (_int, [_vp, _vp, _vp, _vp]),
     "roboy_step": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "roboy_step_many": (_int, [_vp, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "roboy_step_host": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "roboy_set_host_pipeline": (_int, [_vp, _u64, _int]),
     "roboy_set_terminal_obs": (_int, [_vp, _vp]),

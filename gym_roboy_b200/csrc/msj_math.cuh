@@ -104,10 +104,11 @@ __device__ __forceinline__ float normalize32_hot(float v, float hi, float lo, fl
 }
 
 template <bool PENALTY, bool BONUS, bool FASTDIV>
-__device__ __forceinline__ void reward_reached_sampled(float q0, float q1, float q2, float qd0, float qd1, float qd2,
-                                                       float g0, float g1, float g2, const RobotConsts &c,
-                                                       const FastConsts &f, float &reward_out, bool &reached,
-                                                       bool &violation) {
+__device__ __forceinline__ void reward_reached_sampled_ng(float q0, float q1, float q2, float qd0, float qd1, float qd2,
+                                                          float g0, float g1, float g2, float ng0, float ng1,
+                                                          float ng2, const RobotConsts &c, const FastConsts &f,
+                                                          float &reward_out, bool &reached, bool &violation) {
+    // ng0..2: the goal already normalised (normalize32_hot) -- the open-loop kernel keeps it in registers
     // _did_reach_goal (:125-134): angles in float32, velocities in float64 -- evaluated exactly
     // only when the cheap bound cannot rule "close" out.
     reached = false;
@@ -123,12 +124,9 @@ __device__ __forceinline__ void reward_reached_sampled(float q0, float q1, float
         }
     }
     // compute_reward :94-96
-    const float d0 = __fsub_rn(normalize32_hot<FASTDIV>(q0, c.a_hi, c.a_lo, c.a_span, f.a_rc),
-                               normalize32_hot<FASTDIV>(g0, c.a_hi, c.a_lo, c.a_span, f.a_rc));
-    const float d1 = __fsub_rn(normalize32_hot<FASTDIV>(q1, c.a_hi, c.a_lo, c.a_span, f.a_rc),
-                               normalize32_hot<FASTDIV>(g1, c.a_hi, c.a_lo, c.a_span, f.a_rc));
-    const float d2 = __fsub_rn(normalize32_hot<FASTDIV>(q2, c.a_hi, c.a_lo, c.a_span, f.a_rc),
-                               normalize32_hot<FASTDIV>(g2, c.a_hi, c.a_lo, c.a_span, f.a_rc));
+    const float d0 = __fsub_rn(normalize32_hot<FASTDIV>(q0, c.a_hi, c.a_lo, c.a_span, f.a_rc), ng0);
+    const float d1 = __fsub_rn(normalize32_hot<FASTDIV>(q1, c.a_hi, c.a_lo, c.a_span, f.a_rc), ng1);
+    const float d2 = __fsub_rn(normalize32_hot<FASTDIV>(q2, c.a_hi, c.a_lo, c.a_span, f.a_rc), ng2);
     double s = (double)__fmul_rn(d0, d0);                    // OpenBLAS sdot: float products, double sum
     s = __dadd_rn(s, (double)__fmul_rn(d1, d1));
     s = __dadd_rn(s, (double)__fmul_rn(d2, d2));
@@ -147,6 +145,17 @@ __device__ __forceinline__ void reward_reached_sampled(float q0, float q1, float
         reward_out = r32;
         violation = !(r32 >= f.reward_lo_f && r32 <= f.reward_hi_f);  // :109
     }
+}
+
+template <bool PENALTY, bool BONUS, bool FASTDIV>
+__device__ __forceinline__ void reward_reached_sampled(float q0, float q1, float q2, float qd0, float qd1, float qd2,
+                                                       float g0, float g1, float g2, const RobotConsts &c,
+                                                       const FastConsts &f, float &reward_out, bool &reached,
+                                                       bool &violation) {
+    reward_reached_sampled_ng<PENALTY, BONUS, FASTDIV>(
+        q0, q1, q2, qd0, qd1, qd2, g0, g1, g2, normalize32_hot<FASTDIV>(g0, c.a_hi, c.a_lo, c.a_span, f.a_rc),
+        normalize32_hot<FASTDIV>(g1, c.a_hi, c.a_lo, c.a_span, f.a_rc),
+        normalize32_hot<FASTDIV>(g2, c.a_hi, c.a_lo, c.a_span, f.a_rc), c, f, reward_out, reached, violation);
 }
 
 // ---------------------------------------------------------------------------------------------

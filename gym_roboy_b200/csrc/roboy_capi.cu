@@ -191,6 +191,7 @@ CallCounter counter(roboy_env *e, CallCounter::Mode mode, unsigned long long t_f
     c.cta_done = e->cta_done;
     c.t_fixed = t_fixed;
     c.mode = mode;
+    c.advance = 1;
     return c;
 }
 
@@ -418,6 +419,26 @@ int roboy_step(roboy_env *env, const float *actions_dev, float *obs_dev, float *
     fill_step_params(env, p, actions_dev, obs_dev, reward_dev, done_dev);
     CUDA_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset, env->fastdiv,
                          env->sm_count, (cudaStream_t)stream));
+    env->launches++;
+    return ROBOY_OK;
+}
+
+int roboy_step_many(roboy_env *env, uint32_t T, const float *actions_dev, float *obs_dev, float *reward_dev,
+                    uint8_t *done_dev, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(ROBOY_E_ARG, "NULL device pointer");
+    if (T == 0) return ROBOY_OK;
+    if ((uintptr_t)actions_dev & 15) return fail(ROBOY_E_ARG, "actions must be 16-byte aligned");
+    if ((uintptr_t)obs_dev & 3) return fail(ROBOY_E_ARG, "obs must be 4-byte aligned");
+    DeviceGuard g(env->device);
+    env->goal_sub = 1;
+    StepParams p;
+    fill_step_params(env, p, actions_dev, obs_dev, reward_dev, done_dev);
+    p.cc.advance = T;
+    // every [t] slice of obs must be 16-byte aligned for the vector / bulk stores
+    p.obs_aligned = (((uintptr_t)obs_dev & 15) == 0) && (T == 1 || (env->cfg.n_envs * ROBOY_DIM_OBS * sizeof(float)) % 16 == 0);
+    CUDA_TRY(launch_step_many(p, T, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
+                              env->fastdiv, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }

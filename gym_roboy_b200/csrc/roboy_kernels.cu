@@ -71,6 +71,7 @@ struct ChunkIn {
     float4 a0, a1;
     float g0, g1, g2;
     uint32_t sf;
+    float ng0, ng1, ng2;  // normalised goal; only maintained by the open-loop kernel (KEEP_STATE)
 };
 
 // Local env indices are 32-bit (a shard holds < 2^32 envs: 4 Gi envs would need 400 GB of HBM);
@@ -107,6 +108,24 @@ __device__ __forceinline__ ChunkIn load_chunk(const StepParams &p, uint32_t base
         in.sf = live ? p.step_flags[e] : 1u;
     }
     return in;
+}
+
+struct Actions2 {
+    float4 a0, a1;
+};
+template <bool TAIL>
+__device__ __forceinline__ Actions2 load_actions(const float *actions, uint32_t base, uint32_t n_end, int lane) {
+    const float4 *a4 = reinterpret_cast<const float4 *>(actions) + (size_t)base * 2;
+    Actions2 a;
+    if (!TAIL) {
+        a.a0 = ld_stream(a4 + lane);
+        a.a1 = ld_stream(a4 + 32 + lane);
+    } else {
+        const float4 z = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+        a.a0 = (base * 2 + lane < n_end * 2) ? ld_stream(a4 + lane) : z;
+        a.a1 = (base * 2 + 32 + lane < n_end * 2) ? ld_stream(a4 + 32 + lane) : z;
+    }
+    return a;
 }
 
 // Next-chunk prefetch into L2 (no registers held across the compute phase): lanes 0..7 touch the
@@ -219,9 +238,19 @@ __device__ __noinline__ uint32_t finish_episode(const StepParams &p, uint64_t t,
     return 1u;                                                   // :85, with the flags replaced
 }
 
-template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV, bool TAIL>
-__device__ __forceinline__ void process_chunk(const StepParams &p, uint64_t t, const ChunkIn &cur, uint32_t base,
-                                              int lane, float *so, unsigned int *s_cnt, float &sum_reward) {
+// Where one step's outputs go: the handle's / caller's [n] buffers, or slot t of [T][n] rollout buffers.
+struct OutPtrs {
+    float *obs, *reward;
+    uint8_t *done;
+    bool obs_aligned;
+};
+
+// One env-step for the 32 envs of a chunk.  KEEP_STATE: the caller keeps the step word (and goal) in
+// registers across several steps (open-loop rollout) instead of storing it per step.
+template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV, bool TAIL, bool KEEP_STATE>
+__device__ __forceinline__ uint32_t process_chunk(const StepParams &p, uint64_t t, const ChunkIn &cur, uint32_t base,
+                                                  int lane, float *so, unsigned int *s_cnt, float &sum_reward,
+                                                  const OutPtrs &out, bool &done_out) {
     const uint32_t e = base + lane;
     const bool live = TAIL ? (e < (uint32_t)p.e_end) : true;
 
@@ -256,8 +285,12 @@ __device__ __forceinline__ void process_chunk(const StepParams &p, uint64_t t, c
         qd0 = uniform_in21(d.k[3], p.c.a_lo, p.f.a_span21);
         qd1 = uniform_in21(d.k[4], p.c.a_lo, p.f.a_span21);
         qd2 = uniform_in21(d.k[5], p.c.a_lo, p.f.a_span21);
-        reward_reached_sampled<PENALTY, BONUS, FASTDIV>(q0, q1, q2, qd0, qd1, qd2, g0, g1, g2, p.c, p.f, reward,
-                                                        reached, violation);
+        if (KEEP_STATE)
+            reward_reached_sampled_ng<PENALTY, BONUS, FASTDIV>(q0, q1, q2, qd0, qd1, qd2, g0, g1, g2, cur.ng0, cur.ng1,
+                                                               cur.ng2, p.c, p.f, reward, reached, violation);
+        else
+            reward_reached_sampled<PENALTY, BONUS, FASTDIV>(q0, q1, q2, qd0, qd1, qd2, g0, g1, g2, p.c, p.f, reward,
+                                                            reached, violation);
     } else {
         const HoldOut h = hold_branch(p, e, sf, g0, g1, g2, PENALTY, BONUS);
         q0 = h.q0; q1 = h.q1; q2 = h.q2; qd0 = h.qd0; qd1 = h.qd1; qd2 = h.qd2;
@@ -293,14 +326,15 @@ __device__ __forceinline__ void process_chunk(const StepParams &p, uint64_t t, c
     sum_reward += reward;
 #else
     if (live) {
-        p.step_flags[e] = word;
-        st_stream(p.reward + e, reward);
-        p.done[e] = (uint8_t)done;
+        if (!KEEP_STATE) p.step_flags[e] = word;
+        st_stream(out.reward + e, reward);
+        out.done[e] = (uint8_t)done;
         sum_reward += reward;
     }
 #endif
+    done_out = done;
 #if ROBOY_OBS_BULK_STORE
-    if (!TAIL && p.obs_aligned) {
+    if (!TAIL && out.obs_aligned) {
         // every lane publishes its shared-memory writes to the async proxy, then one lane hands the
         // warp's 1152 contiguous bytes to the bulk-copy engine (SASS: UBLKCP); the staging buffer is
         // double-buffered by the caller, so the copy drains while the next chunk is computed
@@ -308,18 +342,18 @@ __device__ __forceinline__ void process_chunk(const StepParams &p, uint64_t t, c
         __syncwarp();
         if (lane == 0) {
             const uint32_t src = (uint32_t)__cvta_generic_to_shared(so);
-            float *dst = p.obs + (size_t)base * kObsDim;
+            float *dst = out.obs + (size_t)base * kObsDim;
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
                          "n"(32 * kObsDim * 4)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        return;
+        return word;
     }
 #endif
     __syncwarp();
-    if (!TAIL && p.obs_aligned) {
-        float4 *dst = reinterpret_cast<float4 *>(p.obs + (size_t)base * kObsDim);  // 1152 B per chunk: 16 B aligned
+    if (!TAIL && out.obs_aligned) {
+        float4 *dst = reinterpret_cast<float4 *>(out.obs + (size_t)base * kObsDim);  // 1152 B per chunk: 16 B aligned
         const float4 *src = reinterpret_cast<const float4 *>(so);
         st_stream(dst + lane, src[lane]);
         st_stream(dst + 32 + lane, src[32 + lane]);
@@ -327,9 +361,10 @@ __device__ __forceinline__ void process_chunk(const StepParams &p, uint64_t t, c
     } else {  // ragged tail, or a caller-supplied obs pointer that is only 4-byte aligned: scalar stores
         const uint32_t rows = TAIL ? (uint32_t)p.e_end - base : 32u;
         const uint32_t n_valid = rows * kObsDim;
-        for (uint32_t i = lane; i < n_valid; i += 32) p.obs[(size_t)base * kObsDim + i] = so[i];
+        for (uint32_t i = lane; i < n_valid; i += 32) out.obs[(size_t)base * kObsDim + i] = so[i];
     }
     __syncwarp();
+    return word;
 }
 
 }  // namespace
@@ -362,6 +397,8 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
     // per-thread reward sum: a thread adds at most a few hundred float32 rewards per launch, the
     // cross-thread reduction below is in double
     float sum_reward = 0.0f;
+    const OutPtrs out{p.obs, p.reward, p.done, p.obs_aligned != 0};
+    bool done_unused;
 
     uint32_t chunk = (uint32_t)(p.e_begin >> 5) + blockIdx.x * kWarpsPerBlock + warp;
 #if ROBOY_PREFETCH == 1
@@ -390,7 +427,8 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
         so = s_obs[parity][warp];
         parity ^= 1;
 #endif
-        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false>(p, t, cur, chunk << 5, lane, so, s_cnt, sum_reward);
+        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false, false>(p, t, cur, chunk << 5, lane, so, s_cnt,
+                                                                         sum_reward, out, done_unused);
         chunk = next;
     }
 #if ROBOY_OBS_BULK_STORE
@@ -400,7 +438,8 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
 #endif
     if (chunk == n_full && (p.e_end & 31)) {  // the ragged last chunk belongs to exactly one warp
         const ChunkIn cur = load_chunk<true>(p, chunk << 5, lane);
-        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true>(p, t, cur, chunk << 5, lane, so, s_cnt, sum_reward);
+        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true, false>(p, t, cur, chunk << 5, lane, so, s_cnt,
+                                                                        sum_reward, out, done_unused);
     }
 
     // ---- K3: episode statistics, one set of atomics per CTA ----
@@ -419,6 +458,99 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
         for (int k = 0; k < ROBOY_STAT_COUNT; ++k)
             if (v[k] != 0.0) atomicAdd(p.stats + k, v[k]);
         counter_end(p.cc, t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Open-loop variant: T consecutive steps on pre-recorded actions.  A warp keeps its 32 envs' goal and
+// step word in registers across the T steps, so per env-step only the action is read and obs /
+// reward / done are written (73 B instead of 93).  Results are bit-identical to T step_kernel launches.
+// ---------------------------------------------------------------------------------------------
+template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV, bool TAIL>
+__device__ __forceinline__ void rollout_chunk(const StepParams &p, uint32_t T, uint64_t t_first, uint32_t base, int lane,
+                                              float (*stage)[kWarpsPerBlock][32 * kObsDim], int warp, uint32_t &parity,
+                                              unsigned int *s_cnt, float &sum_reward) {
+    const uint32_t n_end = (uint32_t)p.e_end;
+    const uint32_t e = base + lane;
+    const bool live = TAIL ? e < n_end : true;
+    ChunkIn cur;
+    cur.g0 = live ? p.goal[e] : 0.f;
+    cur.g1 = live ? p.goal1[e] : 0.f;
+    cur.g2 = live ? p.goal2[e] : 0.f;
+    cur.sf = live ? p.step_flags[e] : 1u;
+    cur.ng0 = normalize32_hot<FASTDIV>(cur.g0, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
+    cur.ng1 = normalize32_hot<FASTDIV>(cur.g1, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
+    cur.ng2 = normalize32_hot<FASTDIV>(cur.g2, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
+    const size_t n = (size_t)p.n;
+    Actions2 nxt = load_actions<TAIL>(p.actions, base, n_end, lane);
+    for (uint32_t tt = 0; tt < T; ++tt) {
+        cur.a0 = nxt.a0;
+        cur.a1 = nxt.a1;
+        if (tt + 1 < T) nxt = load_actions<TAIL>(p.actions + (size_t)(tt + 1) * n * kActDim, base, n_end, lane);
+        const OutPtrs out{p.obs + (size_t)tt * n * kObsDim, p.reward + (size_t)tt * n, p.done + (size_t)tt * n,
+                          p.obs_aligned != 0};
+#if ROBOY_OBS_BULK_STORE
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+#endif
+        float *so = stage[parity][warp];
+        parity ^= 1;
+        bool done;
+        cur.sf = process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, TAIL, true>(p, t_first + tt, cur, base, lane, so, s_cnt,
+                                                                                sum_reward, out, done);
+        if (done && live) {  // rare: the new goal was stored by finish_episode (same thread)
+            cur.g0 = p.goal[e];
+            cur.g1 = p.goal1[e];
+            cur.g2 = p.goal2[e];
+            cur.ng0 = normalize32_hot<FASTDIV>(cur.g0, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
+            cur.ng1 = normalize32_hot<FASTDIV>(cur.g1, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
+            cur.ng2 = normalize32_hot<FASTDIV>(cur.g2, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
+        }
+    }
+    if (live) p.step_flags[e] = cur.sf;
+}
+
+template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV>
+__global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) rollout_kernel(const __grid_constant__ StepParams p,
+                                                                            const uint32_t T) {
+    __shared__ __align__(128) float s_obs[2][kWarpsPerBlock][32 * kObsDim];
+    __shared__ double s_red[kWarpsPerBlock];
+    __shared__ unsigned int s_cnt[5];
+    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint64_t t_first = counter_begin(p.cc);
+    const uint32_t n_full = (uint32_t)(p.e_end >> 5);
+    const uint32_t warp_stride = gridDim.x * kWarpsPerBlock;
+    float sum_reward = 0.0f;
+    uint32_t parity = 0;
+    uint32_t chunk = (uint32_t)(p.e_begin >> 5) + blockIdx.x * kWarpsPerBlock + warp;
+    for (; chunk < n_full; chunk += warp_stride)
+        rollout_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false>(p, T, t_first, chunk << 5, lane, s_obs, warp, parity, s_cnt,
+                                                                  sum_reward);
+    if (chunk == n_full && (p.e_end & 31))
+        rollout_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true>(p, T, t_first, chunk << 5, lane, s_obs, warp, parity, s_cnt,
+                                                                 sum_reward);
+#if ROBOY_OBS_BULK_STORE
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+#endif
+    const double w_reward = warp_sum((double)sum_reward);
+    if (lane == 0) s_red[warp] = w_reward;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; ++w) r += s_red[w];
+        const double done = (double)s_cnt[0], succ = (double)s_cnt[1];
+        const double steps = blockIdx.x == 0 ? (double)(p.e_end - p.e_begin) * (double)T : 0.0;
+        const double v[ROBOY_STAT_COUNT] = {steps, done, succ, done - succ, r, (double)s_cnt[4],
+                                            (double)s_cnt[2], (double)s_cnt[3]};
+#pragma unroll
+        for (int k = 0; k < ROBOY_STAT_COUNT; ++k)
+            if (v[k] != 0.0) atomicAdd(p.stats + k, v[k]);
+        counter_end(p.cc, t_first);
     }
 }
 
@@ -469,7 +601,42 @@ int grid_for(uint64_t n_range, int per_sm, int sm_count) {
     return (int)(want < cap ? want : cap);
 }
 
+using RolloutKernelFn = void (*)(const StepParams, const uint32_t);
+
+template <int SEL>
+RolloutKernelFn rollout_for() {
+    return rollout_kernel<(SEL & 8) != 0, (SEL & 4) != 0, (SEL & 2) != 0, (SEL & 1) != 0>;
+}
+
+RolloutKernelFn select_rollout(int sel) {
+    switch (sel & 15) {
+        case 0: return rollout_for<0>();   case 1: return rollout_for<1>();
+        case 2: return rollout_for<2>();   case 3: return rollout_for<3>();
+        case 4: return rollout_for<4>();   case 5: return rollout_for<5>();
+        case 6: return rollout_for<6>();   case 7: return rollout_for<7>();
+        case 8: return rollout_for<8>();   case 9: return rollout_for<9>();
+        case 10: return rollout_for<10>(); case 11: return rollout_for<11>();
+        case 12: return rollout_for<12>(); case 13: return rollout_for<13>();
+        case 14: return rollout_for<14>(); default: return rollout_for<15>();
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_step_many(const StepParams &p, uint32_t T, bool penalty, bool bonus, bool auto_reset, bool fastdiv,
+                             int sm_count, cudaStream_t stream) {
+    if (p.e_end <= p.e_begin || T == 0) return cudaSuccess;
+    const int sel = selector(penalty, bonus, auto_reset, fastdiv);
+    static int per_sm[16] = {0};
+    if (!per_sm[sel]) {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, select_rollout(sel), kStepBlock, 0) != cudaSuccess || b < 1) b = 1;
+        per_sm[sel] = b;
+    }
+    const int grid = grid_for(p.e_end - p.e_begin, per_sm[sel], sm_count);
+    select_rollout(sel)<<<grid, kStepBlock, 0, stream>>>(p, T);
+    return cudaGetLastError();
+}
 
 LaunchGeom step_geometry(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count) {
     const int sel = selector(penalty, bonus, auto_reset, fastdiv);

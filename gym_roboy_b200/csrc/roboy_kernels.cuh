@@ -30,6 +30,7 @@ struct CallCounter {
     unsigned int *cta_done;  // CTAs of the current launch that have finished
     unsigned long long t_fixed;
     int mode;
+    unsigned int advance;    // how many counter values this launch consumes (T for a T-step rollout; else 1)
 };
 
 __device__ __forceinline__ uint64_t counter_begin(const CallCounter &c) {
@@ -45,7 +46,7 @@ __device__ __forceinline__ void counter_end(const CallCounter &c, uint64_t t) {
     __threadfence();
     if (atomicAdd(c.cta_done, 1u) == gridDim.x - 1) {
         *c.cta_done = 0;
-        *c.t_dev = t;
+        *c.t_dev = t + (c.advance ? c.advance - 1 : 0);   // t is the FIRST value this launch used
     }
 }
 
@@ -89,6 +90,10 @@ struct LaunchGeom {
 LaunchGeom step_geometry(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count);
 cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count,
                         cudaStream_t stream);
+// T consecutive steps on pre-recorded actions [T][n][8] -> obs [T][n][9], reward / done [T][n], with the
+// env state held in registers across the T steps (open loop: 73 B per env-step instead of 93).
+cudaError_t launch_step_many(const StepParams &p, uint32_t T, bool penalty, bool bonus, bool auto_reset, bool fastdiv,
+                             int sm_count, cudaStream_t stream);
 
 struct InitParams {
     uint64_t n, gid_base;

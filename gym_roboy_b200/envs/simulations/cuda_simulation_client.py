@@ -184,6 +184,21 @@ class CudaSimulationClient(SimulationClient):
         _native.check(self._lib.roboy_step(self._h, self._p(actions), self._p(obs), self._p(reward), self._p(done),
                                            self._stream()))
 
+    def step_many(self, actions, obs=None, reward=None, done=None):
+        """Open-loop: T fused steps on pre-recorded `actions` float32 CUDA `[T,N,8]` in ONE launch (the env
+        state stays in registers between steps).  Returns `(obs [T,N,9], reward [T,N], done uint8 [T,N])`,
+        bit-identical to T `step_fused` calls."""
+        T, n = actions.shape[0], self.num_envs
+        if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous() \
+                or actions.numel() != T * n * _native.DIM_ACTION:
+            raise ValueError("actions must be a contiguous float32 CUDA tensor of shape [T, N, 8]")
+        obs = torch.empty((T, n, _native.DIM_OBS), dtype=torch.float32, device=self.device) if obs is None else obs
+        reward = torch.empty((T, n), dtype=torch.float32, device=self.device) if reward is None else reward
+        done = torch.empty((T, n), dtype=torch.uint8, device=self.device) if done is None else done
+        _native.check(self._lib.roboy_step_many(self._h, T, self._p(actions), self._p(obs), self._p(reward),
+                                                self._p(done), self._stream()))
+        return obs, reward, done
+
     def reset_fused(self, mask=None, obs=None):
         m = None if mask is None else self._dev(mask, torch.uint8, (self.num_envs,))
         _native.check(self._lib.roboy_reset(self._h, self._p(m), self._p(obs), self._stream()))

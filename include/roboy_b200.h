@@ -133,6 +133,14 @@ int roboy_reset(roboy_env *env, const uint8_t *mask_dev, float *obs_dev, void *s
 int roboy_step(roboy_env *env, const float *actions_dev, float *obs_dev, float *reward_dev,
                uint8_t *done_dev, void *stream);
 
+/* Open-loop variant: T consecutive RoboyEnv.step calls (roboy_env.py:51-70) on PRE-RECORDED actions
+ * float32 [T][n][8], writing obs [T][n][9], reward [T][n], done [T][n].  One launch: each env's goal and
+ * step counter stay in registers across the T steps (73 algorithmic bytes per env-step instead of
+ * 93).  Bit-identical to T roboy_step calls; the call counter advances by T.  Use it to replay
+ * recorded action sequences; a closed-loop policy needs roboy_step (or a CUDA graph of them). */
+int roboy_step_many(roboy_env *env, uint32_t T, const float *actions_dev, float *obs_dev, float *reward_dev,
+                    uint8_t *done_dev, void *stream);
+
 /* The same step through HOST buffers: pinned staging, chunked H2D -> kernel -> D2H pipelined
  * over internal streams; returns when the outputs are in host memory.  This is the call a
  * host-side (CPU policy) trainer makes, and what bench.py's e2e number times. */

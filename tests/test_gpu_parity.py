@@ -439,3 +439,34 @@ def test_ragged_sizes_with_guarded_output_buffers(n):
     assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
     assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
     assert client.stats()["steps"] == 6 * n and client.stats()["episodes"] == ora.stats()["episodes"] > 0
+
+
+@pytest.mark.parametrize("n,T", [(4096, 37), (1000, 12), (33, 420), (262144, 8)])
+def test_open_loop_step_many_equals_sequential_steps(n, T):
+    """roboy_step_many (state in registers across T steps, 73 B/env-step) must be bit-identical to T
+    roboy_step launches on the same pre-recorded actions -- including episode ends inside the window."""
+    rng = np.random.default_rng(n + T)
+    acts = np.stack([actions_for(rng, n, hold_frac=0.05) for _ in range(T)])
+    env_a, client_a, _ = make_pair(n, seed=31)
+    env_b, client_b, _ = make_pair(n, seed=31)
+    for env, client in ((env_a, client_a), (env_b, client_b)):
+        env._single = False
+        env.reset()
+        client.set_step_num((np.arange(n) % 400 + 1).astype(np.int32))
+    a_dev = torch.as_tensor(acts, device="cuda:0")
+    obs, rew, done = client_a.step_many(a_dev)
+    for t in range(T):
+        client_b.step_fused(a_dev[t])
+        assert torch.equal(obs[t], client_b.obs) and torch.equal(rew[t], client_b.reward), t
+        assert torch.equal(done[t], client_b.done_u8), t
+    assert torch.equal(client_a.goal, client_b.goal) and torch.equal(client_a.step_flags, client_b.step_flags)
+    assert client_a.counter == client_b.counter == 1 + T
+    sa, sb = client_a.stats(), client_b.stats()
+    for k in sa:
+        assert sa[k] == sb[k] if k != "sum_reward" else abs(sa[k] - sb[k]) <= 1e-6 * abs(sb[k]), k
+    assert sa["episodes"] > 0 and sa["holds"] > 0
+    # and a second window continues the same trajectory
+    obs2, _, _ = client_a.step_many(a_dev[:3])
+    for t in range(3):
+        client_b.step_fused(a_dev[t])
+        assert torch.equal(obs2[t], client_b.obs)
