@@ -35,6 +35,12 @@ namespace roboy {
 #ifndef ROBOY_OBS_BULK_STORE
 #define ROBOY_OBS_BULK_STORE 1  // 1 (measured +1%): drain the staged observations with cp.async.bulk (TMA bulk copy smem -> global)
 #endif
+#ifndef ROBOY_HOLD_BRANCHFREE
+#define ROBOY_HOLD_BRANCHFREE 0  // 1: min/max form without a branch (measured: no gain, more spills in the open-loop kernel)
+#endif
+#ifndef ROBOY_ROLLOUT_MIN_BLOCKS
+#define ROBOY_ROLLOUT_MIN_BLOCKS ROBOY_STEP_MIN_BLOCKS
+#endif
 #ifndef ROBOY_LD_HINT
 #define ROBOY_LD_HINT 0  // streamed inputs:  0 default (measured best: +3% over .cs), 1 ld.global.cs, 2 ld.global.nc.L1::no_allocate
 #endif
@@ -159,14 +165,22 @@ __device__ __forceinline__ bool action_ok4(const float4 &v, float hi) {
 
 // simulation_client.py:38 on the rescaled action (roboy_env.py:157-158): all four components
 // inside [hold_lo, hold_hi] -- the exact pre-image of numpy's allclose(rescaled, 0), found on
-// the host by bisection over the monotone float32 map a -> rescaled(a).  A max-magnitude
-// filter keeps the eight compares off the common path (NaN passes the filter and then fails
-// the compares, as it must).
-__device__ __forceinline__ bool action_hold4(const float4 &v, float lo, float hi, float mag) {
+// the host by bisection over the monotone float32 map a -> rescaled(a).  Branch-free: min and max
+// of the four against the interval ends.  fminf/fmaxf drop NaNs, so the verdict is ANDed with the
+// range test of roboy_env.py:52, which is false for NaN (numpy's allclose is false for NaN too).
+#if ROBOY_HOLD_BRANCHFREE
+__device__ __forceinline__ bool action_hold4(const float4 &v, float lo, float hi, float, bool ok4) {
+    const float mn = fminf(fminf(v.x, v.y), fminf(v.z, v.w));
+    const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    return ok4 && mn >= lo && mx <= hi;
+}
+#else
+__device__ __forceinline__ bool action_hold4(const float4 &v, float lo, float hi, float mag, bool) {
     const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
     if (m > mag) return false;
     return v.x >= lo && v.x <= hi && v.y >= lo && v.y <= hi && v.z >= lo && v.z <= hi && v.w >= lo && v.w <= hi;
 }
+#endif
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -257,10 +271,11 @@ __device__ __forceinline__ uint32_t process_chunk(const StepParams &p, uint64_t 
     // ---- roboy_env.py:52 assert + simulation_client.py:38 allclose, as warp ballots ----
     // env `lane` owns float4 2*lane and 2*lane+1 of the chunk's 64
     const float hold_mag = p.hold_mag;
-    const uint32_t okm0 = __ballot_sync(kFull, action_ok4(cur.a0, p.act_in_hi));
-    const uint32_t okm1 = __ballot_sync(kFull, action_ok4(cur.a1, p.act_in_hi));
-    const uint32_t hdm0 = __ballot_sync(kFull, action_hold4(cur.a0, p.hold_lo, p.hold_hi, hold_mag));
-    const uint32_t hdm1 = __ballot_sync(kFull, action_hold4(cur.a1, p.hold_lo, p.hold_hi, hold_mag));
+    const bool ok_a = action_ok4(cur.a0, p.act_in_hi), ok_b = action_ok4(cur.a1, p.act_in_hi);
+    const uint32_t okm0 = __ballot_sync(kFull, ok_a);
+    const uint32_t okm1 = __ballot_sync(kFull, ok_b);
+    const uint32_t hdm0 = __ballot_sync(kFull, action_hold4(cur.a0, p.hold_lo, p.hold_hi, hold_mag, ok_a));
+    const uint32_t hdm1 = __ballot_sync(kFull, action_hold4(cur.a1, p.hold_lo, p.hold_hi, hold_mag, ok_b));
     const uint32_t sh = (lane & 15) << 1;
     const bool act_ok = (((lane < 16 ? okm0 : okm1) >> sh) & 3u) == 3u;
     const bool hold = live && (((lane < 16 ? hdm0 : hdm1) >> sh) & 3u) == 3u;
@@ -511,7 +526,7 @@ __device__ __forceinline__ void rollout_chunk(const StepParams &p, uint32_t T, u
 }
 
 template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV>
-__global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) rollout_kernel(const __grid_constant__ StepParams p,
+__global__ void __launch_bounds__(kStepBlock, ROBOY_ROLLOUT_MIN_BLOCKS) rollout_kernel(const __grid_constant__ StepParams p,
                                                                             const uint32_t T) {
     __shared__ __align__(128) float s_obs[2][kWarpsPerBlock][32 * kObsDim];
     __shared__ double s_red[kWarpsPerBlock];
