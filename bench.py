@@ -403,21 +403,25 @@ def run_b200_arm(args):
         del e, c, a, obs, rew, dn
         torch.cuda.empty_cache()
 
-    # ---- closed-loop policy rollouts (BASELINE configs[1] size and configs[4] shape; N = 1 only) ----
+    # ---- closed-loop policy rollouts (BASELINE configs[1] size and configs[4] shape), every N ----
     rollout = None
-    if world == 1 and not args.no_sweep:
+    if not args.no_sweep:
         from gym_roboy_b200.rollout import MlpPolicy, RolloutCollector
         rollout = []
         for n in (4096, 262144):
             for graph in (False, True):
                 torch.manual_seed(0)
-                e, c = make(n)
+                b0, _ = shard_range(n * world, world, rank)
+                e, c = make(n, b0)
                 col = RolloutCollector(e, MlpPolicy().to(dev), n_steps=128)
                 if graph:
                     col.capture()
                 for _ in range(2):
                     col.collect()
                 torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                    torch.cuda.synchronize()
                 s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 reps = 5
                 s_.record()
@@ -426,10 +430,14 @@ def run_b200_arm(args):
                 e_.record()
                 torch.cuda.synchronize()
                 ms = s_.elapsed_time(e_) / reps
-                rollout.append({"envs": n, "n_steps": 128, "cuda_graph": graph, "ms_per_rollout": ms,
-                                "env_steps_per_s": n * 128 / (ms * 1e-3),
+                if world > 1:
+                    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+                    ms = float(tms.item())
+                rollout.append({"envs_per_gpu": n, "n_gpus": world, "n_steps": 128, "cuda_graph": graph, "ms_per_rollout": ms,
+                                "env_steps_per_s": n * world * 128 / (ms * 1e-3),
                                 "what": "MlpPolicy 9-64-64-8 (+value net) forward, Gaussian sample, device clip, fused env "
-                                        "step writing into [T,N] buffers, GAE kernel"})
+                                        "step writing into [T,N] buffers, GAE kernel; policy replicated per GPU"})
                 del col, e, c
 
     cpu_baseline = None

@@ -228,3 +228,24 @@ class RoboyEnv(_GoalEnvBase):
 
     def close(self):
         self._simulation_client.close()
+
+
+def _l2_distance(joint_angle1, joint_angle2):
+    """Host helper with the reference's semantics (roboy_env.py:137-140): NaN differences count as 0."""
+    diff = np.subtract(joint_angle1, joint_angle2)
+    diff[np.isnan(diff)] = 0
+    return np.linalg.norm(diff, ord=2)
+
+
+def _rescale_from_one_space_to_other(input_val: np.ndarray, input_space: Box, output_space: Box) -> np.ndarray:
+    """Host helper with the reference's semantics (roboy_env.py:143-158): the affine map that sends
+    `input_space` onto `output_space`, evaluated as `slope * (x - in.high) + out.high`.  The step kernel
+    applies the same float32 map to every action (as the pre-image of its hold test); this version
+    exists for callers and tests that use the helper directly."""
+    if not isinstance(input_val, np.ndarray):
+        raise TypeError("input_val must be a numpy array")
+    assert input_space.shape == output_space.shape
+    assert input_space.contains(input_val)
+    slope = (output_space.high - output_space.low) / (input_space.high - input_space.low)
+    return slope * (input_val - input_space.high) + output_space.high
+

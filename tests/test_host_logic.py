@@ -95,3 +95,19 @@ def test_summarize():
     import torch
     s = summarize(torch.tensor([1000.0, 10, 4, 6, -2500.0, 900, 3, 0], dtype=torch.float64))
     assert s["success_rate"] == 0.4 and s["mean_step_reward"] == -2.5 and s["mean_episode_len"] == 90
+
+
+def test_rescale_from_one_space_to_other():                      # test_roboy_env.py:195-207
+    from gym_roboy_b200.envs.roboy_env import _l2_distance, _rescale_from_one_space_to_other
+    np.random.seed(0)
+    mk = lambda: Box(low=-np.random.uniform(size=8), high=np.random.uniform(size=8), dtype="float32")  # noqa: E731
+    src, dst = mk(), mk()
+    assert np.allclose(_rescale_from_one_space_to_other(input_val=src.high, input_space=src, output_space=dst), dst.high)
+    assert np.allclose(_rescale_from_one_space_to_other(input_val=src.low, input_space=src, output_space=dst), dst.low)
+    with pytest.raises(AssertionError):
+        _rescale_from_one_space_to_other(input_val=src.high * 2, input_space=src, output_space=dst)
+    # the MSJ action rescale is the map whose zero set the kernel's hold interval encodes
+    unit, msj = Box(-1, 1, (8,), "float32"), MsjRobot.get_action_space()
+    out = _rescale_from_one_space_to_other(np.zeros(8, np.float32), unit, msj)
+    assert out.dtype == np.float32 and np.allclose(out, 0, atol=1e-8)
+    assert _l2_distance(np.array([np.inf, 1.0, 0.0]), np.array([np.inf, 0.0, 0.0])) == 1.0   # inf - inf counts as 0
