@@ -16,6 +16,11 @@ F_HELD_ZERO64 = 1 << 24
 F_HELD_INFEASIBLE = 1 << 25
 ERR_ACTION, ERR_REWARD_RANGE, ERR_GOAL_BOUNDS = 1, 2, 4
 STAT_NAMES = ("steps", "episodes", "successes", "timeouts", "sum_reward", "sum_episode_len", "holds", "violations")
+# layout of the packed policy image of roboy_policy_rollout (ROBOY_POLICY_* in include/roboy_b200.h), in floats
+POLICY_HIDDEN = 64
+POLICY_OFF_W1, POLICY_OFF_B1, POLICY_OFF_W2, POLICY_OFF_B2, POLICY_OFF_W3, POLICY_OFF_B3 = 0, 576, 640, 4736, 4800, 5312
+POLICY_NET_FLOATS = 5320
+POLICY_OFF_VF, POLICY_OFF_PI, POLICY_OFF_STD, POLICY_OFF_LOGNORM, POLICY_IMAGE_FLOATS = 0, 5320, 10640, 10648, 10652
 (BUF_GOAL, BUF_STEP_FLAGS, BUF_HELD, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_STATS, BUF_TERMINAL_OBS) = range(8)
 
 
@@ -72,6 +77,9 @@ SIGNATURES = {
     "roboy_step_external": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "roboy_reset_external": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "roboy_gae": (_int, [_u64, _u64, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]),
+    "roboy_policy_rollout": (_int, [_vp, ctypes.c_uint32, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "roboy_policy_geometry": (_int, [_vp, _int, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
+                                     ctypes.POINTER(_int)]),
     "roboy_launch_count": (_int, [_vp, ctypes.POINTER(_u64)]),
     "roboy_step_geometry": (_int, [_vp, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
 }

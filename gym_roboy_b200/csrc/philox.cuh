@@ -16,7 +16,7 @@
 
 namespace roboy {
 
-enum : uint32_t { kStreamState = 0, kStreamGoal = 2 };
+enum : uint32_t { kStreamState = 0, kStreamGoal = 2, kStreamNoise = 4 };  // kStreamNoise: the policy's Gaussian noise (own key)
 
 struct PhiloxKeys {
     // the ten round keys, k + r*W, precomputed on the host (uniform across the grid)

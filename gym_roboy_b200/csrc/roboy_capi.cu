@@ -13,6 +13,7 @@
 #include "../../include/roboy_b200.h"
 #include "dlpack_min.h"
 #include "roboy_kernels.cuh"
+#include "roboy_policy.cuh"
 
 using namespace roboy;
 
@@ -864,6 +865,48 @@ int roboy_gae(uint64_t T, uint64_t n, const float *reward_dev, const float *valu
     p.adv = adv_dev;
     p.ret = ret_dev;
     CUDA_TRY(launch_gae(p, (cudaStream_t)stream));
+    return ROBOY_OK;
+}
+
+int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uint64_t noise_seed, float *obs_dev,
+                         float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
+                         float *noise_dev, int envs_per_thread, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!image_dev || !obs_dev || !actions_dev || !logp_dev || !values_dev || !reward_dev || !done_dev)
+        return fail(ROBOY_E_ARG, "NULL device pointer");
+    if (((uintptr_t)image_dev & 15) || ((uintptr_t)actions_dev & 15) || (noise_dev && ((uintptr_t)noise_dev & 15)))
+        return fail(ROBOY_E_ARG, "image, actions and noise must be 16-byte aligned");
+    if ((uintptr_t)obs_dev & 3) return fail(ROBOY_E_ARG, "obs must be 4-byte aligned");
+    if (envs_per_thread < 0 || envs_per_thread > 2) return fail(ROBOY_E_ARG, "envs_per_thread must be 0, 1 or 2");
+    if (T == 0) return ROBOY_OK;
+    DeviceGuard g(env->device);
+    env->goal_sub = 1;
+    StepParams p;
+    fill_step_params(env, p, nullptr, obs_dev, reward_dev, done_dev);
+    p.cc.advance = T;
+    PolicyParams q{};
+    q.image = image_dev;
+    q.T = T;
+    q.obs_aligned = (((uintptr_t)obs_dev & 15) == 0) && (env->cfg.n_envs * ROBOY_DIM_OBS * sizeof(float)) % 16 == 0;
+    q.obs = obs_dev;
+    q.actions = actions_dev;
+    q.logp = logp_dev;
+    q.values = values_dev;
+    q.noise = noise_dev;
+    q.noise_keys = make_philox_keys(noise_seed);
+    CUDA_TRY(launch_policy_rollout(p, q, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
+                                   env->fastdiv, env->sm_count, envs_per_thread, (cudaStream_t)stream));
+    env->launches++;
+    return ROBOY_OK;
+}
+
+int roboy_policy_geometry(roboy_env *env, int envs_per_thread, int *grid, int *block, int *smem_bytes, int *ept) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    const PolicyGeom geo = policy_geometry(env->cfg.n_envs, env->sm_count, envs_per_thread);
+    if (grid) *grid = geo.grid;
+    if (block) *block = geo.block;
+    if (smem_bytes) *smem_bytes = geo.smem;
+    if (ept) *ept = geo.envs_per_thread;
     return ROBOY_OK;
 }
 

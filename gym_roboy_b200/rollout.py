@@ -6,7 +6,10 @@ action crosses a pipe to each env process and the observation comes back the sam
 whole loop stays on one device: a torch policy reads the observation tensor the step kernel wrote,
 actions are clipped on the device, and the step kernel writes observation / reward / done
 straight into the `[T, N]` rollout buffers (its output pointers ARE the buffer slots).
-Advantages come from the `roboy_gae` kernel.  Because the env's call counter is device state, the
+Advantages come from the `roboy_gae` kernel.  With `fused=True` the policy itself runs inside the
+env kernel (`roboy_policy_rollout`: both networks, the Gaussian sample, the clip and the env step for
+all T steps in ONE launch, state in registers), which removes every per-step launch and every
+activation round trip through HBM.  Because the env's call counter is device state, the
 entire T-step loop can be captured in one CUDA graph and replayed, which is what makes small
 populations (e.g. 4,096 envs), otherwise launch-bound, run at speed.
 
@@ -52,13 +55,47 @@ def gae(rewards, values, dones, last_value, gamma=0.99, lam=0.95, adv=None, ret=
     return adv, ret
 
 
-class RolloutCollector:
-    """Collects `[T, N]` rollouts from a batched `RoboyEnv` with a torch policy, all on the device."""
+def pack_policy_image(policy, out=None):
+    """Pack an `MlpPolicy` into the float32 image `roboy_policy_rollout` reads (layout: ROBOY_POLICY_* in
+    include/roboy_b200.h): per network W1^T | b1 | W2^T | b2 | W3^T (8 columns) | b3 (8), value network first,
+    then std = exp(log_std) and the log-density constant."""
+    N = _native
+    dev = policy.log_std.device
+    img = torch.zeros(N.POLICY_IMAGE_FLOATS, dtype=torch.float32, device=dev) if out is None else out
+    for base, net in ((N.POLICY_OFF_VF, policy.vf), (N.POLICY_OFF_PI, policy.pi)):
+        l1, l2, l3 = net[0], net[2], net[4]
+        assert l1.weight.shape == (N.POLICY_HIDDEN, N.DIM_OBS) and l2.weight.shape == (N.POLICY_HIDDEN, N.POLICY_HIDDEN)
+        n_out = l3.weight.shape[0]
+        assert n_out in (1, N.DIM_ACTION)
+        img[base + N.POLICY_OFF_W1: base + N.POLICY_OFF_B1].copy_(l1.weight.detach().t().reshape(-1))
+        img[base + N.POLICY_OFF_B1: base + N.POLICY_OFF_W2].copy_(l1.bias.detach())
+        img[base + N.POLICY_OFF_W2: base + N.POLICY_OFF_B2].copy_(l2.weight.detach().t().reshape(-1))
+        img[base + N.POLICY_OFF_B2: base + N.POLICY_OFF_W3].copy_(l2.bias.detach())
+        w3 = img[base + N.POLICY_OFF_W3: base + N.POLICY_OFF_B3].view(N.POLICY_HIDDEN, 8)
+        w3.zero_()
+        w3[:, :n_out].copy_(l3.weight.detach().t())
+        b3 = img[base + N.POLICY_OFF_B3: base + N.POLICY_NET_FLOATS]
+        b3.zero_()
+        b3[:n_out].copy_(l3.bias.detach())
+    log_std = policy.log_std.detach()
+    img[N.POLICY_OFF_STD: N.POLICY_OFF_STD + 8].copy_(log_std.exp())
+    img[N.POLICY_OFF_LOGNORM] = -0.5 * math.log(2 * math.pi) * log_std.numel() - log_std.sum()
+    return img
 
-    def __init__(self, env, policy, n_steps=128, gamma=0.99, lam=0.95):
+
+class RolloutCollector:
+    """Collects `[T, N]` rollouts from a batched `RoboyEnv` with a torch policy, all on the device.
+
+    `actions` holds the UN-clipped Gaussian samples and `logp` their log-density (what PPO2's runner stores);
+    the env is stepped with `clip(actions, -1, 1)`.  `fused=True` runs policy + env for all T steps in one
+    kernel launch (`roboy_policy_rollout`); the Gaussian noise then comes from Philox keyed by `noise_seed`
+    instead of torch's generator."""
+
+    def __init__(self, env, policy, n_steps=128, gamma=0.99, lam=0.95, fused=False, noise_seed=0, envs_per_thread=0):
         self.env, self.client, self.policy = env, env._simulation_client, policy
         self.T, self.N = int(n_steps), env.num_envs
         self.gamma, self.lam = gamma, lam
+        self.fused, self.noise_seed, self.envs_per_thread = bool(fused), int(noise_seed), int(envs_per_thread)
         dev, T, N = self.client.device, self.T, self.N
         f32 = dict(dtype=torch.float32, device=dev)
         self.obs = torch.zeros((T + 1, N, 9), **f32)
@@ -70,9 +107,26 @@ class RolloutCollector:
         self.adv = torch.zeros((T, N), **f32)
         self.ret = torch.zeros((T, N), **f32)
         self._graph = None
+        self._clipped = torch.zeros((N, 8), **f32)
+        self._image = torch.zeros(_native.POLICY_IMAGE_FLOATS, **f32) if self.fused else None
+        self.noise = None   # tests: set to a [T, N, 8] float32 tensor to have the fused kernel record its noise
         self.obs[0].copy_(env.reset())
 
+    def _fused_loop(self):
+        pack_policy_image(self.policy, out=self._image)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+        dev = self.client.device
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(_native.load().roboy_policy_rollout(
+            self.client._h, self.T, p(self._image), self.noise_seed, p(self.obs), p(self.actions), p(self.logp),
+            p(self.values), p(self.rewards), p(self.dones), p(self.noise) if self.noise is not None else None,
+            self.envs_per_thread, stream))
+        gae(self.rewards, self.values[: self.T], self.dones, self.values[self.T], self.gamma, self.lam, self.adv, self.ret)
+        self.obs[0].copy_(self.obs[self.T])
+
     def _loop(self):
+        if self.fused:
+            return self._fused_loop()
         policy, client = self.policy, self.client
         std = policy.log_std.exp()
         log_norm = -0.5 * math.log(2 * math.pi) * std.numel() - policy.log_std.sum()
@@ -80,10 +134,11 @@ class RolloutCollector:
             mean, value = policy(self.obs[t])
             noise = torch.randn_like(mean)
             self.logp[t] = log_norm - 0.5 * (noise * noise).sum(-1)
-            torch.clamp(mean + std * noise, -1.0, 1.0, out=self.actions[t])   # the runner's np.clip, on the device
+            torch.addcmul(mean, std, noise, out=self.actions[t])
+            torch.clamp(self.actions[t], -1.0, 1.0, out=self._clipped)        # the runner's np.clip, on the device
             self.values[t] = value
             # zero-copy: the step kernel's output pointers are the rollout buffer slots
-            client.step_fused(self.actions[t], obs=self.obs[t + 1], reward=self.rewards[t], done=self.dones[t])
+            client.step_fused(self._clipped, obs=self.obs[t + 1], reward=self.rewards[t], done=self.dones[t])
         self.values[self.T] = policy(self.obs[self.T])[1]
         gae(self.rewards, self.values[: self.T], self.dones, self.values[self.T], self.gamma, self.lam, self.adv, self.ret)
         self.obs[0].copy_(self.obs[self.T])   # next rollout continues where this one stopped

@@ -239,6 +239,45 @@ int roboy_reset_external(roboy_env *env, const uint8_t *mask_dev, const float *q
 int roboy_gae(uint64_t T, uint64_t n, const float *reward_dev, const float *value_dev, const uint8_t *done_dev,
               const float *last_value_dev, float gamma, float lam, float *adv_dev, float *ret_dev, void *stream);
 
+/* Closed-loop rollout with the policy INSIDE the kernel (BASELINE.json configs[4]):
+ * T steps of [MlpPolicy forward -> Gaussian sample -> clip to the action space -> RoboyEnv.step] for every
+ * env in ONE launch -- the loop stable-baselines' PPO2 runner drives over a SubprocVecEnv in
+ * train_parallel.py:28-35.  The policy is stable-baselines' MlpPolicy shape: separate 9-64-64 tanh
+ * networks for the action mean (8 outputs) and the value (1 output), state-independent log-std.
+ * Each env's observation, goal and step counter stay in registers for the T steps; per env-step the
+ * kernel writes action 32 + logp 4 + value 4 + obs 36 + reward 4 + done 1 = 81 bytes and reads nothing.
+ * Env outputs are bit-identical to T roboy_step calls on clip(actions, -1, 1).
+ *
+ * image_dev: the policy packed as float32 [ROBOY_POLICY_IMAGE_FLOATS], 16-byte aligned.  One network
+ * is  W1^T [9][64] | b1 [64] | W2^T [64][64] | b2 [64] | W3^T [64][8] | b3 [8]  (the value network's
+ * output layer zero-padded from 1 to 8 columns); the image is  value net | policy net | std [8]
+ * (= exp(log_std)) | lognorm (= -0.5*8*log(2 pi) - sum(log_std)) | 3 floats of padding.
+ * Noise: Philox4x32-10 keyed by noise_seed, counter (global env id, env call counter, stream 4),
+ * Box-Muller; independent of how envs are sharded.
+ *   obs_dev     float32 [T+1][n][9]  slot 0 = the observation to start from (input), slots 1..T written
+ *   actions_dev float32 [T][n][8]    the UN-clipped samples (what PPO2's runner stores; env.step saw the clip)
+ *   logp_dev    float32 [T][n]       log-density of the sample;  values_dev float32 [T+1][n] (slot T: bootstrap)
+ *   reward_dev  float32 [T][n];  done_dev uint8 [T][n];  noise_dev float32 [T][n][8] or NULL (tests)
+ * envs_per_thread: 0 = automatic (1 while all envs fit on the chip at once, else 2). */
+#define ROBOY_POLICY_HIDDEN 64
+#define ROBOY_POLICY_OFF_W1 0
+#define ROBOY_POLICY_OFF_B1 576
+#define ROBOY_POLICY_OFF_W2 640
+#define ROBOY_POLICY_OFF_B2 4736
+#define ROBOY_POLICY_OFF_W3 4800
+#define ROBOY_POLICY_OFF_B3 5312
+#define ROBOY_POLICY_NET_FLOATS 5320
+#define ROBOY_POLICY_OFF_VF 0
+#define ROBOY_POLICY_OFF_PI 5320
+#define ROBOY_POLICY_OFF_STD 10640
+#define ROBOY_POLICY_OFF_LOGNORM 10648
+#define ROBOY_POLICY_IMAGE_FLOATS 10652
+int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uint64_t noise_seed, float *obs_dev,
+                         float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
+                         float *noise_dev, int envs_per_thread, void *stream);
+/* Launch geometry roboy_policy_rollout uses for this handle (bench.py / tests). */
+int roboy_policy_geometry(roboy_env *env, int envs_per_thread, int *grid, int *block, int *smem_bytes, int *ept);
+
 /* Introspection for bench.py / tests: kernels launched by this handle so far, and the
  * launch geometry the step kernel uses for this n_envs. */
 int roboy_launch_count(roboy_env *env, uint64_t *launches);

@@ -1,0 +1,171 @@
+"""SURVEY.md 8f row 1 / BASELINE.json configs[4], fused form: `roboy_policy_rollout` runs the MlpPolicy, the
+Gaussian sample, the clip and the env step for all T steps inside one kernel.  Checked here:
+  * env outputs (obs / done bit-exact, reward <= 1e-6 rel) against the CPU oracle replaying clip(actions);
+  * policy outputs (action mean via the recorded noise, value, log-density) against the torch float32 MlpPolicy;
+  * the Gaussian noise against a numpy restatement of Philox + Box-Muller, and its moments;
+  * one env per thread vs two envs per thread, and one shard vs two half shards: bit-identical;
+  * CUDA-graph replay and the hand-over to the next rollout.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def make(n, seed, T, fused=True, env_id_base=0, noise_seed=77, envs_per_thread=0, policy_seed=0):
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    from gym_roboy_b200.rollout import MlpPolicy, RolloutCollector
+    torch.manual_seed(policy_seed)
+    policy = MlpPolicy().to(DEV)
+    with torch.no_grad():
+        policy.log_std.copy_(torch.linspace(-1.0, 0.2, 8))     # distinct per-dimension std
+    client = CudaSimulationClient(num_envs=n, seed=seed, device=DEV, env_id_base=env_id_base)
+    env = RoboyEnv(client)
+    col = RolloutCollector(env, policy, n_steps=T, fused=fused, noise_seed=noise_seed, envs_per_thread=envs_per_thread)
+    return policy, client, col
+
+
+def numpy_noise(noise_seed, gids, t):
+    """Restatement of the kernel's noise: two Philox blocks (stream 4, sub 0 / 1) -> four Box-Muller pairs."""
+    z = []
+    for sub in (0, 1):
+        x = orc._block(noise_seed, gids, t, 4, sub)
+        for a, b in ((x[0], x[1]), (x[2], x[3])):
+            u1 = (a >> np.uint32(8)).astype(np.float64) * 2.0 ** -24 + 2.0 ** -25
+            u2 = (b >> np.uint32(8)).astype(np.float64) * 2.0 ** -24
+            r = np.sqrt(-2.0 * np.log(u1))
+            z += [r * np.cos(2 * np.pi * u2), r * np.sin(2 * np.pi * u2)]
+    return np.stack(z, axis=-1)
+
+
+@pytest.mark.parametrize("n,ept", [(4096, 0), (2531, 2), (40000, 0)])
+def test_fused_rollout_against_torch_policy_and_oracle_env(n, ept):
+    T, seed = 10, 21
+    policy, client, col = make(n, seed, T, envs_per_thread=ept)
+    col.noise = torch.zeros((T, n, 8), dtype=torch.float32, device=DEV)
+    client.set_step_num(torch.full((n,), 395, dtype=torch.int32))   # every env times out inside the rollout
+    ora = orc.OracleEnv(n, seed=seed)
+    ora.reset()
+    ora.step_flags[:] = (ora.step_flags & ~np.uint32(orc.STEP_MASK)) | np.uint32(395)
+    t0 = client.counter
+    obs0 = col.obs[0].clone()
+    col.collect()
+    torch.cuda.synchronize()
+    assert client.errors() == (0, None)
+    assert torch.equal(col.obs[0], col.obs[T])                      # handed over to the next rollout
+    std = policy.log_std.detach().exp()
+    lognorm = -0.5 * math.log(2 * math.pi) * 8 - float(policy.log_std.sum())
+    obs_t = obs0
+    with torch.no_grad():
+        for t in range(T):
+            mean, value = policy(obs_t)
+            assert torch.allclose(col.values[t], value, rtol=1e-5, atol=2e-5)
+            z = col.noise[t]
+            assert torch.allclose(col.actions[t], mean + std * z, rtol=1e-5, atol=2e-5)
+            assert torch.allclose(col.logp[t], lognorm - 0.5 * (z * z).sum(-1), rtol=1e-5, atol=1e-4)
+            want_z = numpy_noise(77, np.arange(n, dtype=np.uint64), t0 + 1 + t)
+            assert np.allclose(z.cpu().numpy(), want_z, rtol=0, atol=2e-4)
+            # the env saw the clipped action: replay it through the oracle
+            a = np.clip(col.actions[t].cpu().numpy(), -1.0, 1.0)
+            o, r, d = ora.step(a)
+            assert np.array_equal(col.obs[t + 1].cpu().numpy() if t + 1 < T else col.obs[T].cpu().numpy(), o)
+            assert np.array_equal(col.dones[t].cpu().numpy().astype(bool), d)
+            assert np.allclose(col.rewards[t].cpu().numpy(), r, rtol=1e-6, atol=0)
+            obs_t = col.obs[t + 1]
+        assert torch.allclose(col.values[T], policy(col.obs[T])[1], rtol=1e-5, atol=2e-5)
+    assert int(col.dones.sum()) >= n
+    s, so = client.stats(), ora.stats()
+    assert all(s[k] == so[k] for k in ("steps", "episodes", "successes", "timeouts", "holds", "violations")), (s, so)
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+    assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
+    assert client.counter == t0 + T == ora.counter
+    zz = col.noise.flatten().double()
+    assert abs(float(zz.mean())) < 5e-3 and abs(float(zz.var()) - 1.0) < 1e-2 and abs(float((zz ** 4).mean()) - 3.0) < 0.1
+
+
+def test_one_and_two_envs_per_thread_and_sharding_are_bit_identical():
+    n, T = 6000, 6
+    ref = None
+    for ept in (1, 2):
+        _, client, col = make(n, 5, T, envs_per_thread=ept)
+        col.collect()
+        torch.cuda.synchronize()
+        got = {k: getattr(col, k).clone() for k in ("obs", "actions", "logp", "values", "rewards", "dones", "adv", "ret")}
+        if ref is None:
+            ref = got
+        else:
+            for k in ref:
+                assert torch.equal(ref[k], got[k]), k
+    # two shards of the same population (global env ids 0..2999 and 3000..5999)
+    half = n // 2
+    for base in (0, half):
+        _, client, col = make(half, 5, T, env_id_base=base)
+        col.collect()
+        torch.cuda.synchronize()
+        for k in ("actions", "logp", "values", "rewards", "dones"):
+            assert torch.equal(getattr(col, k), ref[k][:, base:base + half]), k
+        assert torch.equal(col.obs[1:T], ref["obs"][1:T, base:base + half])
+
+
+def test_holds_and_nan_actions_inside_the_fused_kernel():
+    """A zero policy (mean 0, std tiny) makes every env take the Stub's hold branch; a NaN weight trips the
+    action assert (roboy_env.py:52) exactly as T un-fused steps would."""
+    n, T = 1024, 4
+    policy, client, col = make(n, 9, T)
+    with torch.no_grad():
+        for p_ in policy.pi.parameters():
+            p_.zero_()
+        policy.log_std.fill_(-40.0)                                  # std = 4e-18: actions ~ 0 -> hold
+    ora = orc.OracleEnv(n, seed=9)
+    ora.reset()
+    col.collect()
+    torch.cuda.synchronize()
+    for t in range(T):
+        a = np.clip(col.actions[t].cpu().numpy(), -1, 1)
+        assert np.abs(a).max() < 1e-12
+        o, r, d = ora.step(a)
+        assert np.array_equal(col.obs[t + 1].cpu().numpy(), o) and np.array_equal(col.dones[t].cpu().numpy().astype(bool), d)
+        assert np.allclose(col.rewards[t].cpu().numpy(), r, rtol=1e-6, atol=0)
+    assert client.stats()["holds"] == n * T == ora.stats()["holds"]
+    with torch.no_grad():
+        policy.pi[4].bias[3] = float("nan")
+    col.collect()
+    torch.cuda.synchronize()
+    flags, first = client.errors()
+    from gym_roboy_b200 import _native
+    assert flags & _native.ERR_ACTION and first == 0
+    assert torch.isnan(col.actions[:, :, 3]).all()
+
+
+def test_fused_rollout_in_a_cuda_graph_and_against_the_unfused_collector():
+    n, T = 4096, 8
+    policy, client, col = make(n, 3, T)
+    sd = client.state_dict()
+    obs0 = col.obs[0].clone()
+    col.collect()
+    torch.cuda.synchronize()
+    eager = {k: getattr(col, k).clone() for k in ("obs", "actions", "logp", "values", "rewards", "dones", "adv", "ret")}
+    col.capture()
+    client.load_state_dict(sd)
+    col.obs[0].copy_(obs0)
+    col.collect()                                                   # graph replay
+    torch.cuda.synchronize()
+    for k, v in eager.items():
+        if k == "obs":
+            assert torch.equal(col.obs[1:], v[1:]), k
+        else:
+            assert torch.equal(getattr(col, k), v), k
+    # the un-fused collector on the same policy, fed the fused kernel's actions, yields the same env trajectory
+    client.load_state_dict(sd)
+    for t in range(T):
+        client.step_fused(torch.clamp(eager["actions"][t], -1, 1).contiguous())
+        assert torch.equal(client.obs, eager["obs"][t + 1]) and torch.equal(client.reward, eager["rewards"][t])
+        assert torch.equal(client.done_u8, eager["dones"][t])
