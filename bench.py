@@ -408,37 +408,49 @@ def run_b200_arm(args):
     if not args.no_sweep:
         from gym_roboy_b200.rollout import MlpPolicy, RolloutCollector
         rollout = []
-        for n in (4096, 262144):
-            for graph in (False, True):
-                torch.manual_seed(0)
-                b0, _ = shard_range(n * world, world, rank)
-                e, c = make(n, b0)
-                col = RolloutCollector(e, MlpPolicy().to(dev), n_steps=128)
-                if graph:
-                    col.capture()
-                for _ in range(2):
-                    col.collect()
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12   # nominal float32 FMA peak of one B200 at max clock, TFLOP/s
+        for n, mode in ((4096, "torch"), (4096, "torch+graph"), (4096, "fused"), (262144, "torch"), (262144, "torch+graph"),
+                        (262144, "fused"), (1048576, "fused")):
+            torch.manual_seed(0)
+            b0, _ = shard_range(n * world, world, rank)
+            e, c = make(n, b0)
+            fused = mode == "fused"
+            col = RolloutCollector(e, MlpPolicy().to(dev), n_steps=128, fused=fused)
+            if mode == "torch+graph":
+                col.capture()
+            for _ in range(2):
+                col.collect()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
                 torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                    torch.cuda.synchronize()
-                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                reps = 5
-                s_.record()
-                for _ in range(reps):
-                    col.collect()
-                e_.record()
-                torch.cuda.synchronize()
-                ms = s_.elapsed_time(e_) / reps
-                if world > 1:
-                    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-                    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-                    ms = float(tms.item())
-                rollout.append({"envs_per_gpu": n, "n_gpus": world, "n_steps": 128, "cuda_graph": graph, "ms_per_rollout": ms,
-                                "env_steps_per_s": n * world * 128 / (ms * 1e-3),
-                                "what": "MlpPolicy 9-64-64-8 (+value net) forward, Gaussian sample, device clip, fused env "
-                                        "step writing into [T,N] buffers, GAE kernel; policy replicated per GPU"})
-                del col, e, c
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            s_.record()
+            for _ in range(reps):
+                col.collect()
+            e_.record()
+            torch.cuda.synchronize()
+            ms = s_.elapsed_time(e_) / reps
+            if world > 1:
+                tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+                ms = float(tms.item())
+            row = {"envs_per_gpu": n, "n_gpus": world, "n_steps": 128, "mode": mode, "cuda_graph": mode == "torch+graph",
+                   "ms_per_rollout": ms, "env_steps_per_s": n * world * 128 / (ms * 1e-3)}
+            if fused:
+                # 2 networks x (9*64 + 64*64 + 64*8) FMA per env-step (the value head is padded to 8 columns)
+                tflops = 2 * 2 * (9 * 64 + 64 * 64 + 64 * 8) * n * 128 / (ms * 1e-3) / 1e12
+                row.update({"what": "roboy_policy_rollout: both MlpPolicy networks (float32 FFMA2), Philox Gaussian sample, clip "
+                                    "and env step for all 128 steps in ONE launch, state in registers; + GAE kernel",
+                            "bound": "fp32 FMA", "tflops_fp32": tflops, "frac_of_nominal_fp32_peak": tflops / fp32_peak,
+                            "nominal_fp32_peak_tflops": fp32_peak})
+            else:
+                row["what"] = ("torch MlpPolicy 9-64-64-8 (+value net) forward, Gaussian sample, device clip, fused env "
+                               "step writing into [T,N] buffers, GAE kernel; policy replicated per GPU")
+            rollout.append(row)
+            del col, e, c
+            torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

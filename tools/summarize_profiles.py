@@ -23,6 +23,7 @@ sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active sm__inst_executed_pi
 sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
 sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active lts__t_sector_hit_rate.pct
 lts__throughput.avg.pct_of_peak_sustained_elapsed l1tex__throughput.avg.pct_of_peak_sustained_elapsed
+sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed
 sm__throughput.avg.pct_of_peak_sustained_elapsed dram__sectors_read.sum dram__sectors_write.sum""".split()
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -48,7 +49,9 @@ def val(name):
 
 
 traffic = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
-json.dump({"envs": envs, "dram_bytes_per_launch": traffic, "dram_bytes_read": val("dram__bytes_read.sum"),
+STEP_KERNEL = "step_kernel" in kname   # traffic.json feeds bench.py's roofline of the env step kernel only
+if STEP_KERNEL:
+  json.dump({"envs": envs, "dram_bytes_per_launch": traffic, "dram_bytes_read": val("dram__bytes_read.sum"),
            "dram_bytes_write": val("dram__bytes_write.sum"), "algorithmic_bytes_per_launch": 93 * envs,
            "source": os.path.basename(rep), "kernel": kname}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
