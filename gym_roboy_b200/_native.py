@@ -21,6 +21,9 @@ POLICY_HIDDEN = 64
 POLICY_OFF_W1, POLICY_OFF_B1, POLICY_OFF_W2, POLICY_OFF_B2, POLICY_OFF_W3, POLICY_OFF_B3 = 0, 576, 640, 4736, 4800, 5312
 POLICY_NET_FLOATS = 5320
 POLICY_OFF_VF, POLICY_OFF_PI, POLICY_OFF_STD, POLICY_OFF_LOGNORM, POLICY_IMAGE_FLOATS = 0, 5320, 10640, 10648, 10652
+# ... and of the tensor-core variant's image (ROBOY_TC_*)
+TC_OFF_W1, TC_OFF_W2, TC_OFF_W3, TC_OFF_B1, TC_OFF_B2, TC_OFF_B3, TC_NET_FLOATS = 0, 1024, 5120, 6144, 6208, 6272, 6288
+TC_OFF_VF, TC_OFF_PI, TC_OFF_STD, TC_OFF_LOGNORM, TC_IMAGE_FLOATS = 0, 6288, 12576, 12584, 12588
 (BUF_GOAL, BUF_STEP_FLAGS, BUF_HELD, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_STATS, BUF_TERMINAL_OBS) = range(8)
 
 
@@ -78,6 +81,8 @@ SIGNATURES = {
     "roboy_reset_external": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "roboy_gae": (_int, [_u64, _u64, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]),
     "roboy_policy_rollout": (_int, [_vp, ctypes.c_uint32, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "roboy_policy_rollout_tc": (_int, [_vp, ctypes.c_uint32, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "roboy_policy_tc_geometry": (_int, [_vp, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     "roboy_policy_geometry": (_int, [_vp, _int, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
                                      ctypes.POINTER(_int)]),
     "roboy_launch_count": (_int, [_vp, ctypes.POINTER(_u64)]),

@@ -868,9 +868,9 @@ int roboy_gae(uint64_t T, uint64_t n, const float *reward_dev, const float *valu
     return ROBOY_OK;
 }
 
-int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uint64_t noise_seed, float *obs_dev,
-                         float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
-                         float *noise_dev, int envs_per_thread, void *stream) {
+static int policy_rollout_common(roboy_env *env, bool tensor_cores, uint32_t T, const float *image_dev, uint64_t noise_seed,
+                                 float *obs_dev, float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev,
+                                 uint8_t *done_dev, float *noise_dev, int envs_per_thread, void *stream) {
     if (check_env(env)) return ROBOY_E_ARG;
     if (!image_dev || !obs_dev || !actions_dev || !logp_dev || !values_dev || !reward_dev || !done_dev)
         return fail(ROBOY_E_ARG, "NULL device pointer");
@@ -894,9 +894,36 @@ int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uin
     q.values = values_dev;
     q.noise = noise_dev;
     q.noise_keys = make_philox_keys(noise_seed);
-    CUDA_TRY(launch_policy_rollout(p, q, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
-                                   env->fastdiv, env->sm_count, envs_per_thread, (cudaStream_t)stream));
+    if (tensor_cores)
+        CUDA_TRY(launch_policy_rollout_tc(p, q, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
+                                          env->fastdiv, env->sm_count, (cudaStream_t)stream));
+    else
+        CUDA_TRY(launch_policy_rollout(p, q, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
+                                       env->fastdiv, env->sm_count, envs_per_thread, (cudaStream_t)stream));
     env->launches++;
+    return ROBOY_OK;
+}
+
+int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uint64_t noise_seed, float *obs_dev,
+                         float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
+                         float *noise_dev, int envs_per_thread, void *stream) {
+    return policy_rollout_common(env, false, T, image_dev, noise_seed, obs_dev, actions_dev, logp_dev, values_dev, reward_dev,
+                                 done_dev, noise_dev, envs_per_thread, stream);
+}
+
+int roboy_policy_rollout_tc(roboy_env *env, uint32_t T, const float *tc_image_dev, uint64_t noise_seed, float *obs_dev,
+                            float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
+                            float *noise_dev, void *stream) {
+    return policy_rollout_common(env, true, T, tc_image_dev, noise_seed, obs_dev, actions_dev, logp_dev, values_dev, reward_dev,
+                                 done_dev, noise_dev, 0, stream);
+}
+
+int roboy_policy_tc_geometry(roboy_env *env, int *grid, int *block, int *smem_bytes) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    const PolicyGeom geo = policy_tc_geometry(env->cfg.n_envs, env->sm_count);
+    if (grid) *grid = geo.grid;
+    if (block) *block = geo.block;
+    if (smem_bytes) *smem_bytes = geo.smem;
     return ROBOY_OK;
 }
 

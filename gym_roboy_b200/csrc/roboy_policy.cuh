@@ -8,7 +8,9 @@
 
 namespace roboy {
 
-constexpr int kPolicyMaxBlock = 256;  // threads per CTA at most; one CTA per SM (shared memory bound)
+constexpr int kPolicyMaxBlock = 256;
+constexpr int kPolicyTcMaxBlock = 512;      // tensor-core variant: up to four 128-env tiles per CTA
+constexpr int kPolicyTcImagePad = 12608;     // ROBOY_TC_IMAGE_FLOATS rounded up to 128 bytes  // threads per CTA at most; one CTA per SM (shared memory bound)
 
 struct PolicyParams {
     const float *__restrict__ image;  // [ROBOY_POLICY_IMAGE_FLOATS] packed policy (include/roboy_b200.h)
@@ -32,5 +34,10 @@ PolicyGeom policy_geometry(uint64_t n_envs, int sm_count, int envs_per_thread);
 // p: as for launch_step_many (reward / done are [T][n]; p.actions and p.obs are not used)
 cudaError_t launch_policy_rollout(const StepParams &p, const PolicyParams &q, bool penalty, bool bonus, bool auto_reset,
                                   bool fastdiv, int sm_count, int envs_per_thread, cudaStream_t stream);
+
+// tensor-core (tcgen05, TF32) variant: q.image is the ROBOY_TC_* image
+PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count);
+cudaError_t launch_policy_rollout_tc(const StepParams &p, const PolicyParams &q, bool penalty, bool bonus, bool auto_reset,
+                                     bool fastdiv, int sm_count, cudaStream_t stream);
 
 }  // namespace roboy

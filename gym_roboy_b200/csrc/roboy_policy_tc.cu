@@ -1,0 +1,324 @@
+// sm_100a kernel of the closed-loop rollout with the policy's matrix products on the 5th-generation
+// tensor cores (tcgen05.mma, kind::tf32, accumulators in tensor memory).
+//
+// Same contract as policy_rollout_kernel (roboy_policy.cu): T steps of [MlpPolicy forward -> Gaussian
+// sample -> clip -> RoboyEnv.step] per env in ONE launch (train_parallel.py:28-35 is the loop it
+// replaces), env state in registers, env outputs bit-identical to T roboy_step calls on the stored
+// actions.  What differs is where the 10,368 multiply-adds per env-step of the two 9-64-64-{8,1} networks run:
+//
+//   * a CTA holds up to four TILES of 128 envs; thread i of a tile owns env i = row i of every matrix
+//     = lane i of the tile's 128 tensor-memory columns (64 for the activations A, 64 for the accumulator D);
+//   * per layer the tile's threads write their activation row into TMEM (tcgen05.st), one thread issues
+//     K/8 tcgen05.mma (M = 128 envs, N = 64 / 16 outputs, K = 8 per instruction; A from TMEM, the weight
+//     matrix B from shared memory in the canonical K-major core-matrix layout, no swizzle) and commits
+//     them to the tile's mbarrier; every thread then reads its row of D back (tcgen05.ld), adds the
+//     bias, applies tanh (MUFU.TANH) and writes the next layer's A;
+//   * four tiles per SM overlap one tile's MMA round trips with the others' activation math.  The
+//     kernel is bound by the MUFU unit (256 tanh per env-step), not by the tensor pipe or HBM.
+//
+// Arithmetic: operands rounded to TF32 (10-bit mantissa, round-to-nearest), float32 accumulation,
+// tanh.approx.f32: action means and values agree with the float32 policy to ~1e-3 -- the float32 FFMA2
+// kernel (roboy_policy_rollout) stays the exact path.  Tensor cores are used HERE because this IS a
+// dense contraction; the env step itself has none and stays off them.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/roboy_b200.h"
+#include "policy_common.cuh"
+#include "roboy_kernels.cuh"
+#include "roboy_policy.cuh"
+
+namespace roboy {
+
+namespace {
+
+constexpr int kTileEnvs = 128;      // rows of one MMA = TMEM lanes
+constexpr int kTileCols = 128;      // TMEM columns per tile: A [0,64), D [64,128)
+constexpr int kColA = 0, kColD = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_NONE: 8-row x 16-byte core matrices; LBO = byte
+// distance between the two core matrices one MMA reads along K, SBO = between 8-row groups.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+// Instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileEnvs >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void mma_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+            : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a lost arrive must not hang the GPU
+    }
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr) : "memory");
+}
+
+// tcgen05.wait::ld; the loaded registers are threaded through as operands so that no use of them can be
+// scheduled ahead of the wait.
+__device__ __forceinline__ void tmem_ld_wait16(float (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                   "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :: "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :: "r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+           "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct TileCtx {
+    uint32_t tmem_a, tmem_d;   // this warp's view: lane quadrant in bits 31..16, column in bits 15..0
+    uint32_t mma_a, mma_d;     // the issuing thread's view: lane 0
+    uint32_t mbar;             // shared-memory address of the tile's mbarrier
+    uint32_t parity;
+    int bar_id;                // named barrier of the tile's 128 threads
+    bool issuer;
+};
+
+// One layer's matrix product for the tile: D[128][N] = A[128][K] * W[N][K]^T.  Every thread has written
+// its row of A; on return D is readable.
+template <int K, int N>
+__device__ __forceinline__ void tile_gemm(TileCtx &c, uint32_t w_saddr) {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync %0, 128;" :: "r"(c.bar_id) : "memory");
+    if (c.issuer) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < K / 8; ++i)   // one MMA consumes K = 8 (two 16-byte core-matrix columns = 256 B of W)
+            mma_tf32_ts(c.mma_d, c.mma_a + i * 8, smem_desc(w_saddr + i * 256, 128, K * 32), idesc_tf32(N), i > 0);
+        mma_commit(c.mbar);
+    }
+    mbar_wait(c.mbar, c.parity);
+    c.parity ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// A[:, 0..63] = tanh(D[:, 0..63] + b), rounded to TF32.
+__device__ __forceinline__ void tile_activation(const TileCtx &c, const float *__restrict__ bias) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        float v[16];
+        tmem_ld16(c.tmem_d + ch * 16, v);
+        tmem_ld_wait16(v);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            const float4 b = *reinterpret_cast<const float4 *>(bias + ch * 16 + i);
+            v[i] = to_tf32(tanh_approx(__fadd_rn(v[i], b.x)));
+            v[i + 1] = to_tf32(tanh_approx(__fadd_rn(v[i + 1], b.y)));
+            v[i + 2] = to_tf32(tanh_approx(__fadd_rn(v[i + 2], b.z)));
+            v[i + 3] = to_tf32(tanh_approx(__fadd_rn(v[i + 3], b.w)));
+        }
+        tmem_st16(c.tmem_a + ch * 16, v);
+    }
+}
+
+// One network: obs (9) -> 64 -> 64 -> out (first 8 of the 16 padded output columns).
+__device__ __forceinline__ void tile_mlp(TileCtx &c, const float *__restrict__ net, const float (&o)[kObsDim], float (&out)[8]) {
+    {
+        float a[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = k < kObsDim ? to_tf32(o[k]) : 0.0f;
+        tmem_st16(c.tmem_a, a);
+    }
+    tile_gemm<16, 64>(c, smem_u32(net + ROBOY_TC_OFF_W1));
+    tile_activation(c, net + ROBOY_TC_OFF_B1);
+    tile_gemm<64, 64>(c, smem_u32(net + ROBOY_TC_OFF_W2));
+    tile_activation(c, net + ROBOY_TC_OFF_B2);
+    tile_gemm<64, 16>(c, smem_u32(net + ROBOY_TC_OFF_W3));
+    float v[16];
+    tmem_ld16(c.tmem_d, v);
+    tmem_ld_wait16(v);
+    const float4 b0 = *reinterpret_cast<const float4 *>(net + ROBOY_TC_OFF_B3);
+    const float4 b1 = *reinterpret_cast<const float4 *>(net + ROBOY_TC_OFF_B3 + 4);
+    out[0] = __fadd_rn(v[0], b0.x); out[1] = __fadd_rn(v[1], b0.y); out[2] = __fadd_rn(v[2], b0.z); out[3] = __fadd_rn(v[3], b0.w);
+    out[4] = __fadd_rn(v[4], b1.x); out[5] = __fadd_rn(v[5], b1.y); out[6] = __fadd_rn(v[6], b1.z); out[7] = __fadd_rn(v[7], b1.w);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kPolicyTcMaxBlock, 1) policy_rollout_tc_kernel(const __grid_constant__ StepParams p,
+                                                                                  const __grid_constant__ PolicyParams q) {
+    extern __shared__ __align__(128) float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_warps = blockDim.x >> 5;
+    const int tile = warp >> 2, n_tiles = n_warps >> 2;
+    const int row_in_tile = (warp & 3) * 32 + lane;
+    // shared memory: policy image (weights in UMMA layout) | obs stage [32][9] per warp | mbarriers | TMEM base | counters
+    float *img = smem;
+    float *stage = smem + kPolicyTcImagePad + warp * (32 * kObsDim);
+    uint64_t *mbars = reinterpret_cast<uint64_t *>(smem + kPolicyTcImagePad + n_warps * (32 * kObsDim));
+    double *s_red = reinterpret_cast<double *>(mbars + 4);
+    unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_red + n_warps);
+    uint32_t *tmem_base_slot = s_cnt + 6;
+    for (int i = threadIdx.x; i < ROBOY_TC_IMAGE_FLOATS / 4; i += blockDim.x)
+        reinterpret_cast<float4 *>(img)[i] = reinterpret_cast<const float4 *>(q.image)[i];
+    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < n_tiles; ++t)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbars + t)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t tmem_cols = n_tiles <= 1 ? 128u : n_tiles == 2 ? 256u : 512u;   // a power of two >= 32
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_base_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // the weights were written through the generic proxy; the tensor core reads them through the async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_base_slot);
+
+    TileCtx c;
+    c.mma_a = tmem_base + tile * kTileCols + kColA;
+    c.mma_d = tmem_base + tile * kTileCols + kColD;
+    c.tmem_a = c.mma_a + ((uint32_t)((warp & 3) * 32) << 16);
+    c.tmem_d = c.mma_d + ((uint32_t)((warp & 3) * 32) << 16);
+    c.mbar = smem_u32(mbars + tile);
+    c.parity = 0;
+    c.bar_id = 1 + tile;
+    c.issuer = row_in_tile == 0;
+
+    const bool FASTDIV = q.fastdiv;
+    const uint64_t t_first = counter_begin(p.cc);
+    const uint32_t n_end = (uint32_t)p.e_end;
+    const size_t n = (size_t)p.n;
+    const uint32_t n_chunks = (n_end + kTileEnvs - 1) / kTileEnvs;
+    const float *vf_net = img + ROBOY_TC_OFF_VF, *pi_net = img + ROBOY_TC_OFF_PI;
+    float sum_reward = 0.0f;
+
+    // all threads of a tile walk the same chunks (the tile's named barrier needs every one of them)
+    for (uint32_t chunk = blockIdx.x * n_tiles + tile; chunk < n_chunks; chunk += gridDim.x * n_tiles) {
+        const uint32_t env = chunk * kTileEnvs + row_in_tile;
+        const uint32_t wbase = chunk * kTileEnvs + (warp & 3) * 32;   // first env of this warp's 32 rows
+        const bool live = env < n_end;
+        const bool full = wbase + 32 <= n_end;
+        EnvRegs s;
+        s.g0 = live ? p.goal[env] : 0.f;
+        s.g1 = live ? p.goal1[env] : 0.f;
+        s.g2 = live ? p.goal2[env] : 0.f;
+        s.sf = live ? p.step_flags[env] : 1u;
+        if (FASTDIV) normalize_goal<true>(s, p.c, p.f);
+        else normalize_goal<false>(s, p.c, p.f);
+        float o[kObsDim];
+#pragma unroll
+        for (int k = 0; k < kObsDim; ++k) o[k] = live ? q.obs[(size_t)env * kObsDim + k] : 0.f;
+        float *row = stage + lane * kObsDim;
+
+        for (uint32_t tt = 0;; ++tt) {
+            float out[8];
+            tile_mlp(c, vf_net, o, out);                       // value of obs[tt] (bootstrap value at tt == T)
+            if (live) q.values[(size_t)tt * n + env] = out[0];
+            if (tt == q.T) break;
+            tile_mlp(c, pi_net, o, out);                       // mean of the Gaussian
+            sample_and_step(p, q, img + ROBOY_TC_OFF_STD, img[ROBOY_TC_OFF_LOGNORM], out, s, live, env, tt, t_first + tt, row,
+                            s_cnt, sum_reward);
+#pragma unroll
+            for (int k = 0; k < kObsDim; ++k) o[k] = row[k];   // (finish_episode may have replaced the row)
+            // ---- obs[tt + 1]: this warp's 32 rows, stored coalesced ----
+            __syncwarp();
+            float *dst = q.obs + ((size_t)(tt + 1) * n + wbase) * kObsDim;
+            if (full && q.obs_aligned) {
+                const float4 *src = reinterpret_cast<const float4 *>(stage);
+                reinterpret_cast<float4 *>(dst)[lane] = src[lane];
+                reinterpret_cast<float4 *>(dst)[32 + lane] = src[32 + lane];
+                if (lane < 8) reinterpret_cast<float4 *>(dst)[64 + lane] = src[64 + lane];
+            } else if (wbase < n_end) {
+                const uint32_t rows = full ? 32u : n_end - wbase;
+                for (uint32_t i = lane; i < rows * kObsDim; i += 32) dst[i] = stage[i];
+            }
+            __syncwarp();
+        }
+        if (live) p.step_flags[env] = s.sf;
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    policy_stats_tail(p, q.T, t_first, sum_reward, s_red, s_cnt);   // contains a __syncthreads()
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count) {
+    PolicyGeom g;
+    g.envs_per_thread = 1;
+    const uint64_t n_chunks = (n_envs + kTileEnvs - 1) / kTileEnvs;
+    uint64_t tiles = (n_chunks + sm_count - 1) / sm_count;   // spread the tiles over the SMs first
+    if (tiles > kPolicyTcMaxBlock / kTileEnvs) tiles = kPolicyTcMaxBlock / kTileEnvs;
+    if (tiles == 3) tiles = 4;
+    const uint64_t grid = (n_chunks + tiles - 1) / tiles;
+    g.grid = (int)(grid < (uint64_t)sm_count ? grid : (uint64_t)sm_count);
+    g.block = (int)tiles * kTileEnvs;
+    const uint64_t warps = tiles * 4;
+    g.smem = (int)(sizeof(float) * (kPolicyTcImagePad + warps * 32 * kObsDim) + 4 * sizeof(uint64_t) + sizeof(double) * warps +
+                   sizeof(unsigned int) * 8);
+    return g;
+}
+
+cudaError_t launch_policy_rollout_tc(const StepParams &p, const PolicyParams &q, bool penalty, bool bonus, bool auto_reset,
+                                     bool fastdiv, int sm_count, cudaStream_t stream) {
+    if (p.e_end <= p.e_begin) return cudaSuccess;
+    PolicyParams qq = q;
+    qq.penalty = penalty;
+    qq.bonus = bonus;
+    qq.auto_reset = auto_reset;
+    qq.fastdiv = fastdiv;
+    const PolicyGeom g = policy_tc_geometry(p.e_end, sm_count);
+    cudaError_t err = cudaFuncSetAttribute(policy_rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem);
+    if (err != cudaSuccess) return err;
+    policy_rollout_tc_kernel<<<g.grid, g.block, g.smem, stream>>>(p, qq);
+    return cudaGetLastError();
+}
+
+}  // namespace roboy

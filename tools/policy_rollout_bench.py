@@ -1,12 +1,16 @@
-import sys, time, torch
-sys.path.insert(0, '.')
+# closed-loop rollout micro-bench: fused float32 and tensor-core (TF32) kernels at several sizes
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gym_roboy_b200.envs import RoboyEnv
 from gym_roboy_b200.envs.simulations import CudaSimulationClient
 from gym_roboy_b200.rollout import MlpPolicy, RolloutCollector
-for n, ept in ((4096, 0), (32768, 0), (262144, 0), (262144, 1), (1048576, 0)):
+cases = [(4096, "fp32"), (4096, "tf32"), (32768, "tf32"), (262144, "fp32"), (262144, "tf32"), (1048576, "fp32"), (1048576, "tf32")]
+if len(sys.argv) > 1:
+    cases = [(int(a.split(":")[0]), a.split(":")[1]) for a in sys.argv[1:]]
+for n, mode in cases:
     torch.manual_seed(0)
     c = CudaSimulationClient(num_envs=n, seed=1, device='cuda:0')
-    col = RolloutCollector(RoboyEnv(c), MlpPolicy().to('cuda:0'), n_steps=128, fused=True, envs_per_thread=ept)
+    col = RolloutCollector(RoboyEnv(c), MlpPolicy().to('cuda:0'), n_steps=128, fused=mode)
     for _ in range(2): col.collect()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -15,5 +19,5 @@ for n, ept in ((4096, 0), (32768, 0), (262144, 0), (262144, 1), (1048576, 0)):
     for _ in range(reps): col.collect()
     e.record(); torch.cuda.synchronize()
     ms = s.elapsed_time(e) / reps
-    print(n, ept, 'ms/rollout', ms, 'env-steps/s %.3e' % (n * 128 / ms * 1e3), 'GFLOP/s %.1f' % (n*128*20736/ms*1e3/1e9), flush=True)
+    print(n, mode, 'ms/rollout %.3f' % ms, 'env-steps/s %.3e' % (n * 128 / ms * 1e3), 'TFLOP/s %.1f' % (n*128*20736/ms*1e3/1e12), flush=True)
     del col, c
