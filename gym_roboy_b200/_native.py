@@ -21,9 +21,10 @@ POLICY_HIDDEN = 64
 POLICY_OFF_W1, POLICY_OFF_B1, POLICY_OFF_W2, POLICY_OFF_B2, POLICY_OFF_W3, POLICY_OFF_B3 = 0, 576, 640, 4736, 4800, 5312
 POLICY_NET_FLOATS = 5320
 POLICY_OFF_VF, POLICY_OFF_PI, POLICY_OFF_STD, POLICY_OFF_LOGNORM, POLICY_IMAGE_FLOATS = 0, 5320, 10640, 10648, 10652
-# ... and of the tensor-core variant's image (ROBOY_TC_*)
-TC_OFF_W1, TC_OFF_W2, TC_OFF_W3, TC_OFF_B1, TC_OFF_B2, TC_OFF_B3, TC_NET_FLOATS = 0, 1024, 5120, 6144, 6208, 6272, 6288
-TC_OFF_VF, TC_OFF_PI, TC_OFF_STD, TC_OFF_LOGNORM, TC_IMAGE_FLOATS = 0, 6288, 12576, 12584, 12588
+# ... and of the tensor-core variant's image (ROBOY_TC_*): float16 element offsets, then byte offsets
+TC_K_HIDDEN = 80
+TC_OFF_W1, TC_OFF_W2, TC_OFF_W3, TC_NET_HALVES, TC_OFF_VF, TC_OFF_PI = 0, 1024, 6144, 7424, 0, 7424
+TC_OFF_STD_BYTES, TC_IMAGE_BYTES = 29696, 29744
 (BUF_GOAL, BUF_STEP_FLAGS, BUF_HELD, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_STATS, BUF_TERMINAL_OBS) = range(8)
 
 

@@ -1,5 +1,5 @@
 // sm_100a kernel of the closed-loop rollout with the policy's matrix products on the 5th-generation
-// tensor cores (tcgen05.mma, kind::tf32, accumulators in tensor memory).
+// tensor cores (tcgen05.mma, kind::f16, float32 accumulators in tensor memory).
 //
 // Same contract as policy_rollout_kernel (roboy_policy.cu): T steps of [MlpPolicy forward -> Gaussian
 // sample -> clip -> RoboyEnv.step] per env in ONE launch (train_parallel.py:28-35 is the loop it
@@ -7,19 +7,22 @@
 // actions.  What differs is where the 10,368 multiply-adds per env-step of the two 9-64-64-{8,1} networks run:
 //
 //   * a CTA holds up to four TILES of 128 envs; thread i of a tile owns env i = row i of every matrix
-//     = lane i of the tile's 128 tensor-memory columns (64 for the activations A, 64 for the accumulator D);
+//     = lane i of the tile's 128 tensor-memory columns (40 for the activations A, packed two float16
+//     per column, 64 for the float32 accumulator D);
 //   * per layer the tile's threads write their activation row into TMEM (tcgen05.st), one thread issues
-//     K/8 tcgen05.mma (M = 128 envs, N = 64 / 16 outputs, K = 8 per instruction; A from TMEM, the weight
+//     K/16 tcgen05.mma (M = 128 envs, N = 64 / 16 outputs, K = 16 per instruction; A from TMEM, the weight
 //     matrix B from shared memory in the canonical K-major core-matrix layout, no swizzle) and commits
-//     them to the tile's mbarrier; every thread then reads its row of D back (tcgen05.ld), adds the
-//     bias, applies tanh (MUFU.TANH) and writes the next layer's A;
-//   * four tiles per SM overlap one tile's MMA round trips with the others' activation math.  The
-//     kernel is bound by the MUFU unit (256 tanh per env-step), not by the tensor pipe or HBM.
+//     them to the tile's mbarrier; every thread then reads its row of D back (tcgen05.ld) and applies
+//     tanh two at a time (cvt.rn.f16x2 + tanh.approx.f16x2: one MUFU op per two activations) -- the
+//     packed result IS the next layer's A.  Biases ride in the product: A carries a constant 1 in an
+//     extra K column and W the bias in the matching column, so the activation math is two
+//     instructions per two outputs;
+//   * four tiles per SM overlap one tile's MMA round trips with the others' activation math.
 //
-// Arithmetic: operands rounded to TF32 (10-bit mantissa, round-to-nearest), float32 accumulation,
-// tanh.approx.f32: action means and values agree with the float32 policy to ~1e-3 -- the float32 FFMA2
-// kernel (roboy_policy_rollout) stays the exact path.  Tensor cores are used HERE because this IS a
-// dense contraction; the env step itself has none and stays off them.
+// Arithmetic: float16 operands (10-bit mantissa, the precision of TF32; every operand here is far inside
+// float16's range), float32 accumulation, tanh.approx: action means and values agree with the float32
+// policy to ~1e-3 -- the float32 FFMA2 kernel (roboy_policy_rollout) stays the exact path.  Tensor cores
+// are used HERE because this IS a dense contraction; the env step itself has none and stays off them.
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -33,8 +36,9 @@ namespace roboy {
 namespace {
 
 constexpr int kTileEnvs = 128;      // rows of one MMA = TMEM lanes
-constexpr int kTileCols = 128;      // TMEM columns per tile: A [0,64), D [64,128)
-constexpr int kColA = 0, kColD = 64;
+constexpr int kTileCols = 128;      // TMEM columns per tile: A [0,40) (80 float16: 64 activations, 1, 15 zeros), D [64,128)
+constexpr int kColA = 0, kColOnes = 32, kColD = 64;
+constexpr int kKHid = ROBOY_TC_K_HIDDEN;  // 80: K of the 64-input layers including the bias column block
 
 __device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 
@@ -45,17 +49,17 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 
-// Instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major,
+// Instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (bits 7-9, 10-12 = 0), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24.
-__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileEnvs >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileEnvs >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
@@ -92,23 +96,25 @@ __device__ __forceinline__ void tmem_ld_wait16(float (&v)[16]) {
                  :: "memory");
 }
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        :: "r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
-           "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
-        : "memory");
+template <int N>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_st<8>(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
 }
 
-__device__ __forceinline__ float to_tf32(float x) {
+// two float32 -> packed float16 pair: `lo` in bits 15..0 (the lower K index), `hi` in bits 31..16
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 
-__device__ __forceinline__ float tanh_approx(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+__device__ __forceinline__ uint32_t tanh_f16x2(uint32_t x) {
+    uint32_t y;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
 
@@ -131,8 +137,8 @@ __device__ __forceinline__ void tile_gemm(TileCtx &c, uint32_t w_saddr) {
     if (c.issuer) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < K / 8; ++i)   // one MMA consumes K = 8 (two 16-byte core-matrix columns = 256 B of W)
-            mma_tf32_ts(c.mma_d, c.mma_a + i * 8, smem_desc(w_saddr + i * 256, 128, K * 32), idesc_tf32(N), i > 0);
+        for (int i = 0; i < K / 16; ++i)  // one MMA consumes K = 16: 8 TMEM columns of A, two 16-byte core-matrix columns (256 B) of W
+            mma_f16_ts(c.mma_d, c.mma_a + i * 8, smem_desc(w_saddr + i * 256, 128, K * 16), idesc_f16(N), i > 0);
         mma_commit(c.mbar);
     }
     mbar_wait(c.mbar, c.parity);
@@ -140,45 +146,38 @@ __device__ __forceinline__ void tile_gemm(TileCtx &c, uint32_t w_saddr) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-// A[:, 0..63] = tanh(D[:, 0..63] + b), rounded to TF32.
-__device__ __forceinline__ void tile_activation(const TileCtx &c, const float *__restrict__ bias) {
+// A[:, 0..63] = tanh(D[:, 0..63]) as float16 pairs (the bias is already in D).
+__device__ __forceinline__ void tile_activation(const TileCtx &c) {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
         float v[16];
         tmem_ld16(c.tmem_d + ch * 16, v);
         tmem_ld_wait16(v);
+        uint32_t h[8];
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-            const float4 b = *reinterpret_cast<const float4 *>(bias + ch * 16 + i);
-            v[i] = to_tf32(tanh_approx(__fadd_rn(v[i], b.x)));
-            v[i + 1] = to_tf32(tanh_approx(__fadd_rn(v[i + 1], b.y)));
-            v[i + 2] = to_tf32(tanh_approx(__fadd_rn(v[i + 2], b.z)));
-            v[i + 3] = to_tf32(tanh_approx(__fadd_rn(v[i + 3], b.w)));
-        }
-        tmem_st16(c.tmem_a + ch * 16, v);
+        for (int i = 0; i < 8; ++i) h[i] = tanh_f16x2(pack_f16x2(v[2 * i], v[2 * i + 1]));
+        tmem_st<8>(c.tmem_a + ch * 8, h);
     }
 }
 
-// One network: obs (9) -> 64 -> 64 -> out (first 8 of the 16 padded output columns).
-__device__ __forceinline__ void tile_mlp(TileCtx &c, const float *__restrict__ net, const float (&o)[kObsDim], float (&out)[8]) {
+// One network: obs (9) -> 64 -> 64 -> out (first 8 of the 16 padded output columns), biases included.
+__device__ __forceinline__ void tile_mlp(TileCtx &c, const uint16_t *__restrict__ net, const float (&o)[kObsDim], float (&out)[8]) {
     {
-        float a[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) a[k] = k < kObsDim ? to_tf32(o[k]) : 0.0f;
-        tmem_st16(c.tmem_a, a);
+        // K = 16 input block: obs[0..8], 1 (multiplies the bias column of W1), zeros
+        const uint32_t a[8] = {pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]), pack_f16x2(o[4], o[5]), pack_f16x2(o[6], o[7]),
+                               pack_f16x2(o[8], 1.0f), 0u, 0u, 0u};
+        tmem_st<8>(c.tmem_a, a);
     }
     tile_gemm<16, 64>(c, smem_u32(net + ROBOY_TC_OFF_W1));
-    tile_activation(c, net + ROBOY_TC_OFF_B1);
-    tile_gemm<64, 64>(c, smem_u32(net + ROBOY_TC_OFF_W2));
-    tile_activation(c, net + ROBOY_TC_OFF_B2);
-    tile_gemm<64, 16>(c, smem_u32(net + ROBOY_TC_OFF_W3));
+    tile_activation(c);
+    tile_gemm<kKHid, 64>(c, smem_u32(net + ROBOY_TC_OFF_W2));
+    tile_activation(c);
+    tile_gemm<kKHid, 16>(c, smem_u32(net + ROBOY_TC_OFF_W3));
     float v[16];
     tmem_ld16(c.tmem_d, v);
     tmem_ld_wait16(v);
-    const float4 b0 = *reinterpret_cast<const float4 *>(net + ROBOY_TC_OFF_B3);
-    const float4 b1 = *reinterpret_cast<const float4 *>(net + ROBOY_TC_OFF_B3 + 4);
-    out[0] = __fadd_rn(v[0], b0.x); out[1] = __fadd_rn(v[1], b0.y); out[2] = __fadd_rn(v[2], b0.z); out[3] = __fadd_rn(v[3], b0.w);
-    out[4] = __fadd_rn(v[4], b1.x); out[5] = __fadd_rn(v[5], b1.y); out[6] = __fadd_rn(v[6], b1.z); out[7] = __fadd_rn(v[7], b1.w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[k] = v[k];
 }
 
 }  // namespace
@@ -191,14 +190,16 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock, 1) policy_rollout_tc_kernel
     const int n_warps = blockDim.x >> 5;
     const int tile = warp >> 2, n_tiles = n_warps >> 2;
     const int row_in_tile = (warp & 3) * 32 + lane;
-    // shared memory: policy image (weights in UMMA layout) | obs stage [32][9] per warp | mbarriers | TMEM base | counters
+    // shared memory: policy image (float16 weights in UMMA layout, then std / lognorm as float32) | obs stage
+    // [32][9] per warp | mbarriers | TMEM base | counters
     float *img = smem;
+    const uint16_t *img16 = reinterpret_cast<const uint16_t *>(smem);
     float *stage = smem + kPolicyTcImagePad + warp * (32 * kObsDim);
     uint64_t *mbars = reinterpret_cast<uint64_t *>(smem + kPolicyTcImagePad + n_warps * (32 * kObsDim));
     double *s_red = reinterpret_cast<double *>(mbars + 4);
     unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_red + n_warps);
     uint32_t *tmem_base_slot = s_cnt + 6;
-    for (int i = threadIdx.x; i < ROBOY_TC_IMAGE_FLOATS / 4; i += blockDim.x)
+    for (int i = threadIdx.x; i < ROBOY_TC_IMAGE_BYTES / 16; i += blockDim.x)
         reinterpret_cast<float4 *>(img)[i] = reinterpret_cast<const float4 *>(q.image)[i];
     if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
@@ -234,7 +235,9 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock, 1) policy_rollout_tc_kernel
     const uint32_t n_end = (uint32_t)p.e_end;
     const size_t n = (size_t)p.n;
     const uint32_t n_chunks = (n_end + kTileEnvs - 1) / kTileEnvs;
-    const float *vf_net = img + ROBOY_TC_OFF_VF, *pi_net = img + ROBOY_TC_OFF_PI;
+    const uint16_t *vf_net = img16 + ROBOY_TC_OFF_VF, *pi_net = img16 + ROBOY_TC_OFF_PI;
+    const float *sd = img + ROBOY_TC_OFF_STD_BYTES / 4;
+    const float lognorm = sd[8];
     float sum_reward = 0.0f;
 
     // all threads of a tile walk the same chunks (the tile's named barrier needs every one of them)
@@ -254,6 +257,11 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock, 1) policy_rollout_tc_kernel
 #pragma unroll
         for (int k = 0; k < kObsDim; ++k) o[k] = live ? q.obs[(size_t)env * kObsDim + k] : 0.f;
         float *row = stage + lane * kObsDim;
+        {
+            // the constant K block behind the 64 activations: 1 (multiplies the bias column of W2 / W3), then zeros
+            const uint32_t ones[8] = {pack_f16x2(1.0f, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            tmem_st<8>(c.tmem_a + kColOnes, ones);
+        }
 
         for (uint32_t tt = 0;; ++tt) {
             float out[8];
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock, 1) policy_rollout_tc_kernel
             if (live) q.values[(size_t)tt * n + env] = out[0];
             if (tt == q.T) break;
             tile_mlp(c, pi_net, o, out);                       // mean of the Gaussian
-            sample_and_step(p, q, img + ROBOY_TC_OFF_STD, img[ROBOY_TC_OFF_LOGNORM], out, s, live, env, tt, t_first + tt, row,
+            sample_and_step(p, q, sd, lognorm, out, s, live, env, tt, t_first + tt, row,
                             s_cnt, sum_reward);
 #pragma unroll
             for (int k = 0; k < kObsDim; ++k) o[k] = row[k];   // (finish_episode may have replaced the row)

@@ -83,40 +83,34 @@ def pack_policy_image(policy, out=None):
     return img
 
 
-def _round_tf32(w):
-    """Round float32 to TF32 (10-bit mantissa), nearest with ties away from zero -- cvt.rna.tf32.f32."""
-    i = w.contiguous().view(torch.int32)
-    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
-
-
-def _umma_k_major(w, n_pad, k_pad):
-    """[out, in] weight -> zero-padded [n_pad, k_pad], TF32-rounded, in the tensor core's K-major core-matrix
-    layout without swizzle: float index of W[n][k] = (n//8)*(k_pad//4)*32 + (k//4)*32 + (n%8)*4 + (k%4)."""
+def _umma_k_major_f16(w, bias, n_pad, k_pad, bias_col):
+    """[out, in] weight (+ bias as input column `bias_col`) -> zero-padded float16 [n_pad, k_pad] in the tensor
+    core's K-major core-matrix layout without swizzle:
+    element index of W[n][k] = (n//8)*(k_pad//8)*64 + (k//8)*64 + (n%8)*8 + (k%8)."""
     full = torch.zeros((n_pad, k_pad), dtype=torch.float32, device=w.device)
-    full[: w.shape[0], : w.shape[1]] = _round_tf32(w.detach().float())
-    # [n/8, 8, k/4, 4] -> [n/8, k/4, 8, 4]
-    return full.view(n_pad // 8, 8, k_pad // 4, 4).permute(0, 2, 1, 3).reshape(-1)
+    full[: w.shape[0], : w.shape[1]] = w.detach().float()
+    full[: w.shape[0], bias_col] = bias.detach().float()
+    # [n/8, 8, k/8, 8] -> [n/8, k/8, 8, 8]
+    return full.to(torch.float16).view(n_pad // 8, 8, k_pad // 8, 8).permute(0, 2, 1, 3).reshape(-1)
 
 
 def pack_policy_image_tc(policy, out=None):
-    """Pack an `MlpPolicy` into the image `roboy_policy_rollout_tc` reads (layout: ROBOY_TC_* in include/roboy_b200.h)."""
+    """Pack an `MlpPolicy` into the byte image `roboy_policy_rollout_tc` reads (layout: ROBOY_TC_* in
+    include/roboy_b200.h): float16 weights with the biases as an extra input column, then std / lognorm as float32."""
     N = _native
     dev = policy.log_std.device
-    img = torch.zeros(N.TC_IMAGE_FLOATS, dtype=torch.float32, device=dev) if out is None else out
+    img = torch.zeros(N.TC_IMAGE_BYTES, dtype=torch.uint8, device=dev) if out is None else out
+    halves = img[: N.TC_OFF_STD_BYTES].view(torch.float16)
     for base, net in ((N.TC_OFF_VF, policy.vf), (N.TC_OFF_PI, policy.pi)):
         l1, l2, l3 = net[0], net[2], net[4]
         assert l1.weight.shape == (64, N.DIM_OBS) and l2.weight.shape == (64, 64) and l3.weight.shape[0] in (1, 8)
-        img[base + N.TC_OFF_W1: base + N.TC_OFF_W2].copy_(_umma_k_major(l1.weight, 64, 16))
-        img[base + N.TC_OFF_W2: base + N.TC_OFF_W3].copy_(_umma_k_major(l2.weight, 64, 64))
-        img[base + N.TC_OFF_W3: base + N.TC_OFF_B1].copy_(_umma_k_major(l3.weight, 16, 64))
-        img[base + N.TC_OFF_B1: base + N.TC_OFF_B2].copy_(l1.bias.detach())
-        img[base + N.TC_OFF_B2: base + N.TC_OFF_B3].copy_(l2.bias.detach())
-        b3 = img[base + N.TC_OFF_B3: base + N.TC_NET_FLOATS]
-        b3.zero_()
-        b3[: l3.bias.shape[0]].copy_(l3.bias.detach())
+        halves[base + N.TC_OFF_W1: base + N.TC_OFF_W2].copy_(_umma_k_major_f16(l1.weight, l1.bias, 64, 16, N.DIM_OBS))
+        halves[base + N.TC_OFF_W2: base + N.TC_OFF_W3].copy_(_umma_k_major_f16(l2.weight, l2.bias, 64, N.TC_K_HIDDEN, 64))
+        halves[base + N.TC_OFF_W3: base + N.TC_NET_HALVES].copy_(_umma_k_major_f16(l3.weight, l3.bias, 16, N.TC_K_HIDDEN, 64))
+    tail = img[N.TC_OFF_STD_BYTES: N.TC_IMAGE_BYTES].view(torch.float32)
     log_std = policy.log_std.detach()
-    img[N.TC_OFF_STD: N.TC_OFF_STD + 8].copy_(log_std.exp())
-    img[N.TC_OFF_LOGNORM] = -0.5 * math.log(2 * math.pi) * log_std.numel() - log_std.sum()
+    tail[:8].copy_(log_std.exp())
+    tail[8] = -0.5 * math.log(2 * math.pi) * log_std.numel() - log_std.sum()
     return img
 
 
@@ -126,16 +120,16 @@ class RolloutCollector:
     `actions` holds the UN-clipped Gaussian samples and `logp` their log-density (what PPO2's runner stores);
     the env is stepped with `clip(actions, -1, 1)`.  `fused=True` (or "fp32") runs policy + env for all T steps
     in one kernel launch (`roboy_policy_rollout`, float32 FFMA2 -- agrees with the torch policy to ~1e-6);
-    `fused="tf32"` does the same with the matrix products on the tensor cores (`roboy_policy_rollout_tc`,
-    tcgen05 TF32 -- agrees to ~1e-3, several times faster).  Fused, the Gaussian noise comes from Philox keyed by
+    `fused="tc"` does the same with the matrix products on the tensor cores (`roboy_policy_rollout_tc`,
+    tcgen05 with float16 operands and float32 accumulation -- agrees to ~1e-3, several times faster).  Fused, the Gaussian noise comes from Philox keyed by
     `noise_seed` instead of torch's generator."""
 
     def __init__(self, env, policy, n_steps=128, gamma=0.99, lam=0.95, fused=False, noise_seed=0, envs_per_thread=0):
         self.env, self.client, self.policy = env, env._simulation_client, policy
         self.T, self.N = int(n_steps), env.num_envs
         self.gamma, self.lam = gamma, lam
-        if fused not in (False, True, "fp32", "tf32"):
-            raise ValueError('fused must be False, True / "fp32", or "tf32"')
+        if fused not in (False, True, "fp32", "tc"):
+            raise ValueError('fused must be False, True / "fp32", or "tc"')
         self.fused = {True: "fp32", False: None}.get(fused, fused)
         self.noise_seed, self.envs_per_thread = int(noise_seed), int(envs_per_thread)
         dev, T, N = self.client.device, self.T, self.N
@@ -150,7 +144,11 @@ class RolloutCollector:
         self.ret = torch.zeros((T, N), **f32)
         self._graph = None
         self._clipped = torch.zeros((N, 8), **f32)
-        self._image = torch.zeros(max(_native.POLICY_IMAGE_FLOATS, _native.TC_IMAGE_FLOATS), **f32) if self.fused else None
+        self._image = None
+        if self.fused == "fp32":
+            self._image = torch.zeros(_native.POLICY_IMAGE_FLOATS, **f32)
+        elif self.fused == "tc":
+            self._image = torch.zeros(_native.TC_IMAGE_BYTES, dtype=torch.uint8, device=dev)
         self.noise = None   # tests: set to a [T, N, 8] float32 tensor to have the fused kernel record its noise
         self.obs[0].copy_(env.reset())
 
@@ -160,12 +158,12 @@ class RolloutCollector:
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         bufs = (p(self.obs), p(self.actions), p(self.logp), p(self.values), p(self.rewards), p(self.dones),
                 p(self.noise) if self.noise is not None else None)
-        if self.fused == "tf32":
-            pack_policy_image_tc(self.policy, out=self._image[: _native.TC_IMAGE_FLOATS])
+        if self.fused == "tc":
+            pack_policy_image_tc(self.policy, out=self._image)
             _native.check(_native.load().roboy_policy_rollout_tc(self.client._h, self.T, p(self._image), self.noise_seed,
                                                                  *bufs, stream))
         else:
-            pack_policy_image(self.policy, out=self._image[: _native.POLICY_IMAGE_FLOATS])
+            pack_policy_image(self.policy, out=self._image)
             _native.check(_native.load().roboy_policy_rollout(self.client._h, self.T, p(self._image), self.noise_seed,
                                                               *bufs, self.envs_per_thread, stream))
         gae(self.rewards, self.values[: self.T], self.dones, self.values[self.T], self.gamma, self.lam, self.adv, self.ret)

@@ -275,28 +275,28 @@ int roboy_gae(uint64_t T, uint64_t n, const float *reward_dev, const float *valu
 int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uint64_t noise_seed, float *obs_dev,
                          float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
                          float *noise_dev, int envs_per_thread, void *stream);
-/* The same rollout with the two networks' matrix products on the tensor cores (tcgen05.mma kind::tf32, M = 128
- * envs per tile, accumulators in tensor memory): operands rounded to TF32, float32 accumulation, tanh.approx --
- * action means and values agree with the float32 policy to ~1e-3 (roboy_policy_rollout is the exact path).  Env
- * outputs remain bit-identical to T roboy_step calls on clip(actions, -1, 1).
- * tc_image_dev: float32 [ROBOY_TC_IMAGE_FLOATS], 16-byte aligned.  One network is
- *   W1 [64][16] | W2 [64][64] | W3 [16][64] | b1 [64] | b2 [64] | b3 [16]
- * with each W = the torch Linear weight [out][in] (zero-padded: 9 -> 16 inputs, 8 or 1 -> 16 outputs), rounded to
- * TF32 and stored in the tensor core's K-major core-matrix layout without swizzle:
- *   float index of W[n][k] = (n / 8) * (K / 4) * 32 + (k / 4) * 32 + (n % 8) * 4 + (k % 4);
- * the image is  value net | policy net | std [8] | lognorm | 3 floats of padding. */
+/* The same rollout with the two networks' matrix products on the tensor cores (tcgen05.mma kind::f16, M = 128
+ * envs per tile, float32 accumulators in tensor memory): float16 operands (10-bit mantissa, as TF32), float32
+ * accumulation, tanh.approx -- action means and values agree with the float32 policy to ~1e-3
+ * (roboy_policy_rollout is the exact path).  Env outputs remain bit-identical to T roboy_step calls on
+ * clip(actions, -1, 1).
+ * tc_image_dev: ROBOY_TC_IMAGE_BYTES bytes, 16-byte aligned.  One network is, in float16 elements,
+ *   W1 [64][16] | W2 [64][80] | W3 [16][80]
+ * with each W = the torch Linear weight [out][in] zero-padded (9 -> 16 inputs, 64 -> 80 inputs, 8 or 1 -> 16
+ * outputs) and the BIAS stored as input column 9 (W1) / 64 (W2, W3) -- the kernel feeds a constant 1 there --
+ * in the tensor core's K-major core-matrix layout without swizzle:
+ *   element index of W[n][k] = (n / 8) * (K / 8) * 64 + (k / 8) * 64 + (n % 8) * 8 + (k % 8);
+ * the image is  value net | policy net (float16)  then, as float32 at byte ROBOY_TC_OFF_STD_BYTES,
+ * std [8] | lognorm | 3 floats of padding. */
+#define ROBOY_TC_K_HIDDEN 80
 #define ROBOY_TC_OFF_W1 0
 #define ROBOY_TC_OFF_W2 1024
-#define ROBOY_TC_OFF_W3 5120
-#define ROBOY_TC_OFF_B1 6144
-#define ROBOY_TC_OFF_B2 6208
-#define ROBOY_TC_OFF_B3 6272
-#define ROBOY_TC_NET_FLOATS 6288
+#define ROBOY_TC_OFF_W3 6144
+#define ROBOY_TC_NET_HALVES 7424
 #define ROBOY_TC_OFF_VF 0
-#define ROBOY_TC_OFF_PI 6288
-#define ROBOY_TC_OFF_STD 12576
-#define ROBOY_TC_OFF_LOGNORM 12584
-#define ROBOY_TC_IMAGE_FLOATS 12588
+#define ROBOY_TC_OFF_PI 7424
+#define ROBOY_TC_OFF_STD_BYTES 29696
+#define ROBOY_TC_IMAGE_BYTES 29744
 int roboy_policy_rollout_tc(roboy_env *env, uint32_t T, const float *tc_image_dev, uint64_t noise_seed, float *obs_dev,
                             float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
                             float *noise_dev, void *stream);

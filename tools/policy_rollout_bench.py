@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gym_roboy_b200.envs import RoboyEnv
 from gym_roboy_b200.envs.simulations import CudaSimulationClient
 from gym_roboy_b200.rollout import MlpPolicy, RolloutCollector
-cases = [(4096, "fp32"), (4096, "tf32"), (32768, "tf32"), (262144, "fp32"), (262144, "tf32"), (1048576, "fp32"), (1048576, "tf32")]
+cases = [(4096, "fp32"), (4096, "tc"), (32768, "tc"), (262144, "fp32"), (262144, "tc"), (1048576, "fp32"), (1048576, "tc")]
 if len(sys.argv) > 1:
     cases = [(int(a.split(":")[0]), a.split(":")[1]) for a in sys.argv[1:]]
 for n, mode in cases:

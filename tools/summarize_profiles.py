@@ -23,7 +23,7 @@ sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active sm__inst_executed_pi
 sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
 sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active lts__t_sector_hit_rate.pct
 lts__throughput.avg.pct_of_peak_sustained_elapsed l1tex__throughput.avg.pct_of_peak_sustained_elapsed
-sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed
+sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active sm__pipe_tensor_subunit_cycles_active.avg.pct_of_peak_sustained_active l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed
 sm__throughput.avg.pct_of_peak_sustained_elapsed dram__sectors_read.sum dram__sectors_write.sum""".split()
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
