@@ -13,10 +13,9 @@
 //     K/16 tcgen05.mma (M = 128 envs, N = 64 / 16 outputs, K = 16 per instruction; A from TMEM, the weight
 //     matrix B from shared memory in the canonical K-major core-matrix layout, no swizzle) and commits
 //     them to the tile's mbarrier; every thread then reads its row of D back (tcgen05.ld) and applies
-//     tanh two at a time (cvt.rn.f16x2 + tanh.approx.f16x2: one MUFU op per two activations) -- the
-//     packed result IS the next layer's A.  Biases ride in the product: A carries a constant 1 in an
-//     extra K column and W the bias in the matching column, so the activation math is two
-//     instructions per two outputs;
+//     tanh (MUFU.TANH) and packs two results into one float16 pair (F2FP) -- which IS the next layer's A.
+//     Biases ride in the product: A carries a constant 1 in an extra K column and W the bias in the
+//     matching column, so the activation math is three instructions per two outputs;
 //   * four tiles per SM overlap one tile's MMA round trips with the others' activation math.
 //
 // Arithmetic: float16 operands (10-bit mantissa, the precision of TF32; every operand here is far inside
@@ -112,9 +111,11 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     return r;
 }
 
-__device__ __forceinline__ uint32_t tanh_f16x2(uint32_t x) {
-    uint32_t y;
-    asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+// (tanh.approx.f16x2 is two MUFU.TANH.F16 plus a PRMT in SASS -- no cheaper than two float32 MUFU.TANH,
+// and it rounds the argument to float16 first)
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
@@ -155,7 +156,7 @@ __device__ __forceinline__ void tile_activation(const TileCtx &c) {
         tmem_ld_wait16(v);
         uint32_t h[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = tanh_f16x2(pack_f16x2(v[2 * i], v[2 * i + 1]));
+        for (int i = 0; i < 8; ++i) h[i] = pack_f16x2(tanh_approx(v[2 * i]), tanh_approx(v[2 * i + 1]));
         tmem_st<8>(c.tmem_a + ch * 8, h);
     }
 }
