@@ -409,13 +409,15 @@ def run_b200_arm(args):
         from gym_roboy_b200.rollout import MlpPolicy, RolloutCollector
         rollout = []
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12   # nominal float32 FMA peak of one B200 at max clock, TFLOP/s
-        for n, mode in ((4096, "torch"), (4096, "torch+graph"), (4096, "fused"), (262144, "torch"), (262144, "torch+graph"),
-                        (262144, "fused"), (1048576, "fused")):
+        mufu_peak = 148 * 16 * 1.965e9               # MUFU results per second of one B200 at max clock (16 lanes per SM)
+        for n, mode in ((4096, "torch"), (4096, "torch+graph"), (4096, "fused"), (4096, "fused_tc"), (262144, "torch"),
+                        (262144, "torch+graph"), (262144, "fused"), (262144, "fused_tc"), (1048576, "fused"),
+                        (1048576, "fused_tc")):
             torch.manual_seed(0)
             b0, _ = shard_range(n * world, world, rank)
             e, c = make(n, b0)
             fused = mode == "fused"
-            col = RolloutCollector(e, MlpPolicy().to(dev), n_steps=128, fused=fused)
+            col = RolloutCollector(e, MlpPolicy().to(dev), n_steps=128, fused={"fused": "fp32", "fused_tc": "tc"}.get(mode, False))
             if mode == "torch+graph":
                 col.capture()
             for _ in range(2):
@@ -445,6 +447,14 @@ def run_b200_arm(args):
                                     "and env step for all 128 steps in ONE launch, state in registers; + GAE kernel",
                             "bound": "fp32 FMA", "tflops_fp32": tflops, "frac_of_nominal_fp32_peak": tflops / fp32_peak,
                             "nominal_fp32_peak_tflops": fp32_peak})
+            elif mode == "fused_tc":
+                # the MUFU unit bounds this kernel: 256 tanh per env-step (+ ~27 for the Gaussian noise and the env's exp / sqrt)
+                row.update({"what": "roboy_policy_rollout_tc: as `fused`, with the matrix products on the tensor cores (tcgen05.mma "
+                                    "kind::f16, float32 accumulators in TMEM, four 128-env tiles per SM); agrees with the float32 "
+                                    "policy to ~1e-3; + GAE kernel",
+                            "bound": "MUFU (tanh)", "mufu_per_env_step": 283,
+                            "frac_of_nominal_mufu_peak": 283 * n * 128 / (ms * 1e-3) / mufu_peak,
+                            "hbm_GBps_written": 81 * n * 128 / (ms * 1e-3) / 1e9})
             else:
                 row["what"] = ("torch MlpPolicy 9-64-64-8 (+value net) forward, Gaussian sample, device clip, fused env "
                                "step writing into [T,N] buffers, GAE kernel; policy replicated per GPU")
