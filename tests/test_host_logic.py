@@ -111,3 +111,43 @@ def test_rescale_from_one_space_to_other():                      # test_roboy_en
     out = _rescale_from_one_space_to_other(np.zeros(8, np.float32), unit, msj)
     assert out.dtype == np.float32 and np.allclose(out, 0, atol=1e-8)
     assert _l2_distance(np.array([np.inf, 1.0, 0.0]), np.array([np.inf, 0.0, 0.0])) == 1.0   # inf - inf counts as 0
+
+
+def test_policy_image_layouts_match_the_header():
+    """The packed-policy layouts are ABI: _native's constants must equal the #defines of include/roboy_b200.h, and the
+    packers must put every weight where the kernels' index formulas (header comment) say."""
+    import os
+    import re
+    import torch
+    from gym_roboy_b200 import _native as N
+    from gym_roboy_b200.rollout import MlpPolicy, pack_policy_image, pack_policy_image_tc
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "roboy_b200.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define (ROBOY_(?:POLICY|TC)_\w+) (\d+)", hdr)}
+    for name, val in defs.items():
+        assert getattr(N, name[len("ROBOY_"):]) == val, name
+    torch.manual_seed(3)
+    pol = MlpPolicy()
+    img = pack_policy_image(pol)
+    assert img.numel() == N.POLICY_IMAGE_FLOATS
+    for base, net in ((N.POLICY_OFF_VF, pol.vf), (N.POLICY_OFF_PI, pol.pi)):
+        w1, w2, w3 = (net[i].weight.detach() for i in (0, 2, 4))
+        assert img[base + N.POLICY_OFF_W1 + 5 * 64 + 17] == w1[17, 5]                  # W1^T [9][64]
+        assert img[base + N.POLICY_OFF_W2 + 40 * 64 + 3] == w2[3, 40]                  # W2^T [64][64]
+        assert img[base + N.POLICY_OFF_W3 + 63 * 8 + 0] == w3[0, 63]                   # W3^T [64][8]
+        assert img[base + N.POLICY_OFF_B3] == net[4].bias[0]
+    assert torch.equal(img[N.POLICY_OFF_STD:N.POLICY_OFF_STD + 8], pol.log_std.detach().exp())
+    tc = pack_policy_image_tc(pol)
+    assert tc.numel() == N.TC_IMAGE_BYTES and tc.dtype == torch.uint8
+    halves = tc[:N.TC_OFF_STD_BYTES].view(torch.float16)
+
+    def at(base, off, K, n, k):
+        return halves[base + off + (n // 8) * (K // 8) * 64 + (k // 8) * 64 + (n % 8) * 8 + (k % 8)]
+    for base, net in ((N.TC_OFF_VF, pol.vf), (N.TC_OFF_PI, pol.pi)):
+        w1, w2, w3 = (net[i].weight.detach() for i in (0, 2, 4))
+        assert at(base, N.TC_OFF_W1, 16, 17, 5) == w1[17, 5].half() and at(base, N.TC_OFF_W1, 16, 17, 9) == net[0].bias[17].half()
+        assert at(base, N.TC_OFF_W1, 16, 17, 10) == 0
+        assert at(base, N.TC_OFF_W2, 80, 3, 40) == w2[3, 40].half() and at(base, N.TC_OFF_W2, 80, 3, 64) == net[2].bias[3].half()
+        assert at(base, N.TC_OFF_W3, 80, 0, 63) == w3[0, 63].half() and at(base, N.TC_OFF_W3, 80, 0, 64) == net[4].bias[0].half()
+        assert at(base, N.TC_OFF_W3, 80, 15, 63) == 0                                   # output rows padded to 16
+    tail = tc[N.TC_OFF_STD_BYTES:].view(torch.float32)
+    assert torch.equal(tail[:8], pol.log_std.detach().exp())
