@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from gym_roboy_b200.envs import RoboyEnv
 from gym_roboy_b200.envs.simulations import CudaSimulationClient
-from gym_roboy_b200.rollout import gae
+from gym_roboy_b200.rollout import MlpPolicy, RolloutCollector, gae
 rng = np.random.default_rng(0)
 for n in (1, 31, 33, 257, 1000):
     for penalty in (False, True):
@@ -27,4 +27,13 @@ for n in (1, 31, 33, 257, 1000):
         c.compute_reward(q, q * 0.1, np.ones(n, np.uint8), q, None)
         gae(torch.zeros((4, n), device="cuda:0"), torch.zeros((4, n), device="cuda:0"), torch.zeros((4, n), dtype=torch.uint8, device="cuda:0"), torch.zeros(n, device="cuda:0"))
         torch.cuda.synchronize(); c.stats(); c.errors(); c.close()
+# the fused policy rollout kernels (float32 with 1 and 2 envs per thread; tensor cores), ragged sizes
+for n in (1, 33, 257, 1000):
+    for mode, ept in (("fp32", 1), ("fp32", 2), ("tc", 0)):
+        c = CudaSimulationClient(num_envs=n, seed=3, device="cuda:0")
+        col = RolloutCollector(RoboyEnv(c), MlpPolicy().to("cuda:0"), n_steps=3, fused=mode, envs_per_thread=ept)
+        c.set_step_num(np.full(n, 399, np.int32))
+        col.noise = torch.zeros((3, n, 8), device="cuda:0")
+        col.collect(); col.collect()
+        torch.cuda.synchronize(); c.errors(); c.close()
 print("sanitize run ok")
