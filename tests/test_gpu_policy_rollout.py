@@ -192,3 +192,40 @@ def test_fused_rollout_in_a_cuda_graph_and_against_the_unfused_collector(mode):
         client.step_fused(torch.clamp(eager["actions"][t], -1, 1).contiguous())
         assert torch.equal(client.obs, eager["obs"][t + 1]) and torch.equal(client.reward, eager["rewards"][t])
         assert torch.equal(client.done_u8, eager["dones"][t])
+
+
+@pytest.mark.parametrize("mode,ept", [("fp32", 1), ("fp32", 2), ("tc", 0)])
+@pytest.mark.parametrize("n", [2, 33, 257, 1001, 2531])
+def test_ragged_sizes_write_nothing_outside_their_buffers(n, mode, ept):
+    """(compute-sanitizer is not available on the GPU pool.)  Every rollout buffer is carved out of one arena with
+    sentinel-filled guard bands on both sides; after two rollouts at ragged sizes the guards must be untouched and
+    every slot inside must have been written."""
+    T, guard = 3, 256
+    policy, client, col = make(n, 31, T, fused=mode, envs_per_thread=ept)
+    shapes = {"obs": (T + 1, n, 9), "actions": (T, n, 8), "logp": (T, n), "values": (T + 1, n), "rewards": (T, n),
+              "noise": (T, n, 8), "adv": (T, n), "ret": (T, n)}
+    sentinel = -12345.0
+    total = sum(guard + ((int(np.prod(s)) + 3) // 4) * 4 for s in shapes.values()) + guard
+    arena = torch.full((total,), sentinel, dtype=torch.float32, device=DEV)
+    off, spans = guard, {}
+    for k, shp in shapes.items():
+        cnt = int(np.prod(shp))
+        view = arena[off:off + cnt].view(shp)
+        if k == "obs":
+            view[0].copy_(col.obs[0])
+        setattr(col, k, view)
+        spans[k] = (off, cnt)
+        off += ((cnt + 3) // 4) * 4 + guard
+    dones_arena = torch.full((T * n + 2 * guard,), 0x5A, dtype=torch.uint8, device=DEV)
+    col.dones = dones_arena[guard:guard + T * n].view(T, n)
+    col.collect()
+    col.collect()
+    torch.cuda.synchronize()
+    inside = torch.zeros(total, dtype=torch.bool, device=DEV)
+    for k, (o, cnt) in spans.items():
+        inside[o:o + cnt] = True
+        assert not bool((arena[o:o + cnt] == sentinel).any()), k + " has unwritten slots"
+    assert bool((arena[~inside] == sentinel).all()), "a float buffer was written outside its bounds"
+    assert bool((dones_arena[:guard] == 0x5A).all()) and bool((dones_arena[guard + T * n:] == 0x5A).all())
+    assert bool((col.dones <= 1).all())
+    assert client.errors() == (0, None)
