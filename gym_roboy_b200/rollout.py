@@ -144,7 +144,7 @@ class RolloutCollector:
         self.ret = torch.zeros((T, N), **f32)
         self._graph = None
         self._clipped = torch.zeros((N, 8), **f32)
-        self._image = None
+        self._image, self._image_key = None, None
         if self.fused == "fp32":
             self._image = torch.zeros(_native.POLICY_IMAGE_FLOATS, **f32)
         elif self.fused == "tc":
@@ -158,12 +158,16 @@ class RolloutCollector:
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         bufs = (p(self.obs), p(self.actions), p(self.logp), p(self.values), p(self.rewards), p(self.dones),
                 p(self.noise) if self.noise is not None else None)
+        # re-pack the weights only when a parameter changed (in-place updates bump torch's version counters);
+        # inside a CUDA-graph capture the packing is always recorded, so that replays pick up new weights
+        key = tuple((q.data_ptr(), q._version) for q in self.policy.parameters())
+        if key != self._image_key or torch.cuda.is_current_stream_capturing():
+            (pack_policy_image_tc if self.fused == "tc" else pack_policy_image)(self.policy, out=self._image)
+            self._image_key = None if torch.cuda.is_current_stream_capturing() else key
         if self.fused == "tc":
-            pack_policy_image_tc(self.policy, out=self._image)
             _native.check(_native.load().roboy_policy_rollout_tc(self.client._h, self.T, p(self._image), self.noise_seed,
                                                                  *bufs, stream))
         else:
-            pack_policy_image(self.policy, out=self._image)
             _native.check(_native.load().roboy_policy_rollout(self.client._h, self.T, p(self._image), self.noise_seed,
                                                               *bufs, self.envs_per_thread, stream))
         gae(self.rewards, self.values[: self.T], self.dones, self.values[self.T], self.gamma, self.lam, self.adv, self.ret)
