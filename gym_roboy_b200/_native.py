@@ -82,8 +82,9 @@ SIGNATURES = {
     "roboy_reset_external": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "roboy_gae": (_int, [_u64, _u64, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]),
     "roboy_policy_rollout": (_int, [_vp, ctypes.c_uint32, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
-    "roboy_policy_rollout_tc": (_int, [_vp, ctypes.c_uint32, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "roboy_policy_tc_geometry": (_int, [_vp, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
+    "roboy_policy_rollout_tc": (_int, [_vp, ctypes.c_uint32, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "roboy_policy_tc_geometry": (_int, [_vp, _int, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
+                                        ctypes.POINTER(_int)]),
     "roboy_policy_geometry": (_int, [_vp, _int, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
                                      ctypes.POINTER(_int)]),
     "roboy_launch_count": (_int, [_vp, ctypes.POINTER(_u64)]),

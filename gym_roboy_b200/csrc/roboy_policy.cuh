@@ -36,8 +36,10 @@ cudaError_t launch_policy_rollout(const StepParams &p, const PolicyParams &q, bo
                                   bool fastdiv, int sm_count, int envs_per_thread, cudaStream_t stream);
 
 // tensor-core (tcgen05, TF32) variant: q.image is the ROBOY_TC_* image
-PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count);
+// tiles_per_group: 0 = choose; 1 = one 128-env tile per group of 128 threads; 2 = two tiles per group, ping-pong
+// (PolicyGeom::envs_per_thread returns the choice)
+PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count, int tiles_per_group);
 cudaError_t launch_policy_rollout_tc(const StepParams &p, const PolicyParams &q, bool penalty, bool bonus, bool auto_reset,
-                                     bool fastdiv, int sm_count, cudaStream_t stream);
+                                     bool fastdiv, int sm_count, int tiles_per_group, cudaStream_t stream);
 
 }  // namespace roboy

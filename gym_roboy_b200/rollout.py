@@ -166,7 +166,7 @@ class RolloutCollector:
             self._image_key = None if torch.cuda.is_current_stream_capturing() else key
         if self.fused == "tc":
             _native.check(_native.load().roboy_policy_rollout_tc(self.client._h, self.T, p(self._image), self.noise_seed,
-                                                                 *bufs, stream))
+                                                                 *bufs, self.envs_per_thread, stream))
         else:
             _native.check(_native.load().roboy_policy_rollout(self.client._h, self.T, p(self._image), self.noise_seed,
                                                               *bufs, self.envs_per_thread, stream))

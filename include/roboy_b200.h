@@ -287,7 +287,9 @@ int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uin
  * in the tensor core's K-major core-matrix layout without swizzle:
  *   element index of W[n][k] = (n / 8) * (K / 8) * 64 + (k / 8) * 64 + (n % 8) * 8 + (k % 8);
  * the image is  value net | policy net (float16)  then, as float32 at byte ROBOY_TC_OFF_STD_BYTES,
- * std [8] | lognorm | 3 floats of padding. */
+ * std [8] | lognorm | 3 floats of padding.
+ * tiles_per_group: 0 = default (1); 1 = each group of 128 threads owns one 128-env tile; 2 = two tiles per group, worked
+ * on alternately (an experiment: measured 35 % slower than 1 on B200; results are bit-identical). */
 #define ROBOY_TC_K_HIDDEN 80
 #define ROBOY_TC_OFF_W1 0
 #define ROBOY_TC_OFF_W2 1024
@@ -299,10 +301,10 @@ int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uin
 #define ROBOY_TC_IMAGE_BYTES 29744
 int roboy_policy_rollout_tc(roboy_env *env, uint32_t T, const float *tc_image_dev, uint64_t noise_seed, float *obs_dev,
                             float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
-                            float *noise_dev, void *stream);
+                            float *noise_dev, int tiles_per_group, void *stream);
 /* Launch geometry roboy_policy_rollout uses for this handle (bench.py / tests). */
 int roboy_policy_geometry(roboy_env *env, int envs_per_thread, int *grid, int *block, int *smem_bytes, int *ept);
-int roboy_policy_tc_geometry(roboy_env *env, int *grid, int *block, int *smem_bytes);
+int roboy_policy_tc_geometry(roboy_env *env, int tiles_per_group, int *grid, int *block, int *smem_bytes, int *tpg);
 
 /* Introspection for bench.py / tests: kernels launched by this handle so far, and the
  * launch geometry the step kernel uses for this n_envs. */
