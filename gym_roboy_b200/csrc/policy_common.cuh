@@ -15,6 +15,17 @@ namespace {
 
 constexpr uint32_t kFullMask = 0xffffffffu;
 
+__device__ __forceinline__ float tanh_mufu(float x) {
+    // tanh x = 1 - 2 / (e^{2x} + 1); ex2.approx and rcp.approx are accurate to ~1 ulp, so the
+    // absolute error is a few 1e-7 everywhere (the cancellation near 0 costs relative, not absolute,
+    // accuracy).  e = inf gives 1, e = 0 gives -1, NaN propagates.
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(x, 2.885390081777927f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(e, 1.0f)));
+    return fmaf(-2.0f, r, 1.0f);
+}
+
+
 // Two standard normals from two 32-bit words (Box-Muller on the MUFU unit).
 __device__ __forceinline__ float2 box_muller(uint32_t x, uint32_t y) {
     const float u1 = fmaf(__uint2float_rn(x >> 8), 0x1p-24f, 0x1p-25f);  // (0, 1)

@@ -868,7 +868,7 @@ int roboy_gae(uint64_t T, uint64_t n, const float *reward_dev, const float *valu
     return ROBOY_OK;
 }
 
-static int policy_rollout_common(roboy_env *env, bool tensor_cores, uint32_t T, const float *image_dev, uint64_t noise_seed,
+static int policy_rollout_common(roboy_env *env, bool tensor_cores, bool exact, uint32_t T, const float *image_dev, uint64_t noise_seed,
                                  float *obs_dev, float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev,
                                  uint8_t *done_dev, float *noise_dev, int envs_per_thread, void *stream) {
     if (check_env(env)) return ROBOY_E_ARG;
@@ -896,7 +896,7 @@ static int policy_rollout_common(roboy_env *env, bool tensor_cores, uint32_t T, 
     q.noise_keys = make_philox_keys(noise_seed);
     if (tensor_cores)
         CUDA_TRY(launch_policy_rollout_tc(p, q, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
-                                          env->fastdiv, env->sm_count, envs_per_thread, (cudaStream_t)stream));
+                                          env->fastdiv, env->sm_count, envs_per_thread, exact, (cudaStream_t)stream));
     else
         CUDA_TRY(launch_policy_rollout(p, q, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
                                        env->fastdiv, env->sm_count, envs_per_thread, (cudaStream_t)stream));
@@ -907,20 +907,20 @@ static int policy_rollout_common(roboy_env *env, bool tensor_cores, uint32_t T, 
 int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uint64_t noise_seed, float *obs_dev,
                          float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
                          float *noise_dev, int envs_per_thread, void *stream) {
-    return policy_rollout_common(env, false, T, image_dev, noise_seed, obs_dev, actions_dev, logp_dev, values_dev, reward_dev,
+    return policy_rollout_common(env, false, true, T, image_dev, noise_seed, obs_dev, actions_dev, logp_dev, values_dev, reward_dev,
                                  done_dev, noise_dev, envs_per_thread, stream);
 }
 
 int roboy_policy_rollout_tc(roboy_env *env, uint32_t T, const float *tc_image_dev, uint64_t noise_seed, float *obs_dev,
                             float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
-                            float *noise_dev, int tiles_per_group, void *stream) {
-    return policy_rollout_common(env, true, T, tc_image_dev, noise_seed, obs_dev, actions_dev, logp_dev, values_dev, reward_dev,
+                            float *noise_dev, int tiles_per_group, int exact, void *stream) {
+    return policy_rollout_common(env, true, exact != 0, T, tc_image_dev, noise_seed, obs_dev, actions_dev, logp_dev, values_dev, reward_dev,
                                  done_dev, noise_dev, tiles_per_group, stream);
 }
 
-int roboy_policy_tc_geometry(roboy_env *env, int tiles_per_group, int *grid, int *block, int *smem_bytes, int *tpg) {
+int roboy_policy_tc_geometry(roboy_env *env, int tiles_per_group, int exact, int *grid, int *block, int *smem_bytes, int *tpg) {
     if (check_env(env)) return ROBOY_E_ARG;
-    const PolicyGeom geo = policy_tc_geometry(env->cfg.n_envs, env->sm_count, tiles_per_group);
+    const PolicyGeom geo = policy_tc_geometry(env->cfg.n_envs, env->sm_count, tiles_per_group, exact != 0);
     if (grid) *grid = geo.grid;
     if (block) *block = geo.block;
     if (smem_bytes) *smem_bytes = geo.smem;

@@ -38,16 +38,6 @@ namespace {
 
 constexpr int kHid = ROBOY_POLICY_HIDDEN;  // 64
 
-__device__ __forceinline__ float tanh_mufu(float x) {
-    // tanh x = 1 - 2 / (e^{2x} + 1); ex2.approx and rcp.approx are accurate to ~1 ulp, so the
-    // absolute error is a few 1e-7 everywhere (the cancellation near 0 costs relative, not absolute,
-    // accuracy).  e = inf gives 1, e = 0 gives -1, NaN propagates.
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(x, 2.885390081777927f)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(e, 1.0f)));
-    return fmaf(-2.0f, r, 1.0f);
-}
-
 // acc[e][j2] (outputs 2*j2, 2*j2+1 of env e) += sum_k x_e[k] * W[k][.]; W is [K][64] in shared memory
 // (every lane reads the same 16 bytes: a broadcast), x_e[k] sits at x[k * ks + e * es] (thread-private).
 template <int E>

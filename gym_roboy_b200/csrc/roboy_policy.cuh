@@ -10,7 +10,7 @@ namespace roboy {
 
 constexpr int kPolicyMaxBlock = 256;
 constexpr int kPolicyTcMaxBlock = 512;      // tensor-core variant: up to four 128-env tiles per CTA
-constexpr int kPolicyTcImagePad = 7456;      // ROBOY_TC_IMAGE_BYTES rounded up to 128 bytes, in floats  // threads per CTA at most; one CTA per SM (shared memory bound)
+constexpr int kPolicyTcImagePad = 14880;     // ROBOY_TC_IMAGE_BYTES rounded up to 128 bytes, in floats  // threads per CTA at most; one CTA per SM (shared memory bound)
 
 struct PolicyParams {
     const float *__restrict__ image;  // [ROBOY_POLICY_IMAGE_FLOATS] packed policy (include/roboy_b200.h)
@@ -38,8 +38,9 @@ cudaError_t launch_policy_rollout(const StepParams &p, const PolicyParams &q, bo
 // tensor-core (tcgen05, TF32) variant: q.image is the ROBOY_TC_* image
 // tiles_per_group: 0 = choose; 1 = one 128-env tile per group of 128 threads; 2 = two tiles per group, ping-pong
 // (PolicyGeom::envs_per_thread returns the choice)
-PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count, int tiles_per_group);
+// exact: split-float16 operands (float32-level accuracy) instead of single float16 operands
+PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count, int tiles_per_group, bool exact);
 cudaError_t launch_policy_rollout_tc(const StepParams &p, const PolicyParams &q, bool penalty, bool bonus, bool auto_reset,
-                                     bool fastdiv, int sm_count, int tiles_per_group, cudaStream_t stream);
+                                     bool fastdiv, int sm_count, int tiles_per_group, bool exact, cudaStream_t stream);
 
 }  // namespace roboy

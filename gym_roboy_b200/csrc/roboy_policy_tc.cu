@@ -37,8 +37,19 @@ namespace roboy {
 namespace {
 
 constexpr int kTileEnvs = 128;      // rows of one MMA = TMEM lanes
-constexpr int kTileCols = 128;      // TMEM columns per tile: A [0,40) (80 float16: 64 activations, 1, 15 zeros), input [40,48), D [64,128)
-constexpr int kColA = 0, kColOnes = 32, kColIn = 40, kColD = 64;   // A: activations | constant-1 block | input block
+// TMEM columns of one tile (float16 pairs for A, float32 for D):
+//   fast : activations [0,32) | constant-1 block [32,40) | input block [40,48) | D [64,128)                    -> 128 per tile
+//   exact: the same plus the LOW halves of the split operands, activations [40,72) and input [80,88); D [96,160) -> 160 per tile
+template <bool EXACT>
+struct Cols {
+    static constexpr int A = 0, Ones = 32;
+    static constexpr int ALo = 40;                       // exact only
+    static constexpr int In = EXACT ? 72 : 40;
+    static constexpr int InLo = 80;                      // exact only
+    static constexpr int D = EXACT ? 96 : 64;
+    static constexpr int Tile = EXACT ? 160 : 128;
+    static constexpr int MaxGroups = EXACT ? 3 : 4;      // 512 TMEM columns per SM
+};
 constexpr int kKHid = ROBOY_TC_K_HIDDEN;  // 80: K of the 64-input layers including the bias column block
 
 __device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
@@ -122,8 +133,8 @@ __device__ __forceinline__ float tanh_approx(float x) {
 }
 
 struct TileCtx {
-    uint32_t tmem_a, tmem_d;   // this warp's view: lane quadrant in bits 31..16, column in bits 15..0
-    uint32_t mma_a, mma_d;     // the issuing thread's view: lane 0
+    uint32_t tmem_a;           // first column of the tile as this warp addresses it: lane quadrant in bits 31..16
+    uint32_t mma_a, mma_d;     // first column of the tile / of its accumulator as the issuing thread addresses them (lane 0)
     uint32_t mbar;             // shared-memory address of the tile's mbarrier
     uint32_t parity;
     int bar_id;                // named barrier of the tile's 128 threads
@@ -133,16 +144,29 @@ struct TileCtx {
 // One layer's matrix product for a tile, D[128][N] = A[128][K] * W[N][K]^T, split in two so that the threads
 // can work on their other tile while it runs.  issue: every thread has written its row of A; the group's
 // threads meet, one of them issues the MMAs and commits them to the tile's mbarrier.  wait: D is readable.
-template <int K, int N>
-__device__ __forceinline__ void gemm_issue(const TileCtx &c, uint32_t a_col, uint32_t w_saddr) {
+// EXACT: every operand is split x = hi + lo with hi = float16(x), lo = float16(x - hi) (22 mantissa bits together), and
+// the product is accumulated as A_hi W_hi + A_hi W_lo + A_lo W_hi in float32 -- float32-level accuracy from float16 MMAs.
+// a_col / lo_col: first TMEM column of the (high / low) A block; K_LO: K of the low block (it has no constant-1 columns).
+template <int K, int K_LO, int N, bool EXACT>
+__device__ __forceinline__ void gemm_issue(const TileCtx &c, uint32_t a_col, uint32_t lo_col, uint32_t w_saddr) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("bar.sync %0, 128;" :: "r"(c.bar_id) : "memory");
     if (c.issuer) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // one MMA consumes K = 16: 8 TMEM columns of A, two 16-byte core-matrix columns (256 B) of W
 #pragma unroll
-        for (int i = 0; i < K / 16; ++i)  // one MMA consumes K = 16: 8 TMEM columns of A, two 16-byte core-matrix columns (256 B) of W
+        for (int i = 0; i < K / 16; ++i)
             mma_f16_ts(c.mma_d, c.mma_a + a_col + i * 8, smem_desc(w_saddr + i * 256, 128, K * 16), idesc_f16(N), i > 0);
+        if (EXACT) {
+#pragma unroll
+            for (int i = 0; i < K / 16; ++i)
+                mma_f16_ts(c.mma_d, c.mma_a + a_col + i * 8, smem_desc(w_saddr + ROBOY_TC_OFF_LO_BYTES + i * 256, 128, K * 16),
+                           idesc_f16(N), 1);
+#pragma unroll
+            for (int i = 0; i < K_LO / 16; ++i)
+                mma_f16_ts(c.mma_d, c.mma_a + lo_col + i * 8, smem_desc(w_saddr + i * 256, 128, K * 16), idesc_f16(N), 1);
+        }
         mma_commit(c.mbar);
     }
 }
@@ -153,45 +177,70 @@ __device__ __forceinline__ void gemm_wait(TileCtx &c) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-// A[:, 0..63] = tanh(D[:, 0..63]) as float16 pairs (the bias is already in D).
+__device__ __forceinline__ float f16_lo_to_f32(uint32_t pair) {
+    float r;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(r) : "r"(pair));
+    return r;
+}
+__device__ __forceinline__ float f16_hi_to_f32(uint32_t pair) {
+    float r;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(r) : "r"(pair));
+    return r;
+}
+
+// (x0, x1) -> float16 pairs hi = f16(x), lo = f16(x - hi)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    hi = pack_f16x2(x0, x1);
+    lo = pack_f16x2(__fsub_rn(x0, f16_lo_to_f32(hi)), __fsub_rn(x1, f16_hi_to_f32(hi)));
+}
+
+// A[:, 0..63] = tanh(D[:, 0..63]) as float16 pairs (the bias is already in D).  Fast: MUFU.TANH; exact: the
+// float32 kernel's tanh (ex2 + rcp, abs error ~3e-7) and the result split into high and low halves.
+template <bool EXACT>
 __device__ __forceinline__ void tile_activation(const TileCtx &c) {
+    using L = Cols<EXACT>;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
         float v[16];
-        tmem_ld16(c.tmem_d + ch * 16, v);
+        tmem_ld16(c.tmem_a + L::D + ch * 16, v);
         tmem_ld_wait16(v);
-        uint32_t h[8];
+        uint32_t h[8], l[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = pack_f16x2(tanh_approx(v[2 * i]), tanh_approx(v[2 * i + 1]));
-        tmem_st<8>(c.tmem_a + ch * 8, h);
+        for (int i = 0; i < 8; ++i) {
+            if (EXACT) split_f16x2(tanh_mufu(v[2 * i]), tanh_mufu(v[2 * i + 1]), h[i], l[i]);
+            else h[i] = pack_f16x2(tanh_approx(v[2 * i]), tanh_approx(v[2 * i + 1]));
+        }
+        tmem_st<8>(c.tmem_a + L::A + ch * 8, h);
+        if (EXACT) tmem_st<8>(c.tmem_a + L::ALo + ch * 8, l);
     }
 }
 
 // One network for the group's U tiles: obs (9) -> 64 -> 64 -> out (first 8 of the 16 padded output columns),
-// biases included.  The input block [obs, 1, 0...] already sits in TMEM columns kColIn.. of every tile.  With
-// U = 2 the tiles ping-pong: while one tile's MMAs run, the threads do the other tile's activation math.
-template <int U>
+// biases included.  The input block [obs, 1, 0...] already sits in TMEM of every tile.  With U = 2 the tiles
+// ping-pong: while one tile's MMAs run, the threads do the other tile's activation math.
+template <int U, bool EXACT>
 __device__ __forceinline__ void group_mlp(TileCtx (&c)[U], const uint16_t *__restrict__ net, float (&out)[U][8]) {
+    using L = Cols<EXACT>;
     const uint32_t w1 = smem_u32(net + ROBOY_TC_OFF_W1), w2 = smem_u32(net + ROBOY_TC_OFF_W2), w3 = smem_u32(net + ROBOY_TC_OFF_W3);
 #pragma unroll
-    for (int u = 0; u < U; ++u) gemm_issue<16, 64>(c[u], kColIn, w1);
+    for (int u = 0; u < U; ++u) gemm_issue<16, 16, 64, EXACT>(c[u], L::In, L::InLo, w1);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         gemm_wait(c[u]);
-        tile_activation(c[u]);
-        gemm_issue<kKHid, 64>(c[u], kColA, w2);
+        tile_activation<EXACT>(c[u]);
+        gemm_issue<kKHid, 64, 64, EXACT>(c[u], L::A, L::ALo, w2);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         gemm_wait(c[u]);
-        tile_activation(c[u]);
-        gemm_issue<kKHid, 16>(c[u], kColA, w3);
+        tile_activation<EXACT>(c[u]);
+        gemm_issue<kKHid, 64, 16, EXACT>(c[u], L::A, L::ALo, w3);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         gemm_wait(c[u]);
         float v[16];
-        tmem_ld16(c[u].tmem_d, v);
+        tmem_ld16(c[u].tmem_a + L::D, v);
         tmem_ld_wait16(v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) out[u][k] = v[k];
@@ -199,16 +248,28 @@ __device__ __forceinline__ void group_mlp(TileCtx (&c)[U], const uint16_t *__res
 }
 
 // K = 16 input block of a tile: obs[0..8], 1 (multiplies the bias column of W1), zeros.  Written once per step.
+template <bool EXACT>
 __device__ __forceinline__ void store_input(const TileCtx &c, const float (&o)[kObsDim]) {
-    const uint32_t a[8] = {pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]), pack_f16x2(o[4], o[5]), pack_f16x2(o[6], o[7]),
-                           pack_f16x2(o[8], 1.0f), 0u, 0u, 0u};
-    tmem_st<8>(c.tmem_a + kColIn, a);
+    using L = Cols<EXACT>;
+    uint32_t a[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, l[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (EXACT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_f16x2(o[2 * i], o[2 * i + 1], a[i], l[i]);
+        split_f16x2(o[8], 1.0f, a[4], l[4]);
+        tmem_st<8>(c.tmem_a + L::InLo, l);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = pack_f16x2(o[2 * i], o[2 * i + 1]);
+        a[4] = pack_f16x2(o[8], 1.0f);
+    }
+    tmem_st<8>(c.tmem_a + L::In, a);
 }
 
 }  // namespace
 
-// U = tiles per group of 128 threads (thread i of the group owns row i of each of its U tiles).
-template <int U>
+// U = tiles per group of 128 threads (thread i of the group owns row i of each of its U tiles); EXACT: split-float16
+// operands and the accurate tanh (float32-level accuracy) instead of single float16 operands and tanh.approx.
+template <int U, bool EXACT>
 __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_kernel(const __grid_constant__ StepParams p,
                                                                                       const __grid_constant__ PolicyParams q) {
     extern __shared__ __align__(128) float smem[];
@@ -226,8 +287,11 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
     double *s_red = reinterpret_cast<double *>(mbars + 4);
     unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_red + n_warps);
     uint32_t *tmem_base_slot = s_cnt + 6;
+    using L = Cols<EXACT>;
+    // fast: the high halves of the weights and the float32 tail; exact: the whole image
     for (int i = threadIdx.x; i < ROBOY_TC_IMAGE_BYTES / 16; i += blockDim.x)
-        reinterpret_cast<float4 *>(img)[i] = reinterpret_cast<const float4 *>(q.image)[i];
+        if (EXACT || i < ROBOY_TC_OFF_LO_BYTES / 16 || i >= ROBOY_TC_OFF_STD_BYTES / 16)
+            reinterpret_cast<float4 *>(img)[i] = reinterpret_cast<const float4 *>(q.image)[i];
     if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
         for (int t = 0; t < n_groups * U; ++t)
@@ -235,7 +299,8 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int n_tiles = n_groups * U;
-    const uint32_t tmem_cols = n_tiles <= 1 ? 128u : n_tiles == 2 ? 256u : 512u;   // a power of two >= 32
+    const uint32_t need_cols = (uint32_t)n_tiles * L::Tile;
+    const uint32_t tmem_cols = need_cols <= 128 ? 128u : need_cols <= 256 ? 256u : 512u;   // a power of two >= 32
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(smem_u32(tmem_base_slot)), "r"(tmem_cols) : "memory");
@@ -252,10 +317,9 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int tile = group * U + u;
-        c[u].mma_a = tmem_base + tile * kTileCols + kColA;
-        c[u].mma_d = tmem_base + tile * kTileCols + kColD;
+        c[u].mma_a = tmem_base + tile * L::Tile;
+        c[u].mma_d = c[u].mma_a + L::D;
         c[u].tmem_a = c[u].mma_a + ((uint32_t)((warp & 3) * 32) << 16);
-        c[u].tmem_d = c[u].mma_d + ((uint32_t)((warp & 3) * 32) << 16);
         c[u].mbar = smem_u32(mbars + tile);
         c[u].parity = 0;
         c[u].bar_id = 1 + group;
@@ -268,10 +332,16 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
     const size_t n = (size_t)p.n;
     const uint32_t n_chunks = (n_end + U * kTileEnvs - 1) / (U * kTileEnvs);
     const uint16_t *vf_net = img16 + ROBOY_TC_OFF_VF, *pi_net = img16 + ROBOY_TC_OFF_PI;
-    const float *sd = img + ROBOY_TC_OFF_STD_BYTES / 4;
+    const float *sd = img + ROBOY_TC_OFF_STD_BYTES / 4;   // (the image keeps its layout in shared memory)
     const float lognorm = sd[8];
     float sum_reward = 0.0f;
 
+#ifdef ROBOY_TC_STAGGER  // experiment: start the groups out of phase
+    {
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)group * ROBOY_TC_STAGGER) {}
+    }
+#endif
     // all threads of a group walk the same chunks of U * 128 envs (the group's named barrier needs every one of them)
     for (uint32_t chunk = blockIdx.x * n_groups + group; chunk < n_chunks; chunk += gridDim.x * n_groups) {
         uint32_t env[U], wbase[U];   // this thread's env in tile u; first env of this warp's 32 rows of tile u
@@ -293,19 +363,19 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
             for (int k = 0; k < kObsDim; ++k) o[u][k] = live[u] ? q.obs[(size_t)env[u] * kObsDim + k] : 0.f;
             // the constant K block behind the 64 activations: 1 (multiplies the bias column of W2 / W3), then zeros
             const uint32_t ones[8] = {pack_f16x2(1.0f, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            tmem_st<8>(c[u].tmem_a + kColOnes, ones);
+            tmem_st<8>(c[u].tmem_a + L::Ones, ones);
         }
 
         for (uint32_t tt = 0;; ++tt) {
             float out[U][8];
 #pragma unroll
-            for (int u = 0; u < U; ++u) store_input(c[u], o[u]);
-            group_mlp<U>(c, vf_net, out);                      // value of obs[tt] (bootstrap value at tt == T)
+            for (int u = 0; u < U; ++u) store_input<EXACT>(c[u], o[u]);
+            group_mlp<U, EXACT>(c, vf_net, out);                      // value of obs[tt] (bootstrap value at tt == T)
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (live[u]) q.values[(size_t)tt * n + env[u]] = out[u][0];
             if (tt == q.T) break;
-            group_mlp<U>(c, pi_net, out);                      // mean of the Gaussian
+            group_mlp<U, EXACT>(c, pi_net, out);                      // mean of the Gaussian
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 float *row = stage + (u * 32 + lane) * kObsDim;
@@ -345,19 +415,17 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
     }
 }
 
-PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count, int tiles_per_group) {
+PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count, int tiles_per_group, bool exact) {
     PolicyGeom g;
     // one tile per thread group by default: four groups (16 warps) per SM hide the MMA round trips and the TMEM / MUFU
     // latencies better than two groups ping-ponging two tiles each (measured on B200 at 1,048,576 envs: 1.09e10 vs
-    // 7.1e9 env-steps/s); the two-tile form stays selectable for experiments
-    const int U = tiles_per_group ? tiles_per_group : 1;
-    (void)n_envs;
+    // 7.1e9 env-steps/s); the two-tile form stays selectable for experiments (fast mode only)
+    const int U = (tiles_per_group == 2 && !exact) ? 2 : 1;
     g.envs_per_thread = U;
     const uint64_t n_chunks = (n_envs + U * kTileEnvs - 1) / (U * kTileEnvs);
-    const uint64_t max_groups = kPolicyTcMaxBlock / kTileEnvs / U;   // TMEM: 4 tiles of 128 columns per SM
+    const uint64_t max_groups = (exact ? Cols<true>::MaxGroups : Cols<false>::MaxGroups) / U;   // TMEM: 512 columns per SM
     uint64_t groups = (n_chunks + sm_count - 1) / sm_count;          // spread the groups over the SMs first
     if (groups > max_groups) groups = max_groups;
-    if (groups == 3) groups = 4;
     const uint64_t grid = (n_chunks + groups - 1) / groups;
     g.grid = (int)(grid < (uint64_t)sm_count ? grid : (uint64_t)sm_count);
     g.block = (int)groups * kTileEnvs;
@@ -368,16 +436,17 @@ PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count, int tiles_per_group
 }
 
 cudaError_t launch_policy_rollout_tc(const StepParams &p, const PolicyParams &q, bool penalty, bool bonus, bool auto_reset,
-                                     bool fastdiv, int sm_count, int tiles_per_group, cudaStream_t stream) {
+                                     bool fastdiv, int sm_count, int tiles_per_group, bool exact, cudaStream_t stream) {
     if (p.e_end <= p.e_begin) return cudaSuccess;
     PolicyParams qq = q;
     qq.penalty = penalty;
     qq.bonus = bonus;
     qq.auto_reset = auto_reset;
     qq.fastdiv = fastdiv;
-    const PolicyGeom g = policy_tc_geometry(p.e_end, sm_count, tiles_per_group);
+    const PolicyGeom g = policy_tc_geometry(p.e_end, sm_count, tiles_per_group, exact);
     void (*fn)(const StepParams, const PolicyParams) =
-        g.envs_per_thread == 1 ? policy_rollout_tc_kernel<1> : policy_rollout_tc_kernel<2>;
+        exact ? policy_rollout_tc_kernel<1, true>
+              : (g.envs_per_thread == 1 ? policy_rollout_tc_kernel<1, false> : policy_rollout_tc_kernel<2, false>);
     cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem);
     if (err != cudaSuccess) return err;
     fn<<<g.grid, g.block, g.smem, stream>>>(p, qq);

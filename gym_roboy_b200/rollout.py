@@ -84,29 +84,37 @@ def pack_policy_image(policy, out=None):
 
 
 def _umma_k_major_f16(w, bias, n_pad, k_pad, bias_col):
-    """[out, in] weight (+ bias as input column `bias_col`) -> zero-padded float16 [n_pad, k_pad] in the tensor
-    core's K-major core-matrix layout without swizzle:
-    element index of W[n][k] = (n//8)*(k_pad//8)*64 + (k//8)*64 + (n%8)*8 + (k%8)."""
+    """[out, in] weight (+ bias as input column `bias_col`) -> zero-padded [n_pad, k_pad] split into float16 halves
+    (hi = float16(w), lo = float16(w - hi)), each in the tensor core's K-major core-matrix layout without swizzle:
+    element index of W[n][k] = (n//8)*(k_pad//8)*64 + (k//8)*64 + (n%8)*8 + (k%8).  Returns (hi, lo), flat."""
     full = torch.zeros((n_pad, k_pad), dtype=torch.float32, device=w.device)
     full[: w.shape[0], : w.shape[1]] = w.detach().float()
     full[: w.shape[0], bias_col] = bias.detach().float()
+    hi = full.to(torch.float16)
+    lo = (full - hi.float()).to(torch.float16)
     # [n/8, 8, k/8, 8] -> [n/8, k/8, 8, 8]
-    return full.to(torch.float16).view(n_pad // 8, 8, k_pad // 8, 8).permute(0, 2, 1, 3).reshape(-1)
+    lay = lambda t: t.view(n_pad // 8, 8, k_pad // 8, 8).permute(0, 2, 1, 3).reshape(-1)  # noqa: E731
+    return lay(hi), lay(lo)
 
 
 def pack_policy_image_tc(policy, out=None):
     """Pack an `MlpPolicy` into the byte image `roboy_policy_rollout_tc` reads (layout: ROBOY_TC_* in
-    include/roboy_b200.h): float16 weights with the biases as an extra input column, then std / lognorm as float32."""
+    include/roboy_b200.h): float16 weights (high halves, then low halves) with the biases as an extra input column,
+    then std / lognorm as float32."""
     N = _native
     dev = policy.log_std.device
     img = torch.zeros(N.TC_IMAGE_BYTES, dtype=torch.uint8, device=dev) if out is None else out
-    halves = img[: N.TC_OFF_STD_BYTES].view(torch.float16)
+    his = img[: N.TC_OFF_LO_BYTES].view(torch.float16)
+    los = img[N.TC_OFF_LO_BYTES: N.TC_OFF_STD_BYTES].view(torch.float16)
     for base, net in ((N.TC_OFF_VF, policy.vf), (N.TC_OFF_PI, policy.pi)):
         l1, l2, l3 = net[0], net[2], net[4]
         assert l1.weight.shape == (64, N.DIM_OBS) and l2.weight.shape == (64, 64) and l3.weight.shape[0] in (1, 8)
-        halves[base + N.TC_OFF_W1: base + N.TC_OFF_W2].copy_(_umma_k_major_f16(l1.weight, l1.bias, 64, 16, N.DIM_OBS))
-        halves[base + N.TC_OFF_W2: base + N.TC_OFF_W3].copy_(_umma_k_major_f16(l2.weight, l2.bias, 64, N.TC_K_HIDDEN, 64))
-        halves[base + N.TC_OFF_W3: base + N.TC_NET_HALVES].copy_(_umma_k_major_f16(l3.weight, l3.bias, 16, N.TC_K_HIDDEN, 64))
+        for (lo_, hi_), layer, n_pad, k_pad, bias_col in (
+                ((N.TC_OFF_W1, N.TC_OFF_W2), l1, 64, 16, N.DIM_OBS), ((N.TC_OFF_W2, N.TC_OFF_W3), l2, 64, N.TC_K_HIDDEN, 64),
+                ((N.TC_OFF_W3, N.TC_NET_HALVES), l3, 16, N.TC_K_HIDDEN, 64)):
+            hi, lo = _umma_k_major_f16(layer.weight, layer.bias, n_pad, k_pad, bias_col)
+            his[base + lo_: base + hi_].copy_(hi)
+            los[base + lo_: base + hi_].copy_(lo)
     tail = img[N.TC_OFF_STD_BYTES: N.TC_IMAGE_BYTES].view(torch.float32)
     log_std = policy.log_std.detach()
     tail[:8].copy_(log_std.exp())
@@ -121,15 +129,17 @@ class RolloutCollector:
     the env is stepped with `clip(actions, -1, 1)`.  `fused=True` (or "fp32") runs policy + env for all T steps
     in one kernel launch (`roboy_policy_rollout`, float32 FFMA2 -- agrees with the torch policy to ~1e-6);
     `fused="tc"` does the same with the matrix products on the tensor cores (`roboy_policy_rollout_tc`,
-    tcgen05 with float16 operands and float32 accumulation -- agrees to ~1e-3, several times faster).  Fused, the Gaussian noise comes from Philox keyed by
+    tcgen05 with float16 operands and float32 accumulation -- agrees to ~1e-3, several times faster);
+    `fused="tc_exact"` splits every operand into two float16 halves (three MMAs per product) and keeps the accurate
+    tanh -- agrees to ~1e-6 like "fp32", at more than twice its speed.  Fused, the Gaussian noise comes from Philox keyed by
     `noise_seed` instead of torch's generator."""
 
     def __init__(self, env, policy, n_steps=128, gamma=0.99, lam=0.95, fused=False, noise_seed=0, envs_per_thread=0):
         self.env, self.client, self.policy = env, env._simulation_client, policy
         self.T, self.N = int(n_steps), env.num_envs
         self.gamma, self.lam = gamma, lam
-        if fused not in (False, True, "fp32", "tc"):
-            raise ValueError('fused must be False, True / "fp32", or "tc"')
+        if fused not in (False, True, "fp32", "tc", "tc_exact"):
+            raise ValueError('fused must be False, True / "fp32", "tc" or "tc_exact"')
         self.fused = {True: "fp32", False: None}.get(fused, fused)
         self.noise_seed, self.envs_per_thread = int(noise_seed), int(envs_per_thread)
         dev, T, N = self.client.device, self.T, self.N
@@ -147,7 +157,7 @@ class RolloutCollector:
         self._image, self._image_key = None, None
         if self.fused == "fp32":
             self._image = torch.zeros(_native.POLICY_IMAGE_FLOATS, **f32)
-        elif self.fused == "tc":
+        elif self.fused in ("tc", "tc_exact"):
             self._image = torch.zeros(_native.TC_IMAGE_BYTES, dtype=torch.uint8, device=dev)
         self.noise = None   # tests: set to a [T, N, 8] float32 tensor to have the fused kernel record its noise
         self.obs[0].copy_(env.reset())
@@ -162,11 +172,12 @@ class RolloutCollector:
         # inside a CUDA-graph capture the packing is always recorded, so that replays pick up new weights
         key = tuple((q.data_ptr(), q._version) for q in self.policy.parameters())
         if key != self._image_key or torch.cuda.is_current_stream_capturing():
-            (pack_policy_image_tc if self.fused == "tc" else pack_policy_image)(self.policy, out=self._image)
+            (pack_policy_image if self.fused == "fp32" else pack_policy_image_tc)(self.policy, out=self._image)
             self._image_key = None if torch.cuda.is_current_stream_capturing() else key
-        if self.fused == "tc":
+        if self.fused != "fp32":
             _native.check(_native.load().roboy_policy_rollout_tc(self.client._h, self.T, p(self._image), self.noise_seed,
-                                                                 *bufs, self.envs_per_thread, stream))
+                                                                 *bufs, self.envs_per_thread, int(self.fused == "tc_exact"),
+                                                                 stream))
         else:
             _native.check(_native.load().roboy_policy_rollout(self.client._h, self.T, p(self._image), self.noise_seed,
                                                               *bufs, self.envs_per_thread, stream))

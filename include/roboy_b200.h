@@ -276,20 +276,24 @@ int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uin
                          float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
                          float *noise_dev, int envs_per_thread, void *stream);
 /* The same rollout with the two networks' matrix products on the tensor cores (tcgen05.mma kind::f16, M = 128
- * envs per tile, float32 accumulators in tensor memory): float16 operands (10-bit mantissa, as TF32), float32
- * accumulation, tanh.approx -- action means and values agree with the float32 policy to ~1e-3
- * (roboy_policy_rollout is the exact path).  Env outputs remain bit-identical to T roboy_step calls on
- * clip(actions, -1, 1).
+ * envs per tile, float32 accumulators in tensor memory).  Env outputs remain bit-identical to T roboy_step calls on
+ * clip(actions, -1, 1).  Two precisions:
+ *   exact = 0  float16 operands (10-bit mantissa, as TF32), float32 accumulation, tanh.approx: action means and values
+ *              agree with the float32 policy to ~1e-3.  The fastest path.
+ *   exact = 1  every operand split x = hi + lo into two float16 (22 mantissa bits), products accumulated as
+ *              A_hi W_hi + A_hi W_lo + A_lo W_hi in float32, and the float32 kernel's tanh: agrees with the float32
+ *              policy to ~1e-6, like roboy_policy_rollout, at more than twice its speed.
  * tc_image_dev: ROBOY_TC_IMAGE_BYTES bytes, 16-byte aligned.  One network is, in float16 elements,
  *   W1 [64][16] | W2 [64][80] | W3 [16][80]
  * with each W = the torch Linear weight [out][in] zero-padded (9 -> 16 inputs, 64 -> 80 inputs, 8 or 1 -> 16
  * outputs) and the BIAS stored as input column 9 (W1) / 64 (W2, W3) -- the kernel feeds a constant 1 there --
  * in the tensor core's K-major core-matrix layout without swizzle:
  *   element index of W[n][k] = (n / 8) * (K / 8) * 64 + (k / 8) * 64 + (n % 8) * 8 + (k % 8);
- * the image is  value net | policy net (float16)  then, as float32 at byte ROBOY_TC_OFF_STD_BYTES,
- * std [8] | lognorm | 3 floats of padding.
+ * the image is  value net | policy net  (HIGH halves: float16(w)),  then the same two networks again with the LOW
+ * halves float16(w - high) at byte ROBOY_TC_OFF_LO_BYTES (read only when exact = 1),  then, as float32 at byte
+ * ROBOY_TC_OFF_STD_BYTES,  std [8] | lognorm | 3 floats of padding.
  * tiles_per_group: 0 = default (1); 1 = each group of 128 threads owns one 128-env tile; 2 = two tiles per group, worked
- * on alternately (an experiment: measured 35 % slower than 1 on B200; results are bit-identical). */
+ * on alternately (an experiment, exact = 0 only: measured 35 % slower than 1 on B200; results are bit-identical). */
 #define ROBOY_TC_K_HIDDEN 80
 #define ROBOY_TC_OFF_W1 0
 #define ROBOY_TC_OFF_W2 1024
@@ -297,14 +301,15 @@ int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uin
 #define ROBOY_TC_NET_HALVES 7424
 #define ROBOY_TC_OFF_VF 0
 #define ROBOY_TC_OFF_PI 7424
-#define ROBOY_TC_OFF_STD_BYTES 29696
-#define ROBOY_TC_IMAGE_BYTES 29744
+#define ROBOY_TC_OFF_LO_BYTES 29696
+#define ROBOY_TC_OFF_STD_BYTES 59392
+#define ROBOY_TC_IMAGE_BYTES 59440
 int roboy_policy_rollout_tc(roboy_env *env, uint32_t T, const float *tc_image_dev, uint64_t noise_seed, float *obs_dev,
                             float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
-                            float *noise_dev, int tiles_per_group, void *stream);
+                            float *noise_dev, int tiles_per_group, int exact, void *stream);
 /* Launch geometry roboy_policy_rollout uses for this handle (bench.py / tests). */
 int roboy_policy_geometry(roboy_env *env, int envs_per_thread, int *grid, int *block, int *smem_bytes, int *ept);
-int roboy_policy_tc_geometry(roboy_env *env, int tiles_per_group, int *grid, int *block, int *smem_bytes, int *tpg);
+int roboy_policy_tc_geometry(roboy_env *env, int tiles_per_group, int exact, int *grid, int *block, int *smem_bytes, int *tpg);
 
 /* Introspection for bench.py / tests: kernels launched by this handle so far, and the
  * launch geometry the step kernel uses for this n_envs. */

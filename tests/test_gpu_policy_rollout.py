@@ -48,11 +48,13 @@ def numpy_noise(noise_seed, gids, t):
 
 # the float32 FFMA2 kernel agrees with the torch float32 policy to ~1e-6; the tensor-core kernel computes with
 # float16 operands (10-bit mantissa), float32 accumulation and tanh.approx: ~1e-3
-POLICY_TOL = {"fp32": dict(rtol=1e-5, atol=2e-5), "tc": dict(rtol=0, atol=4e-3)}
+# ("tc_exact": split float16 operands, three MMAs per product, accurate tanh: float32-level again)
+POLICY_TOL = {"fp32": dict(rtol=1e-5, atol=2e-5), "tc": dict(rtol=0, atol=4e-3), "tc_exact": dict(rtol=1e-5, atol=2e-5)}
 
 
 @pytest.mark.parametrize("n,ept,mode", [(4096, 0, "fp32"), (2531, 2, "fp32"), (40000, 0, "fp32"),
-                                        (4096, 0, "tc"), (2531, 2, "tc"), (80000, 0, "tc")])
+                                        (4096, 0, "tc"), (2531, 2, "tc"), (80000, 0, "tc"),
+                                        (4096, 0, "tc_exact"), (2531, 0, "tc_exact"), (80000, 0, "tc_exact")])
 def test_fused_rollout_against_torch_policy_and_oracle_env(n, ept, mode):
     T, seed = 10, 21
     tol = POLICY_TOL[mode]
@@ -116,7 +118,7 @@ def test_one_and_two_envs_per_thread_and_sharding_are_bit_identical(mode):
     shards_of_one_population(n, T, ref, mode)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tc"])
+@pytest.mark.parametrize("mode", ["fp32", "tc", "tc_exact"])
 def test_sharding_invariance(mode):
     n, T = 6000, 6
     _, client, col = make(n, 5, T, fused=mode)
@@ -138,7 +140,7 @@ def shards_of_one_population(n, T, ref, mode):
         assert torch.equal(col.obs[1:T], ref["obs"][1:T, base:base + half])
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tc"])
+@pytest.mark.parametrize("mode", ["fp32", "tc", "tc_exact"])
 def test_holds_and_nan_actions_inside_the_fused_kernel(mode):
     """A zero policy (mean 0, std tiny) makes every env take the Stub's hold branch; a NaN weight trips the
     action assert (roboy_env.py:52) exactly as T un-fused steps would."""
@@ -169,7 +171,7 @@ def test_holds_and_nan_actions_inside_the_fused_kernel(mode):
     assert torch.isnan(col.actions[:, :, 3]).all()
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tc"])
+@pytest.mark.parametrize("mode", ["fp32", "tc", "tc_exact"])
 def test_fused_rollout_in_a_cuda_graph_and_against_the_unfused_collector(mode):
     n, T = 4096, 8
     policy, client, col = make(n, 3, T, fused=mode)
@@ -196,7 +198,7 @@ def test_fused_rollout_in_a_cuda_graph_and_against_the_unfused_collector(mode):
         assert torch.equal(client.done_u8, eager["dones"][t])
 
 
-@pytest.mark.parametrize("mode,ept", [("fp32", 1), ("fp32", 2), ("tc", 1), ("tc", 2)])
+@pytest.mark.parametrize("mode,ept", [("fp32", 1), ("fp32", 2), ("tc", 1), ("tc", 2), ("tc_exact", 0)])
 @pytest.mark.parametrize("n", [2, 33, 257, 1001, 2531])
 def test_ragged_sizes_write_nothing_outside_their_buffers(n, mode, ept):
     """(compute-sanitizer is not available on the GPU pool.)  Every rollout buffer is carved out of one arena with

@@ -138,7 +138,8 @@ def test_policy_image_layouts_match_the_header():
     assert torch.equal(img[N.POLICY_OFF_STD:N.POLICY_OFF_STD + 8], pol.log_std.detach().exp())
     tc = pack_policy_image_tc(pol)
     assert tc.numel() == N.TC_IMAGE_BYTES and tc.dtype == torch.uint8
-    halves = tc[:N.TC_OFF_STD_BYTES].view(torch.float16)
+    halves = tc[:N.TC_OFF_LO_BYTES].view(torch.float16)
+    lows = tc[N.TC_OFF_LO_BYTES:N.TC_OFF_STD_BYTES].view(torch.float16)
 
     def at(base, off, K, n, k):
         return halves[base + off + (n // 8) * (K // 8) * 64 + (k // 8) * 64 + (n % 8) * 8 + (k % 8)]
@@ -149,5 +150,9 @@ def test_policy_image_layouts_match_the_header():
         assert at(base, N.TC_OFF_W2, 80, 3, 40) == w2[3, 40].half() and at(base, N.TC_OFF_W2, 80, 3, 64) == net[2].bias[3].half()
         assert at(base, N.TC_OFF_W3, 80, 0, 63) == w3[0, 63].half() and at(base, N.TC_OFF_W3, 80, 0, 64) == net[4].bias[0].half()
         assert at(base, N.TC_OFF_W3, 80, 15, 63) == 0                                   # output rows padded to 16
+        i = base + N.TC_OFF_W2 + (3 // 8) * (80 // 8) * 64 + (40 // 8) * 64 + (3 % 8) * 8 + (40 % 8)
+        assert lows[i] == (w2[3, 40] - w2[3, 40].half().float()).half()                 # low half of the split
+        # (a small weight's low half is a float16 subnormal: absolute spacing 2^-24)
+        assert abs(float(halves[i].float() + lows[i].float() - w2[3, 40])) <= 2.0 ** -21 * abs(float(w2[3, 40])) + 2.0 ** -25
     tail = tc[N.TC_OFF_STD_BYTES:].view(torch.float32)
     assert torch.equal(tail[:8], pol.log_std.detach().exp())
