@@ -410,14 +410,14 @@ def run_b200_arm(args):
         rollout = []
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12   # nominal float32 FMA peak of one B200 at max clock, TFLOP/s
         mufu_peak = 148 * 16 * 1.965e9               # MUFU results per second of one B200 at max clock (16 lanes per SM)
-        for n, mode in ((4096, "torch"), (4096, "torch+graph"), (4096, "fused"), (4096, "fused_tc"), (262144, "torch"),
-                        (262144, "torch+graph"), (262144, "fused"), (262144, "fused_tc"), (1048576, "fused"),
-                        (1048576, "fused_tc")):
+        for n, mode in ((4096, "torch"), (4096, "torch+graph"), (4096, "fused"), (4096, "fused_tc_exact"), (4096, "fused_tc"),
+                        (262144, "torch"), (262144, "torch+graph"), (262144, "fused"), (262144, "fused_tc_exact"),
+                        (262144, "fused_tc"), (1048576, "fused"), (1048576, "fused_tc_exact"), (1048576, "fused_tc")):
             torch.manual_seed(0)
             b0, _ = shard_range(n * world, world, rank)
             e, c = make(n, b0)
             fused = mode == "fused"
-            col = RolloutCollector(e, MlpPolicy().to(dev), n_steps=128, fused={"fused": "fp32", "fused_tc": "tc"}.get(mode, False))
+            col = RolloutCollector(e, MlpPolicy().to(dev), n_steps=128, fused={"fused": "fp32", "fused_tc": "tc", "fused_tc_exact": "tc_exact"}.get(mode, False))
             if mode == "torch+graph":
                 col.capture()
             for _ in range(2):
@@ -447,6 +447,12 @@ def run_b200_arm(args):
                                     "and env step for all 128 steps in ONE launch, state in registers; + GAE kernel",
                             "bound": "fp32 FMA", "tflops_fp32": tflops, "frac_of_nominal_fp32_peak": tflops / fp32_peak,
                             "nominal_fp32_peak_tflops": fp32_peak})
+            elif mode == "fused_tc_exact":
+                row.update({"what": "roboy_policy_rollout_tc(exact=1): tensor cores with every operand split into two float16 "
+                                    "halves (three MMAs per product) and the accurate tanh; agrees with the float32 policy to "
+                                    "~1e-6 like `fused`; + GAE kernel",
+                            "bound": "MUFU (tanh = ex2 + rcp)", "mufu_per_env_step": 539,
+                            "frac_of_nominal_mufu_peak": 539 * n * 128 / (ms * 1e-3) / mufu_peak})
             elif mode == "fused_tc":
                 # the MUFU unit bounds this kernel: 256 tanh per env-step (+ ~27 for the Gaussian noise and the env's exp / sqrt)
                 row.update({"what": "roboy_policy_rollout_tc: as `fused`, with the matrix products on the tensor cores (tcgen05.mma "

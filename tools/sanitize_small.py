@@ -29,7 +29,7 @@ for n in (1, 31, 33, 257, 1000):
         torch.cuda.synchronize(); c.stats(); c.errors(); c.close()
 # the fused policy rollout kernels (float32 with 1 and 2 envs per thread; tensor cores), ragged sizes
 for n in (2, 33, 257, 1000):
-    for mode, ept in (("fp32", 1), ("fp32", 2), ("tc", 0)):
+    for mode, ept in (("fp32", 1), ("fp32", 2), ("tc", 1), ("tc", 2), ("tc_exact", 0)):
         c = CudaSimulationClient(num_envs=n, seed=3, device="cuda:0")
         col = RolloutCollector(RoboyEnv(c), MlpPolicy().to("cuda:0"), n_steps=3, fused=mode, envs_per_thread=ept)
         c.set_step_num(np.full(n, 399, np.int32))
