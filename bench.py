@@ -189,9 +189,10 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
-def device_timed(env, client, actions, steps, warmup, torch, dist, world, stats_every=100):
+def device_timed(env, client, actions, steps, warmup, torch, dist, world, stats_every=100, per_step_events=True):
     """K steps, barrier + synchronize on both sides, CUDA events on the launching stream.
-    Returns (elapsed_ms_total_max_over_ranks, mean_kernel_ms, launches)."""
+    Returns (elapsed_ms_total_max_over_ranks, mean_kernel_ms, median_kernel_ms, launches).  per_step_events=False
+    records only the first and the last event (host-bound sizes: an event record per step costs more than the step)."""
     from gym_roboy_b200.sharding import all_reduce_stats
     side = torch.cuda.Stream()
     for i in range(warmup):
@@ -205,7 +206,8 @@ def device_timed(env, client, actions, steps, warmup, torch, dist, world, stats_
     ev[0].record()
     for i in range(steps):
         env.step(actions[i % len(actions)])
-        ev[i + 1].record()
+        if per_step_events or i == steps - 1:
+            ev[i + 1].record()
         if world > 1 and (i + 1) % stats_every == 0:      # tiny episode-stat reduction, off the step stream
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -215,7 +217,7 @@ def device_timed(env, client, actions, steps, warmup, torch, dist, world, stats_
         dist.barrier()
         torch.cuda.synchronize()
     total_ms = ev[0].elapsed_time(ev[steps])
-    per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+    per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps)) if per_step_events else [total_ms / steps]
     mean_kernel_ms = sum(per) / len(per)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -336,7 +338,9 @@ def run_b200_arm(args):
             e, c = make(n)
             acts = make_actions(n)
             k = max(20, min(args.steps, 200))
-            tot, mean_ms, med_ms, _ = device_timed(e, c, acts, k, max(3, args.warmup), torch, dist, 1)
+            # (below ~1M envs the eager loop is bound by the host, where a CUDA event per step would dominate)
+            tot, mean_ms, med_ms, _ = device_timed(e, c, acts, k, max(3, args.warmup), torch, dist, 1,
+                                                   per_step_events=n > 1048576)
             row = {"envs": n, "env_steps_per_s": n * k / (tot * 1e-3), "ms_per_step": tot / k,
                    "GBps_algorithmic": BYTES_PER_ENV_STEP * n / (mean_ms * 1e-3) / 1e9,
                    "frac_of_peak": BYTES_PER_ENV_STEP * n / (mean_ms * 1e-3) / 1e9 / peak,
