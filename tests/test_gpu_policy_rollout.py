@@ -233,3 +233,28 @@ def test_ragged_sizes_write_nothing_outside_their_buffers(n, mode, ept):
     assert bool((dones_arena[:guard] == 0x5A).all()) and bool((dones_arena[guard + T * n:] == 0x5A).all())
     assert bool((col.dones <= 1).all())
     assert client.errors() == (0, None)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc", "tc_exact"])
+def test_long_fused_rollout_crosses_several_episode_ends(mode):
+    """T = 900 steps in one launch: every env times out at least twice inside the kernel (goal re-draw, reset
+    observation, step counter restart), all of it replayed through the oracle on the stored actions."""
+    n, T, seed = 384, 900, 17
+    policy, client, col = make(n, seed, T, fused=mode)
+    ora = orc.OracleEnv(n, seed=seed)
+    assert np.array_equal(ora.reset(), col.obs[0].cpu().numpy())
+    col.collect()
+    torch.cuda.synchronize()
+    acts = np.clip(col.actions.cpu().numpy(), -1.0, 1.0)
+    obs, rew, done = col.obs.cpu().numpy(), col.rewards.cpu().numpy(), col.dones.cpu().numpy().astype(bool)
+    for t in range(T):
+        o, r, d = ora.step(acts[t])
+        assert np.array_equal(obs[t + 1] if t + 1 < T else col.obs[T].cpu().numpy(), o), t
+        assert np.array_equal(done[t], d), t
+        assert np.allclose(rew[t], r, rtol=1e-6, atol=0), t
+    assert done.sum(axis=0).min() >= 2
+    s, so = client.stats(), ora.stats()
+    assert all(s[k] == so[k] for k in ("steps", "episodes", "successes", "timeouts", "holds", "violations")), (s, so)
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+    assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
+    assert client.errors() == (0, None)
