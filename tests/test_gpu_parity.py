@@ -470,3 +470,39 @@ def test_open_loop_step_many_equals_sequential_steps(n, T):
     for t in range(3):
         client_b.step_fused(a_dev[t])
         assert torch.equal(obs2[t], client_b.obs)
+
+
+def test_maximum_size_shard_matches_the_oracle_at_both_ends():
+    """134,217,728 envs on one GPU (the largest total of SURVEY.md 8d config C4; ~15 GB of HBM, observation offsets
+    beyond 4 GiB): because draws depend only on the global env id, the first and the last 4,096 envs must equal a
+    4,096-env oracle shard with the matching env_id_base, bit for bit."""
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    n, k, seed = 1 << 27, 4096, 77
+    free, _ = torch.cuda.mem_get_info()
+    if free < 24 << 30:
+        pytest.skip("needs 24 GB of free HBM")
+    client = CudaSimulationClient(num_envs=n, seed=seed, device="cuda:0")
+    env = RoboyEnv(client)
+    obs0 = env.reset()
+    ends = {0: orc.OracleEnv(k, seed=seed, env_id_base=0), n - k: orc.OracleEnv(k, seed=seed, env_id_base=n - k)}
+    for base, ora in ends.items():
+        assert np.array_equal(ora.reset(), obs0[base:base + k].cpu().numpy())
+        ora.step_flags[:] = (ora.step_flags & ~np.uint32(orc.STEP_MASK)) | np.uint32(399)
+    client.set_step_num(torch.full((k,), 399, dtype=torch.int32), idx=torch.arange(0, k))
+    client.set_step_num(torch.full((k,), 399, dtype=torch.int32), idx=torch.arange(n - k, n))
+    gen = torch.Generator(device="cuda:0"); gen.manual_seed(5)
+    a = torch.empty((n, 8), device="cuda:0")
+    for t in range(3):
+        a.uniform_(-1, 1, generator=gen)
+        a[n - 7:] = 0.0                                                   # hold branch at the very end of the shard
+        obs, rew, done, _ = env.step(a)
+        for base, ora in ends.items():
+            o, r, d = ora.step(a[base:base + k].cpu().numpy())
+            assert np.array_equal(obs[base:base + k].cpu().numpy(), o), (t, base)
+            assert np.array_equal(done[base:base + k].cpu().numpy(), d), (t, base)
+            assert np.allclose(rew[base:base + k].cpu().numpy(), r, rtol=1e-6, atol=0), (t, base)
+    s = client.stats()
+    assert s["steps"] == 3 * n and s["holds"] >= 3 * 7 and s["violations"] == 0
+    assert client.errors() == (0, None)
+    client.close()
