@@ -87,7 +87,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
             "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
             : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
         if (ok) break;
-        if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a lost arrive must not hang the GPU
+        if (clock64() - t0 > 20000000000ll) __trap();  // ~10 s: a lost arrive must not hang the GPU for good
     }
 }
 
