@@ -131,7 +131,9 @@ class RolloutCollector:
     `fused="tc"` does the same with the matrix products on the tensor cores (`roboy_policy_rollout_tc`,
     tcgen05 with float16 operands and float32 accumulation -- agrees to ~1e-3, several times faster);
     `fused="tc_exact"` splits every operand into two float16 halves (three MMAs per product) and keeps the accurate
-    tanh -- agrees to ~1e-6 like "fp32", at more than twice its speed.  Fused, the Gaussian noise comes from Philox keyed by
+    tanh -- agrees to ~1e-6 like "fp32", at more than twice its speed.  (`logp` is always the density of the stored
+    sample under the mean the kernel computed; with "tc" that mean differs from the float32 policy's by ~1e-3, so a
+    PPO ratio evaluated in float32 starts within ~1e-3 * |z| / std of 1 -- use "tc_exact" or "fp32" where that matters.)  Fused, the Gaussian noise comes from Philox keyed by
     `noise_seed` instead of torch's generator."""
 
     def __init__(self, env, policy, n_steps=128, gamma=0.99, lam=0.95, fused=False, noise_seed=0, envs_per_thread=0):
