@@ -1,0 +1,12 @@
+# profiling driver: a few fused steps with joint_vel_penalty=True (used under ncu)
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gym_roboy_b200.envs import RoboyEnv
+from gym_roboy_b200.envs.simulations import CudaSimulationClient
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 24
+c = CudaSimulationClient(num_envs=n, seed=1234, device="cuda:0")
+e = RoboyEnv(c, joint_vel_penalty=True, strict=False); e.reset()
+g = torch.Generator(device="cuda:0"); g.manual_seed(0)
+a = [torch.rand((n, 8), device="cuda:0", generator=g) * 2 - 1 for _ in range(2)]
+for i in range(6): e.step(a[i & 1])
+torch.cuda.synchronize(); print("ok", c.stats()["steps"])
