@@ -7,8 +7,8 @@
 // actions.  What differs is where the 10,368 multiply-adds per env-step of the two 9-64-64-{8,1} networks run:
 //
 //   * a CTA holds up to four TILES of 128 envs; thread i of a tile owns env i = row i of every matrix
-//     = lane i of the tile's 128 tensor-memory columns (40 for the activations A, packed two float16
-//     per column, 64 for the float32 accumulator D);
+//     = lane i of the tile's 128 tensor-memory columns (48 for the activations A and the input block, packed
+//     two float16 per column, 64 for the float32 accumulator D; 160 columns and three tiles in exact mode);
 //   * per layer the tile's threads write their activation row into TMEM (tcgen05.st), one thread issues
 //     K/16 tcgen05.mma (M = 128 envs, N = 64 / 16 outputs, K = 16 per instruction; A from TMEM, the weight
 //     matrix B from shared memory in the canonical K-major core-matrix layout, no swizzle) and commits
@@ -20,10 +20,13 @@
 //     variant in which each group of 128 threads ping-pongs TWO tiles, template parameter U = 2, measured 35 %
 //     slower: with the same four tiles in flight it has half the warps to hide TMEM / MUFU latency behind.)
 //
-// Arithmetic: float16 operands (10-bit mantissa, the precision of TF32; every operand here is far inside
-// float16's range), float32 accumulation, tanh.approx: action means and values agree with the float32
-// policy to ~1e-3 -- the float32 FFMA2 kernel (roboy_policy_rollout) stays the exact path.  Tensor cores
-// are used HERE because this IS a dense contraction; the env step itself has none and stays off them.
+// Arithmetic, two modes (template parameter EXACT):
+//   fast   float16 operands (10-bit mantissa, the precision of TF32; every operand here is far inside float16's
+//          range), float32 accumulation, tanh.approx: action means and values agree with the float32 policy to ~1e-3;
+//   exact  every operand split x = hi + lo into two float16 (22 mantissa bits), each product accumulated in float32 as
+//          A_hi W_hi + A_hi W_lo + A_lo W_hi (three MMA groups into the same accumulator), and the float32 kernel's
+//          tanh (ex2 + rcp): ~1e-6, the accuracy of torch's own float32 forward, at 2.5x the float32 FFMA2 kernel.
+// Tensor cores are used HERE because this IS a dense contraction; the env step itself has none and stays off them.
 #include <cuda_runtime.h>
 #include <math.h>
 
