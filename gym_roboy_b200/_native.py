@@ -24,7 +24,7 @@ POLICY_OFF_VF, POLICY_OFF_PI, POLICY_OFF_STD, POLICY_OFF_LOGNORM, POLICY_IMAGE_F
 # ... and of the tensor-core variant's image (ROBOY_TC_*): float16 element offsets, then byte offsets
 TC_K_HIDDEN = 80
 TC_OFF_W1, TC_OFF_W2, TC_OFF_W3, TC_NET_HALVES, TC_OFF_VF, TC_OFF_PI = 0, 1024, 6144, 7424, 0, 7424
-TC_OFF_LO_BYTES, TC_OFF_STD_BYTES, TC_IMAGE_BYTES = 29696, 59392, 59440
+TC_OFF_LO_BYTES, TC_OFF_STD_BYTES, TC_BIAS32_NET_FLOATS, TC_IMAGE_BYTES = 29696, 59392, 80, 60080
 (BUF_GOAL, BUF_STEP_FLAGS, BUF_HELD, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_STATS, BUF_TERMINAL_OBS) = range(8)
 
 

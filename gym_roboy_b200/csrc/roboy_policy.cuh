@@ -10,7 +10,7 @@ namespace roboy {
 
 constexpr int kPolicyMaxBlock = 256;
 constexpr int kPolicyTcMaxBlock = 512;      // tensor-core variant: up to four 128-env tiles per CTA
-constexpr int kPolicyTcImagePad = 14880;     // ROBOY_TC_IMAGE_BYTES rounded up to 128 bytes, in floats  // threads per CTA at most; one CTA per SM (shared memory bound)
+constexpr int kPolicyTcImagePad = 15040;     // ROBOY_TC_IMAGE_BYTES rounded up to 128 bytes, in floats  // threads per CTA at most; one CTA per SM (shared memory bound)
 
 struct PolicyParams {
     const float *__restrict__ image;  // [ROBOY_POLICY_IMAGE_FLOATS] packed policy (include/roboy_b200.h)

@@ -8,7 +8,7 @@
 //
 //   * a CTA holds up to four TILES of 128 envs; thread i of a tile owns env i = row i of every matrix
 //     = lane i of the tile's 128 tensor-memory columns (48 for the activations A and the input block, packed
-//     two float16 per column, 64 for the float32 accumulator D; 160 columns and three tiles in exact mode);
+//     two float16 per column, 64 for the float32 accumulator D);
 //   * per layer the tile's threads write their activation row into TMEM (tcgen05.st), one thread issues
 //     K/16 tcgen05.mma (M = 128 envs, N = 64 / 16 outputs, K = 16 per instruction; A from TMEM, the weight
 //     matrix B from shared memory in the canonical K-major core-matrix layout, no swizzle) and commits
@@ -25,7 +25,7 @@
 //          range), float32 accumulation, tanh.approx: action means and values agree with the float32 policy to ~1e-3;
 //   exact  every operand split x = hi + lo into two float16 (22 mantissa bits), each product accumulated in float32 as
 //          A_hi W_hi + A_hi W_lo + A_lo W_hi (three MMA groups into the same accumulator), and the float32 kernel's
-//          tanh (ex2 + rcp): ~1e-6, the accuracy of torch's own float32 forward, at 2.5x the float32 FFMA2 kernel.
+//          tanh (ex2 + rcp): ~1e-6, the accuracy of torch's own float32 forward, at 2.8x the float32 FFMA2 kernel.
 // Tensor cores are used HERE because this IS a dense contraction; the env step itself has none and stays off them.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -40,18 +40,23 @@ namespace roboy {
 namespace {
 
 constexpr int kTileEnvs = 128;      // rows of one MMA = TMEM lanes
-// TMEM columns of one tile (float16 pairs for A, float32 for D):
-//   fast : activations [0,32) | constant-1 block [32,40) | input block [40,48) | D [64,128)                    -> 128 per tile
-//   exact: the same plus the LOW halves of the split operands, activations [40,72) and input [80,88); D [96,160) -> 160 per tile
+// TMEM columns of one tile (float16 pairs for A, float32 for D), 128 per tile in both modes -> four tiles per SM:
+//   fast : activations [0,32) | constant-1 block [32,40) | input block [40,48) | D [64,128)
+//          (biases ride in the product: the constant-1 block multiplies the bias column of W2 / W3)
+//   exact: HIGH halves of the activations [0,32) | LOW halves [32,64) | D [64,128); the input block is written over the
+//          first 8 columns of each half before every network's first layer, and the biases of the 64-input layers
+//          are added in float32 by the epilogue (no room for a constant-1 block)
 template <bool EXACT>
 struct Cols {
-    static constexpr int A = 0, Ones = 32;
-    static constexpr int ALo = 40;                       // exact only
-    static constexpr int In = EXACT ? 72 : 40;
-    static constexpr int InLo = 80;                      // exact only
-    static constexpr int D = EXACT ? 96 : 64;
-    static constexpr int Tile = EXACT ? 160 : 128;
-    static constexpr int MaxGroups = EXACT ? 3 : 4;      // 512 TMEM columns per SM
+    static constexpr int A = 0;
+    static constexpr int Ones = 32;                      // fast only
+    static constexpr int ALo = 32;                       // exact only
+    static constexpr int In = EXACT ? 0 : 40;
+    static constexpr int InLo = 32;                      // exact only
+    static constexpr int D = 64;
+    static constexpr int Tile = 128;
+    static constexpr int MaxGroups = 4;                  // 512 TMEM columns per SM
+    static constexpr int KHid = EXACT ? 64 : ROBOY_TC_K_HIDDEN;   // K the 64-input layers' MMAs run over
 };
 constexpr int kKHid = ROBOY_TC_K_HIDDEN;  // 80: K of the 64-input layers including the bias column block
 
@@ -149,8 +154,9 @@ struct TileCtx {
 // threads meet, one of them issues the MMAs and commits them to the tile's mbarrier.  wait: D is readable.
 // EXACT: every operand is split x = hi + lo with hi = float16(x), lo = float16(x - hi) (22 mantissa bits together), and
 // the product is accumulated as A_hi W_hi + A_hi W_lo + A_lo W_hi in float32 -- float32-level accuracy from float16 MMAs.
-// a_col / lo_col: first TMEM column of the (high / low) A block; K_LO: K of the low block (it has no constant-1 columns).
-template <int K, int K_LO, int N, bool EXACT>
+// a_col / lo_col: first TMEM column of the (high / low) A block.
+// K: the K range the MMAs cover; K_LAYOUT: K of W's layout in shared memory (its 8-row groups are K_LAYOUT * 16 bytes apart).
+template <int K, int K_LAYOUT, int N, bool EXACT>
 __device__ __forceinline__ void gemm_issue(const TileCtx &c, uint32_t a_col, uint32_t lo_col, uint32_t w_saddr) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -160,15 +166,15 @@ __device__ __forceinline__ void gemm_issue(const TileCtx &c, uint32_t a_col, uin
         // one MMA consumes K = 16: 8 TMEM columns of A, two 16-byte core-matrix columns (256 B) of W
 #pragma unroll
         for (int i = 0; i < K / 16; ++i)
-            mma_f16_ts(c.mma_d, c.mma_a + a_col + i * 8, smem_desc(w_saddr + i * 256, 128, K * 16), idesc_f16(N), i > 0);
+            mma_f16_ts(c.mma_d, c.mma_a + a_col + i * 8, smem_desc(w_saddr + i * 256, 128, K_LAYOUT * 16), idesc_f16(N), i > 0);
         if (EXACT) {
 #pragma unroll
             for (int i = 0; i < K / 16; ++i)
-                mma_f16_ts(c.mma_d, c.mma_a + a_col + i * 8, smem_desc(w_saddr + ROBOY_TC_OFF_LO_BYTES + i * 256, 128, K * 16),
-                           idesc_f16(N), 1);
+                mma_f16_ts(c.mma_d, c.mma_a + a_col + i * 8,
+                           smem_desc(w_saddr + ROBOY_TC_OFF_LO_BYTES + i * 256, 128, K_LAYOUT * 16), idesc_f16(N), 1);
 #pragma unroll
-            for (int i = 0; i < K_LO / 16; ++i)
-                mma_f16_ts(c.mma_d, c.mma_a + lo_col + i * 8, smem_desc(w_saddr + i * 256, 128, K * 16), idesc_f16(N), 1);
+            for (int i = 0; i < K / 16; ++i)
+                mma_f16_ts(c.mma_d, c.mma_a + lo_col + i * 8, smem_desc(w_saddr + i * 256, 128, K_LAYOUT * 16), idesc_f16(N), 1);
         }
         mma_commit(c.mbar);
     }
@@ -197,16 +203,25 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t &hi, ui
     lo = pack_f16x2(__fsub_rn(x0, f16_lo_to_f32(hi)), __fsub_rn(x1, f16_hi_to_f32(hi)));
 }
 
-// A[:, 0..63] = tanh(D[:, 0..63]) as float16 pairs (the bias is already in D).  Fast: MUFU.TANH; exact: the
-// float32 kernel's tanh (ex2 + rcp, abs error ~3e-7) and the result split into high and low halves.
+// A[:, 0..63] = tanh(D[:, 0..63] + bias) as float16 pairs.  Fast: MUFU.TANH, the bias is already in D (bias = nullptr);
+// exact: the float32 kernel's tanh (ex2 + rcp, abs error ~3e-7), the result split into high and low halves, and the
+// float32 bias of a 64-input layer added here.
 template <bool EXACT>
-__device__ __forceinline__ void tile_activation(const TileCtx &c) {
+__device__ __forceinline__ void tile_activation(const TileCtx &c, const float *__restrict__ bias) {
     using L = Cols<EXACT>;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
         float v[16];
         tmem_ld16(c.tmem_a + L::D + ch * 16, v);
         tmem_ld_wait16(v);
+        if (EXACT && bias) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 b = *reinterpret_cast<const float4 *>(bias + ch * 16 + i);
+                v[i] = __fadd_rn(v[i], b.x); v[i + 1] = __fadd_rn(v[i + 1], b.y);
+                v[i + 2] = __fadd_rn(v[i + 2], b.z); v[i + 3] = __fadd_rn(v[i + 3], b.w);
+            }
+        }
         uint32_t h[8], l[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -218,39 +233,7 @@ __device__ __forceinline__ void tile_activation(const TileCtx &c) {
     }
 }
 
-// One network for the group's U tiles: obs (9) -> 64 -> 64 -> out (first 8 of the 16 padded output columns),
-// biases included.  The input block [obs, 1, 0...] already sits in TMEM of every tile.  With U = 2 the tiles
-// ping-pong: while one tile's MMAs run, the threads do the other tile's activation math.
-template <int U, bool EXACT>
-__device__ __forceinline__ void group_mlp(TileCtx (&c)[U], const uint16_t *__restrict__ net, float (&out)[U][8]) {
-    using L = Cols<EXACT>;
-    const uint32_t w1 = smem_u32(net + ROBOY_TC_OFF_W1), w2 = smem_u32(net + ROBOY_TC_OFF_W2), w3 = smem_u32(net + ROBOY_TC_OFF_W3);
-#pragma unroll
-    for (int u = 0; u < U; ++u) gemm_issue<16, 16, 64, EXACT>(c[u], L::In, L::InLo, w1);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        gemm_wait(c[u]);
-        tile_activation<EXACT>(c[u]);
-        gemm_issue<kKHid, 64, 64, EXACT>(c[u], L::A, L::ALo, w2);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        gemm_wait(c[u]);
-        tile_activation<EXACT>(c[u]);
-        gemm_issue<kKHid, 64, 16, EXACT>(c[u], L::A, L::ALo, w3);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        gemm_wait(c[u]);
-        float v[16];
-        tmem_ld16(c[u].tmem_a + L::D, v);
-        tmem_ld_wait16(v);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) out[u][k] = v[k];
-    }
-}
-
-// K = 16 input block of a tile: obs[0..8], 1 (multiplies the bias column of W1), zeros.  Written once per step.
+// K = 16 input block of a tile: obs[0..8], 1 (multiplies the bias column of W1), zeros.
 template <bool EXACT>
 __device__ __forceinline__ void store_input(const TileCtx &c, const float (&o)[kObsDim]) {
     using L = Cols<EXACT>;
@@ -266,6 +249,43 @@ __device__ __forceinline__ void store_input(const TileCtx &c, const float (&o)[k
         a[4] = pack_f16x2(o[8], 1.0f);
     }
     tmem_st<8>(c.tmem_a + L::In, a);
+}
+
+// One network for the group's U tiles: obs (9) -> 64 -> 64 -> out (first 8 of the 16 padded output columns), biases
+// included.  Fast: the input block [obs, 1, 0...] already sits in its own TMEM columns; exact: it is written here, over
+// the first columns of the activation blocks.  `bias32`: the float32 biases b2 [64] | b3 [16] of this network (exact).
+// With U = 2 the tiles ping-pong: while one tile's MMAs run, the threads do the other tile's activation math.
+template <int U, bool EXACT>
+__device__ __forceinline__ void group_mlp(TileCtx (&c)[U], const uint16_t *__restrict__ net, const float *__restrict__ bias32,
+                                          const float (&o)[U][kObsDim], float (&out)[U][8]) {
+    using L = Cols<EXACT>;
+    const uint32_t w1 = smem_u32(net + ROBOY_TC_OFF_W1), w2 = smem_u32(net + ROBOY_TC_OFF_W2), w3 = smem_u32(net + ROBOY_TC_OFF_W3);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (EXACT) store_input<EXACT>(c[u], o[u]);
+        gemm_issue<16, 16, 64, EXACT>(c[u], L::In, L::InLo, w1);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        gemm_wait(c[u]);
+        tile_activation<EXACT>(c[u], nullptr);                       // b1 rides in the product in both modes
+        gemm_issue<L::KHid, kKHid, 64, EXACT>(c[u], L::A, L::ALo, w2);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        gemm_wait(c[u]);
+        tile_activation<EXACT>(c[u], bias32);
+        gemm_issue<L::KHid, kKHid, 16, EXACT>(c[u], L::A, L::ALo, w3);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        gemm_wait(c[u]);
+        float v[16];
+        tmem_ld16(c[u].tmem_a + L::D, v);
+        tmem_ld_wait16(v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[u][k] = EXACT ? __fadd_rn(v[k], bias32[64 + k]) : v[k];
+    }
 }
 
 }  // namespace
@@ -337,6 +357,7 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
     const uint16_t *vf_net = img16 + ROBOY_TC_OFF_VF, *pi_net = img16 + ROBOY_TC_OFF_PI;
     const float *sd = img + ROBOY_TC_OFF_STD_BYTES / 4;   // (the image keeps its layout in shared memory)
     const float lognorm = sd[8];
+    const float *bias32 = sd + 12;   // float32 b2 | b3 per network (exact mode)
     float sum_reward = 0.0f;
 
 #ifdef ROBOY_TC_STAGGER  // experiment: start the groups out of phase
@@ -364,22 +385,24 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
             else normalize_goal<false>(s[u], p.c, p.f);
 #pragma unroll
             for (int k = 0; k < kObsDim; ++k) o[u][k] = live[u] ? q.obs[(size_t)env[u] * kObsDim + k] : 0.f;
-            // the constant K block behind the 64 activations: 1 (multiplies the bias column of W2 / W3), then zeros
-            const uint32_t ones[8] = {pack_f16x2(1.0f, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            tmem_st<8>(c[u].tmem_a + L::Ones, ones);
+            if (!EXACT) {   // the constant K block behind the 64 activations: 1 (multiplies the bias column of W2 / W3), then zeros
+                const uint32_t ones[8] = {pack_f16x2(1.0f, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                tmem_st<8>(c[u].tmem_a + L::Ones, ones);
+            }
         }
 
         for (uint32_t tt = 0;; ++tt) {
             float out[U][8];
 #pragma unroll
-            for (int u = 0; u < U; ++u) store_input<EXACT>(c[u], o[u]);
+            for (int u = 0; u < U; ++u)
+                if (!EXACT) store_input<EXACT>(c[u], o[u]);   // (exact: written per network, it shares columns with the activations)
             if constexpr (EXACT) {
                 // one copy of the network code for both nets: the exact kernel is three times the size of the fast one
                 // and instruction-cache misses showed in its profile (measured +12 %; the fast kernel loses 1 % this way)
                 bool last = false;
 #pragma unroll 1
                 for (int net = 0; net < 2; ++net) {
-                    group_mlp<U, EXACT>(c, net == 0 ? vf_net : pi_net, out);   // value of obs[tt], then the Gaussian's mean
+                    group_mlp<U, EXACT>(c, net == 0 ? vf_net : pi_net, bias32 + net * ROBOY_TC_BIAS32_NET_FLOATS, o, out);   // value of obs[tt], then the mean
                     if (net == 0) {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
@@ -389,12 +412,12 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
                 }
                 if (last) break;
             } else {
-                group_mlp<U, EXACT>(c, vf_net, out);                      // value of obs[tt] (bootstrap value at tt == T)
+                group_mlp<U, EXACT>(c, vf_net, bias32, o, out);           // value of obs[tt] (bootstrap value at tt == T)
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if (live[u]) q.values[(size_t)tt * n + env[u]] = out[u][0];
                 if (tt == q.T) break;
-                group_mlp<U, EXACT>(c, pi_net, out);                      // mean of the Gaussian
+                group_mlp<U, EXACT>(c, pi_net, bias32 + ROBOY_TC_BIAS32_NET_FLOATS, o, out);   // mean of the Gaussian
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {

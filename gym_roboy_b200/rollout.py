@@ -119,6 +119,11 @@ def pack_policy_image_tc(policy, out=None):
     log_std = policy.log_std.detach()
     tail[:8].copy_(log_std.exp())
     tail[8] = -0.5 * math.log(2 * math.pi) * log_std.numel() - log_std.sum()
+    for i, net in enumerate((policy.vf, policy.pi)):    # float32 biases of the 64-input layers (exact mode's epilogue)
+        b = tail[12 + i * N.TC_BIAS32_NET_FLOATS: 12 + (i + 1) * N.TC_BIAS32_NET_FLOATS]
+        b.zero_()
+        b[:64].copy_(net[2].bias.detach())
+        b[64: 64 + net[4].bias.shape[0]].copy_(net[4].bias.detach())
     return img
 
 

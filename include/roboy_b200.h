@@ -291,7 +291,8 @@ int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uin
  *   element index of W[n][k] = (n / 8) * (K / 8) * 64 + (k / 8) * 64 + (n % 8) * 8 + (k % 8);
  * the image is  value net | policy net  (HIGH halves: float16(w)),  then the same two networks again with the LOW
  * halves float16(w - high) at byte ROBOY_TC_OFF_LO_BYTES (read only when exact = 1),  then, as float32 at byte
- * ROBOY_TC_OFF_STD_BYTES,  std [8] | lognorm | 3 floats of padding.
+ * ROBOY_TC_OFF_STD_BYTES,  std [8] | lognorm | 3 floats of padding | b2 [64] | b3 [16] of the value net | the same of
+ * the policy net (float32 biases of the 64-input layers: exact = 1 adds them in its epilogue instead of the product).
  * tiles_per_group: 0 = default (1); 1 = each group of 128 threads owns one 128-env tile; 2 = two tiles per group, worked
  * on alternately (an experiment, exact = 0 only: measured 35 % slower than 1 on B200; results are bit-identical). */
 #define ROBOY_TC_K_HIDDEN 80
@@ -303,7 +304,8 @@ int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uin
 #define ROBOY_TC_OFF_PI 7424
 #define ROBOY_TC_OFF_LO_BYTES 29696
 #define ROBOY_TC_OFF_STD_BYTES 59392
-#define ROBOY_TC_IMAGE_BYTES 59440
+#define ROBOY_TC_BIAS32_NET_FLOATS 80
+#define ROBOY_TC_IMAGE_BYTES 60080
 int roboy_policy_rollout_tc(roboy_env *env, uint32_t T, const float *tc_image_dev, uint64_t noise_seed, float *obs_dev,
                             float *actions_dev, float *logp_dev, float *values_dev, float *reward_dev, uint8_t *done_dev,
                             float *noise_dev, int tiles_per_group, int exact, void *stream);
