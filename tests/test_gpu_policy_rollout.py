@@ -278,3 +278,28 @@ def test_env_trajectory_is_identical_across_the_three_fused_kernels():
         for a, b in zip(outs["fp32"], outs[mode]):
             assert torch.equal(a, b), mode
     # ... while the policy outputs agree only to the kernels' tolerances (checked elsewhere)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc", "tc_exact"])
+def test_saturated_policy(mode):
+    """Weights scaled up until most tanh units saturate (|pre-activation| up to ~60): no NaN / inf anywhere, values and
+    means still track the torch float32 policy (relative to their now larger magnitude)."""
+    n, T = 2048, 3
+    policy, client, col = make(n, 41, T, fused=mode)
+    with torch.no_grad():
+        for net in (policy.pi, policy.vf):
+            net[0].weight.mul_(8.0); net[2].weight.mul_(8.0); net[4].weight.mul_(4.0)
+    col.noise = torch.zeros((T, n, 8), dtype=torch.float32, device=DEV)
+    obs0 = col.obs[0].clone()
+    col.collect()
+    torch.cuda.synchronize()
+    for k in ("actions", "logp", "values", "rewards", "adv", "ret"):
+        assert bool(torch.isfinite(getattr(col, k)).all()), k
+    with torch.no_grad():
+        mean, value = policy(obs0)
+    scale = float(mean.abs().max())
+    tol = 5e-3 if mode == "tc" else 5e-5
+    got_mean = col.actions[0] - policy.log_std.detach().exp() * col.noise[0]
+    assert float((got_mean - mean).abs().max()) <= tol * max(scale, 1.0)
+    assert float((col.values[0] - value).abs().max()) <= tol * max(float(value.abs().max()), 1.0)
+    assert client.errors() == (0, None)
