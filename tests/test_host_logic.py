@@ -156,3 +156,58 @@ def test_policy_image_layouts_match_the_header():
         assert abs(float(halves[i].float() + lows[i].float() - w2[3, 40])) <= 2.0 ** -21 * abs(float(w2[3, 40])) + 2.0 ** -25
     tail = tc[N.TC_OFF_STD_BYTES:].view(torch.float32)
     assert torch.equal(tail[:8], pol.log_std.detach().exp())
+
+
+def test_packed_policy_images_reproduce_the_policy_on_the_cpu():
+    """Decode both packed images with nothing but the header's layout formulas and run the forward pass from them:
+    the float32 image must reproduce the torch policy to rounding, the tensor-core image (hi + lo halves, bias as an
+    extra input column) to float32 level with both halves and to ~1e-3 with the high halves alone."""
+    import torch
+    from gym_roboy_b200 import _native as N
+    from gym_roboy_b200.rollout import MlpPolicy, pack_policy_image, pack_policy_image_tc
+    torch.manual_seed(11)
+    pol = MlpPolicy()
+    with torch.no_grad():
+        pol.log_std.copy_(torch.linspace(-0.5, 0.3, 8))
+    obs = torch.rand(257, 9) * 6.0 - 3.0
+    with torch.no_grad():
+        want_mean, want_value = pol(obs)
+
+    img = pack_policy_image(pol).double()
+
+    def fwd32(base, n_out):
+        w1 = img[base + N.POLICY_OFF_W1: base + N.POLICY_OFF_B1].view(9, 64)
+        w2 = img[base + N.POLICY_OFF_W2: base + N.POLICY_OFF_B2].view(64, 64)
+        w3 = img[base + N.POLICY_OFF_W3: base + N.POLICY_OFF_B3].view(64, 8)
+        b1, b2 = img[base + N.POLICY_OFF_B1: base + N.POLICY_OFF_W2], img[base + N.POLICY_OFF_B2: base + N.POLICY_OFF_W3]
+        b3 = img[base + N.POLICY_OFF_B3: base + N.POLICY_NET_FLOATS]
+        h = torch.tanh(torch.tanh(obs.double() @ w1 + b1) @ w2 + b2) @ w3 + b3
+        return h[:, :n_out]
+    assert torch.allclose(fwd32(N.POLICY_OFF_PI, 8).float(), want_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(fwd32(N.POLICY_OFF_VF, 1)[:, 0].float(), want_value, rtol=1e-5, atol=1e-6)
+
+    tc = pack_policy_image_tc(pol)
+    halves = (tc[:N.TC_OFF_LO_BYTES].view(torch.float16).double(), tc[N.TC_OFF_LO_BYTES:N.TC_OFF_STD_BYTES].view(torch.float16).double())
+
+    def dense(part, base, off, n_pad, k_pad):      # undo the K-major core-matrix layout: [n/8, k/8, 8, 8] -> [n, k]
+        flat = part[base + off: base + off + n_pad * k_pad]
+        return flat.view(n_pad // 8, k_pad // 8, 8, 8).permute(0, 2, 1, 3).reshape(n_pad, k_pad)
+
+    def fwd_tc(base, n_out, use_lo):
+        def lin(x, off, n_pad, k_pad):             # x: [batch, k_pad] with the constant 1 already in place
+            w = dense(halves[0], base, off, n_pad, k_pad) + (dense(halves[1], base, off, n_pad, k_pad) if use_lo else 0)
+            return x @ w.t()
+        x = torch.zeros(obs.shape[0], 16, dtype=torch.float64); x[:, :9] = obs; x[:, 9] = 1.0
+        h = torch.tanh(lin(x, N.TC_OFF_W1, 64, 16))
+        for off, n_pad in ((N.TC_OFF_W2, 64), (N.TC_OFF_W3, 16)):
+            x = torch.zeros(obs.shape[0], 80, dtype=torch.float64); x[:, :64] = h; x[:, 64] = 1.0
+            h = lin(x, off, n_pad, 80)
+            if n_pad == 64:
+                h = torch.tanh(h)
+        return h[:, :n_out]
+    assert torch.allclose(fwd_tc(N.TC_OFF_PI, 8, True).float(), want_mean, rtol=1e-5, atol=2e-6)
+    assert torch.allclose(fwd_tc(N.TC_OFF_VF, 1, True)[:, 0].float(), want_value, rtol=1e-5, atol=2e-6)
+    assert float((fwd_tc(N.TC_OFF_PI, 8, False).float() - want_mean).abs().max()) < 2e-3    # high halves alone: float16 weights
+    tail = tc[N.TC_OFF_STD_BYTES:].view(torch.float32)
+    assert torch.equal(tail[12:76], pol.vf[2].bias.detach()) and torch.equal(tail[12 + 80:12 + 80 + 64], pol.pi[2].bias.detach())
+    assert tail[12 + 64] == pol.vf[4].bias.detach()[0] and torch.equal(tail[12 + 80 + 64:12 + 80 + 72], pol.pi[4].bias.detach())
