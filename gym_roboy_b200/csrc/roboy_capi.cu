@@ -877,7 +877,8 @@ static int policy_rollout_common(roboy_env *env, bool tensor_cores, bool exact, 
     if (((uintptr_t)image_dev & 15) || ((uintptr_t)actions_dev & 15) || (noise_dev && ((uintptr_t)noise_dev & 15)))
         return fail(ROBOY_E_ARG, "image, actions and noise must be 16-byte aligned");
     if ((uintptr_t)obs_dev & 3) return fail(ROBOY_E_ARG, "obs must be 4-byte aligned");
-    if (envs_per_thread < 0 || envs_per_thread > 2) return fail(ROBOY_E_ARG, "envs_per_thread must be 0, 1 or 2");
+    if (envs_per_thread < 0 || envs_per_thread > (tensor_cores ? 3 : 2))
+        return fail(ROBOY_E_ARG, "envs_per_thread must be 0, 1 or 2 (tensor-core variant: 0..3)");
     if (T == 0) return ROBOY_OK;
     DeviceGuard g(env->device);
     env->goal_sub = 1;

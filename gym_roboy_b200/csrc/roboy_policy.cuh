@@ -36,8 +36,8 @@ cudaError_t launch_policy_rollout(const StepParams &p, const PolicyParams &q, bo
                                   bool fastdiv, int sm_count, int envs_per_thread, cudaStream_t stream);
 
 // tensor-core (tcgen05, TF32) variant: q.image is the ROBOY_TC_* image
-// tiles_per_group: 0 = choose; 1 = one 128-env tile per group of 128 threads; 2 = two tiles per group, ping-pong
-// (PolicyGeom::envs_per_thread returns the choice)
+// variant: 0 = choose; 1 = one 128-env tile per group of 128 threads; 2 = two tiles per group, ping-pong; 3 = merged
+// (both networks of a tile advance together: small populations).  PolicyGeom::envs_per_thread returns the choice.
 // exact: split-float16 operands (float32-level accuracy) instead of single float16 operands
 PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count, int tiles_per_group, bool exact);
 cudaError_t launch_policy_rollout_tc(const StepParams &p, const PolicyParams &q, bool penalty, bool bonus, bool auto_reset,

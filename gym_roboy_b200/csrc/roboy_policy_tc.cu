@@ -19,6 +19,8 @@
 //   * four tiles (16 warps) per SM overlap one tile's MMA round trips with the others' activation math.  (A
 //     variant in which each group of 128 threads ping-pongs TWO tiles, template parameter U = 2, measured 35 %
 //     slower: with the same four tiles in flight it has half the warps to hide TMEM / MUFU latency behind.)
+//     Small populations (at most two tiles per SM) run the MERGED form instead: both networks of a tile advance
+//     together, three round trips per step instead of six (+11 % at 4,096 envs).
 //
 // Arithmetic, two modes (template parameter EXACT):
 //   fast   float16 operands (10-bit mantissa, the precision of TF32; every operand here is far inside float16's
@@ -55,8 +57,13 @@ struct Cols {
     static constexpr int InLo = 32;                      // exact only
     static constexpr int D = 64;
     static constexpr int Tile = 128;
-    static constexpr int MaxGroups = 4;                  // 512 TMEM columns per SM
     static constexpr int KHid = EXACT ? 64 : ROBOY_TC_K_HIDDEN;   // K the 64-input layers' MMAs run over
+};
+// merged (fast arithmetic, small populations): both networks advance together, one MMA round trip per layer instead of
+// two -- activations of the value net [0,32) | of the policy net [32,64) | constant-1 block [64,72) | input block
+// [72,80) | D of the value net [128,192) | D of the policy net [192,256): 256 columns per tile, two tiles per SM
+struct ColsMerged {
+    static constexpr int AVf = 0, APi = 32, Ones = 64, In = 72, DVf = 128, DPi = 192, Tile = 256, MaxGroups = 2;
 };
 constexpr int kKHid = ROBOY_TC_K_HIDDEN;  // 80: K of the 64-input layers including the bias column block
 
@@ -288,12 +295,77 @@ __device__ __forceinline__ void group_mlp(TileCtx (&c)[U], const uint16_t *__res
     }
 }
 
+// ---- merged form: the value and the policy network of one tile advance together ----
+// One round trip: for each network K/16 (+1 for the constant-1 block) MMAs into its own accumulator, ONE commit.
+template <int N, bool HIDDEN>
+__device__ __forceinline__ void merged_issue(const TileCtx &c, uint32_t w_vf, uint32_t w_pi) {
+    using M = ColsMerged;
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync %0, 128;" :: "r"(c.bar_id) : "memory");
+    if (c.issuer) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int net = 0; net < 2; ++net) {
+            const uint32_t d = c.mma_a + (net ? M::DPi : M::DVf), a = c.mma_a + (net ? M::APi : M::AVf), w = net ? w_pi : w_vf;
+            if (HIDDEN) {   // 64 activations (4 MMAs) + the constant-1 block against the bias columns of W (K layout 80)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mma_f16_ts(d, a + i * 8, smem_desc(w + i * 256, 128, kKHid * 16), idesc_f16(N), i > 0);
+                mma_f16_ts(d, c.mma_a + M::Ones, smem_desc(w + 4 * 256, 128, kKHid * 16), idesc_f16(N), 1);
+            } else {        // the K = 16 input block, shared by both networks
+                mma_f16_ts(d, c.mma_a + M::In, smem_desc(w, 128, 16 * 16), idesc_f16(N), 0);
+            }
+        }
+        mma_commit(c.mbar);
+    }
+}
+
+__device__ __forceinline__ void merged_activation(const TileCtx &c) {
+    using M = ColsMerged;
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            float v[16];
+            tmem_ld16(c.tmem_a + (net ? M::DPi : M::DVf) + ch * 16, v);
+            tmem_ld_wait16(v);
+            uint32_t h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = pack_f16x2(tanh_approx(v[2 * i]), tanh_approx(v[2 * i + 1]));
+            tmem_st<8>(c.tmem_a + (net ? M::APi : M::AVf) + ch * 8, h);
+        }
+    }
+}
+
+// value = first output of the value net, mean = the 8 outputs of the policy net; three round trips
+__device__ __forceinline__ void merged_mlp(TileCtx &c, const uint16_t *__restrict__ vf, const uint16_t *__restrict__ pi, float &value,
+                                           float (&mean)[8]) {
+    using M = ColsMerged;
+    merged_issue<64, false>(c, smem_u32(vf + ROBOY_TC_OFF_W1), smem_u32(pi + ROBOY_TC_OFF_W1));
+    gemm_wait(c);
+    merged_activation(c);
+    merged_issue<64, true>(c, smem_u32(vf + ROBOY_TC_OFF_W2), smem_u32(pi + ROBOY_TC_OFF_W2));
+    gemm_wait(c);
+    merged_activation(c);
+    merged_issue<16, true>(c, smem_u32(vf + ROBOY_TC_OFF_W3), smem_u32(pi + ROBOY_TC_OFF_W3));
+    gemm_wait(c);
+    float v[16], m[16];
+    tmem_ld16(c.tmem_a + M::DVf, v);
+    tmem_ld16(c.tmem_a + M::DPi, m);
+    tmem_ld_wait16(v);
+    tmem_ld_wait16(m);
+    value = v[0];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mean[k] = m[k];
+}
+
 }  // namespace
 
 // U = tiles per group of 128 threads (thread i of the group owns row i of each of its U tiles); EXACT: split-float16
 // operands and the accurate tanh (float32-level accuracy) instead of single float16 operands and tanh.approx.
-template <int U, bool EXACT>
-__global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_kernel(const __grid_constant__ StepParams p,
+// MERGED (fast arithmetic, U = 1): both networks of a tile advance together, three MMA round trips per step instead of six.
+template <int U, bool EXACT, bool MERGED = false>
+__global__ void __launch_bounds__(kPolicyTcMaxBlock / (MERGED ? 2 : U), 1) policy_rollout_tc_kernel(const __grid_constant__ StepParams p,
                                                                                       const __grid_constant__ PolicyParams q) {
     extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31;
@@ -322,7 +394,8 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int n_tiles = n_groups * U;
-    const uint32_t need_cols = (uint32_t)n_tiles * L::Tile;
+    constexpr int kTile = MERGED ? ColsMerged::Tile : L::Tile;
+    const uint32_t need_cols = (uint32_t)n_tiles * kTile;
     const uint32_t tmem_cols = need_cols <= 128 ? 128u : need_cols <= 256 ? 256u : 512u;   // a power of two >= 32
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -340,7 +413,7 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int tile = group * U + u;
-        c[u].mma_a = tmem_base + tile * L::Tile;
+        c[u].mma_a = tmem_base + tile * kTile;
         c[u].mma_d = c[u].mma_a + L::D;
         c[u].tmem_a = c[u].mma_a + ((uint32_t)((warp & 3) * 32) << 16);
         c[u].mbar = smem_u32(mbars + tile);
@@ -387,12 +460,23 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
             for (int k = 0; k < kObsDim; ++k) o[u][k] = live[u] ? q.obs[(size_t)env[u] * kObsDim + k] : 0.f;
             if (!EXACT) {   // the constant K block behind the 64 activations: 1 (multiplies the bias column of W2 / W3), then zeros
                 const uint32_t ones[8] = {pack_f16x2(1.0f, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                tmem_st<8>(c[u].tmem_a + L::Ones, ones);
+                tmem_st<8>(c[u].tmem_a + (MERGED ? ColsMerged::Ones : L::Ones), ones);
             }
         }
 
         for (uint32_t tt = 0;; ++tt) {
             float out[U][8];
+            if constexpr (MERGED) {
+                {
+                    const uint32_t a[8] = {pack_f16x2(o[0][0], o[0][1]), pack_f16x2(o[0][2], o[0][3]), pack_f16x2(o[0][4], o[0][5]),
+                                           pack_f16x2(o[0][6], o[0][7]), pack_f16x2(o[0][8], 1.0f), 0u, 0u, 0u};
+                    tmem_st<8>(c[0].tmem_a + ColsMerged::In, a);
+                }
+                float value;
+                merged_mlp(c[0], vf_net, pi_net, value, out[0]);
+                if (live[0]) q.values[(size_t)tt * n + env[0]] = value;
+                if (tt == q.T) break;
+            } else {
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (!EXACT) store_input<EXACT>(c[u], o[u]);   // (exact: written per network, it shares columns with the activations)
@@ -419,6 +503,7 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
                 if (tt == q.T) break;
                 group_mlp<U, EXACT>(c, pi_net, bias32 + ROBOY_TC_BIAS32_NET_FLOATS, o, out);   // mean of the Gaussian
             }
+            }   // !MERGED
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 float *row = stage + (u * 32 + lane) * kObsDim;
@@ -458,15 +543,20 @@ __global__ void __launch_bounds__(kPolicyTcMaxBlock / U, 1) policy_rollout_tc_ke
     }
 }
 
-PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count, int tiles_per_group, bool exact) {
+PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count, int variant, bool exact) {
     PolicyGeom g;
-    // one tile per thread group by default: four groups (16 warps) per SM hide the MMA round trips and the TMEM / MUFU
-    // latencies better than two groups ping-ponging two tiles each (measured on B200 at 1,048,576 envs: 1.09e10 vs
-    // 7.1e9 env-steps/s); the two-tile form stays selectable for experiments (fast mode only)
-    const int U = (tiles_per_group == 2 && !exact) ? 2 : 1;
-    g.envs_per_thread = U;
+    const uint64_t n_tiles = (n_envs + kTileEnvs - 1) / kTileEnvs;
+    // variant 0 = choose: small populations (at most two 128-env tiles per SM) are bound by the MMA round trips of
+    // a step, so both networks advance together (3, "merged": three round trips instead of six; fast arithmetic only);
+    // otherwise one tile per thread group (1): four groups (16 warps) per SM hide the round trips and the TMEM / MUFU
+    // latencies better than two groups ping-ponging two tiles each (2; measured at 1,048,576 envs: 1.09e10 vs 7.1e9
+    // env-steps/s), which stays selectable for experiments.
+    if (variant == 0) variant = (!exact && n_tiles <= 2ull * sm_count) ? 3 : 1;
+    if (exact) variant = 1;
+    const int U = variant == 2 ? 2 : 1;
+    g.envs_per_thread = variant;
     const uint64_t n_chunks = (n_envs + U * kTileEnvs - 1) / (U * kTileEnvs);
-    const uint64_t max_groups = (exact ? Cols<true>::MaxGroups : Cols<false>::MaxGroups) / U;   // TMEM: 512 columns per SM
+    const uint64_t max_groups = variant == 3 ? ColsMerged::MaxGroups : 4 / U;   // TMEM: 512 columns per SM
     uint64_t groups = (n_chunks + sm_count - 1) / sm_count;          // spread the groups over the SMs first
     if (groups > max_groups) groups = max_groups;
     const uint64_t grid = (n_chunks + groups - 1) / groups;
@@ -479,17 +569,18 @@ PolicyGeom policy_tc_geometry(uint64_t n_envs, int sm_count, int tiles_per_group
 }
 
 cudaError_t launch_policy_rollout_tc(const StepParams &p, const PolicyParams &q, bool penalty, bool bonus, bool auto_reset,
-                                     bool fastdiv, int sm_count, int tiles_per_group, bool exact, cudaStream_t stream) {
+                                     bool fastdiv, int sm_count, int variant, bool exact, cudaStream_t stream) {
     if (p.e_end <= p.e_begin) return cudaSuccess;
     PolicyParams qq = q;
     qq.penalty = penalty;
     qq.bonus = bonus;
     qq.auto_reset = auto_reset;
     qq.fastdiv = fastdiv;
-    const PolicyGeom g = policy_tc_geometry(p.e_end, sm_count, tiles_per_group, exact);
+    const PolicyGeom g = policy_tc_geometry(p.e_end, sm_count, variant, exact);
     void (*fn)(const StepParams, const PolicyParams) =
         exact ? policy_rollout_tc_kernel<1, true>
-              : (g.envs_per_thread == 1 ? policy_rollout_tc_kernel<1, false> : policy_rollout_tc_kernel<2, false>);
+              : g.envs_per_thread == 3 ? policy_rollout_tc_kernel<1, false, true>
+              : g.envs_per_thread == 2 ? policy_rollout_tc_kernel<2, false> : policy_rollout_tc_kernel<1, false>;
     cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem);
     if (err != cudaSuccess) return err;
     fn<<<g.grid, g.block, g.smem, stream>>>(p, qq);

@@ -293,8 +293,11 @@ int roboy_policy_rollout(roboy_env *env, uint32_t T, const float *image_dev, uin
  * halves float16(w - high) at byte ROBOY_TC_OFF_LO_BYTES (read only when exact = 1),  then, as float32 at byte
  * ROBOY_TC_OFF_STD_BYTES,  std [8] | lognorm | 3 floats of padding | b2 [64] | b3 [16] of the value net | the same of
  * the policy net (float32 biases of the 64-input layers: exact = 1 adds them in its epilogue instead of the product).
- * tiles_per_group: 0 = default (1); 1 = each group of 128 threads owns one 128-env tile; 2 = two tiles per group, worked
- * on alternately (an experiment, exact = 0 only: measured 35 % slower than 1 on B200; results are bit-identical). */
+ * tiles_per_group selects the kernel variant (results are bit-identical across variants): 0 = choose; 1 = each group of
+ * 128 threads owns one 128-env tile, four tiles per SM (large populations); 2 = two tiles per group, worked on
+ * alternately (an experiment, exact = 0 only: measured 35 % slower than 1 on B200); 3 = "merged" (exact = 0 only): the
+ * value and the policy network of a tile advance together, three tensor-core round trips per step instead of six --
+ * chosen automatically while the population is at most two tiles per SM, where those round trips bound the step. */
 #define ROBOY_TC_K_HIDDEN 80
 #define ROBOY_TC_OFF_W1 0
 #define ROBOY_TC_OFF_W2 1024

@@ -53,7 +53,7 @@ POLICY_TOL = {"fp32": dict(rtol=1e-5, atol=2e-5), "tc": dict(rtol=0, atol=4e-3),
 
 
 @pytest.mark.parametrize("n,ept,mode", [(4096, 0, "fp32"), (2531, 2, "fp32"), (40000, 0, "fp32"),
-                                        (4096, 0, "tc"), (2531, 2, "tc"), (80000, 0, "tc"),
+                                        (4096, 0, "tc"), (2531, 2, "tc"), (80000, 0, "tc"), (4096, 1, "tc"), (80000, 3, "tc"),
                                         (4096, 0, "tc_exact"), (2531, 0, "tc_exact"), (80000, 0, "tc_exact")])
 def test_fused_rollout_against_torch_policy_and_oracle_env(n, ept, mode):
     T, seed = 10, 21
@@ -102,10 +102,10 @@ def test_fused_rollout_against_torch_policy_and_oracle_env(n, ept, mode):
 
 @pytest.mark.parametrize("mode", ["fp32", "tc"])
 def test_one_and_two_envs_per_thread_and_sharding_are_bit_identical(mode):
-    """fp32: one or two envs per thread; tc: one or two 128-env tiles per thread group (ping-pong)."""
+    """fp32: one or two envs per thread; tc: one or two 128-env tiles per thread group (ping-pong), or the merged form."""
     n, T = 6000, 6
     ref = None
-    for ept in (1, 2):
+    for ept in ((1, 2) if mode == "fp32" else (1, 2, 3)):
         _, client, col = make(n, 5, T, fused=mode, envs_per_thread=ept)
         col.collect()
         torch.cuda.synchronize()
@@ -198,7 +198,7 @@ def test_fused_rollout_in_a_cuda_graph_and_against_the_unfused_collector(mode):
         assert torch.equal(client.done_u8, eager["dones"][t])
 
 
-@pytest.mark.parametrize("mode,ept", [("fp32", 1), ("fp32", 2), ("tc", 1), ("tc", 2), ("tc_exact", 0)])
+@pytest.mark.parametrize("mode,ept", [("fp32", 1), ("fp32", 2), ("tc", 1), ("tc", 2), ("tc", 3), ("tc_exact", 0)])
 @pytest.mark.parametrize("n", [2, 33, 257, 1001, 2531])
 def test_ragged_sizes_write_nothing_outside_their_buffers(n, mode, ept):
     """(compute-sanitizer is not available on the GPU pool.)  Every rollout buffer is carved out of one arena with
