@@ -42,6 +42,9 @@ namespace roboy {
 #ifndef ROBOY_ROLLOUT_MIN_BLOCKS
 #define ROBOY_ROLLOUT_MIN_BLOCKS ROBOY_STEP_MIN_BLOCKS
 #endif
+#ifndef ROBOY_PDL
+#define ROBOY_PDL 1  // programmatic dependent launch of the step kernel (measured: +0.7 % at 16,777,216 envs, -4 % step time at 65,536, -9 % eager at 4,096)
+#endif
 #ifndef ROBOY_LD_HINT
 #define ROBOY_LD_HINT 0  // streamed inputs:  0 default (measured best: +3% over .cs), 1 ld.global.cs, 2 ld.global.nc.L1::no_allocate
 #endif
@@ -334,6 +337,13 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
     __shared__ unsigned int s_cnt[5];  // done, success, hold, violation, sum of episode lengths
     if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
     __syncthreads();
+#if ROBOY_PDL
+    // programmatic dependent launch: this grid may have been started while its predecessor in the stream (the policy
+    // that produced the actions, or the previous step) was still draining; everything above overlapped with that.
+    // From here on the predecessor's writes (actions, state, call counter) are complete and visible.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -601,8 +611,22 @@ cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto
     if (p.e_end <= p.e_begin) return cudaSuccess;
     const int sel = selector(penalty, bonus, auto_reset, fastdiv);
     const int grid = grid_for(p.e_end - p.e_begin, blocks_per_sm(sel), sm_count);
+#if ROBOY_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kStepBlock);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, select_kernel(sel), p);
+#else
     select_kernel(sel)<<<grid, kStepBlock, 0, stream>>>(p);
     return cudaGetLastError();
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
