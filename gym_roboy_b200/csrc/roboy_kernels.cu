@@ -19,6 +19,7 @@
 // grid-stride loop, so the atomics are per CTA, not per env.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/roboy_b200.h"
 #include "roboy_kernels.cuh"
@@ -612,6 +613,14 @@ cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto
     const int sel = selector(penalty, bonus, auto_reset, fastdiv);
     const int grid = grid_for(p.e_end - p.e_begin, blocks_per_sm(sel), sm_count);
 #if ROBOY_PDL
+    static const bool pdl = [] {   // ROBOY_B200_PDL=0 in the environment turns the launch attribute off (A/B measurements)
+        const char *v = getenv("ROBOY_B200_PDL");
+        return !(v && v[0] == '0');
+    }();
+    if (!pdl) {
+        select_kernel(sel)<<<grid, kStepBlock, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kStepBlock);
