@@ -8,7 +8,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 DIM_JOINT, DIM_ACTION, DIM_OBS = 3, 8, 9
 
 STEP_MASK = 0x00FFFFFF
@@ -25,7 +25,8 @@ POLICY_OFF_VF, POLICY_OFF_PI, POLICY_OFF_STD, POLICY_OFF_LOGNORM, POLICY_IMAGE_F
 TC_K_HIDDEN = 80
 TC_OFF_W1, TC_OFF_W2, TC_OFF_W3, TC_NET_HALVES, TC_OFF_VF, TC_OFF_PI = 0, 1024, 6144, 7424, 0, 7424
 TC_OFF_LO_BYTES, TC_OFF_STD_BYTES, TC_BIAS32_NET_FLOATS, TC_IMAGE_BYTES = 29696, 59392, 80, 60080
-(BUF_GOAL, BUF_STEP_FLAGS, BUF_HELD, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_STATS, BUF_TERMINAL_OBS) = range(8)
+(BUF_GOAL, BUF_STEP_FLAGS, BUF_HELD, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_STATS, BUF_TERMINAL_OBS, BUF_DONE_BITS) = range(9)
+HOST_STAGED, HOST_MAPPED_OUT, HOST_MAPPED_ALL = 0, 1, 2
 
 
 class RoboyCfg(ctypes.Structure):
@@ -59,6 +60,14 @@ SIGNATURES = {
     "roboy_step_many": (_int, [_vp, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "roboy_step_host": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "roboy_set_host_pipeline": (_int, [_vp, _u64, _int]),
+    "roboy_set_host_ramp": (_int, [_vp, _int]),
+    "roboy_set_host_mode": (_int, [_vp, _int]),
+    "roboy_host_alloc": (_int, [_u64, _int, ctypes.POINTER(_vp)]),
+    "roboy_host_free": (_int, [_vp]),
+    "roboy_host_copy_probe": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, ctypes.POINTER(ctypes.c_double)]),
+    "roboy_enable_done_index": (_int, [_vp, _int]),
+    "roboy_done_indices": (_int, [_vp, _vp, _u64, _vp, _vp, _vp]),
+    "roboy_reseed": (_int, [_vp, _u64]),
     "roboy_set_terminal_obs": (_int, [_vp, _vp]),
     "roboy_compute_reward": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "roboy_set_goal": (_int, [_vp, _u64, _vp, _vp, _vp]),
@@ -88,6 +97,7 @@ SIGNATURES = {
     "roboy_policy_geometry": (_int, [_vp, _int, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
                                      ctypes.POINTER(_int)]),
     "roboy_launch_count": (_int, [_vp, ctypes.POINTER(_u64)]),
+    "roboy_null_step": (_int, [_vp, _vp]),
     "roboy_step_geometry": (_int, [_vp, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
 }
 

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 
 #include <atomic>
 #include <new>
@@ -159,6 +160,13 @@ struct roboy_env {
     int host_streams = kHostStreamsDefault;
     uint64_t host_stage_envs = kHostStageEnvsDefault;
     bool host_ready = false;
+    cudaEvent_t hev[kHostStreamsMax] = {};
+    bool host_ramp = true;  // shorter first stages (pipeline fill)
+    int host_mode = 0;  // ROBOY_HOST_STAGED / ROBOY_HOST_MAPPED_OUT / ROBOY_HOST_MAPPED_ALL
+    // done-index list (lazily allocated by roboy_enable_done_index)
+    uint32_t *done_bits = nullptr;
+    uint32_t *done_tile_off = nullptr;
+    unsigned int *done_ticket = nullptr;
 };
 
 namespace {
@@ -177,8 +185,14 @@ void free_env(roboy_env *e) {
     cudaFree(e->t_dev);
     cudaFree(e->cta_done);
     cudaFree(e->actions_stage);
+    cudaFree(e->done_bits);
+    cudaFree(e->done_tile_off);
+    cudaFree(e->done_ticket);
     if (e->host_ready)
-        for (int i = 0; i < kHostStreamsMax; ++i) cudaStreamDestroy(e->hs[i]);
+        for (int i = 0; i < kHostStreamsMax; ++i) {
+            cudaStreamDestroy(e->hs[i]);
+            cudaEventDestroy(e->hev[i]);
+        }
     delete e;
 }
 
@@ -226,6 +240,7 @@ void fill_step_params(roboy_env *e, StepParams &p, const float *actions, float *
     p.reward = reward ? reward : e->reward;
     p.done = done ? done : e->done;
     p.terminal_obs = e->terminal_obs;
+    p.done_bits = e->done_bits;
     p.stats = e->stats;
     p.err_flags = e->err_flags;
     p.first_bad = e->first_bad;
@@ -354,9 +369,12 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
         ip.held = e->held;
         ip.mask = nullptr;
         ip.obs = nullptr;
-        err = launch_init_or_reset(ip, 0);
+        err = launch_init_or_reset(ip, e->sm_count, 0);
         e->launches++;
-        e->goal_sub = 1;  // construction consumed goal draw 0 of counter 0
+        // Goal draw 0 of counter 0 is the goal the env starts with.  The first get_new_goal_joint_angles() after
+        // construction hands out that same draw, so the reference's RoboyEnv.__init__ (roboy_env.py:37), which asks the
+        // client for its first goal, starts from the goal the fused env starts from.
+        e->goal_sub = 0;
     }
     if (err == cudaSuccess) err = cudaStreamSynchronize(0);
     if (err != cudaSuccess) {
@@ -403,7 +421,7 @@ int roboy_reset(roboy_env *env, const uint8_t *mask_dev, float *obs_dev, void *s
     ip.held = nullptr;
     ip.mask = mask_dev;
     ip.obs = obs_dev ? obs_dev : env->obs;
-    CUDA_TRY(launch_init_or_reset(ip, (cudaStream_t)stream));
+    CUDA_TRY(launch_init_or_reset(ip, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -436,6 +454,7 @@ int roboy_step_many(roboy_env *env, uint32_t T, const float *actions_dev, float 
     StepParams p;
     fill_step_params(env, p, actions_dev, obs_dev, reward_dev, done_dev);
     p.cc.advance = T;
+    p.done_bits = nullptr;  // the done-index list belongs to single steps
     // every [t] slice of obs must be 16-byte aligned for the vector / bulk stores
     p.obs_aligned = (((uintptr_t)obs_dev & 15) == 0) && (T == 1 || (env->cfg.n_envs * ROBOY_DIM_OBS * sizeof(float)) % 16 == 0);
     CUDA_TRY(launch_step_many(p, T, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
@@ -444,49 +463,178 @@ int roboy_step_many(roboy_env *env, uint32_t T, const float *actions_dev, float 
     return ROBOY_OK;
 }
 
+// ---- the host-buffer path: H2D(actions) -> step kernel -> D2H(obs, reward, done), pipelined in stages ----
+enum { kHostH2D = 1, kHostKernel = 2, kHostD2H = 4, kHostSplitDirections = 8 };
+
+static int host_pipeline(roboy_env *env, const float *actions_host, float *obs_host, float *reward_host,
+                         uint8_t *done_host, int what) {
+    const uint64_t n = env->cfg.n_envs;
+    // The stages run on internal non-blocking streams.  Order them after everything queued on this device before the
+    // call (roboy_reset / roboy_set_* / roboy_step on ANY stream, blocking or not): the call is device-synchronous.
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (!env->host_ready) {
+        CUDA_TRY(cudaMalloc((void **)&env->actions_stage, sizeof(float) * ROBOY_DIM_ACTION * n));
+        for (int i = 0; i < kHostStreamsMax; ++i) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&env->hs[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&env->hev[i], cudaEventDisableTiming));
+        }
+        env->host_ready = true;
+    }
+    const bool run_kernel = (what & kHostKernel) != 0;
+    if (run_kernel) env->goal_sub = 1;
+    StepParams p;
+    fill_step_params(env, p, env->actions_stage, nullptr, nullptr, nullptr);
+    // All stages of one call use the same counter value *t_dev + 1 (they run concurrently on several streams, so none of
+    // them may store it back); a one-thread kernel advances the device counter once they have all finished.
+    p.cc = counter(env, CallCounter::kPeekNext);
+    const int mode = run_kernel ? env->host_mode : ROBOY_HOST_STAGED;
+    if (mode != ROBOY_HOST_STAGED) {
+        // zero-copy: the kernel addresses the caller's page-locked buffers directly over PCIe
+        void *o = nullptr, *r = nullptr, *d = nullptr, *a = nullptr;
+        if (cudaHostGetDevicePointer(&o, obs_host, 0) != cudaSuccess || cudaHostGetDevicePointer(&r, reward_host, 0) != cudaSuccess ||
+            cudaHostGetDevicePointer(&d, done_host, 0) != cudaSuccess ||
+            (mode == ROBOY_HOST_MAPPED_ALL && cudaHostGetDevicePointer(&a, (void *)actions_host, 0) != cudaSuccess)) {
+            cudaGetLastError();
+            return fail(ROBOY_E_ARG, "host mode %d needs page-locked host buffers (cudaHostAlloc / cudaHostRegister / roboy_host_alloc)", mode);
+        }
+        p.obs = (float *)o;
+        p.reward = (float *)r;
+        p.done = (uint8_t *)d;
+        p.obs_aligned = ((uintptr_t)o & 15) == 0;
+        if (mode == ROBOY_HOST_MAPPED_ALL) {
+            if ((uintptr_t)a & 15) return fail(ROBOY_E_ARG, "actions must be 16-byte aligned");
+            p.actions = (const float *)a;
+        }
+    }
+    cudaError_t err = cudaSuccess;
+#define HOST_TRY(expr) do { if (err == cudaSuccess) err = (expr); } while (0)
+    int used = 0;
+    if (mode == ROBOY_HOST_MAPPED_ALL) {
+        // one launch over the whole shard: PCIe reads and posted writes overlap inside the kernel, no staging at all
+        HOST_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset, env->fastdiv,
+                             env->sm_count, env->hs[0]));
+        env->launches++;
+        used = 1;
+    } else if (what & kHostSplitDirections) {
+        // copy-ceiling probe only: both directions as one monolithic copy each, on two independent streams
+        if (what & kHostH2D)
+            HOST_TRY(cudaMemcpyAsync(env->actions_stage, actions_host, sizeof(float) * ROBOY_DIM_ACTION * n, cudaMemcpyHostToDevice, env->hs[0]));
+        if (what & kHostD2H) {
+            HOST_TRY(cudaMemcpyAsync(obs_host, env->obs, sizeof(float) * ROBOY_DIM_OBS * n, cudaMemcpyDeviceToHost, env->hs[1]));
+            HOST_TRY(cudaMemcpyAsync(reward_host, env->reward, sizeof(float) * n, cudaMemcpyDeviceToHost, env->hs[1]));
+            HOST_TRY(cudaMemcpyAsync(done_host, env->done, n, cudaMemcpyDeviceToHost, env->hs[1]));
+        }
+        used = 2;
+    } else {
+        // Pipeline: per stage H2D(actions) -> step kernel -> D2H(obs, reward, done) on one stream of a ring, so the
+        // copy engines of both directions and the SMs overlap across stages.  The first stages are shorter: the D2H
+        // engine (the longer leg, 41 of the 73 bytes) idles until the first kernel has run.
+        int stage = 0;
+        const uint64_t stage_envs = env->host_stage_envs;
+        uint64_t b = 0;
+        while (b < n && err == cudaSuccess) {
+            uint64_t len = stage_envs;
+            if (env->host_ramp && stage < 3 && n > 4 * stage_envs) len = (stage_envs >> (3 - stage)) & ~31ull;  // 1/8, 1/4, 1/2
+            if (len == 0) len = stage_envs;
+            const uint64_t eend = b + len < n ? b + len : n;
+            const uint64_t cnt = eend - b;
+            cudaStream_t st = env->hs[stage % env->host_streams];
+            if (what & kHostH2D)
+                HOST_TRY(cudaMemcpyAsync(env->actions_stage + b * ROBOY_DIM_ACTION, actions_host + b * ROBOY_DIM_ACTION,
+                                         sizeof(float) * ROBOY_DIM_ACTION * cnt, cudaMemcpyHostToDevice, st));
+            if (run_kernel) {
+                p.e_begin = b;
+                p.e_end = eend;
+                HOST_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
+                                     env->fastdiv, env->sm_count, st));
+                env->launches++;
+            }
+            if ((what & kHostD2H) && mode == ROBOY_HOST_STAGED) {
+                HOST_TRY(cudaMemcpyAsync(obs_host + b * ROBOY_DIM_OBS, env->obs + b * ROBOY_DIM_OBS,
+                                         sizeof(float) * ROBOY_DIM_OBS * cnt, cudaMemcpyDeviceToHost, st));
+                HOST_TRY(cudaMemcpyAsync(reward_host + b, env->reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, st));
+                HOST_TRY(cudaMemcpyAsync(done_host + b, env->done + b, cnt, cudaMemcpyDeviceToHost, st));
+            }
+            b = eend;
+            ++stage;
+        }
+        used = stage < env->host_streams ? stage : env->host_streams;
+    }
+    if (err == cudaSuccess && run_kernel) {
+        // join the ring on stream 0, advance the device counter there, wait once
+        for (int i = 1; i < used; ++i) {
+            HOST_TRY(cudaEventRecord(env->hev[i], env->hs[i]));
+            HOST_TRY(cudaStreamWaitEvent(env->hs[0], env->hev[i], 0));
+        }
+        HOST_TRY(launch_counter_bump(env->t_dev, 1, env->hs[0]));
+        HOST_TRY(cudaStreamSynchronize(env->hs[0]));
+    }
+    // Whatever happened, nothing may still be copying into the caller's buffers when this returns.
+    const bool drain_all = err != cudaSuccess || !run_kernel;
+    if (drain_all)
+        for (int i = 0; i < kHostStreamsMax; ++i) {
+            const cudaError_t e2 = cudaStreamSynchronize(env->hs[i]);
+            if (err == cudaSuccess) err = e2;
+        }
+#undef HOST_TRY
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ROBOY_E_CUDA, "roboy_step_host: %s", cudaGetErrorString(err));
+    }
+    return ROBOY_OK;
+}
+
 int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, float *reward_host,
                     uint8_t *done_host) {
     if (check_env(env)) return ROBOY_E_ARG;
     if (!actions_host || !obs_host || !reward_host || !done_host) return fail(ROBOY_E_ARG, "NULL host buffer");
     DeviceGuard g(env->device);
-    const uint64_t n = env->cfg.n_envs;
-    if (!env->host_ready) {
-        CUDA_TRY(cudaMalloc((void **)&env->actions_stage, sizeof(float) * ROBOY_DIM_ACTION * n));
-        for (int i = 0; i < kHostStreamsMax; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&env->hs[i], cudaStreamNonBlocking));
-        env->host_ready = true;
+    return host_pipeline(env, actions_host, obs_host, reward_host, done_host, kHostH2D | kHostKernel | kHostD2H);
+}
+
+int roboy_host_copy_probe(roboy_env *env, const float *actions_host, float *obs_host, float *reward_host,
+                          uint8_t *done_host, int directions, int monolithic, int iters, double *ms_per_pass) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!actions_host || !obs_host || !reward_host || !done_host || !ms_per_pass) return fail(ROBOY_E_ARG, "NULL argument");
+    if (!(directions & 3) || iters < 1) return fail(ROBOY_E_ARG, "directions: 1 = H2D, 2 = D2H, 3 = both; iters >= 1");
+    DeviceGuard g(env->device);
+    const int what = ((directions & 1) ? kHostH2D : 0) | ((directions & 2) ? kHostD2H : 0) | (monolithic ? kHostSplitDirections : 0);
+    int rc = host_pipeline(env, actions_host, obs_host, reward_host, done_host, what);  // warm-up (stream creation, page touch)
+    if (rc) return rc;
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < iters; ++i) {
+        rc = host_pipeline(env, actions_host, obs_host, reward_host, done_host, what);
+        if (rc) return rc;
     }
-    env->goal_sub = 1;
-    // The stages run on several streams at once, so they all get the new counter value from the
-    // host (this call is synchronous anyway) and the device copy is updated when they are done.
-    unsigned long long t_now = 0;
-    CUDA_TRY(cudaMemcpy(&t_now, env->t_dev, sizeof(t_now), cudaMemcpyDeviceToHost));
-    t_now += 1;
-    StepParams p;
-    fill_step_params(env, p, env->actions_stage, nullptr, nullptr, nullptr);
-    p.cc = counter(env, CallCounter::kFixed, t_now);
-    // Pipeline: per stage H2D(actions) -> step kernel -> D2H(obs, reward, done) on one stream of a
-    // ring, so the copy engines of both directions and the SMs overlap across stages.
-    int stage = 0;
-    const uint64_t stage_envs = env->host_stage_envs;
-    for (uint64_t b = 0; b < n; b += stage_envs, ++stage) {
-        const uint64_t eend = b + stage_envs < n ? b + stage_envs : n;
-        const uint64_t cnt = eend - b;
-        cudaStream_t s = env->hs[stage % env->host_streams];
-        CUDA_TRY(cudaMemcpyAsync(env->actions_stage + b * ROBOY_DIM_ACTION, actions_host + b * ROBOY_DIM_ACTION,
-                                 sizeof(float) * ROBOY_DIM_ACTION * cnt, cudaMemcpyHostToDevice, s));
-        p.e_begin = b;
-        p.e_end = eend;
-        CUDA_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset, env->fastdiv,
-                             env->sm_count, s));
-        env->launches++;
-        CUDA_TRY(cudaMemcpyAsync(obs_host + b * ROBOY_DIM_OBS, env->obs + b * ROBOY_DIM_OBS,
-                                 sizeof(float) * ROBOY_DIM_OBS * cnt, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(reward_host + b, env->reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(done_host + b, env->done + b, cnt, cudaMemcpyDeviceToHost, s));
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    *ms_per_pass = ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6) / iters;
+    return ROBOY_OK;
+}
+
+int roboy_set_host_mode(roboy_env *env, int mode) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (mode < ROBOY_HOST_STAGED || mode > ROBOY_HOST_MAPPED_ALL) return fail(ROBOY_E_ARG, "unknown host mode %d", mode);
+    env->host_mode = mode;
+    return ROBOY_OK;
+}
+
+int roboy_host_alloc(uint64_t bytes, int write_combined, void **out_host) {
+    if (!out_host || bytes == 0) return fail(ROBOY_E_ARG, "NULL argument / zero size");
+    *out_host = nullptr;
+    const unsigned flags = cudaHostAllocPortable | cudaHostAllocMapped | (write_combined ? cudaHostAllocWriteCombined : 0u);
+    const cudaError_t e = cudaHostAlloc(out_host, bytes, flags);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? ROBOY_E_ALLOC : ROBOY_E_CUDA, "cudaHostAlloc(%llu): %s",
+                    (unsigned long long)bytes, cudaGetErrorString(e));
     }
-    const int used = stage < env->host_streams ? stage : env->host_streams;
-    for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamSynchronize(env->hs[i]));
-    CUDA_TRY(cudaMemcpy(env->t_dev, &t_now, sizeof(t_now), cudaMemcpyHostToDevice));
+    return ROBOY_OK;
+}
+
+int roboy_host_free(void *host) {
+    if (!host) return ROBOY_OK;
+    CUDA_TRY(cudaFreeHost(host));
     return ROBOY_OK;
 }
 
@@ -496,6 +644,12 @@ int roboy_set_host_pipeline(roboy_env *env, uint64_t stage_envs, int n_streams) 
         return fail(ROBOY_E_ARG, "stage_envs must be a positive multiple of 32 and 1 <= n_streams <= %d", kHostStreamsMax);
     env->host_stage_envs = stage_envs;
     env->host_streams = n_streams;
+    return ROBOY_OK;
+}
+
+int roboy_set_host_ramp(roboy_env *env, int enable) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    env->host_ramp = enable != 0;
     return ROBOY_OK;
 }
 
@@ -528,7 +682,7 @@ int roboy_compute_reward(roboy_env *env, uint64_t k, const float *q_dev, const f
     p.stats = env->stats;
     p.err_flags = env->err_flags;
     p.first_bad = env->first_bad;
-    CUDA_TRY(launch_compute_reward(p, (cudaStream_t)stream));
+    CUDA_TRY(launch_compute_reward(p, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -546,7 +700,7 @@ static int scatter_common(roboy_env *env, ScatterParams &p, uint64_t k, const in
     p.step_flags = env->step_flags;
     p.err_flags = env->err_flags;
     p.first_bad = env->first_bad;
-    CUDA_TRY(launch_scatter(p, (cudaStream_t)stream));
+    CUDA_TRY(launch_scatter(p, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -616,7 +770,7 @@ int roboy_sim_step(roboy_env *env, const float *actions_dev, float *q_dev, float
     p.out_q = q_dev;
     p.out_qd = qd_dev;
     p.out_feasible = feasible_dev;
-    CUDA_TRY(launch_sim(p, (cudaStream_t)stream));
+    CUDA_TRY(launch_sim(p, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -628,7 +782,7 @@ int roboy_sim_reset(roboy_env *env, const uint8_t *mask_dev, void *stream) {
     SimParams p{};
     fill_sim_params(env, p, 1);
     p.mask = mask_dev;
-    CUDA_TRY(launch_sim(p, (cudaStream_t)stream));
+    CUDA_TRY(launch_sim(p, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -641,7 +795,7 @@ int roboy_new_goal(roboy_env *env, float *goal_q_dev, void *stream) {
     SimParams p{};
     fill_sim_params(env, p, 2);
     p.out_q = goal_q_dev;
-    CUDA_TRY(launch_sim(p, (cudaStream_t)stream));
+    CUDA_TRY(launch_sim(p, env->sm_count, (cudaStream_t)stream));
     env->goal_sub += 1;
     env->launches++;
     return ROBOY_OK;
@@ -662,6 +816,31 @@ int roboy_set_seed(roboy_env *env, uint64_t seed) {
     return ROBOY_OK;
 }
 
+int roboy_reseed(roboy_env *env, uint64_t seed) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    DeviceGuard g(env->device);
+    env->cfg.seed = seed;
+    env->keys = make_philox_keys(seed);
+    CUDA_TRY(cudaDeviceSynchronize());
+    const unsigned long long zero = 0;
+    CUDA_TRY(cudaMemcpy(env->t_dev, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+    InitParams ip{};
+    ip.n = env->cfg.n_envs;
+    ip.gid_base = env->cfg.env_id_base;
+    ip.cc = counter(env, CallCounter::kFixed, 0);
+    ip.keys = env->keys;
+    ip.a_lo = env->consts.a_lo;
+    ip.a_span = env->consts.a_span;
+    ip.goal = env->goal;
+    ip.step_flags = env->step_flags;
+    ip.held = env->held;
+    CUDA_TRY(launch_init_or_reset(ip, env->sm_count, 0));
+    env->launches++;
+    env->goal_sub = 0;
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return ROBOY_OK;
+}
+
 int roboy_buffer(roboy_env *env, int which, void **dev_ptr, uint64_t *nbytes) {
     if (check_env(env)) return ROBOY_E_ARG;
     const uint64_t n = env->cfg.n_envs;
@@ -676,6 +855,7 @@ int roboy_buffer(roboy_env *env, int which, void **dev_ptr, uint64_t *nbytes) {
         case ROBOY_BUF_DONE: p = env->done; b = n; break;
         case ROBOY_BUF_STATS: p = env->stats; b = 8 * ROBOY_STAT_COUNT; break;
         case ROBOY_BUF_TERMINAL_OBS: p = env->terminal_obs; b = env->terminal_obs ? 36 * n : 0; break;
+        case ROBOY_BUF_DONE_BITS: p = env->done_bits; b = env->done_bits ? 4 * ((n + 31) / 32) : 0; break;
         default: return fail(ROBOY_E_ARG, "unknown buffer id %d", which);
     }
     if (dev_ptr) *dev_ptr = p;
@@ -732,6 +912,16 @@ void *roboy_export_dlpack(roboy_env *env, int which) {
         case ROBOY_BUF_STATS:
             t.data = env->stats; t.ndim = 1; ctx->shape[0] = ROBOY_STAT_COUNT;
             t.dtype.bits = 64;
+            break;
+        case ROBOY_BUF_DONE_BITS:
+            if (!env->done_bits) {
+                delete m;
+                delete ctx;
+                fail(ROBOY_E_ARG, "the done index is not enabled");
+                return nullptr;
+            }
+            t.data = env->done_bits; t.ndim = 1; ctx->shape[0] = (n + 31) / 32;
+            t.dtype.code = kDLInt;
             break;
         default:
             delete m;
@@ -834,7 +1024,7 @@ static int external_common(roboy_env *env, int reset, const uint8_t *mask, const
     p.stats = env->stats;
     p.err_flags = env->err_flags;
     p.first_bad = env->first_bad;
-    CUDA_TRY(launch_external(p, (cudaStream_t)stream));
+    CUDA_TRY(launch_external(p, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -864,7 +1054,10 @@ int roboy_gae(uint64_t T, uint64_t n, const float *reward_dev, const float *valu
     p.lam = lam;
     p.adv = adv_dev;
     p.ret = ret_dev;
-    CUDA_TRY(launch_gae(p, (cudaStream_t)stream));
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(launch_gae(p, sms, (cudaStream_t)stream));
     return ROBOY_OK;
 }
 
@@ -885,6 +1078,7 @@ static int policy_rollout_common(roboy_env *env, bool tensor_cores, bool exact, 
     StepParams p;
     fill_step_params(env, p, nullptr, obs_dev, reward_dev, done_dev);
     p.cc.advance = T;
+    p.done_bits = nullptr;
     PolicyParams q{};
     q.image = image_dev;
     q.T = T;
@@ -939,9 +1133,70 @@ int roboy_policy_geometry(roboy_env *env, int envs_per_thread, int *grid, int *b
     return ROBOY_OK;
 }
 
+int roboy_enable_done_index(roboy_env *env, int enable) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    DeviceGuard g(env->device);
+    if (enable && !env->done_bits) {
+        const uint64_t n_words = (env->cfg.n_envs + 31) / 32;
+        const uint64_t n_tiles = (n_words + kDoneTileWords - 1) / kDoneTileWords;
+        uint32_t *bits = nullptr, *tile_off = nullptr;
+        unsigned int *ticket = nullptr;
+        cudaError_t err = cudaMalloc((void **)&bits, sizeof(uint32_t) * n_words);
+        if (err == cudaSuccess) err = cudaMalloc((void **)&tile_off, sizeof(uint32_t) * (n_tiles + 1));
+        if (err == cudaSuccess) err = cudaMalloc((void **)&ticket, sizeof(unsigned int));
+        if (err == cudaSuccess) err = cudaMemset(bits, 0, sizeof(uint32_t) * n_words);
+        if (err == cudaSuccess) err = cudaMemset(ticket, 0, sizeof(unsigned int));
+        if (err != cudaSuccess) {
+            cudaFree(bits); cudaFree(tile_off); cudaFree(ticket);
+            cudaGetLastError();
+            return fail(ROBOY_E_ALLOC, "roboy_enable_done_index: %s", cudaGetErrorString(err));
+        }
+        env->done_bits = bits;
+        env->done_tile_off = tile_off;
+        env->done_ticket = ticket;
+    } else if (!enable && env->done_bits) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(env->done_bits); cudaFree(env->done_tile_off); cudaFree(env->done_ticket);
+        env->done_bits = nullptr; env->done_tile_off = nullptr; env->done_ticket = nullptr;
+    }
+    return ROBOY_OK;
+}
+
+int roboy_done_indices(roboy_env *env, int32_t *idx_dev, uint64_t capacity, uint32_t *count_dev, float *terminal_rows_dev,
+                       void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!env->done_bits) return fail(ROBOY_E_ARG, "roboy_enable_done_index(env, 1) first");
+    if (!count_dev || (!idx_dev && capacity)) return fail(ROBOY_E_ARG, "NULL device pointer");
+    if (terminal_rows_dev && !env->terminal_obs) return fail(ROBOY_E_ARG, "terminal rows requested but no terminal-obs buffer is set");
+    DeviceGuard g(env->device);
+    DoneIndexParams p{};
+    p.bits = env->done_bits;
+    p.n_words = (uint32_t)((env->cfg.n_envs + 31) / 32);
+    p.n_envs = (uint32_t)env->cfg.n_envs;
+    p.tile_off = env->done_tile_off;
+    p.ticket = env->done_ticket;
+    p.idx = idx_dev;
+    p.capacity = capacity > 0xffffffffull ? 0xffffffffu : (uint32_t)capacity;
+    p.count = count_dev;
+    p.terminal_obs = env->terminal_obs;
+    p.terminal_rows = terminal_rows_dev;
+    p.obs_dim = ROBOY_DIM_OBS;
+    CUDA_TRY(launch_done_index(p, (cudaStream_t)stream));
+    env->launches += 2;
+    return ROBOY_OK;
+}
+
 int roboy_launch_count(roboy_env *env, uint64_t *launches) {
     if (check_env(env) || !launches) return fail(ROBOY_E_ARG, "NULL argument");
     *launches = env->launches;
+    return ROBOY_OK;
+}
+
+int roboy_null_step(roboy_env *env, void *stream) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    DeviceGuard g(env->device);
+    CUDA_TRY(launch_null_step(env->cfg.n_envs, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
+                              env->fastdiv, env->sm_count, (cudaStream_t)stream));
     return ROBOY_OK;
 }
 

@@ -289,6 +289,10 @@ __device__ __forceinline__ uint32_t process_chunk(const StepParams &p, uint64_t 
     }
 #endif
     done_out = done;
+    if (!KEEP_STATE && p.done_bits != nullptr) {  // done mask as bits for the done-index list (uniform branch)
+        const uint32_t dm = __ballot_sync(kFull, done && live);
+        if (lane == 0) p.done_bits[base >> 5] = dm;
+    }
 #if ROBOY_OBS_BULK_STORE
     if (!TAIL && out.obs_aligned) {
         // every lane publishes its shared-memory writes to the async proxy, then one lane hands the
@@ -638,6 +642,38 @@ cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto
 #endif
 }
 
+__global__ void counter_bump_kernel(unsigned long long *t_dev, unsigned int advance) { *t_dev += advance; }
+
+cudaError_t launch_counter_bump(unsigned long long *t_dev, unsigned int advance, cudaStream_t stream) {
+    counter_bump_kernel<<<1, 1, 0, stream>>>(t_dev, advance);
+    return cudaGetLastError();
+}
+
+// Measurement only: an EMPTY kernel launched exactly like the step kernel (same grid, block, programmatic-dependent-launch
+// attribute) -- the launch floor bench.py prints next to the launch-bound sizes.
+__global__ void __launch_bounds__(kStepBlock) null_step_kernel() {
+#if ROBOY_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+cudaError_t launch_null_step(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count,
+                             cudaStream_t stream) {
+    const int sel = selector(penalty, bonus, auto_reset, fastdiv);
+    const int grid = grid_for(n_range, blocks_per_sm(sel), sm_count);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kStepBlock);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = ROBOY_PDL;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, null_step_kernel);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2: construction and reset
 // ---------------------------------------------------------------------------------------------
@@ -676,10 +712,10 @@ __global__ void __launch_bounds__(256) init_or_reset_kernel(const __grid_constan
     if (threadIdx.x == 0) counter_end(p.cc, t);
 }
 
-cudaError_t launch_init_or_reset(const InitParams &p, cudaStream_t stream) {
+cudaError_t launch_init_or_reset(const InitParams &p, int sm_count, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
     const uint64_t want = (p.n + 255) / 256;
-    const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    const int grid = (int)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
     init_or_reset_kernel<<<grid, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
@@ -719,10 +755,10 @@ __global__ void __launch_bounds__(256) compute_reward_kernel(const __grid_consta
     }
 }
 
-cudaError_t launch_compute_reward(const RewardParams &p, cudaStream_t stream) {
+cudaError_t launch_compute_reward(const RewardParams &p, int sm_count, cudaStream_t stream) {
     if (p.k == 0) return cudaSuccess;
     const uint64_t want = (p.k + 255) / 256;
-    const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    const int grid = (int)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
     compute_reward_kernel<<<grid, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
@@ -771,7 +807,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ Sc
                 p.out_q[i * 3 + k] = z ? 0.0f : p.held[(uint64_t)k * p.n + e];
                 p.out_qd[i * 3 + k] = z ? 0.0f : p.held[(uint64_t)(3 + k) * p.n + e];
             }
-            if (p.out_feasible) p.out_feasible[i] = z ? 1 : !(sf & ROBOY_F_HELD_INFEASIBLE);
+            // bit 0: is_feasible; bit 1: the state is the reference's FLOAT64 zero state (roboy_robot.py:41-45)
+            if (p.out_feasible) p.out_feasible[i] = z ? 3 : !(sf & ROBOY_F_HELD_INFEASIBLE);
         }
     }
 }
@@ -806,9 +843,10 @@ __global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ SimPar
             for (int k = 0; k < 8; ++k) hold = hold && (fabs((double)a[k]) <= 1e-8);
         }
         float q[3], qd[3];
-        bool feasible = true;
+        bool feasible = true, is64 = false;
         if (hold) {
             const bool z = sf & ROBOY_F_HELD_ZERO64;
+            is64 = z;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 q[k] = z ? 0.0f : p.held[(uint64_t)k * p.n + e];
@@ -830,25 +868,25 @@ __global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ SimPar
                 p.out_q[e * 3 + k] = q[k];
                 p.out_qd[e * 3 + k] = qd[k];
             }
-            if (p.out_feasible) p.out_feasible[e] = (uint8_t)feasible;
+            if (p.out_feasible) p.out_feasible[e] = (uint8_t)feasible | (is64 ? 2 : 0);
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) counter_end(p.cc, t);
 }
 
-cudaError_t launch_sim(const SimParams &p, cudaStream_t stream) {
+cudaError_t launch_sim(const SimParams &p, int sm_count, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
     const uint64_t want = (p.n + 255) / 256;
-    const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    const int grid = (int)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
     sim_kernel<<<grid, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_scatter(const ScatterParams &p, cudaStream_t stream) {
+cudaError_t launch_scatter(const ScatterParams &p, int sm_count, cudaStream_t stream) {
     if (p.k == 0) return cudaSuccess;
     const uint64_t want = (p.k + 255) / 256;
-    const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    const int grid = (int)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
     scatter_kernel<<<grid, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
@@ -892,6 +930,7 @@ __global__ void __launch_bounds__(256) external_kernel(const __grid_constant__ E
             if (done) {
                 atomicAdd(p.stats + ROBOY_STAT_EPISODES, 1.0);
                 atomicAdd(p.stats + (reached ? ROBOY_STAT_SUCCESSES : ROBOY_STAT_TIMEOUTS), 1.0);
+                atomicAdd(p.stats + ROBOY_STAT_SUM_EPLEN, (double)(step - 1));
             }
             if (violation) {
                 atomicOr(p.err_flags, ROBOY_ERR_REWARD_RANGE);
@@ -925,10 +964,10 @@ __global__ void __launch_bounds__(256) external_kernel(const __grid_constant__ E
     if (threadIdx.x == 0) counter_end(p.cc, t);
 }
 
-cudaError_t launch_external(const ExternalParams &p, cudaStream_t stream) {
+cudaError_t launch_external(const ExternalParams &p, int sm_count, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
     const uint64_t want = (p.n + 255) / 256;
-    const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    const int grid = (int)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
     external_kernel<<<grid, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
@@ -956,11 +995,124 @@ __global__ void __launch_bounds__(256) gae_kernel(const __grid_constant__ GaePar
     }
 }
 
-cudaError_t launch_gae(const GaeParams &p, cudaStream_t stream) {
+cudaError_t launch_gae(const GaeParams &p, int sm_count, cudaStream_t stream) {
     if (p.n == 0 || p.T == 0) return cudaSuccess;
     const uint64_t want = (p.n + 255) / 256;
-    const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    const int grid = (int)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
     gae_kernel<<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Done-index list: ascending env ids of the envs that finished in the last step (roboy_env.py:65-68),
+// from the bit mask the step kernel published.  Two tiny launches (2 MB of mask words at 16,777,216 envs).
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int kDoneBlock = 256;
+constexpr int kDoneWordsPerThread = kDoneTileWords / kDoneBlock;  // 4 consecutive words per thread
+
+__device__ __forceinline__ uint32_t done_word(const DoneIndexParams &p, uint32_t w) {
+    if (w >= p.n_words) return 0u;
+    uint32_t v = p.bits[w];
+    const uint32_t rem = p.n_envs - w * 32u;  // envs covered by this word
+    if (rem < 32u) v &= (1u << rem) - 1u;
+    return v;
+}
+
+// exclusive prefix sum of one value per thread over the CTA; `total` gets the CTA sum
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s_warp, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kDoneBlock / 32; ++w) {
+        const uint32_t x = s_warp[w];
+        if (w < warp) base += x;
+        tot += x;
+    }
+    __syncthreads();
+    total = tot;
+    return base + inc - v;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kDoneBlock) done_count_kernel(const __grid_constant__ DoneIndexParams p) {
+    __shared__ uint32_t s_warp[kDoneBlock / 32];
+    __shared__ bool s_last;
+    const uint32_t w0 = (blockIdx.x * kDoneBlock + threadIdx.x) * kDoneWordsPerThread;
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < kDoneWordsPerThread; ++k) c += __popc(done_word(p, w0 + k));
+    uint32_t total;
+    block_exclusive_scan(c, s_warp, total);
+    if (threadIdx.x == 0) {
+        p.tile_off[blockIdx.x] = total;
+        __threadfence();
+        s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // last CTA: exclusive scan of the tile sums in place (tile order = env order), total -> *count
+    __threadfence();
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < gridDim.x; b += kDoneBlock) {
+        const uint32_t i = b + threadIdx.x;
+        const uint32_t v = i < gridDim.x ? *reinterpret_cast<volatile uint32_t *>(p.tile_off + i) : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_exclusive_scan(v, s_warp, tot);
+        if (i < gridDim.x) p.tile_off[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        p.tile_off[gridDim.x] = carry;
+        *p.count = carry;
+        *p.ticket = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kDoneBlock) done_emit_kernel(const __grid_constant__ DoneIndexParams p) {
+    __shared__ uint32_t s_warp[kDoneBlock / 32];
+    const uint32_t w0 = (blockIdx.x * kDoneBlock + threadIdx.x) * kDoneWordsPerThread;
+    uint32_t word[kDoneWordsPerThread];
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < kDoneWordsPerThread; ++k) {
+        word[k] = done_word(p, w0 + k);
+        c += __popc(word[k]);
+    }
+    uint32_t total;
+    uint32_t pos = p.tile_off[blockIdx.x] + block_exclusive_scan(c, s_warp, total);
+    if (c == 0) return;
+#pragma unroll
+    for (int k = 0; k < kDoneWordsPerThread; ++k) {
+        uint32_t m = word[k];
+        while (m) {
+            const uint32_t b = __ffs(m) - 1;
+            m &= m - 1;
+            if (pos < p.capacity) {
+                const uint32_t e = (w0 + k) * 32u + b;
+                p.idx[pos] = (int32_t)e;
+                if (p.terminal_rows)
+                    for (int j = 0; j < p.obs_dim; ++j)
+                        p.terminal_rows[(size_t)pos * p.obs_dim + j] = p.terminal_obs[(size_t)e * p.obs_dim + j];
+            }
+            ++pos;
+        }
+    }
+}
+
+cudaError_t launch_done_index(const DoneIndexParams &p, cudaStream_t stream) {
+    if (p.n_words == 0) return cudaSuccess;
+    const int grid = (int)((p.n_words + kDoneTileWords - 1) / kDoneTileWords);
+    done_count_kernel<<<grid, kDoneBlock, 0, stream>>>(p);
+    done_emit_kernel<<<grid, kDoneBlock, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

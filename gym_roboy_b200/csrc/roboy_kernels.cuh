@@ -24,8 +24,10 @@ constexpr int kObsDim = 9, kActDim = 8;
 //   kFixed    t = t_fixed (host supplied; the multi-stream host-buffer path, construction)
 //   kAdvance  t = *t_dev + 1, and the LAST CTA of the launch to finish stores it back
 //   kPeek     t = *t_dev (get_new_goal_joint_angles between steps)
+//   kPeekNext t = *t_dev + 1 without storing it (the concurrent stages of the host-buffer pipeline; one
+//             launch_counter_bump after them advances the counter)
 struct CallCounter {
-    enum Mode : int { kFixed = 0, kAdvance = 1, kPeek = 2 };
+    enum Mode : int { kFixed = 0, kAdvance = 1, kPeek = 2, kPeekNext = 3 };
     unsigned long long *t_dev;
     unsigned int *cta_done;  // CTAs of the current launch that have finished
     unsigned long long t_fixed;
@@ -36,7 +38,7 @@ struct CallCounter {
 __device__ __forceinline__ uint64_t counter_begin(const CallCounter &c) {
     if (c.mode == CallCounter::kFixed) return c.t_fixed;
     const unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(c.t_dev);
-    return c.mode == CallCounter::kAdvance ? t + 1 : t;
+    return c.mode == CallCounter::kPeek ? t : t + 1;
 }
 
 // Call once per CTA, by one thread, after the CTA's last use of the counter value.  Every CTA read
@@ -78,10 +80,15 @@ struct StepParams {
     float *__restrict__ reward;         // [n]
     uint8_t *__restrict__ done;         // [n]
     float *__restrict__ terminal_obs;   // [n][9] or nullptr
+    uint32_t *__restrict__ done_bits;   // [ceil(n/32)] or nullptr: the done mask of this step as bits (bit l of word c = env 32c+l)
     double *__restrict__ stats;         // [ROBOY_STAT_COUNT]
     uint32_t *__restrict__ err_flags;
     unsigned long long *__restrict__ first_bad;
 };
+
+cudaError_t launch_null_step(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count,
+                             cudaStream_t stream);
+cudaError_t launch_counter_bump(unsigned long long *t_dev, unsigned int advance, cudaStream_t stream);
 
 struct LaunchGeom {
     int grid, block, smem;
@@ -107,7 +114,7 @@ struct InitParams {
     float *obs;              // nullptr: do not write observations
 };
 // init (held != nullptr): RoboyEnv.__init__ / Stub.__init__;  reset (held == nullptr): RoboyEnv.reset
-cudaError_t launch_init_or_reset(const InitParams &p, cudaStream_t stream);
+cudaError_t launch_init_or_reset(const InitParams &p, int sm_count, cudaStream_t stream);
 
 struct RewardParams {
     uint64_t k;
@@ -122,7 +129,7 @@ struct RewardParams {
     uint32_t *err_flags;
     unsigned long long *first_bad;
 };
-cudaError_t launch_compute_reward(const RewardParams &p, cudaStream_t stream);
+cudaError_t launch_compute_reward(const RewardParams &p, int sm_count, cudaStream_t stream);
 
 struct ScatterParams {
     uint64_t k, n;
@@ -143,7 +150,7 @@ struct ScatterParams {
     float *out_q, *out_qd;
     uint8_t *out_feasible;
 };
-cudaError_t launch_scatter(const ScatterParams &p, cudaStream_t stream);
+cudaError_t launch_scatter(const ScatterParams &p, int sm_count, cudaStream_t stream);
 
 // The un-fused plug-in calls of SimulationClient (simulation_client.py:11-23), batched:
 //   mode 0  forward_step_command(action in robot units)  -> state      (:36-40)
@@ -164,7 +171,7 @@ struct SimParams {
     uint8_t *out_feasible;  // [n] or nullptr
     double *stats;
 };
-cudaError_t launch_sim(const SimParams &p, cudaStream_t stream);
+cudaError_t launch_sim(const SimParams &p, int sm_count, cudaStream_t stream);
 
 // RoboyEnv.step / reset when the states come from an EXTERNAL simulator (the role of
 // RosSimulationClient, ros_simulation_client.py:40-60: q, qdot, feasible arrive over the wire and
@@ -189,7 +196,7 @@ struct ExternalParams {
     uint32_t *err_flags;
     unsigned long long *first_bad;
 };
-cudaError_t launch_external(const ExternalParams &p, cudaStream_t stream);
+cudaError_t launch_external(const ExternalParams &p, int sm_count, cudaStream_t stream);
 
 // Generalised advantage estimation over rollout buffers [T][n] that the step kernel filled in place
 // (the PPO2 runner of train_parallel.py:31-34 does this on the host; stable-baselines is external).
@@ -201,6 +208,28 @@ struct GaeParams {
     float gamma, lam;
     float *adv, *ret;              // [T][n]
 };
-cudaError_t launch_gae(const GaeParams &p, cudaStream_t stream);
+cudaError_t launch_gae(const GaeParams &p, int sm_count, cudaStream_t stream);
+
+// Done-index list (roboy_env.py:65-68: which envs finished): the step kernel publishes its done mask as bits
+// (StepParams::done_bits, one warp ballot per 32-env chunk); these two small kernels turn the words into the
+// ascending list of env ids -- deterministic, no atomics on the output order:
+//   count: per-tile popcounts (a tile = kDoneTileWords words = 32,768 envs); the last CTA to finish scans the tile sums
+//   emit : every set bit writes its env id at tile offset + rank inside the tile, and (optionally) gathers that env's
+//          pre-reset observation row into a packed [count][obs_dim] buffer (the vec-env `terminal_observation`s)
+constexpr int kDoneTileWords = 1024;
+struct DoneIndexParams {
+    const uint32_t *bits;      // [n_words]
+    uint32_t n_words;
+    uint32_t n_envs;           // bits beyond n_envs in the last word are ignored
+    uint32_t *tile_off;        // [n_tiles + 1] scratch: tile sums, then exclusive offsets
+    unsigned int *ticket;      // zero between launches
+    int32_t *idx;              // [capacity] out: ascending local env ids
+    uint32_t capacity;
+    uint32_t *count;           // out: number of done envs (may exceed capacity; only capacity entries are written)
+    const float *terminal_obs; // [n][obs_dim] or nullptr
+    float *terminal_rows;      // [capacity][obs_dim] or nullptr
+    int obs_dim;
+};
+cudaError_t launch_done_index(const DoneIndexParams &p, cudaStream_t stream);
 
 }  // namespace roboy

@@ -64,6 +64,7 @@ static __device__ __noinline__ uint32_t finish_episode(const StepParams &p, uint
     p.goal2[e] = ng2;
     atomicAdd(&s_cnt[0], 1u);
     if (reached) atomicAdd(&s_cnt[1], 1u);
+    atomicAdd(&s_cnt[4], step - 1);              // episode length (steps taken since reset(): step_num starts at 1)
     if (!auto_reset) return step | 0x80000000u;  // top bit: keep the flag bits
     if (p.terminal_obs) {
 #pragma unroll
@@ -71,7 +72,6 @@ static __device__ __noinline__ uint32_t finish_episode(const StepParams &p, uint
     }
     row[0] = row[1] = row[2] = row[3] = row[4] = row[5] = 0.0f;  // reset(): zero state, :83-84,87
     row[6] = ng0; row[7] = ng1; row[8] = ng2;
-    atomicAdd(&s_cnt[4], step - 1);
     return 1u;                                                   // :85, with the flags replaced
 }
 

@@ -58,7 +58,8 @@ class RoboyEnv(_GoalEnvBase):
         self._strict = self._single if strict is None else bool(strict)
         self._robot = robot = client.robot
         if seed is not None:
-            self.seed(seed)
+            # the reference seeds before it draws its first goal (roboy_env.py:15 then :37): redo the construction draws
+            client.reseed(seed)
         client.configure_env(self._joint_vel_penalty, self._is_agent_getting_bonus_for_reaching_goal, self._auto_reset)
 
         angles, vels = robot.get_joint_angles_space(), robot.get_joint_vels_space()

@@ -75,6 +75,8 @@ class CudaSimulationClient(SimulationClient):
         self.terminal_obs = None
         self.info_sink = None
         self._all_idx = None
+        self._host_allocs = []
+        self._done_index, self._done_idx, self._done_count, self._done_rows = False, None, None, None
 
     # ------------------------------------------------------------------ plumbing
     def _view(self, which):
@@ -86,6 +88,9 @@ class CudaSimulationClient(SimulationClient):
         destroy = getattr(getattr(self, "_lib", None), "roboy_destroy", None)
         if h and destroy is not None:   # (None during interpreter shutdown)
             destroy(h)
+            for ptr in getattr(self, "_host_allocs", []):
+                self._lib.roboy_host_free(ctypes.c_void_p(ptr))
+            self._host_allocs = []
 
     def __del__(self):
         try:
@@ -114,9 +119,12 @@ class CudaSimulationClient(SimulationClient):
         return None if t is None else ctypes.c_void_p(t.data_ptr())
 
     def _state_out(self, q, qd, feasible):
+        # feasible byte: bit 0 is_feasible, bit 1 "this is the float64 zero state" (roboy_robot.py:41-45)
         if self.num_envs == 1:
-            return RobotState(q[0].cpu().numpy(), qd[0].cpu().numpy(), bool(feasible[0].item()))
-        return RobotState(q, qd, feasible.view(torch.bool))
+            f = int(feasible[0].item())
+            dt = np.float64 if f & 2 else np.float32   # numpy then promotes as it does over the reference's Stub
+            return RobotState(q[0].cpu().numpy().astype(dt), qd[0].cpu().numpy().astype(dt), bool(f & 1))
+        return RobotState(q, qd, (feasible & 1).view(torch.bool))
 
     # ------------------------------------------------------------------ SimulationClient API
     def read_state(self) -> RobotState:
@@ -163,6 +171,11 @@ class CudaSimulationClient(SimulationClient):
     def set_seed(self, seed):
         self.seed_value = int(seed) & (2 ** 64 - 1)
         _native.check(self._lib.roboy_set_seed(self._h, self.seed_value))
+
+    def reseed(self, seed):
+        """Re-key and redo the construction draws (held state, first goal, counter 0): `RoboyEnv(client, seed=s)`."""
+        self.seed_value = int(seed) & (2 ** 64 - 1)
+        _native.check(self._lib.roboy_reseed(self._h, self.seed_value))
 
     def enable_terminal_obs(self, enable=True):
         if enable and self.terminal_obs is None:
@@ -218,8 +231,61 @@ class CudaSimulationClient(SimulationClient):
         _native.check(self._lib.roboy_reset_external(self._h, self._p(m), self._p(q), self._p(qd), self._p(obs),
                                                      self._stream()))
 
-    def set_host_pipeline(self, stage_envs=1 << 19, n_streams=2):
+    def set_host_pipeline(self, stage_envs=1 << 19, n_streams=2, ramp=True):
         _native.check(self._lib.roboy_set_host_pipeline(self._h, int(stage_envs), int(n_streams)))
+        _native.check(self._lib.roboy_set_host_ramp(self._h, int(bool(ramp))))
+
+    def set_host_mode(self, mode):
+        """`_native.HOST_STAGED` (copy engines both ways), `HOST_MAPPED_OUT` (the kernel stores its outputs straight into
+        the page-locked host buffers) or `HOST_MAPPED_ALL` (it also reads the actions from them)."""
+        _native.check(self._lib.roboy_set_host_mode(self._h, int(mode)))
+
+    def host_buffers(self, write_combined_actions=False):
+        """Page-locked, device-mapped numpy buffers `(actions [N,8], obs [N,9], reward [N], done [N])` for `step_host`
+        (`roboy_host_alloc`); freed when the client closes."""
+        n, out = self.num_envs, []
+        for shape, dt, wc in (((n, _native.DIM_ACTION), np.float32, write_combined_actions),
+                              ((n, _native.DIM_OBS), np.float32, False), ((n,), np.float32, False), ((n,), np.uint8, False)):
+            nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
+            ptr = ctypes.c_void_p()
+            _native.check(self._lib.roboy_host_alloc(nbytes, int(wc), ctypes.byref(ptr)))
+            self._host_allocs.append(ptr.value)
+            buf = (ctypes.c_char * nbytes).from_address(ptr.value)
+            out.append(np.frombuffer(buf, dtype=dt).reshape(shape))
+        return tuple(out)
+
+    def copy_probe(self, actions, obs, reward, done, directions=3, monolithic=False, iters=3):
+        """Milliseconds per pass of `step_host`'s copies WITHOUT the kernel (bench.py's e2e.copy_ceiling)."""
+        ms = ctypes.c_double()
+        _native.check(self._lib.roboy_host_copy_probe(self._h, actions.ctypes.data, obs.ctypes.data, reward.ctypes.data,
+                                                      done.ctypes.data, int(directions), int(monolithic), int(iters),
+                                                      ctypes.byref(ms)))
+        return ms.value
+
+    # ------------------------------------------------------------------ done-index list
+    def enable_done_index(self, enable=True):
+        _native.check(self._lib.roboy_enable_done_index(self._h, int(bool(enable))))
+        self._done_index = bool(enable)
+        if enable and self._done_idx is None:
+            self._done_idx = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+            self._done_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def done_indices(self, with_terminal_obs=False, capacity=None):
+        """Ascending local ids of the envs the last step finished (roboy_env.py:65-68), computed on the device from the
+        step kernel's done bits.  Returns `(idx int32 [k], terminal_rows float32 [k, 9] or None)`; one small D2H read
+        (the count) synchronises the stream."""
+        if not getattr(self, "_done_index", False):
+            self.enable_done_index(True)
+        cap = self.num_envs if capacity is None else int(capacity)
+        rows = None
+        if with_terminal_obs:
+            if self._done_rows is None or self._done_rows.shape[0] < cap:
+                self._done_rows = torch.empty((cap, _native.DIM_OBS), dtype=torch.float32, device=self.device)
+            rows = self._done_rows
+        _native.check(self._lib.roboy_done_indices(self._h, self._p(self._done_idx), cap, self._p(self._done_count),
+                                                   self._p(rows), self._stream()))
+        k = min(int(self._done_count.item()), cap)
+        return self._done_idx[:k], (rows[:k] if rows is not None else None)
 
     def step_host(self, actions, obs, reward, done):
         """The fused step through HOST numpy buffers (pinned for full speed); synchronous."""
@@ -299,6 +365,10 @@ class CudaSimulationClient(SimulationClient):
         _native.check(self._lib.roboy_launch_count(self._h, ctypes.byref(n)))
         return n.value
 
+    def null_step(self):
+        """An empty kernel launched like the step kernel (launch-floor measurements)."""
+        _native.check(self._lib.roboy_null_step(self._h, self._stream()))
+
     def step_geometry(self):
         g, b, s = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         _native.check(self._lib.roboy_step_geometry(self._h, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
@@ -306,14 +376,26 @@ class CudaSimulationClient(SimulationClient):
 
     # ------------------------------------------------------------------ checkpoint
     def state_dict(self):
+        """The complete checkpoint of the shard: SoA state, call counter, seed, statistics, the error word and the
+        CURRENT observation (the Stub never stores a sampled state, so the last observation exists only in `obs`)."""
+        flags, first = self.errors()
         return dict(goal=self.goal.clone(), step_flags=self.step_flags.clone(), held=self.held.clone(),
-                    counter=self.counter, seed=self.seed_value, env_id_base=self.env_id_base,
-                    stats=self.stats_tensor.clone())
+                    obs=self.obs.clone(), counter=self.counter, seed=self.seed_value, env_id_base=self.env_id_base,
+                    num_envs=self.num_envs, stats=self.stats_tensor.clone(), err_flags=flags, first_bad=first)
 
     def load_state_dict(self, sd):
+        if int(sd.get("num_envs", self.num_envs)) != self.num_envs or int(sd["env_id_base"]) != self.env_id_base:
+            raise ValueError("checkpoint is for {} envs at env_id_base {}, this client holds {} at {}".format(
+                sd.get("num_envs"), sd["env_id_base"], self.num_envs, self.env_id_base))
         self.goal.copy_(sd["goal"])
         self.step_flags.copy_(sd["step_flags"])
         self.held.copy_(sd["held"])
+        if "obs" in sd:
+            self.obs.copy_(sd["obs"])
         self.stats_tensor.copy_(sd["stats"])
+        self.clear_errors()   # the error word is not restorable through the C-ABI; a checkpoint taken with errors says so
+        if sd.get("err_flags"):
+            raise ValueError("checkpoint was taken with a non-zero error word ({}, first env {})".format(
+                sd["err_flags"], sd.get("first_bad")))
         self.set_seed(sd["seed"])
         self.counter = sd["counter"]

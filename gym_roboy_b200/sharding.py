@@ -60,8 +60,10 @@ def summarize(stats: torch.Tensor) -> dict:
         steps=steps, episodes=episodes, successes=successes, timeouts=timeouts, holds=holds, violations=violations,
         success_rate=successes / episodes if episodes else 0.0,
         mean_step_reward=sum_reward / steps if steps else 0.0,
-        mean_episode_len=sum_eplen / episodes if episodes else 0.0,
-        mean_episode_return=(sum_reward / steps) * (sum_eplen / episodes) if steps and episodes else 0.0,
+        mean_episode_len=sum_eplen / episodes if episodes else None,
+        # total reward per finished episode: exact once many episodes have finished (the steps of episodes still in
+        # flight are in the numerator only)
+        mean_episode_return=sum_reward / episodes if episodes else None,
     )
 
 

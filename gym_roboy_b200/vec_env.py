@@ -2,20 +2,29 @@
 
 `train_parallel.py:29` wraps one reference env per process in `SubprocVecEnv`.  This adapter offers
 the same calling convention -- `reset()`, `step_async(actions)` / `step_wait()`, `step(actions)`,
-`num_envs`, spaces, `infos[i]['terminal_observation']` on done -- on top of ONE fused kernel launch
-per step.  Data crosses PCIe once per step through pinned buffers (`roboy_step_host`).
+`num_envs`, spaces, `infos[i]['terminal_observation']` on done, per-env `get_attr` / `set_attr` /
+`env_method` -- on top of ONE fused kernel launch per step.  Data crosses PCIe once per step through
+page-locked buffers (`roboy_step_host`); which envs finished, and their pre-reset observations, are
+compacted on the device (`roboy_done_indices`), so the host never scans the done mask.
 stable-baselines is external to the reference; the contract followed is its
 documented worker behaviour: on done the env is reset and the reset observation is returned.
+
+Actions are NOT clipped here: stable-baselines' runner clips before `env.step`, and the reference env
+asserts (`roboy_env.py:52`).  An out-of-range or NaN action raises the same `AssertionError` from
+`step_wait()` (the device error word), unless the adapter is built with `clip_actions=True`.
 """
 import numpy as np
-import torch
 
 from .envs import RoboyEnv
 from .envs.simulations import CudaSimulationClient
 
+# attributes of RoboyEnv that differ per env: get_attr returns one value per selected env
+_PER_ENV_ATTRS = ("step_num",)
+
 
 class RoboyVecEnv:
-    def __init__(self, num_envs, seed=0, device=None, env_id_base=0, terminal_observation=True, **env_kwargs):
+    def __init__(self, num_envs, seed=0, device=None, env_id_base=0, terminal_observation=True, clip_actions=False,
+                 **env_kwargs):
         client = CudaSimulationClient(num_envs=num_envs, seed=seed, device=device, env_id_base=env_id_base)
         self.env = RoboyEnv(client, auto_reset=True, strict=False, **env_kwargs)
         if num_envs == 1:
@@ -24,14 +33,12 @@ class RoboyVecEnv:
         self.num_envs = num_envs
         self.observation_space, self.action_space = self.env.observation_space, self.env.action_space
         self.reward_range = self.env.reward_range
-        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
-        self._actions = pin((num_envs, 8), torch.float32)
-        self._obs = pin((num_envs, 9), torch.float32)
-        self._rew = pin((num_envs,), torch.float32)
-        self._done = pin((num_envs,), torch.uint8)
+        self._actions, self._obs, self._rew, self._done = client.host_buffers()
+        self._clip = bool(clip_actions)
         self._want_terminal = terminal_observation
         if terminal_observation:
             client.enable_terminal_obs(True)
+            client.enable_done_index(True)
         self._pending = False
 
     def seed(self, seed=None):
@@ -41,31 +48,62 @@ class RoboyVecEnv:
         return self.env.reset().cpu().numpy().reshape(self.num_envs, 9)
 
     def step_async(self, actions):
-        np.clip(np.asarray(actions, np.float32).reshape(self.num_envs, 8), -1.0, 1.0, out=self._actions)
+        a = np.asarray(actions, np.float32).reshape(self.num_envs, 8)
+        if self._clip:
+            np.clip(a, -1.0, 1.0, out=self._actions)
+        else:
+            self._actions[...] = a
         self._pending = True
 
     def step_wait(self):
         assert self._pending, "step_async() first"
         self._pending = False
         self.client.step_host(self._actions, self._obs, self._rew, self._done)
-        done = self._done.astype(bool)
+        self.env.check_errors()   # roboy_env.py:52 / :109 -> AssertionError, as the worker's env.step would raise
         infos = [{} for _ in range(self.num_envs)]
-        if self._want_terminal and done.any():
-            idx = np.flatnonzero(done)
-            term = self.client.terminal_obs[torch.as_tensor(idx, device=self.client.device)].cpu().numpy()
-            for i, row in zip(idx, term):
-                infos[i]["terminal_observation"] = row
-        return self._obs.copy(), self._rew.copy(), done, infos
+        if self._want_terminal:
+            idx, rows = self.client.done_indices(with_terminal_obs=True)   # device-side compaction + gather
+            if idx.numel():
+                for i, row in zip(idx.cpu().numpy(), rows.cpu().numpy()):
+                    infos[int(i)]["terminal_observation"] = row
+        return self._obs.copy(), self._rew.copy(), self._done.astype(bool), infos
 
     def step(self, actions):
         self.step_async(actions)
         return self.step_wait()
 
+    # ---- per-env accessors (stable-baselines VecEnv.get_attr / set_attr / env_method) ----
+    def _indices(self, indices):
+        if indices is None:
+            return list(range(self.num_envs))
+        if isinstance(indices, (int, np.integer)):
+            return [int(indices)]
+        return [int(i) for i in indices]
+
     def get_attr(self, name, indices=None):
-        return [getattr(self.env, name)] * (self.num_envs if indices is None else len(indices))
+        """One value PER selected env, as SubprocVecEnv returns them."""
+        idx = self._indices(indices)
+        value = getattr(self.env, name)
+        if name in _PER_ENV_ATTRS:
+            per_env = value.cpu().numpy()
+            return [int(per_env[i]) for i in idx]
+        return [value for _ in idx]
+
+    def set_attr(self, name, value, indices=None):
+        idx = self._indices(indices)
+        if name == "step_num":
+            self.client.set_step_num(np.full(len(idx), int(value), np.int32), idx=idx)
+        else:
+            setattr(self.env, name, value)
 
     def env_method(self, name, *args, indices=None, **kwargs):
-        return [getattr(self.env, name)(*args, **kwargs)]
+        """Call `name` once for the batch and hand every selected env its own result (batched results are split)."""
+        idx = self._indices(indices)
+        out = getattr(self.env, name)(*args, **kwargs)
+        if hasattr(out, "shape") and len(getattr(out, "shape", ())) >= 1 and out.shape[0] == self.num_envs:
+            out = out.cpu().numpy() if hasattr(out, "cpu") else np.asarray(out)
+            return [out[i] for i in idx]
+        return [out for _ in idx]
 
     def close(self):
         self.env.close()

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ROBOY_B200_ABI_VERSION 1
+#define ROBOY_B200_ABI_VERSION 2
 
 #define ROBOY_DIM_JOINT 3  /* msj_robot.py:8  */
 #define ROBOY_DIM_ACTION 8 /* msj_robot.py:12 */
@@ -75,7 +75,8 @@ enum {
 enum {
     ROBOY_BUF_GOAL = 0, ROBOY_BUF_STEP_FLAGS = 1, ROBOY_BUF_HELD = 2, ROBOY_BUF_OBS = 3,
     ROBOY_BUF_REWARD = 4, ROBOY_BUF_DONE = 5, ROBOY_BUF_STATS = 6, ROBOY_BUF_TERMINAL_OBS = 7,
-    ROBOY_BUF_COUNT = 8
+    ROBOY_BUF_DONE_BITS = 8, /* uint32 [ceil(n/32)], after roboy_enable_done_index */
+    ROBOY_BUF_COUNT = 9
 };
 
 /* Constructor arguments of RoboyEnv (roboy_env.py:12-14) + the robot's bounds
@@ -141,19 +142,58 @@ int roboy_step(roboy_env *env, const float *actions_dev, float *obs_dev, float *
 int roboy_step_many(roboy_env *env, uint32_t T, const float *actions_dev, float *obs_dev, float *reward_dev,
                     uint8_t *done_dev, void *stream);
 
-/* The same step through HOST buffers: pinned staging, chunked H2D -> kernel -> D2H pipelined
- * over internal streams; returns when the outputs are in host memory.  This is the call a
- * host-side (CPU policy) trainer makes, and what bench.py's e2e number times. */
+/* The same step through HOST buffers -- the hop train_parallel.py:29 makes through SubprocVecEnv's pipes, once per
+ * step for the whole population: chunked H2D(actions) -> kernel -> D2H(obs, reward, done) pipelined over internal
+ * streams; returns when the outputs are in host memory.  This is the call a host-side (CPU policy) trainer makes, and
+ * what bench.py's e2e number times.  The call is DEVICE-SYNCHRONOUS: it first waits for all work queued on the device
+ * (whatever stream a preceding roboy_reset / roboy_set_* / roboy_step was issued on), and on a CUDA error it drains its
+ * internal streams before returning, so no copy into the caller's buffers is ever left in flight. */
 int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, float *reward_host,
                     uint8_t *done_host);
 
 /* Tuning of roboy_step_host's pipeline: envs per stage (multiple of 32) and streams in the ring
- * (1..8).  Defaults: 524,288 envs, 2 streams (measured best on PCIe Gen5). */
+ * (1..8).  Defaults: 524,288 envs, 2 streams (measured best on PCIe Gen5).  roboy_set_host_ramp: run the first three
+ * stages at 1/8, 1/4 and 1/2 of the stage size so the D2H engine starts sooner (default on). */
 int roboy_set_host_pipeline(roboy_env *env, uint64_t stage_envs, int n_streams);
+int roboy_set_host_ramp(roboy_env *env, int enable);
+
+/* How roboy_step_host moves the outputs (and inputs):
+ *   ROBOY_HOST_STAGED      copy engines both ways (default; any host memory, pinned for full speed)
+ *   ROBOY_HOST_MAPPED_OUT  H2D by copy engine; the step kernel stores obs / reward / done straight into the caller's
+ *                          page-locked buffers over PCIe (no HBM round trip, no D2H stage)
+ *   ROBOY_HOST_MAPPED_ALL  one launch over the shard that also READS the actions from page-locked host memory
+ * The mapped modes need buffers from cudaHostAlloc / cudaHostRegister / roboy_host_alloc. */
+#define ROBOY_HOST_STAGED 0
+#define ROBOY_HOST_MAPPED_OUT 1
+#define ROBOY_HOST_MAPPED_ALL 2
+int roboy_set_host_mode(roboy_env *env, int mode);
+
+/* Page-locked, device-mapped host memory for the calls above (cudaHostAlloc portable | mapped, optionally
+ * write-combined: faster for the GPU to read, slow for the CPU to read -- action buffers only). */
+int roboy_host_alloc(uint64_t bytes, int write_combined, void **out_host);
+int roboy_host_free(void *host);
+
+/* Measurement only (bench.py's e2e.copy_ceiling): the copies of roboy_step_host WITHOUT the kernel, same buffers, same
+ * 32 / 41 byte split per env.  directions: 1 = H2D, 2 = D2H, 3 = both concurrently.  monolithic = 0: the staged
+ * pipeline's copy pattern; 1: one copy per array, the two directions on two independent streams.  Env state is not
+ * touched.  Returns the wall-clock milliseconds per pass over all n envs, averaged over `iters` passes. */
+int roboy_host_copy_probe(roboy_env *env, const float *actions_host, float *obs_host, float *reward_host,
+                          uint8_t *done_host, int directions, int monolithic, int iters, double *ms_per_pass);
 
 /* Optional side buffer float32 [n][9] receiving the pre-reset observation of envs that
  * finish an episode (the vec-env `terminal_observation`).  NULL disables. */
 int roboy_set_terminal_obs(roboy_env *env, float *terminal_obs_dev);
+
+/* The done list of the LAST roboy_step / roboy_step_host as indices (roboy_env.py:65-68 `if done:` -- which envs
+ * finished; north_star: "bit-exact for done/reset masks and indices").  Once enabled, the step kernel also publishes its
+ * done mask as bits (one warp ballot per 32 envs; ROBOY_BUF_DONE_BITS), and roboy_done_indices turns them into the
+ * ASCENDING list of local env ids on the device: idx_dev int32 [capacity], *count_dev = number of done envs (entries
+ * beyond capacity are dropped, the count is not clipped).  terminal_rows_dev (optional, float32 [capacity][9]) receives
+ * the pre-reset observation of each listed env, gathered from the terminal-obs side buffer -- the rows a vec-env
+ * returns as infos[i]["terminal_observation"].  Asynchronous on `stream`; deterministic. */
+int roboy_enable_done_index(roboy_env *env, int enable);
+int roboy_done_indices(roboy_env *env, int32_t *idx_dev, uint64_t capacity, uint32_t *count_dev, float *terminal_rows_dev,
+                       void *stream);
 
 /* Stand-alone GoalEnv.compute_reward(current_state, goal_state) (roboy_env.py:92-112) and
  * _did_reach_goal (:125-134) over float32 device arrays [k][3]; feasible_dev uint8 [k] or NULL
@@ -173,7 +213,9 @@ int roboy_set_state(roboy_env *env, uint64_t k, const int64_t *idx_dev, const fl
 int roboy_set_step_num(roboy_env *env, uint64_t k, const int64_t *idx_dev, const int32_t *step_dev, void *stream);
 
 /* SimulationClient.read_state (simulation_client.py:33-34) for k envs: the held state as
- * float32 [k][3] q, [k][3] qd, uint8 [k] feasible. */
+ * float32 [k][3] q, [k][3] qd, uint8 [k] feasible.  feasible byte: bit 0 = is_feasible, bit 1 = the state is the
+ * reference's FLOAT64 zero state (roboy_robot.py:41-45 after forward_reset_command) -- a caller that keeps the
+ * reference's RoboyEnv on top hands it float64 arrays then, so numpy promotes exactly as it does over the Stub. */
 int roboy_read_state(roboy_env *env, uint64_t k, const int64_t *idx_dev, float *q_dev, float *qd_dev,
                      uint8_t *feasible_dev, void *stream);
 
@@ -181,12 +223,14 @@ int roboy_read_state(roboy_env *env, uint64_t k, const int64_t *idx_dev, float *
  * shard, for callers that keep the reference's own RoboyEnv on top:
  *   roboy_sim_step   forward_step_command(action) -- simulation_client.py:36-40.  actions_dev is
  *                    float32 [n][8] in ROBOT units (after roboy_env.py:54-57); advances the call
- *                    counter; writes the returned state (q, qd [n][3], feasible [n] or NULL).
+ *                    counter; writes the returned state (q, qd [n][3], feasible [n] or NULL; same two bits as
+ *                    roboy_read_state).
  *   roboy_sim_reset  forward_reset_command()      -- simulation_client.py:42-44, envs with
  *                    mask_dev[i] != 0 (NULL: all); advances the call counter.
  *   roboy_new_goal   get_new_goal_joint_angles()  -- simulation_client.py:46-47; writes [n][3]
  *                    draws to goal_q_dev and does NOT change the env's goal (RoboyEnv._set_new_goal
- *                    does that, via roboy_set_goal).  Repeated calls give fresh draws. */
+ *                    does that, via roboy_set_goal).  Repeated calls give fresh draws; the first call after
+ *                    roboy_create / roboy_reseed returns the goal the env was constructed with (roboy_env.py:37). */
 int roboy_sim_step(roboy_env *env, const float *actions_dev, float *q_dev, float *qd_dev, uint8_t *feasible_dev,
                    void *stream);
 int roboy_sim_reset(roboy_env *env, const uint8_t *mask_dev, void *stream);
@@ -196,6 +240,9 @@ int roboy_new_goal(roboy_env *env, float *goal_q_dev, void *stream);
 int roboy_set_flags(roboy_env *env, int joint_vel_penalty, int bonus_for_goal, int auto_reset);
 /* RoboyEnv.seed (roboy_env.py:114-115): re-key the Philox generator; state is left as is. */
 int roboy_set_seed(roboy_env *env, uint64_t seed);
+/* RoboyEnv(client, seed=s) (roboy_env.py:12,15 then :37): re-key AND redo the construction draws (held state, first
+ * goal, step_num = 1, call counter = 0), so the first episode is reproducible from the env seed.  Synchronises. */
+int roboy_reseed(roboy_env *env, uint64_t seed);
 
 /* Zero-copy access to the handle's buffers (ROBOY_BUF_*): raw device pointer + byte size, or
  * a DLPack DLManagedTensor* (consume with PyCapsule "dltensor" -> torch.from_dlpack). */
@@ -320,6 +367,10 @@ int roboy_policy_tc_geometry(roboy_env *env, int tiles_per_group, int exact, int
  * launch geometry the step kernel uses for this n_envs. */
 int roboy_launch_count(roboy_env *env, uint64_t *launches);
 int roboy_step_geometry(roboy_env *env, int *grid, int *block, int *smem_bytes);
+/* Measurement only: an EMPTY kernel launched exactly like roboy_step launches the step kernel (grid, block,
+ * programmatic dependent launch) -- the launch-latency floor bench.py reports next to the launch-bound sizes.
+ * Not counted by roboy_launch_count. */
+int roboy_null_step(roboy_env *env, void *stream);
 
 #ifdef __cplusplus
 }

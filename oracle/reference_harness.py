@@ -1,9 +1,10 @@
 """Runs the UNMODIFIED reference (gym-roboy) on injected draws -- TEST INFRASTRUCTURE.
 
-Container-only: needs /root/reference (read-only) plus the test-only import shim under
-tests/_shim (gym / rclpy stand-ins; see tests/_shim/README.md).  It is how the oracle is
-pinned and how tests/golden/*.npz are generated (oracle/gen_golden.py).  Never imported by the
-product package, and never at run time on the GPU box (where /root/reference does not exist).
+Needs the reference -- /root/reference (read-only, build container) or the unmodified copy under
+baseline/_ref/ that __graft_entry__.build() installs with pip (git-ignored; it travels to the GPU
+box) -- plus the test-only import shim under tests/_shim (gym / rclpy stand-ins; see
+tests/_shim/README.md).  It is how the oracle is pinned and how tests/golden/*.npz are generated
+(oracle/gen_golden.py).  Never imported by the product package.
 
 The reference's random draws (gym Box.sample) are unpinned, so parity is established by
 INJECTION: a `ReplayRobot(MsjRobot)` overrides only `new_random_state()` to return the
@@ -20,7 +21,19 @@ import sys
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("ROBOY_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference():
+    """The read-only checkout in the build container, else the unmodified copy __graft_entry__.build() installs
+    under baseline/_ref/ (git-ignored; it travels to the GPU box with the tree, /root/reference does not)."""
+    for cand in (os.environ.get("ROBOY_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "gym_roboy")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 _SHIM = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "_shim")
 
 

@@ -427,7 +427,7 @@ void orc_external(orc_env *e, int reset, const uint8_t *mask, const float *q, co
             new_goal = dn;
             e->stats[ST_STEPS] += 1.0;
             e->stats[ST_SUM_REWARD] += (double)(float)r;
-            if (dn) { e->stats[ST_EPISODES] += 1.0; e->stats[reached ? ST_SUCCESSES : ST_TIMEOUTS] += 1.0; }
+            if (dn) { e->stats[ST_EPISODES] += 1.0; e->stats[reached ? ST_SUCCESSES : ST_TIMEOUTS] += 1.0; e->stats[ST_SUM_EPLEN] += (double)step - 1.0; }
             if (viol) { e->stats[ST_VIOLATIONS] += 1.0; note_error(e, ORC_ERR_REWARD_RANGE, gid); }
             for (int k = 0; k < 3; ++k) { obs[9 * i + k] = (float)s.q[k]; obs[9 * i + 3 + k] = (float)s.qd[k]; obs[9 * i + 6 + k] = g[k]; }
         } else {
@@ -520,11 +520,11 @@ static void step_range(step_job *j) {
              * again and only that second goal is observable, so one draw is materialised. */
             orc_draw_goal(cfg, gid, t, ng);
             for (int k = 0; k < 3; ++k) e->goal[(size_t)k * n + i] = ng[k];
+            j->stats[ST_SUM_EPLEN] += (double)step - 1.0;   /* steps taken since reset(): step_num starts at 1 */
             if (cfg->auto_reset) {
                 if (j->terminal_obs) memcpy(j->terminal_obs + 9 * i, o, sizeof(o));
                 for (int k = 0; k < 6; ++k) o[k] = 0.0f;
                 for (int k = 0; k < 3; ++k) o[6 + k] = ng[k];
-                j->stats[ST_SUM_EPLEN] += (double)step - 1.0;
                 step = 1;
                 flags = ORC_F_HELD_ZERO64;
             }

@@ -1,13 +1,17 @@
 """Time the UNMODIFIED Python reference on this machine's CPU -- TEST/BENCH INFRASTRUCTURE.
 
-    python -m oracle.time_reference        (build container only: needs /root/reference)
+    python -m oracle.time_reference            full run, writes profiles/r1_reference_python_cpu.json
+    python -m oracle.time_reference --quick    ~5 s, prints ONE JSON line (bench.py runs this on the bench box)
+
+Needs the reference: /root/reference in the build container, or the unmodified copy under baseline/_ref/ that
+__graft_entry__.build() installs and that travels to the GPU box.
 
 SURVEY.md 8d CPU baseline: (i) one reference RoboyEnv(StubSimulationClient(MsjRobot())) on one core,
 U(-1,1) float32 actions, reset() on done; (ii) the "vectorised-env path": stable-baselines is not
 installable, so SubprocVecEnv is restated as P worker processes each owning one reference env,
 lock-stepped through pipes with reset-on-done in the worker; (iii) the no-pipe upper bound
-(P independent loops).  Writes profiles/r1_reference_python_cpu.json, which bench.py attaches to
-its cpu_baseline object as context (it is measured HERE, not on the GPU box).
+(P independent loops).  bench.py attaches the --quick numbers, measured on the box it runs on, to its
+cpu_baseline object (`reference_python`).
 """
 import contextlib
 import io
@@ -105,6 +109,26 @@ def independent(P, steps):
         p.join()
     return sum(rates), time.perf_counter() - t0
 
+
+def quick():
+    """Bounded (~5 s) version for bench.py: measured on whatever box runs it, core count stated."""
+    from oracle import reference_harness as rh
+    cores = len(os.sched_getaffinity(0))
+    single = sorted(single_env(3000, warmup=300) for _ in range(2))
+    vec = vec_env(cores, 400)
+    ind, _ = independent(cores, 3000)
+    return {"what": "unmodified Python reference (gym-roboy RoboyEnv + StubSimulationClient) through tests/_shim",
+            "where": "this box", "reference_root": rh.REFERENCE_ROOT, "cores": cores,
+            "python": sys.version.split()[0], "numpy": np.__version__,
+            "single_env_steps_per_s": single[-1], "vec_env_restated_steps_per_s": vec,
+            "independent_processes_steps_per_s": ind,
+            "note": "restated SubprocVecEnv (stable-baselines is not installable): one process per core, pipes, lock-step, "
+                    "reset in the worker; `independent` = the same processes without pipes (upper bound)"}
+
+
+if __name__ == "__main__" and "--quick" in sys.argv:
+    print(json.dumps(quick()))
+    sys.exit(0)
 
 if __name__ == "__main__":
     cores = len(os.sched_getaffinity(0))

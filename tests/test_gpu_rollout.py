@@ -85,7 +85,7 @@ def test_collector_buffers_are_what_the_env_produced_and_graph_replay_matches_ea
 def test_vec_env_adapter():
     from gym_roboy_b200.vec_env import RoboyVecEnv
     n = 1000
-    venv = RoboyVecEnv(n, seed=4)
+    venv = RoboyVecEnv(n, seed=4, clip_actions=True)
     ora = orc.OracleEnv(n, seed=4)
     obs = venv.reset()
     assert obs.shape == (n, 9) and np.array_equal(obs, ora.reset())
@@ -102,4 +102,27 @@ def test_vec_env_adapter():
             assert np.array_equal(infos[i]["terminal_observation"], term[i])
         assert all("terminal_observation" not in infos[i] for i in np.flatnonzero(~d))
     assert venv.client.errors() == (0, None)
+    # per-env accessors, stable-baselines style
+    assert venv.get_attr("step_num", indices=[0, 5]) == [int(venv.client.step_num[0]), int(venv.client.step_num[5])]
+    assert len(venv.get_attr("reward_range")) == n and len(venv.env_method("render", indices=[1, 2, 3])) == 3
+    venv.set_attr("step_num", 7, indices=[3])
+    assert venv.get_attr("step_num", indices=3) == [7]
+    venv.close()
+
+
+def test_vec_env_adapter_asserts_like_the_reference_env_when_not_clipping():
+    """roboy_env.py:52: the env asserts the action range (the SB runner clips BEFORE env.step); a NaN fails too."""
+    from gym_roboy_b200.vec_env import RoboyVecEnv
+    venv = RoboyVecEnv(64, seed=1)
+    venv.reset()
+    a = np.zeros((64, 8), np.float32)
+    venv.step(a)
+    a[17, 3] = 1.0000001
+    with pytest.raises(AssertionError, match="17"):
+        venv.step(a)
+    a[17, 3] = np.nan
+    with pytest.raises(AssertionError):
+        venv.step(a)
+    a[17, 3] = 1.0
+    venv.step(a)
     venv.close()
