@@ -522,7 +522,7 @@ def run_b200_arm(args):
         e2e = {"value": rate, "unit": UNIT, "h2d_bytes_per_step": H2D_BYTES * n,
                "d2h_bytes_per_step": D2H_BYTES * n, "steps": k2, "ms_per_step": 1e3 * dt / k2,
                "api": "roboy_step_host (C-ABI), mode {}: page-locked host actions -> H2D -> step kernel -> D2H obs+reward+done, "
-                      "pipelined over 2 streams in 524,288-env stages (first stages shorter)".format(default_mode),
+                      "524,288-env stages (first stages shorter) on a ring of 2 streams".format(default_mode),
                "gpu_launches": e2e_launches,
                "copy_ceiling": {"value": ceiling, "unit": UNIT, "ms_per_pass": best_ms,
                                 "what": "roboy_host_copy_probe: the same H2D (32 B/env) and D2H (41 B/env) copies over the same "

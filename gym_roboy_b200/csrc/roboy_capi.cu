@@ -38,7 +38,7 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 constexpr int kHostStreamsMax = 8;         // ring of streams for the host-buffer pipeline
-constexpr int kHostStreamsDefault = 2;                // measured best on PCIe Gen5 (tools/e2e_sweep.py)
+constexpr int kHostStreamsDefault = 2;                // ring of two streams, each stage entirely on one of them (measured best)
 constexpr uint64_t kHostStageEnvsDefault = 1u << 19;  // 524,288 envs per pipeline stage (16 MiB in, 20.5 MiB out)
 
 struct DeviceGuard {
@@ -162,6 +162,7 @@ struct roboy_env {
     bool host_ready = false;
     cudaEvent_t hev[kHostStreamsMax] = {};
     bool host_ramp = true;  // shorter first stages (pipeline fill)
+    int host_pattern = ROBOY_HOST_PATTERN_RING;
     int host_mode = 0;  // ROBOY_HOST_STAGED / ROBOY_HOST_MAPPED_OUT / ROBOY_HOST_MAPPED_ALL
     // done-index list (lazily allocated by roboy_enable_done_index)
     uint32_t *done_bits = nullptr;
@@ -526,11 +527,19 @@ static int host_pipeline(roboy_env *env, const float *actions_host, float *obs_h
         }
         used = 2;
     } else {
-        // Pipeline: per stage H2D(actions) -> step kernel -> D2H(obs, reward, done) on one stream of a ring, so the
-        // copy engines of both directions and the SMs overlap across stages.  The first stages are shorter: the D2H
-        // engine (the longer leg, 41 of the 73 bytes) idles until the first kernel has run.
+        // Pipeline over stages of the env range.  ROBOY_HOST_PATTERN_RING (default): stage i runs H2D(actions_i) -> step
+        // kernel_i -> D2H(obs_i, reward_i, done_i) on stream i % n_streams, so the copy engines of both directions and the
+        // SMs overlap across stages.  ROBOY_HOST_PATTERN_SPLIT: one "up" stream carries every H2D and kernel, a ring of
+        // "down" streams the D2H copies behind per-stage events.  Measured on PCIe Gen5 x16 (16,777,216 envs, 1.22 GB per
+        // pass; the two directions as one monolithic copy each take 13.4-13.9 ms): ring of 2 streams 14.0-14.2 ms, split
+        // with 1 / 2 / 3 down streams 15.9 / 15.3 / 15.4 ms -- an H2D engine that never waits takes link bandwidth from
+        // the D2H leg, which is the longer one (41 of the 73 bytes).  The first stages are shorter: the D2H engine idles
+        // until the first kernel has run.
         int stage = 0;
         const uint64_t stage_envs = env->host_stage_envs;
+        cudaStream_t up = env->hs[0];
+        const int n_down = env->host_streams > 1 ? env->host_streams - 1 : 0;   // 0: D2H on the up stream too
+        const bool ring = env->host_pattern == ROBOY_HOST_PATTERN_RING && env->host_streams > 1;
         uint64_t b = 0;
         while (b < n && err == cudaSuccess) {
             uint64_t len = stage_envs;
@@ -538,44 +547,50 @@ static int host_pipeline(roboy_env *env, const float *actions_host, float *obs_h
             if (len == 0) len = stage_envs;
             const uint64_t eend = b + len < n ? b + len : n;
             const uint64_t cnt = eend - b;
-            cudaStream_t st = env->hs[stage % env->host_streams];
+            if (ring) up = env->hs[stage % env->host_streams];   // ROBOY_HOST_PATTERN_RING: stage i entirely on stream i % n
             if (what & kHostH2D)
                 HOST_TRY(cudaMemcpyAsync(env->actions_stage + b * ROBOY_DIM_ACTION, actions_host + b * ROBOY_DIM_ACTION,
-                                         sizeof(float) * ROBOY_DIM_ACTION * cnt, cudaMemcpyHostToDevice, st));
+                                         sizeof(float) * ROBOY_DIM_ACTION * cnt, cudaMemcpyHostToDevice, up));
             if (run_kernel) {
                 p.e_begin = b;
                 p.e_end = eend;
                 HOST_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
-                                     env->fastdiv, env->sm_count, st));
+                                     env->fastdiv, env->sm_count, up));
                 env->launches++;
             }
             if ((what & kHostD2H) && mode == ROBOY_HOST_STAGED) {
+                cudaStream_t down = n_down ? env->hs[1 + stage % n_down] : up;
+                if (ring) down = up;
+                if (down != up && ((what & kHostH2D) || run_kernel)) {
+                    cudaEvent_t ev = env->hev[stage % kHostStreamsMax];   // re-recording an event is fine: waits already
+                    HOST_TRY(cudaEventRecord(ev, up));                    // queued keep the record they saw
+                    HOST_TRY(cudaStreamWaitEvent(down, ev, 0));
+                }
                 HOST_TRY(cudaMemcpyAsync(obs_host + b * ROBOY_DIM_OBS, env->obs + b * ROBOY_DIM_OBS,
-                                         sizeof(float) * ROBOY_DIM_OBS * cnt, cudaMemcpyDeviceToHost, st));
-                HOST_TRY(cudaMemcpyAsync(reward_host + b, env->reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, st));
-                HOST_TRY(cudaMemcpyAsync(done_host + b, env->done + b, cnt, cudaMemcpyDeviceToHost, st));
+                                         sizeof(float) * ROBOY_DIM_OBS * cnt, cudaMemcpyDeviceToHost, down));
+                HOST_TRY(cudaMemcpyAsync(reward_host + b, env->reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, down));
+                HOST_TRY(cudaMemcpyAsync(done_host + b, env->done + b, cnt, cudaMemcpyDeviceToHost, down));
             }
             b = eend;
             ++stage;
         }
-        used = stage < env->host_streams ? stage : env->host_streams;
+        used = ring ? env->host_streams : 1 + n_down;
     }
     if (err == cudaSuccess && run_kernel) {
-        // join the ring on stream 0, advance the device counter there, wait once
-        for (int i = 1; i < used; ++i) {
-            HOST_TRY(cudaEventRecord(env->hev[i], env->hs[i]));
-            HOST_TRY(cudaStreamWaitEvent(env->hs[0], env->hev[i], 0));
-        }
+        // all kernels of this call are on stream 0 (mapped modes: one stream per stage ring is not needed either), so the
+        // device counter is advanced there, in stream order, without a join
+        if (env->host_pattern == ROBOY_HOST_PATTERN_RING && mode != ROBOY_HOST_MAPPED_ALL)
+            for (int i = 1; i < used; ++i) {
+                HOST_TRY(cudaEventRecord(env->hev[i], env->hs[i]));
+                HOST_TRY(cudaStreamWaitEvent(env->hs[0], env->hev[i], 0));
+            }
         HOST_TRY(launch_counter_bump(env->t_dev, 1, env->hs[0]));
-        HOST_TRY(cudaStreamSynchronize(env->hs[0]));
     }
     // Whatever happened, nothing may still be copying into the caller's buffers when this returns.
-    const bool drain_all = err != cudaSuccess || !run_kernel;
-    if (drain_all)
-        for (int i = 0; i < kHostStreamsMax; ++i) {
-            const cudaError_t e2 = cudaStreamSynchronize(env->hs[i]);
-            if (err == cudaSuccess) err = e2;
-        }
+    for (int i = 0; i < used; ++i) {
+        const cudaError_t e2 = cudaStreamSynchronize(env->hs[i]);
+        if (err == cudaSuccess) err = e2;
+    }
 #undef HOST_TRY
     if (err != cudaSuccess) {
         cudaGetLastError();
@@ -644,6 +659,13 @@ int roboy_set_host_pipeline(roboy_env *env, uint64_t stage_envs, int n_streams) 
         return fail(ROBOY_E_ARG, "stage_envs must be a positive multiple of 32 and 1 <= n_streams <= %d", kHostStreamsMax);
     env->host_stage_envs = stage_envs;
     env->host_streams = n_streams;
+    return ROBOY_OK;
+}
+
+int roboy_set_host_pattern(roboy_env *env, int pattern) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (pattern != ROBOY_HOST_PATTERN_SPLIT && pattern != ROBOY_HOST_PATTERN_RING) return fail(ROBOY_E_ARG, "unknown pattern %d", pattern);
+    env->host_pattern = pattern;
     return ROBOY_OK;
 }
 

@@ -46,6 +46,10 @@ namespace roboy {
 #ifndef ROBOY_PDL
 #define ROBOY_PDL 1  // programmatic dependent launch of the step kernel (measured: +0.7 % at 16,777,216 envs, -4 % step time at 65,536, -9 % eager at 4,096)
 #endif
+#ifndef ROBOY_DEFER_DONE
+#define ROBOY_DEFER_DONE 0  // 1: queue finished envs in shared memory and resample their goals at the end of the CTA (measured SLOWER:
+                            // 0.2606 vs 0.2563 ms per 16,777,216-env step with 1/400 of the envs finishing -- the pass is a serial tail)
+#endif
 #ifndef ROBOY_LD_HINT
 #define ROBOY_LD_HINT 0  // streamed inputs:  0 default (measured best: +3% over .cs), 1 ld.global.cs, 2 ld.global.nc.L1::no_allocate
 #endif
@@ -202,10 +206,23 @@ struct OutPtrs {
 
 // One env-step for the 32 envs of a chunk.  KEEP_STATE: the caller keeps the step word (and goal) in
 // registers across several steps (open-loop rollout) instead of storing it per step.
-template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV, bool TAIL, bool KEEP_STATE>
+// EXPERIMENT (ROBOY_DEFER_DONE=1, not the product build): finished envs of one CTA, queued by the hot loop and worked off
+// by all threads of the CTA at its end.  An episode end costs a Philox block, three scattered goal stores and, under
+// auto-reset, a rewritten observation row: ~150 instructions that one lane of a warp executes alone, and with 1/400 of the
+// envs finishing per step 7.7 % of the 32-env chunks contain one (2.5 % of the step time at 16,777,216 envs).  Queued, the
+// instructions shrink, but the pass runs when every CTA of the persistent grid has drained its memory pipeline -- a serial
+// tail that costs more than it saves (0.2606 vs 0.2563 ms).  Entries beyond the capacity take the inline path.
+constexpr uint32_t kDoneQueueCap = 512;
+struct DoneQueue {
+    unsigned int n;
+    uint32_t env[kDoneQueueCap];   // local env id | reached << 31
+    uint32_t step[kDoneQueueCap];  // step_num at the episode end
+};
+
+template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV, bool TAIL, bool KEEP_STATE, bool DEFER = false>
 __device__ __forceinline__ uint32_t process_chunk(const StepParams &p, uint64_t t, const ChunkIn &cur, uint32_t base,
                                                   int lane, float *so, unsigned int *s_cnt, float &sum_reward,
-                                                  const OutPtrs &out, bool &done_out) {
+                                                  const OutPtrs &out, bool &done_out, DoneQueue *dq = nullptr) {
     const uint32_t e = base + lane;
     const bool live = TAIL ? (e < (uint32_t)p.e_end) : true;
 
@@ -267,8 +284,20 @@ __device__ __forceinline__ uint32_t process_chunk(const StepParams &p, uint64_t 
     row[6] = g0; row[7] = g1; row[8] = g2;
 
     if (done && live) {
-        const uint32_t r = finish_episode(p, t, e, step, reached, AUTO_RESET, row, s_cnt);
-        word = (r & 0x80000000u) ? word : (r | ROBOY_F_HELD_ZERO64);
+        bool queued = false;
+        if (DEFER) {
+            const unsigned int slot = atomicAdd(&dq->n, 1u);
+            if (slot < kDoneQueueCap) {
+                dq->env[slot] = e | (reached ? 0x80000000u : 0u);
+                dq->step[slot] = step;
+                if (AUTO_RESET) word = 1u | ROBOY_F_HELD_ZERO64;   // roboy_env.py:85 + the zero state of :83
+                queued = true;
+            }
+        }
+        if (!queued) {
+            const uint32_t r = finish_episode(p, t, e, step, reached, AUTO_RESET, row, s_cnt);
+            word = (r & 0x80000000u) ? word : (r | ROBOY_F_HELD_ZERO64);
+        }
     }
     if (live && (violation || !act_ok)) {
         atomicOr(p.err_flags, (violation ? ROBOY_ERR_REWARD_RANGE : 0u) | (!act_ok ? ROBOY_ERR_ACTION : 0u));
@@ -341,6 +370,15 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
     // atomics where they happen instead of tying up registers in the hot loop
     __shared__ unsigned int s_cnt[5];  // done, success, hold, violation, sum of episode lengths
     if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
+#if ROBOY_DEFER_DONE
+    __shared__ DoneQueue s_dq;
+    if (threadIdx.x == 0) s_dq.n = 0;
+    constexpr bool kDefer = true;
+    DoneQueue *dq = &s_dq;
+#else
+    constexpr bool kDefer = false;
+    DoneQueue *dq = nullptr;
+#endif
     __syncthreads();
 #if ROBOY_PDL
     // programmatic dependent launch: this grid may have been started while its predecessor in the stream (the policy
@@ -394,20 +432,36 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
         so = s_obs[parity][warp];
         parity ^= 1;
 #endif
-        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false, false>(p, t, cur, chunk << 5, lane, so, s_cnt,
-                                                                         sum_reward, out, done_unused);
+        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false, false, kDefer>(p, t, cur, chunk << 5, lane, so, s_cnt,
+                                                                                 sum_reward, out, done_unused, dq);
         chunk = next;
     }
 #if ROBOY_OBS_BULK_STORE
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    // all bulk copies of this warp have completed (their global writes included: the queued episode ends below rewrite
+    // observation rows they wrote)
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
     so = s_obs[0][warp];
 #endif
     if (chunk == n_full && (p.e_end & 31)) {  // the ragged last chunk belongs to exactly one warp
         const ChunkIn cur = load_chunk<true>(p, chunk << 5, lane);
-        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true, false>(p, t, cur, chunk << 5, lane, so, s_cnt,
-                                                                        sum_reward, out, done_unused);
+        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true, false, kDefer>(p, t, cur, chunk << 5, lane, so, s_cnt,
+                                                                                sum_reward, out, done_unused, dq);
     }
+#if ROBOY_DEFER_DONE
+    // ---- queued episode ends: one pass of the whole CTA ----
+    __syncthreads();
+    {
+        const unsigned int qn = s_dq.n < kDoneQueueCap ? s_dq.n : kDoneQueueCap;
+        if (qn) {
+            asm volatile("fence.proxy.async;" ::: "memory");  // the rows were written through the async proxy (bulk copies)
+            for (unsigned int i = threadIdx.x; i < qn; i += kStepBlock) {
+                const uint32_t ew = s_dq.env[i];
+                finish_episode_queued(p, t, ew & 0x7fffffffu, s_dq.step[i], (ew >> 31) != 0, AUTO_RESET, out.obs, s_cnt);
+            }
+        }
+    }
+#endif
 
     // ---- K3: episode statistics, one set of atomics per CTA ----
     const double w_reward = warp_sum((double)sum_reward);

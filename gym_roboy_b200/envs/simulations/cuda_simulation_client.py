@@ -231,9 +231,10 @@ class CudaSimulationClient(SimulationClient):
         _native.check(self._lib.roboy_reset_external(self._h, self._p(m), self._p(q), self._p(qd), self._p(obs),
                                                      self._stream()))
 
-    def set_host_pipeline(self, stage_envs=1 << 19, n_streams=2, ramp=True):
+    def set_host_pipeline(self, stage_envs=1 << 19, n_streams=2, ramp=True, ring=True):
         _native.check(self._lib.roboy_set_host_pipeline(self._h, int(stage_envs), int(n_streams)))
         _native.check(self._lib.roboy_set_host_ramp(self._h, int(bool(ramp))))
+        _native.check(self._lib.roboy_set_host_pattern(self._h, int(bool(ring))))
 
     def set_host_mode(self, mode):
         """`_native.HOST_STAGED` (copy engines both ways), `HOST_MAPPED_OUT` (the kernel stores its outputs straight into

@@ -151,11 +151,19 @@ int roboy_step_many(roboy_env *env, uint32_t T, const float *actions_dev, float 
 int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, float *reward_host,
                     uint8_t *done_host);
 
-/* Tuning of roboy_step_host's pipeline: envs per stage (multiple of 32) and streams in the ring
- * (1..8).  Defaults: 524,288 envs, 2 streams (measured best on PCIe Gen5).  roboy_set_host_ramp: run the first three
- * stages at 1/8, 1/4 and 1/2 of the stage size so the D2H engine starts sooner (default on). */
+/* Tuning of roboy_step_host's pipeline: envs per stage (multiple of 32; default 524,288), streams (1..8, default 2)
+ * and the pattern:
+ *   ROBOY_HOST_PATTERN_RING (default)  stage i runs H2D(actions_i) -> kernel_i -> D2H(obs_i, reward_i, done_i) on
+ *                                      stream i % n_streams
+ *   ROBOY_HOST_PATTERN_SPLIT           one "up" stream carries every H2D and kernel, n_streams - 1 "down" streams the
+ *                                      D2H copies behind per-stage events
+ * (measured: the ring of two streams is 7 % faster -- roboy_capi.cu).  roboy_set_host_ramp: run the first three stages
+ * at 1/8, 1/4 and 1/2 of the stage size so the D2H engine starts sooner (default on). */
 int roboy_set_host_pipeline(roboy_env *env, uint64_t stage_envs, int n_streams);
 int roboy_set_host_ramp(roboy_env *env, int enable);
+#define ROBOY_HOST_PATTERN_SPLIT 0
+#define ROBOY_HOST_PATTERN_RING 1
+int roboy_set_host_pattern(roboy_env *env, int pattern);
 
 /* How roboy_step_host moves the outputs (and inputs):
  *   ROBOY_HOST_STAGED      copy engines both ways (default; any host memory, pinned for full speed)

