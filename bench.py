@@ -473,10 +473,13 @@ def run_b200_arm(args):
             torch.from_numpy(a).copy_(src)
         modes = {"staged": _native.HOST_STAGED, "mapped_out": _native.HOST_MAPPED_OUT, "mapped_all": _native.HOST_MAPPED_ALL}
 
-        def time_e2e(mode, ramp=True, steps=k2):
+        def time_e2e(mode, ramp=True, steps=k2, streams=None):
             client.set_host_mode(modes[mode])
-            client.set_host_pipeline(ramp=ramp)
-            for i in range(2):
+            if streams is None:
+                client.set_host_autotune(True)     # the library's default: ring, stream count tuned on calls 2 and 3
+            else:
+                client.set_host_pipeline(n_streams=streams, ramp=ramp)
+            for i in range(3):
                 client.step_host(a_host[i & 1], obs_h, rew_h, done_h)
             torch.cuda.synchronize()
             if world > 1:
@@ -503,17 +506,15 @@ def run_b200_arm(args):
                 ms = float(t.item())
             return ms
 
-        default_mode = os.environ.get("ROBOY_BENCH_E2E_MODE", "staged")
         variants = {}
-        for mode, ramp in (("staged", False), ("mapped_out", True), ("mapped_all", True), ("staged", True)):
-            if mode == default_mode and ramp:
-                continue
+        for name, mode, ramp, streams in (("ring2_noramp", "staged", False, 2), ("ring2", "staged", True, 2), ("one_stream", "staged", True, 1),
+                                          ("mapped_out", "mapped_out", True, 2), ("mapped_all", "mapped_all", True, 1)):
             try:
-                v, _, _ = time_e2e(mode, ramp, steps=max(3, k2 // 2))
-                variants[mode + ("" if ramp else "_noramp")] = v
+                variants[name] = time_e2e(mode, ramp, steps=max(3, k2 // 2), streams=streams)[0]
             except Exception as exc:
-                variants[mode] = "failed: %s" % str(exc)[:120]
-        rate, dt, e2e_launches = time_e2e(default_mode, True)          # the library's default configuration: THE e2e number
+                variants[name] = "failed: %s" % str(exc)[:120]
+        rate, dt, e2e_launches = time_e2e("staged")          # the library's default configuration: THE e2e number
+        pipeline = client.host_pipeline()
         # the copy ceiling: the same bytes over the same buffers without the kernel, all ranks at once
         both_staged, both_mono = probe(3, False), probe(3, True)
         h2d_ms, d2h_ms = probe(1, True), probe(2, True)
@@ -521,8 +522,9 @@ def run_b200_arm(args):
         ceiling = envs * world / (best_ms * 1e-3)
         e2e = {"value": rate, "unit": UNIT, "h2d_bytes_per_step": H2D_BYTES * n,
                "d2h_bytes_per_step": D2H_BYTES * n, "steps": k2, "ms_per_step": 1e3 * dt / k2,
-               "api": "roboy_step_host (C-ABI), mode {}: page-locked host actions -> H2D -> step kernel -> D2H obs+reward+done, "
-                      "524,288-env stages (first stages shorter) on a ring of 2 streams".format(default_mode),
+               "api": "roboy_step_host (C-ABI), library defaults: page-locked host actions -> H2D -> step kernel -> D2H obs+reward+done, "
+                      "{:,}-env stages (first stages shorter) on a ring of {} stream(s) -- the stream count is tuned by the "
+                      "library on its 2nd and 3rd call".format(pipeline["stage_envs"], pipeline["n_streams"]),
                "gpu_launches": e2e_launches,
                "copy_ceiling": {"value": ceiling, "unit": UNIT, "ms_per_pass": best_ms,
                                 "what": "roboy_host_copy_probe: the same H2D (32 B/env) and D2H (41 B/env) copies over the same "

@@ -62,6 +62,8 @@ SIGNATURES = {
     "roboy_set_host_pipeline": (_int, [_vp, _u64, _int]),
     "roboy_set_host_ramp": (_int, [_vp, _int]),
     "roboy_set_host_pattern": (_int, [_vp, _int]),
+    "roboy_set_host_autotune": (_int, [_vp, _int]),
+    "roboy_get_host_pipeline": (_int, [_vp, ctypes.POINTER(_u64), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     "roboy_set_host_mode": (_int, [_vp, _int]),
     "roboy_host_alloc": (_int, [_u64, _int, ctypes.POINTER(_vp)]),
     "roboy_host_free": (_int, [_vp]),

@@ -236,6 +236,15 @@ class CudaSimulationClient(SimulationClient):
         _native.check(self._lib.roboy_set_host_ramp(self._h, int(bool(ramp))))
         _native.check(self._lib.roboy_set_host_pattern(self._h, int(bool(ring))))
 
+    def set_host_autotune(self, enable=True):
+        """Default pipeline, stream count tuned by measurement on the next calls (`roboy_set_host_autotune`)."""
+        _native.check(self._lib.roboy_set_host_autotune(self._h, int(bool(enable))))
+
+    def host_pipeline(self):
+        stage, streams, pattern = ctypes.c_uint64(), ctypes.c_int(), ctypes.c_int()
+        _native.check(self._lib.roboy_get_host_pipeline(self._h, ctypes.byref(stage), ctypes.byref(streams), ctypes.byref(pattern)))
+        return dict(stage_envs=stage.value, n_streams=streams.value, pattern="ring" if pattern.value else "split")
+
     def set_host_mode(self, mode):
         """`_native.HOST_STAGED` (copy engines both ways), `HOST_MAPPED_OUT` (the kernel stores its outputs straight into
         the page-locked host buffers) or `HOST_MAPPED_ALL` (it also reads the actions from them)."""

@@ -161,6 +161,13 @@ int roboy_step_host(roboy_env *env, const float *actions_host, float *obs_host, 
  * at 1/8, 1/4 and 1/2 of the stage size so the D2H engine starts sooner (default on). */
 int roboy_set_host_pipeline(roboy_env *env, uint64_t stage_envs, int n_streams);
 int roboy_set_host_ramp(roboy_env *env, int enable);
+/* Unless the caller fixed the pipeline with roboy_set_host_pipeline, the stream count of the ring is tuned by measurement:
+ * the second and third roboy_step_host calls of a handle time a ring of two streams and a single stream and the faster
+ * one is kept (one GPU on its own PCIe link wants two; eight GPUs saturating the host's memory path want one).
+ * roboy_set_host_autotune(env, 1) restores the defaults and re-arms the tuning; roboy_get_host_pipeline reads the
+ * configuration in force (any pointer may be NULL). */
+int roboy_set_host_autotune(roboy_env *env, int enable);
+int roboy_get_host_pipeline(roboy_env *env, uint64_t *stage_envs, int *n_streams, int *pattern);
 #define ROBOY_HOST_PATTERN_SPLIT 0
 #define ROBOY_HOST_PATTERN_RING 1
 int roboy_set_host_pattern(roboy_env *env, int pattern);
