@@ -9,7 +9,8 @@ import os
 from . import build as _build
 
 ABI_VERSION = 2
-DIM_JOINT, DIM_ACTION, DIM_OBS = 3, 8, 9
+DIM_JOINT, DIM_ACTION, DIM_OBS = 3, 8, 9          # the MSJ robot; other robots: RoboyCfg.dim_joint / dim_action
+MAX_JOINT, JOINT_PAD, MAX_ACTION = 15, 16, 64    # ROBOY_MAX_JOINT, ROBOY_JOINT_PAD, ROBOY_MAX_ACTION
 
 STEP_MASK = 0x00FFFFFF
 F_HELD_ZERO64 = 1 << 24
@@ -40,6 +41,11 @@ class RoboyCfg(ctypes.Structure):
         ("bonus_for_goal", ctypes.c_int32), ("auto_reset", ctypes.c_int32),
         ("penalty_boundary", ctypes.c_float), ("bonus_goal", ctypes.c_float),
         ("reward_lo", ctypes.c_double), ("reward_hi", ctypes.c_double),
+        ("dim_joint", ctypes.c_int32), ("dim_action", ctypes.c_int32),
+        ("per_component_bounds", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("angle_low_v", ctypes.c_float * JOINT_PAD), ("angle_high_v", ctypes.c_float * JOINT_PAD),
+        ("vel_low_v", ctypes.c_float * JOINT_PAD), ("vel_high_v", ctypes.c_float * JOINT_PAD),
+        ("act_low_v", ctypes.c_float * MAX_ACTION), ("act_high_v", ctypes.c_float * MAX_ACTION),
     ]
 
 
@@ -52,6 +58,8 @@ SIGNATURES = {
     "roboy_last_error": (ctypes.c_char_p, []),
     "roboy_cfg_msj": (_int, [_cfgp]),
     "roboy_hold_interval": (_int, [_cfgp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    "roboy_hold_intervals": (_int, [_cfgp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    "roboy_robot_dims": (_int, [_vp, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     "roboy_create": (_int, [_cfgp, _int, ctypes.POINTER(_vp)]),
     "roboy_destroy": (_int, [_vp]),
     "roboy_set_reward_range": (_int, [_vp, ctypes.c_double, ctypes.c_double]),

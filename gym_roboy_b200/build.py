@@ -12,8 +12,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 LIB_DIR = os.path.join(_PKG, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libroboy_b200.so")
-SOURCES = ("roboy_kernels.cu", "roboy_policy.cu", "roboy_policy_tc.cu", "roboy_capi.cu")
-HEADERS = ("roboy_kernels.cuh", "roboy_policy.cuh", "policy_common.cuh", "step_rare.cuh", "msj_math.cuh", "philox.cuh", "dlpack_min.h", os.path.join("..", "..", "include", "roboy_b200.h"))
+SOURCES = ("roboy_kernels.cu", "roboy_generic.cu", "roboy_policy.cu", "roboy_policy_tc.cu", "roboy_capi.cu")
+HEADERS = ("roboy_kernels.cuh", "roboy_generic.cuh", "roboy_policy.cuh", "policy_common.cuh", "step_rare.cuh", "msj_math.cuh", "philox.cuh", "dlpack_min.h", os.path.join("..", "..", "include", "roboy_b200.h"))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -7,7 +7,7 @@
 //   compute_reward  envs/roboy_env.py:92-112
 //   _did_reach_goal envs/roboy_env.py:125-134
 // np.linalg.norm(float32[3]) accumulates the float32 products in a double (OpenBLAS sdot) and
-// rounds once to float32 before the float32 sqrt; float64 operands sum sequentially.  All
+// rounds once to float32 before the float32 sqrt; float64 operands accumulate sequentially with FMA.  All
 // arithmetic below uses the round-to-nearest intrinsics so nvcc never contracts a multiply and
 // an add into an FMA (numpy does not fuse).
 #pragma once
@@ -59,9 +59,12 @@ __device__ __forceinline__ double l2_f64(double a0, double a1, double a2, double
     const double d0 = nan_to_zero(__dsub_rn(a0, b0));
     const double d1 = nan_to_zero(__dsub_rn(a1, b1));
     const double d2 = nan_to_zero(__dsub_rn(a2, b2));
+    // OpenBLAS ddot's scalar tail (n < 16) is compiled with FMA contraction: s = fma(d, d, s), sequentially -- pinned
+    // against numpy in oracle/roboy_oracle.c's header.  (With float32-valued operands the products are exact and the
+    // unfused sum gives the same bits; with the float64 normalised zero of an asymmetric velocity space it does not.)
     double s = __dmul_rn(d0, d0);
-    s = __dadd_rn(s, __dmul_rn(d1, d1));
-    s = __dadd_rn(s, __dmul_rn(d2, d2));
+    s = __fma_rn(d1, d1, s);
+    s = __fma_rn(d2, d2, s);
     return __dsqrt_rn(s);
 }
 

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
@@ -13,6 +14,7 @@
 
 #include "../../include/roboy_b200.h"
 #include "dlpack_min.h"
+#include "roboy_generic.cuh"
 #include "roboy_kernels.cuh"
 #include "roboy_policy.cuh"
 
@@ -56,11 +58,13 @@ struct DeviceGuard {
 
 // roboy_env.py:24-25 _l2_distance(space.low, space.high) in float32, numpy evaluation order
 // (float32 products accumulated in double, rounded to float32, float32 sqrt).
-float box_diagonal_f32(float lo, float hi, int dim) {
-    volatile float d = lo - hi;
-    volatile float p = d * d;
+float box_diagonal_f32(const float *lo, const float *hi, int dim) {
     double s = 0.0;
-    for (int k = 0; k < dim; ++k) s += (double)p;
+    for (int k = 0; k < dim; ++k) {
+        volatile float d = lo[k] - hi[k];
+        volatile float p = d * d;
+        s += (double)p;
+    }
     return sqrtf((float)s);
 }
 
@@ -119,9 +123,63 @@ float round_down_f32(double x) {
 
 // The 3-instruction division of the sampled-state path is proved bit-exact (oracle/verify_fastdiv.c)
 // for the MSJ spans only: 2*pi_f32 (0x40c90fdb) and (pi/3)_f32 (0x3f860a92).
-bool spans_are_proved(const roboy_cfg &c) {
-    return f2u(c.angle_high - c.angle_low) == 0x40c90fdbu && c.angle_low == -c.angle_high &&
-           f2u(c.vel_high - c.vel_low) == 0x3f860a92u && c.vel_low == -c.vel_high;
+bool spans_are_proved(float a_lo, float a_hi, float v_lo, float v_hi) {
+    return f2u(a_hi - a_lo) == 0x40c90fdbu && a_lo == -a_hi && f2u(v_hi - v_lo) == 0x3f860a92u && v_lo == -v_hi;
+}
+
+int cfg_dim_joint(const roboy_cfg &c) { return c.dim_joint > 0 ? c.dim_joint : ROBOY_DIM_JOINT; }
+int cfg_dim_action(const roboy_cfg &c) { return c.dim_action > 0 ? c.dim_action : ROBOY_DIM_ACTION; }
+
+// The robot's spaces as per-component arrays, whichever way the caller gave them
+void fill_robot_spec(const roboy_cfg &c, RobotSpec &r) {
+    memset(&r, 0, sizeof(r));
+    r.J = cfg_dim_joint(c);
+    r.A = cfg_dim_action(c);
+    for (int k = 0; k < r.J; ++k) {
+        r.a_lo[k] = c.per_component_bounds ? c.angle_low_v[k] : c.angle_low;
+        r.a_hi[k] = c.per_component_bounds ? c.angle_high_v[k] : c.angle_high;
+        r.v_lo[k] = c.per_component_bounds ? c.vel_low_v[k] : c.vel_low;
+        r.v_hi[k] = c.per_component_bounds ? c.vel_high_v[k] : c.vel_high;
+    }
+    for (int k = 0; k < r.A; ++k) {
+        const float lo = c.per_component_bounds ? c.act_low_v[k] : c.act_low;
+        const float hi = c.per_component_bounds ? c.act_high_v[k] : c.act_high;
+        const float slope = (hi - lo) / (1.0f - (-1.0f));  // roboy_env.py:157, float32, per component
+        hold_interval(-1.0f, 1.0f, slope, hi, &r.hold_lo[k], &r.hold_hi[k]);
+    }
+    r.thr_angle = box_diagonal_f32(r.a_lo, r.a_hi, r.J) / 200.0f;  // roboy_env.py:127
+    r.thr_vel = box_diagonal_f32(r.v_lo, r.v_hi, r.J) / 5.0f;      // roboy_env.py:130
+    r.penalty_boundary = fabsf(c.penalty_boundary);
+    r.bonus_goal = c.bonus_goal;
+    r.reward_lo = c.reward_lo;
+    r.reward_hi = c.reward_hi;
+}
+
+// MSJ's dims and the same bounds on every component: the tuned kernels apply
+bool is_msj_shaped(const roboy_cfg &c, const RobotSpec &r) {
+    if (r.J != ROBOY_DIM_JOINT || r.A != ROBOY_DIM_ACTION) return false;
+    for (int k = 1; k < r.J; ++k)
+        if (r.a_lo[k] != r.a_lo[0] || r.a_hi[k] != r.a_hi[0] || r.v_lo[k] != r.v_lo[0] || r.v_hi[k] != r.v_hi[0]) return false;
+    if (c.per_component_bounds)
+        for (int k = 1; k < r.A; ++k)
+            if (c.act_low_v[k] != c.act_low_v[0] || c.act_high_v[k] != c.act_high_v[0]) return false;
+    return true;
+}
+
+const char *check_robot(const roboy_cfg &c) {
+    const int J = cfg_dim_joint(c), A = cfg_dim_action(c);
+    if (J < 1 || J > ROBOY_MAX_JOINT) return "dim_joint must be 1..15 (numpy sums longer vectors in a CPU-dependent order)";
+    if (A < 1 || A > ROBOY_MAX_ACTION) return "dim_action must be 1..64";
+    for (int k = 0; k < J; ++k) {
+        const float al = c.per_component_bounds ? c.angle_low_v[k] : c.angle_low, ah = c.per_component_bounds ? c.angle_high_v[k] : c.angle_high;
+        const float vl = c.per_component_bounds ? c.vel_low_v[k] : c.vel_low, vh = c.per_component_bounds ? c.vel_high_v[k] : c.vel_high;
+        if (!(ah > al) || !(vh > vl)) return "empty robot space";
+    }
+    for (int k = 0; k < A; ++k) {
+        const float tl = c.per_component_bounds ? c.act_low_v[k] : c.act_low, th = c.per_component_bounds ? c.act_high_v[k] : c.act_high;
+        if (!(th > tl)) return "empty robot space";
+    }
+    return nullptr;
 }
 
 }  // namespace
@@ -138,9 +196,12 @@ struct roboy_env {
     uint32_t goal_sub = 0;  // goal draws already made at this call counter (un-fused API)
     uint64_t launches = 0;  // kernels launched through this handle
     PhiloxKeys keys;
-    RobotConsts consts;
+    RobotSpec spec;         // the robot, per component (generic kernels; all robots)
+    int J = ROBOY_DIM_JOINT, A = ROBOY_DIM_ACTION, D = ROBOY_DIM_OBS;
+    bool msj_shaped = true;  // MSJ's dims with uniform bounds: the tuned step / rollout kernels apply
+    RobotConsts consts;     // ... and their scalar constants
     FastConsts fast;
-    float act_slope = 0.f;
+    float act_slope = 0.f, act_hi = 0.f;
     float hold_lo = 1.f, hold_hi = -1.f;
     bool fastdiv = false;
     // HBM
@@ -233,7 +294,7 @@ void fill_step_params(roboy_env *e, StepParams &p, const float *actions, float *
     p.hold_mag = fmaxf(fabsf(e->hold_lo), fabsf(e->hold_hi));
     p.act_in_hi = 1.0f;   // roboy_env.py:31
     p.act_in_lo = -1.0f;
-    p.act_hi = e->cfg.act_high;
+    p.act_hi = e->act_hi;
     p.act_slope = e->act_slope;
     p.max_len = e->cfg.max_episode_len;
     p.actions = actions;
@@ -251,6 +312,54 @@ void fill_step_params(roboy_env *e, StepParams &p, const float *actions, float *
     p.stats = e->stats;
     p.err_flags = e->err_flags;
     p.first_bad = e->first_bad;
+}
+
+void fill_generic_step_params(roboy_env *e, GStepParams &p, const float *actions, float *obs, float *reward, uint8_t *done) {
+    p.n = e->cfg.n_envs;
+    p.e_begin = 0;
+    p.e_end = e->cfg.n_envs;
+    p.gid_base = e->cfg.env_id_base;
+    p.cc = counter(e, CallCounter::kAdvance);
+    p.keys = e->keys;
+    p.r = e->spec;
+    p.max_len = e->cfg.max_episode_len;
+    p.penalty = e->cfg.joint_vel_penalty;
+    p.bonus = e->cfg.bonus_for_goal;
+    p.auto_reset = e->cfg.auto_reset;
+    p.actions = actions;
+    p.goal = e->goal;
+    p.step_flags = e->step_flags;
+    p.held = e->held;
+    p.obs = obs ? obs : e->obs;
+    p.reward = reward ? reward : e->reward;
+    p.done = done ? done : e->done;
+    p.terminal_obs = e->terminal_obs;
+    p.done_bits = e->done_bits;
+    p.stats = e->stats;
+    p.err_flags = e->err_flags;
+    p.first_bad = e->first_bad;
+}
+
+// One fused step over local envs [e_begin, e_end): the tuned kernel for MSJ-shaped robots, the generic one otherwise.
+// obs / reward / done: full-array base pointers (NULL = the handle's buffers).
+cudaError_t launch_env_step(roboy_env *e, const float *actions, float *obs, float *reward, uint8_t *done, uint64_t e_begin,
+                            uint64_t e_end, const CallCounter &cc, bool with_done_bits, cudaStream_t stream) {
+    if (e->msj_shaped) {
+        StepParams p;
+        fill_step_params(e, p, actions, obs, reward, done);
+        p.e_begin = e_begin;
+        p.e_end = e_end;
+        p.cc = cc;
+        if (!with_done_bits) p.done_bits = nullptr;
+        return launch_step(p, e->cfg.joint_vel_penalty, e->cfg.bonus_for_goal, e->cfg.auto_reset, e->fastdiv, e->sm_count, stream);
+    }
+    GStepParams p;
+    fill_generic_step_params(e, p, actions, obs, reward, done);
+    p.e_begin = e_begin;
+    p.e_end = e_end;
+    p.cc = cc;
+    if (!with_done_bits) p.done_bits = nullptr;
+    return launch_generic_step(p, e->sm_count, stream);
 }
 
 int check_env(roboy_env *e) {
@@ -284,13 +393,33 @@ int roboy_cfg_msj(roboy_cfg *cfg) {
     cfg->bonus_goal = 1000.0f;       // roboy_env.py:27
     cfg->reward_lo = -INFINITY;
     cfg->reward_hi = INFINITY;
+    cfg->dim_joint = ROBOY_DIM_JOINT;    // msj_robot.py:8
+    cfg->dim_action = ROBOY_DIM_ACTION;  // msj_robot.py:12
+    cfg->per_component_bounds = 0;
+    for (int k = 0; k < ROBOY_DIM_JOINT; ++k) {
+        cfg->angle_low_v[k] = cfg->angle_low; cfg->angle_high_v[k] = cfg->angle_high;
+        cfg->vel_low_v[k] = cfg->vel_low; cfg->vel_high_v[k] = cfg->vel_high;
+    }
+    for (int k = 0; k < ROBOY_DIM_ACTION; ++k) { cfg->act_low_v[k] = cfg->act_low; cfg->act_high_v[k] = cfg->act_high; }
+    return ROBOY_OK;
+}
+
+int roboy_hold_intervals(const roboy_cfg *cfg, float *lo, float *hi) {
+    if (!cfg || !lo || !hi) return fail(ROBOY_E_ARG, "NULL argument");
+    if (const char *why = check_robot(*cfg)) return fail(ROBOY_E_ARG, "%s", why);
+    RobotSpec r;
+    fill_robot_spec(*cfg, r);
+    for (int k = 0; k < r.A; ++k) { lo[k] = r.hold_lo[k]; hi[k] = r.hold_hi[k]; }
     return ROBOY_OK;
 }
 
 int roboy_hold_interval(const roboy_cfg *cfg, float *lo, float *hi) {
     if (!cfg || !lo || !hi) return fail(ROBOY_E_ARG, "NULL argument");
-    const float slope = (cfg->act_high - cfg->act_low) / (1.0f - (-1.0f));
-    hold_interval(-1.0f, 1.0f, slope, cfg->act_high, lo, hi);
+    float l[ROBOY_MAX_ACTION], h[ROBOY_MAX_ACTION];
+    const int rc = roboy_hold_intervals(cfg, l, h);
+    if (rc) return rc;
+    *lo = l[0];
+    *hi = h[0];
     return ROBOY_OK;
 }
 
@@ -299,8 +428,7 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
     *out = nullptr;
     if (cfg->n_envs == 0) return fail(ROBOY_E_ARG, "n_envs must be > 0");
     if (cfg->n_envs > 0x7fffff00ull) return fail(ROBOY_E_ARG, "a shard holds fewer than 2^31 envs");
-    if (!(cfg->angle_high > cfg->angle_low) || !(cfg->vel_high > cfg->vel_low) || !(cfg->act_high > cfg->act_low))
-        return fail(ROBOY_E_ARG, "empty robot space");
+    if (const char *why = check_robot(*cfg)) return fail(ROBOY_E_ARG, "%s", why);
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
         cudaGetLastError();
@@ -317,21 +445,34 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
     e->keys = make_philox_keys(cfg->seed);
+    fill_robot_spec(*cfg, e->spec);
+    const RobotSpec &r = e->spec;
+    e->J = r.J;
+    e->A = r.A;
+    e->D = 3 * r.J;
+    e->msj_shaped = is_msj_shaped(*cfg, r);
+    if (const char *force = getenv("ROBOY_B200_FORCE_GENERIC"))   // tests: run an MSJ-shaped robot through the generic kernels
+        if (force[0] == '1') e->msj_shaped = false;
+    // scalar constants of the tuned MSJ-shaped kernels (component 0 stands for all when msj_shaped)
     RobotConsts &c = e->consts;
-    c.a_hi = cfg->angle_high;
-    c.a_lo = cfg->angle_low;
-    c.a_span = cfg->angle_high - cfg->angle_low;
-    c.v_hi = cfg->vel_high;
-    c.v_lo = cfg->vel_low;
-    c.v_span = cfg->vel_high - cfg->vel_low;
-    c.thr_angle = box_diagonal_f32(cfg->angle_low, cfg->angle_high, ROBOY_DIM_JOINT) / 200.0f;  // roboy_env.py:127
-    c.thr_vel = box_diagonal_f32(cfg->vel_low, cfg->vel_high, ROBOY_DIM_JOINT) / 5.0f;          // roboy_env.py:130
-    c.penalty_boundary = fabsf(cfg->penalty_boundary);
-    c.bonus_goal = cfg->bonus_goal;
+    c.a_hi = r.a_hi[0];
+    c.a_lo = r.a_lo[0];
+    c.a_span = r.a_hi[0] - r.a_lo[0];
+    c.v_hi = r.v_hi[0];
+    c.v_lo = r.v_lo[0];
+    c.v_span = r.v_hi[0] - r.v_lo[0];
+    c.thr_angle = r.thr_angle;
+    c.thr_vel = r.thr_vel;
+    c.penalty_boundary = r.penalty_boundary;
+    c.bonus_goal = r.bonus_goal;
     c.reward_lo = cfg->reward_lo;
     c.reward_hi = cfg->reward_hi;
-    e->act_slope = (cfg->act_high - cfg->act_low) / (1.0f - (-1.0f));  // roboy_env.py:157, float32
-    hold_interval(-1.0f, 1.0f, e->act_slope, cfg->act_high, &e->hold_lo, &e->hold_hi);
+    const float act_lo0 = cfg->per_component_bounds ? cfg->act_low_v[0] : cfg->act_low;
+    const float act_hi0 = cfg->per_component_bounds ? cfg->act_high_v[0] : cfg->act_high;
+    e->act_hi = act_hi0;
+    e->act_slope = (act_hi0 - act_lo0) / (1.0f - (-1.0f));  // roboy_env.py:157, float32
+    e->hold_lo = r.hold_lo[0];
+    e->hold_hi = r.hold_hi[0];
     e->fast.a_rc = (float)(1.0 / (double)c.a_span);
     e->fast.v_rc = (float)(1.0 / (double)c.v_span);
     e->fast.thr_angle_sq_hi = round_up_f32((double)c.thr_angle * (double)c.thr_angle * (1.0 + 1e-5));
@@ -339,17 +480,17 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
     e->fast.a_span21 = c.a_span * 0x1p-21f;
     e->fast.reward_lo_f = -INFINITY;
     e->fast.reward_hi_f = INFINITY;
-    e->fastdiv = spans_are_proved(*cfg);
+    e->fastdiv = e->msj_shaped && spans_are_proved(c.a_lo, c.a_hi, c.v_lo, c.v_hi);
 
     const uint64_t n = cfg->n_envs;
     cudaError_t err = cudaSuccess;
     auto alloc = [&](void **p, size_t bytes) {
         if (err == cudaSuccess) err = cudaMalloc(p, bytes);
     };
-    alloc((void **)&e->goal, sizeof(float) * 3 * n);
+    alloc((void **)&e->goal, sizeof(float) * e->J * n);
     alloc((void **)&e->step_flags, sizeof(uint32_t) * n);
-    alloc((void **)&e->held, sizeof(float) * 6 * n);
-    alloc((void **)&e->obs, sizeof(float) * ROBOY_DIM_OBS * n);
+    alloc((void **)&e->held, sizeof(float) * 2 * e->J * n);
+    alloc((void **)&e->obs, sizeof(float) * e->D * n);
     alloc((void **)&e->reward, sizeof(float) * n);
     alloc((void **)&e->done, n);
     alloc((void **)&e->stats, sizeof(double) * ROBOY_STAT_COUNT);
@@ -364,19 +505,18 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
     if (err == cudaSuccess) err = cudaMemset(e->first_bad, 0xff, sizeof(unsigned long long));
     if (err == cudaSuccess) err = cudaMemset(e->done, 0, n);
     if (err == cudaSuccess) {
-        InitParams ip{};
+        GInitParams ip{};
         ip.n = n;
         ip.gid_base = cfg->env_id_base;
         ip.cc = counter(e, CallCounter::kFixed, 0);
         ip.keys = e->keys;
-        ip.a_lo = c.a_lo;
-        ip.a_span = c.a_span;
+        ip.r = e->spec;
         ip.goal = e->goal;
         ip.step_flags = e->step_flags;
         ip.held = e->held;
         ip.mask = nullptr;
         ip.obs = nullptr;
-        err = launch_init_or_reset(ip, e->sm_count, 0);
+        err = launch_generic_init_or_reset(ip, e->sm_count, 0);
         e->launches++;
         // Goal draw 0 of counter 0 is the goal the env starts with.  The first get_new_goal_joint_angles() after
         // construction hands out that same draw, so the reference's RoboyEnv.__init__ (roboy_env.py:37), which asks the
@@ -407,8 +547,8 @@ int roboy_destroy(roboy_env *env) {
 
 int roboy_set_reward_range(roboy_env *env, double lo, double hi) {
     if (check_env(env)) return ROBOY_E_ARG;
-    env->cfg.reward_lo = env->consts.reward_lo = lo;
-    env->cfg.reward_hi = env->consts.reward_hi = hi;
+    env->cfg.reward_lo = env->consts.reward_lo = env->spec.reward_lo = lo;
+    env->cfg.reward_hi = env->consts.reward_hi = env->spec.reward_hi = hi;
     return ROBOY_OK;
 }
 
@@ -416,19 +556,18 @@ int roboy_reset(roboy_env *env, const uint8_t *mask_dev, float *obs_dev, void *s
     if (check_env(env)) return ROBOY_E_ARG;
     DeviceGuard g(env->device);
     env->goal_sub = 1;  // the reset itself consumes goal draw 0 of the new counter value
-    InitParams ip{};
+    GInitParams ip{};
     ip.n = env->cfg.n_envs;
     ip.gid_base = env->cfg.env_id_base;
     ip.cc = counter(env, CallCounter::kAdvance);
     ip.keys = env->keys;
-    ip.a_lo = env->consts.a_lo;
-    ip.a_span = env->consts.a_span;
+    ip.r = env->spec;
     ip.goal = env->goal;
     ip.step_flags = env->step_flags;
     ip.held = nullptr;
     ip.mask = mask_dev;
     ip.obs = obs_dev ? obs_dev : env->obs;
-    CUDA_TRY(launch_init_or_reset(ip, env->sm_count, (cudaStream_t)stream));
+    CUDA_TRY(launch_generic_init_or_reset(ip, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -441,10 +580,8 @@ int roboy_step(roboy_env *env, const float *actions_dev, float *obs_dev, float *
     if (obs_dev && ((uintptr_t)obs_dev & 3)) return fail(ROBOY_E_ARG, "obs must be 4-byte aligned");
     DeviceGuard g(env->device);
     env->goal_sub = 1;  // done envs consume goal draw 0 of the new counter value
-    StepParams p;
-    fill_step_params(env, p, actions_dev, obs_dev, reward_dev, done_dev);
-    CUDA_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset, env->fastdiv,
-                         env->sm_count, (cudaStream_t)stream));
+    CUDA_TRY(launch_env_step(env, actions_dev, obs_dev, reward_dev, done_dev, 0, env->cfg.n_envs,
+                             counter(env, CallCounter::kAdvance), true, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -458,6 +595,17 @@ int roboy_step_many(roboy_env *env, uint32_t T, const float *actions_dev, float 
     if ((uintptr_t)obs_dev & 3) return fail(ROBOY_E_ARG, "obs must be 4-byte aligned");
     DeviceGuard g(env->device);
     env->goal_sub = 1;
+    if (!env->msj_shaped) {
+        // other robots: T launches of the generic step kernel over the [t] slices (same results, state through HBM)
+        const uint64_t n = env->cfg.n_envs;
+        for (uint32_t t = 0; t < T; ++t) {
+            CUDA_TRY(launch_env_step(env, actions_dev + (size_t)t * n * env->A, obs_dev + (size_t)t * n * env->D,
+                                     reward_dev + (size_t)t * n, done_dev + (size_t)t * n, 0, n,
+                                     counter(env, CallCounter::kAdvance), false, (cudaStream_t)stream));
+            env->launches++;
+        }
+        return ROBOY_OK;
+    }
     StepParams p;
     fill_step_params(env, p, actions_dev, obs_dev, reward_dev, done_dev);
     p.cc.advance = T;
@@ -480,7 +628,7 @@ static int host_pipeline(roboy_env *env, const float *actions_host, float *obs_h
     // call (roboy_reset / roboy_set_* / roboy_step on ANY stream, blocking or not): the call is device-synchronous.
     CUDA_TRY(cudaDeviceSynchronize());
     if (!env->host_ready) {
-        CUDA_TRY(cudaMalloc((void **)&env->actions_stage, sizeof(float) * ROBOY_DIM_ACTION * n));
+        CUDA_TRY(cudaMalloc((void **)&env->actions_stage, sizeof(float) * env->A * n));
         for (int i = 0; i < kHostStreamsMax; ++i) {
             CUDA_TRY(cudaStreamCreateWithFlags(&env->hs[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&env->hev[i], cudaEventDisableTiming));
@@ -489,11 +637,13 @@ static int host_pipeline(roboy_env *env, const float *actions_host, float *obs_h
     }
     const bool run_kernel = (what & kHostKernel) != 0;
     if (run_kernel) env->goal_sub = 1;
-    StepParams p;
-    fill_step_params(env, p, env->actions_stage, nullptr, nullptr, nullptr);
+    const size_t A = (size_t)env->A, D = (size_t)env->D;
     // All stages of one call use the same counter value *t_dev + 1 (they run concurrently on several streams, so none of
     // them may store it back); a one-thread kernel advances the device counter once they have all finished.
-    p.cc = counter(env, CallCounter::kPeekNext);
+    const CallCounter cc = counter(env, CallCounter::kPeekNext);
+    const float *k_actions = env->actions_stage;   // what the stage kernels read and write (full-array base pointers)
+    float *k_obs = nullptr, *k_reward = nullptr;
+    uint8_t *k_done = nullptr;
     const int mode = run_kernel ? env->host_mode : ROBOY_HOST_STAGED;
     if (mode != ROBOY_HOST_STAGED) {
         // zero-copy: the kernel addresses the caller's page-locked buffers directly over PCIe
@@ -504,13 +654,12 @@ static int host_pipeline(roboy_env *env, const float *actions_host, float *obs_h
             cudaGetLastError();
             return fail(ROBOY_E_ARG, "host mode %d needs page-locked host buffers (cudaHostAlloc / cudaHostRegister / roboy_host_alloc)", mode);
         }
-        p.obs = (float *)o;
-        p.reward = (float *)r;
-        p.done = (uint8_t *)d;
-        p.obs_aligned = ((uintptr_t)o & 15) == 0;
+        k_obs = (float *)o;
+        k_reward = (float *)r;
+        k_done = (uint8_t *)d;
         if (mode == ROBOY_HOST_MAPPED_ALL) {
             if ((uintptr_t)a & 15) return fail(ROBOY_E_ARG, "actions must be 16-byte aligned");
-            p.actions = (const float *)a;
+            k_actions = (const float *)a;
         }
     }
     cudaError_t err = cudaSuccess;
@@ -518,16 +667,15 @@ static int host_pipeline(roboy_env *env, const float *actions_host, float *obs_h
     int used = 0;
     if (mode == ROBOY_HOST_MAPPED_ALL) {
         // one launch over the whole shard: PCIe reads and posted writes overlap inside the kernel, no staging at all
-        HOST_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset, env->fastdiv,
-                             env->sm_count, env->hs[0]));
+        HOST_TRY(launch_env_step(env, k_actions, k_obs, k_reward, k_done, 0, n, cc, true, env->hs[0]));
         env->launches++;
         used = 1;
     } else if (what & kHostSplitDirections) {
         // copy-ceiling probe only: both directions as one monolithic copy each, on two independent streams
         if (what & kHostH2D)
-            HOST_TRY(cudaMemcpyAsync(env->actions_stage, actions_host, sizeof(float) * ROBOY_DIM_ACTION * n, cudaMemcpyHostToDevice, env->hs[0]));
+            HOST_TRY(cudaMemcpyAsync(env->actions_stage, actions_host, sizeof(float) * A * n, cudaMemcpyHostToDevice, env->hs[0]));
         if (what & kHostD2H) {
-            HOST_TRY(cudaMemcpyAsync(obs_host, env->obs, sizeof(float) * ROBOY_DIM_OBS * n, cudaMemcpyDeviceToHost, env->hs[1]));
+            HOST_TRY(cudaMemcpyAsync(obs_host, env->obs, sizeof(float) * D * n, cudaMemcpyDeviceToHost, env->hs[1]));
             HOST_TRY(cudaMemcpyAsync(reward_host, env->reward, sizeof(float) * n, cudaMemcpyDeviceToHost, env->hs[1]));
             HOST_TRY(cudaMemcpyAsync(done_host, env->done, n, cudaMemcpyDeviceToHost, env->hs[1]));
         }
@@ -555,13 +703,10 @@ static int host_pipeline(roboy_env *env, const float *actions_host, float *obs_h
             const uint64_t cnt = eend - b;
             if (ring) up = env->hs[stage % env->host_streams];   // ROBOY_HOST_PATTERN_RING: stage i entirely on stream i % n
             if (what & kHostH2D)
-                HOST_TRY(cudaMemcpyAsync(env->actions_stage + b * ROBOY_DIM_ACTION, actions_host + b * ROBOY_DIM_ACTION,
-                                         sizeof(float) * ROBOY_DIM_ACTION * cnt, cudaMemcpyHostToDevice, up));
+                HOST_TRY(cudaMemcpyAsync(env->actions_stage + b * A, actions_host + b * A, sizeof(float) * A * cnt,
+                                         cudaMemcpyHostToDevice, up));
             if (run_kernel) {
-                p.e_begin = b;
-                p.e_end = eend;
-                HOST_TRY(launch_step(p, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
-                                     env->fastdiv, env->sm_count, up));
+                HOST_TRY(launch_env_step(env, k_actions, k_obs, k_reward, k_done, b, eend, cc, true, up));
                 env->launches++;
             }
             if ((what & kHostD2H) && mode == ROBOY_HOST_STAGED) {
@@ -572,8 +717,7 @@ static int host_pipeline(roboy_env *env, const float *actions_host, float *obs_h
                     HOST_TRY(cudaEventRecord(ev, up));                    // queued keep the record they saw
                     HOST_TRY(cudaStreamWaitEvent(down, ev, 0));
                 }
-                HOST_TRY(cudaMemcpyAsync(obs_host + b * ROBOY_DIM_OBS, env->obs + b * ROBOY_DIM_OBS,
-                                         sizeof(float) * ROBOY_DIM_OBS * cnt, cudaMemcpyDeviceToHost, down));
+                HOST_TRY(cudaMemcpyAsync(obs_host + b * D, env->obs + b * D, sizeof(float) * D * cnt, cudaMemcpyDeviceToHost, down));
                 HOST_TRY(cudaMemcpyAsync(reward_host + b, env->reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, down));
                 HOST_TRY(cudaMemcpyAsync(done_host + b, env->done + b, cnt, cudaMemcpyDeviceToHost, down));
             }
@@ -728,9 +872,9 @@ int roboy_compute_reward(roboy_env *env, uint64_t k, const float *q_dev, const f
     if (check_env(env)) return ROBOY_E_ARG;
     if (!q_dev || !qd_dev || !goal_q_dev || !reward_dev) return fail(ROBOY_E_ARG, "NULL device pointer");
     DeviceGuard g(env->device);
-    RewardParams p{};
+    GRewardParams p{};
     p.k = k;
-    p.c = env->consts;
+    p.r = env->spec;
     p.penalty = env->cfg.joint_vel_penalty != 0;
     p.bonus = env->cfg.bonus_for_goal != 0;
     p.check_range = check_range != 0;
@@ -745,25 +889,24 @@ int roboy_compute_reward(roboy_env *env, uint64_t k, const float *q_dev, const f
     p.stats = env->stats;
     p.err_flags = env->err_flags;
     p.first_bad = env->first_bad;
-    CUDA_TRY(launch_compute_reward(p, env->sm_count, (cudaStream_t)stream));
+    CUDA_TRY(launch_generic_compute_reward(p, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
 
-static int scatter_common(roboy_env *env, ScatterParams &p, uint64_t k, const int64_t *idx, void *stream) {
+static int scatter_common(roboy_env *env, GScatterParams &p, uint64_t k, const int64_t *idx, void *stream) {
     DeviceGuard g(env->device);
     p.k = k;
     p.n = env->cfg.n_envs;
     p.idx = idx;
-    p.a_lo = env->consts.a_lo;
-    p.a_hi = env->consts.a_hi;
+    p.r = env->spec;
     p.gid_base = env->cfg.env_id_base;
     p.goal = env->goal;
     p.held = env->held;
     p.step_flags = env->step_flags;
     p.err_flags = env->err_flags;
     p.first_bad = env->first_bad;
-    CUDA_TRY(launch_scatter(p, env->sm_count, (cudaStream_t)stream));
+    CUDA_TRY(launch_generic_scatter(p, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -771,7 +914,7 @@ static int scatter_common(roboy_env *env, ScatterParams &p, uint64_t k, const in
 int roboy_set_goal(roboy_env *env, uint64_t k, const int64_t *idx_dev, const float *goal_q_dev, void *stream) {
     if (check_env(env)) return ROBOY_E_ARG;
     if (!goal_q_dev) return fail(ROBOY_E_ARG, "goal_q_dev is NULL");
-    ScatterParams p{};
+    GScatterParams p{};
     p.goal_q = goal_q_dev;
     return scatter_common(env, p, k, idx_dev, stream);
 }
@@ -780,7 +923,7 @@ int roboy_set_state(roboy_env *env, uint64_t k, const int64_t *idx_dev, const fl
                     const uint8_t *feasible_dev, void *stream) {
     if (check_env(env)) return ROBOY_E_ARG;
     if (!q_dev || !qd_dev) return fail(ROBOY_E_ARG, "q_dev/qd_dev is NULL");
-    ScatterParams p{};
+    GScatterParams p{};
     p.q = q_dev;
     p.qd = qd_dev;
     p.feasible = feasible_dev;
@@ -790,7 +933,7 @@ int roboy_set_state(roboy_env *env, uint64_t k, const int64_t *idx_dev, const fl
 int roboy_set_step_num(roboy_env *env, uint64_t k, const int64_t *idx_dev, const int32_t *step_dev, void *stream) {
     if (check_env(env)) return ROBOY_E_ARG;
     if (!step_dev) return fail(ROBOY_E_ARG, "step_dev is NULL");
-    ScatterParams p{};
+    GScatterParams p{};
     p.step = step_dev;
     return scatter_common(env, p, k, idx_dev, stream);
 }
@@ -799,22 +942,21 @@ int roboy_read_state(roboy_env *env, uint64_t k, const int64_t *idx_dev, float *
                      uint8_t *feasible_dev, void *stream) {
     if (check_env(env)) return ROBOY_E_ARG;
     if (!q_dev || !qd_dev) return fail(ROBOY_E_ARG, "q_dev/qd_dev is NULL");
-    ScatterParams p{};
+    GScatterParams p{};
     p.out_q = q_dev;
     p.out_qd = qd_dev;
     p.out_feasible = feasible_dev;
     return scatter_common(env, p, k, idx_dev, stream);
 }
 
-static void fill_sim_params(roboy_env *env, SimParams &p, int mode) {
+static void fill_sim_params(roboy_env *env, GSimParams &p, int mode) {
     p.mode = mode;
     p.n = env->cfg.n_envs;
     p.gid_base = env->cfg.env_id_base;
     p.cc = counter(env, mode == 2 ? CallCounter::kPeek : CallCounter::kAdvance);
     p.sub = env->goal_sub;
     p.keys = env->keys;
-    p.a_lo = env->consts.a_lo;
-    p.a_span = env->consts.a_span;
+    p.r = env->spec;
     p.step_flags = env->step_flags;
     p.held = env->held;
     p.stats = env->stats;
@@ -827,13 +969,13 @@ int roboy_sim_step(roboy_env *env, const float *actions_dev, float *q_dev, float
     if ((uintptr_t)actions_dev & 15) return fail(ROBOY_E_ARG, "actions must be 16-byte aligned");
     DeviceGuard g(env->device);
     env->goal_sub = 0;
-    SimParams p{};
+    GSimParams p{};
     fill_sim_params(env, p, 0);
     p.actions = actions_dev;
     p.out_q = q_dev;
     p.out_qd = qd_dev;
     p.out_feasible = feasible_dev;
-    CUDA_TRY(launch_sim(p, env->sm_count, (cudaStream_t)stream));
+    CUDA_TRY(launch_generic_sim(p, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -842,10 +984,10 @@ int roboy_sim_reset(roboy_env *env, const uint8_t *mask_dev, void *stream) {
     if (check_env(env)) return ROBOY_E_ARG;
     DeviceGuard g(env->device);
     env->goal_sub = 0;
-    SimParams p{};
+    GSimParams p{};
     fill_sim_params(env, p, 1);
     p.mask = mask_dev;
-    CUDA_TRY(launch_sim(p, env->sm_count, (cudaStream_t)stream));
+    CUDA_TRY(launch_generic_sim(p, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -855,10 +997,10 @@ int roboy_new_goal(roboy_env *env, float *goal_q_dev, void *stream) {
     if (!goal_q_dev) return fail(ROBOY_E_ARG, "goal_q_dev is NULL");
     DeviceGuard g(env->device);
     if (env->goal_sub >= 255) return fail(ROBOY_E_ARG, "more than 255 goal draws without a step or reset in between");
-    SimParams p{};
+    GSimParams p{};
     fill_sim_params(env, p, 2);
     p.out_q = goal_q_dev;
-    CUDA_TRY(launch_sim(p, env->sm_count, (cudaStream_t)stream));
+    CUDA_TRY(launch_generic_sim(p, env->sm_count, (cudaStream_t)stream));
     env->goal_sub += 1;
     env->launches++;
     return ROBOY_OK;
@@ -887,17 +1029,16 @@ int roboy_reseed(roboy_env *env, uint64_t seed) {
     CUDA_TRY(cudaDeviceSynchronize());
     const unsigned long long zero = 0;
     CUDA_TRY(cudaMemcpy(env->t_dev, &zero, sizeof(zero), cudaMemcpyHostToDevice));
-    InitParams ip{};
+    GInitParams ip{};
     ip.n = env->cfg.n_envs;
     ip.gid_base = env->cfg.env_id_base;
     ip.cc = counter(env, CallCounter::kFixed, 0);
     ip.keys = env->keys;
-    ip.a_lo = env->consts.a_lo;
-    ip.a_span = env->consts.a_span;
+    ip.r = env->spec;
     ip.goal = env->goal;
     ip.step_flags = env->step_flags;
     ip.held = env->held;
-    CUDA_TRY(launch_init_or_reset(ip, env->sm_count, 0));
+    CUDA_TRY(launch_generic_init_or_reset(ip, env->sm_count, 0));
     env->launches++;
     env->goal_sub = 0;
     CUDA_TRY(cudaStreamSynchronize(0));
@@ -910,14 +1051,14 @@ int roboy_buffer(roboy_env *env, int which, void **dev_ptr, uint64_t *nbytes) {
     void *p = nullptr;
     uint64_t b = 0;
     switch (which) {
-        case ROBOY_BUF_GOAL: p = env->goal; b = 12 * n; break;
+        case ROBOY_BUF_GOAL: p = env->goal; b = 4ull * env->J * n; break;
         case ROBOY_BUF_STEP_FLAGS: p = env->step_flags; b = 4 * n; break;
-        case ROBOY_BUF_HELD: p = env->held; b = 24 * n; break;
-        case ROBOY_BUF_OBS: p = env->obs; b = 36 * n; break;
+        case ROBOY_BUF_HELD: p = env->held; b = 8ull * env->J * n; break;
+        case ROBOY_BUF_OBS: p = env->obs; b = 4ull * env->D * n; break;
         case ROBOY_BUF_REWARD: p = env->reward; b = 4 * n; break;
         case ROBOY_BUF_DONE: p = env->done; b = n; break;
         case ROBOY_BUF_STATS: p = env->stats; b = 8 * ROBOY_STAT_COUNT; break;
-        case ROBOY_BUF_TERMINAL_OBS: p = env->terminal_obs; b = env->terminal_obs ? 36 * n : 0; break;
+        case ROBOY_BUF_TERMINAL_OBS: p = env->terminal_obs; b = env->terminal_obs ? 4ull * env->D * n : 0; break;
         case ROBOY_BUF_DONE_BITS: p = env->done_bits; b = env->done_bits ? 4 * ((n + 31) / 32) : 0; break;
         default: return fail(ROBOY_E_ARG, "unknown buffer id %d", which);
     }
@@ -960,9 +1101,9 @@ void *roboy_export_dlpack(roboy_env *env, int which) {
     t.dtype.bits = 32;
     t.ndim = 2;
     switch (which) {
-        case ROBOY_BUF_GOAL: t.data = env->goal; ctx->shape[0] = 3; ctx->shape[1] = n; break;
-        case ROBOY_BUF_HELD: t.data = env->held; ctx->shape[0] = 6; ctx->shape[1] = n; break;
-        case ROBOY_BUF_OBS: t.data = env->obs; ctx->shape[0] = n; ctx->shape[1] = ROBOY_DIM_OBS; break;
+        case ROBOY_BUF_GOAL: t.data = env->goal; ctx->shape[0] = env->J; ctx->shape[1] = n; break;
+        case ROBOY_BUF_HELD: t.data = env->held; ctx->shape[0] = 2 * env->J; ctx->shape[1] = n; break;
+        case ROBOY_BUF_OBS: t.data = env->obs; ctx->shape[0] = n; ctx->shape[1] = env->D; break;
         case ROBOY_BUF_REWARD: t.data = env->reward; t.ndim = 1; ctx->shape[0] = n; break;
         case ROBOY_BUF_STEP_FLAGS:
             t.data = env->step_flags; t.ndim = 1; ctx->shape[0] = n;
@@ -1064,14 +1205,13 @@ static int external_common(roboy_env *env, int reset, const uint8_t *mask, const
     if (!q || !qd) return fail(ROBOY_E_ARG, "q_dev/qd_dev is NULL");
     DeviceGuard g(env->device);
     env->goal_sub = 1;
-    ExternalParams p{};
+    GExternalParams p{};
     p.reset = reset;
     p.n = env->cfg.n_envs;
     p.gid_base = env->cfg.env_id_base;
     p.cc = counter(env, CallCounter::kAdvance);
     p.keys = env->keys;
-    p.c = env->consts;
-    p.a_span24 = env->fast.a_span24;
+    p.r = env->spec;
     p.penalty = env->cfg.joint_vel_penalty != 0;
     p.bonus = env->cfg.bonus_for_goal != 0;
     p.max_len = env->cfg.max_episode_len;
@@ -1087,7 +1227,7 @@ static int external_common(roboy_env *env, int reset, const uint8_t *mask, const
     p.stats = env->stats;
     p.err_flags = env->err_flags;
     p.first_bad = env->first_bad;
-    CUDA_TRY(launch_external(p, env->sm_count, (cudaStream_t)stream));
+    CUDA_TRY(launch_generic_external(p, env->sm_count, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -1135,6 +1275,9 @@ static int policy_rollout_common(roboy_env *env, bool tensor_cores, bool exact, 
     if ((uintptr_t)obs_dev & 3) return fail(ROBOY_E_ARG, "obs must be 4-byte aligned");
     if (envs_per_thread < 0 || envs_per_thread > (tensor_cores ? 3 : 2))
         return fail(ROBOY_E_ARG, "envs_per_thread must be 0, 1 or 2 (tensor-core variant: 0..3)");
+    if (!env->msj_shaped)
+        return fail(ROBOY_E_ARG, "the fused policy rollouts are built for MSJ-shaped robots (3 joints, 8 tendons, uniform bounds: "
+                                 "a 9-64-64-8 MlpPolicy); other robots step with roboy_step under a host-side policy");
     if (T == 0) return ROBOY_OK;
     DeviceGuard g(env->device);
     env->goal_sub = 1;
@@ -1243,7 +1386,7 @@ int roboy_done_indices(roboy_env *env, int32_t *idx_dev, uint64_t capacity, uint
     p.count = count_dev;
     p.terminal_obs = env->terminal_obs;
     p.terminal_rows = terminal_rows_dev;
-    p.obs_dim = ROBOY_DIM_OBS;
+    p.obs_dim = env->D;
     CUDA_TRY(launch_done_index(p, (cudaStream_t)stream));
     env->launches += 2;
     return ROBOY_OK;
@@ -1252,6 +1395,15 @@ int roboy_done_indices(roboy_env *env, int32_t *idx_dev, uint64_t capacity, uint
 int roboy_launch_count(roboy_env *env, uint64_t *launches) {
     if (check_env(env) || !launches) return fail(ROBOY_E_ARG, "NULL argument");
     *launches = env->launches;
+    return ROBOY_OK;
+}
+
+int roboy_robot_dims(roboy_env *env, int *dim_joint, int *dim_action, int *dim_obs, int *msj_kernels) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (dim_joint) *dim_joint = env->J;
+    if (dim_action) *dim_action = env->A;
+    if (dim_obs) *dim_obs = env->D;
+    if (msj_kernels) *msj_kernels = env->msj_shaped ? 1 : 0;
     return ROBOY_OK;
 }
 

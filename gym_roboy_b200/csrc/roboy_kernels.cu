@@ -4,7 +4,8 @@
 //                  (envs/simulations/simulation_client.py:36-40), normalisation
 //                  (envs/robots/roboy_robot.py:80-95), compute_reward (:92-112), the done test
 //                  (:65-66,:125-134), goal resampling (:117-123) and the vec-env reset-on-done.
-// K2 init_or_reset RoboyEnv.__init__ / reset (:12-38, :82-87) over the Stub (:29-31, :42-44).
+// K2 construction / reset, the un-fused SimulationClient calls, state injection, stand-alone compute_reward and the
+//    external-simulator feed are robot-generic kernels: roboy_generic.cu (this file is the MSJ-shaped hot step).
 // K3 episode statistics are folded into K1's tail (warp reduce -> one atomic set per CTA).
 //
 // The path is elementwise and HBM-bound (93 algorithmic bytes, ~0.6 flop/B): no tensor cores.
@@ -726,304 +727,6 @@ cudaError_t launch_null_step(uint64_t n_range, bool penalty, bool bonus, bool au
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, null_step_kernel);
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2: construction and reset
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) init_or_reset_kernel(const __grid_constant__ InitParams p) {
-    const uint64_t t = counter_begin(p.cc);
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += stride) {
-        if (p.mask && !p.mask[e]) continue;
-        const uint64_t gid = p.gid_base + e;
-        const uint4 rg = philox_draw(gid, t, kStreamGoal, p.keys);
-        const float g0 = uniform_in(rg.x, p.a_lo, p.a_span);
-        const float g1 = uniform_in(rg.y, p.a_lo, p.a_span);
-        const float g2 = uniform_in(rg.z, p.a_lo, p.a_span);
-        p.goal[e] = g0;
-        p.goal[p.n + e] = g1;
-        p.goal[2 * p.n + e] = g2;
-        if (p.held) {
-            // StubSimulationClient.__init__ (simulation_client.py:31): _state = new_random_state()
-            const Draw6 d = split6x21(philox_draw(gid, t, kStreamState, p.keys));
-#pragma unroll
-            for (int k = 0; k < 6; ++k) p.held[(size_t)k * p.n + e] = uniform_in21(d.k[k], p.a_lo, p.a_span * 0x1p-21f);
-            p.step_flags[e] = 1u;  // roboy_env.py:38
-        } else {
-            // forward_reset_command (simulation_client.py:42-44): _state = float64 zero state
-            p.step_flags[e] = 1u | ROBOY_F_HELD_ZERO64;  // roboy_env.py:85
-        }
-        if (p.obs) {
-            float *o = p.obs + e * kObsDim;
-            o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.0f;
-            o[6] = g0;
-            o[7] = g1;
-            o[8] = g2;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) counter_end(p.cc, t);
-}
-
-cudaError_t launch_init_or_reset(const InitParams &p, int sm_count, cudaStream_t stream) {
-    if (p.n == 0) return cudaSuccess;
-    const uint64_t want = (p.n + 255) / 256;
-    const int grid = (int)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
-    init_or_reset_kernel<<<grid, 256, 0, stream>>>(p);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------
-// Stand-alone compute_reward / _did_reach_goal
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) compute_reward_kernel(const __grid_constant__ RewardParams p) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.k; i += stride) {
-        HeldState s;
-        float g[3], gqd[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            s.q[k] = (double)p.q[i * 3 + k];
-            s.qd[k] = (double)p.qd[i * 3 + k];
-            g[k] = p.goal_q[i * 3 + k];
-            if (p.goal_qd) gqd[k] = p.goal_qd[i * 3 + k];
-        }
-        s.is64 = false;
-        s.feasible = p.feasible ? p.feasible[i] != 0 : true;
-        RobotConsts c = p.c;
-        if (!p.check_range) {
-            c.reward_lo = -INFINITY;
-            c.reward_hi = INFINITY;
-        }
-        double r;
-        bool reached, violation;
-        reward_reached_general(s, g, p.goal_qd != nullptr, gqd, p.penalty, p.bonus, c, r, reached, violation);
-        p.reward[i] = r;
-        if (p.reached) p.reached[i] = (uint8_t)reached;
-        if (violation) {
-            atomicOr(p.err_flags, ROBOY_ERR_REWARD_RANGE);
-            atomicMin(p.first_bad, (unsigned long long)(p.gid_base + i));
-            atomicAdd(p.stats + ROBOY_STAT_VIOLATIONS, 1.0);
-        }
-    }
-}
-
-cudaError_t launch_compute_reward(const RewardParams &p, int sm_count, cudaStream_t stream) {
-    if (p.k == 0) return cudaSuccess;
-    const uint64_t want = (p.k + 255) / 256;
-    const int grid = (int)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
-    compute_reward_kernel<<<grid, 256, 0, stream>>>(p);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------
-// Indexed state injection / read-back
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ ScatterParams p) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.k; i += stride) {
-        const int64_t e64 = p.idx ? p.idx[i] : (int64_t)i;
-        if (e64 < 0 || (uint64_t)e64 >= p.n) continue;
-        const uint64_t e = (uint64_t)e64;
-        if (p.goal_q) {
-            bool inside = true;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float v = p.goal_q[i * 3 + k];
-                inside = inside && (v >= p.a_lo && v <= p.a_hi);  // roboy_robot.py:76
-                p.goal[(uint64_t)k * p.n + e] = v;
-            }
-            if (!inside) {
-                atomicOr(p.err_flags, ROBOY_ERR_GOAL_BOUNDS);
-                atomicMin(p.first_bad, (unsigned long long)(p.gid_base + e));
-            }
-        }
-        if (p.q) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                p.held[(uint64_t)k * p.n + e] = p.q[i * 3 + k];
-                p.held[(uint64_t)(3 + k) * p.n + e] = p.qd[i * 3 + k];
-            }
-            uint32_t sf = p.step_flags[e] & ROBOY_STEP_MASK;
-            if (p.feasible && !p.feasible[i]) sf |= ROBOY_F_HELD_INFEASIBLE;
-            p.step_flags[e] = sf;
-        }
-        if (p.step) {
-            const uint32_t s = (uint32_t)p.step[i] & ROBOY_STEP_MASK;
-            p.step_flags[e] = (p.step_flags[e] & ~ROBOY_STEP_MASK) | s;
-        }
-        if (p.out_q) {  // SimulationClient.read_state
-            const uint32_t sf = p.step_flags[e];
-            const bool z = sf & ROBOY_F_HELD_ZERO64;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                p.out_q[i * 3 + k] = z ? 0.0f : p.held[(uint64_t)k * p.n + e];
-                p.out_qd[i * 3 + k] = z ? 0.0f : p.held[(uint64_t)(3 + k) * p.n + e];
-            }
-            // bit 0: is_feasible; bit 1: the state is the reference's FLOAT64 zero state (roboy_robot.py:41-45)
-            if (p.out_feasible) p.out_feasible[i] = z ? 3 : !(sf & ROBOY_F_HELD_INFEASIBLE);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Un-fused SimulationClient calls (the plug-in API the reference's own RoboyEnv drives)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ SimParams p) {
-    const uint64_t t = counter_begin(p.cc);
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += stride) {
-        const uint64_t gid = p.gid_base + e;
-        if (p.mode == 2) {
-            const uint4 rg = philox_draw(gid, t, kStreamGoal, p.keys, p.sub);
-            p.out_q[e * 3 + 0] = uniform_in(rg.x, p.a_lo, p.a_span);
-            p.out_q[e * 3 + 1] = uniform_in(rg.y, p.a_lo, p.a_span);
-            p.out_q[e * 3 + 2] = uniform_in(rg.z, p.a_lo, p.a_span);
-            continue;
-        }
-        uint32_t sf = p.step_flags[e];
-        bool hold = true;
-        if (p.mode == 1) {
-            if (p.mask && !p.mask[e]) continue;
-            sf = (sf & ROBOY_STEP_MASK) | ROBOY_F_HELD_ZERO64;  // _state = new_zero_state()
-            p.step_flags[e] = sf;
-        } else {
-            // simulation_client.py:38 np.allclose(action, 0): |a| <= 1e-8 in float64, NaN fails
-            const float4 a0 = reinterpret_cast<const float4 *>(p.actions)[e * 2];
-            const float4 a1 = reinterpret_cast<const float4 *>(p.actions)[e * 2 + 1];
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) hold = hold && (fabs((double)a[k]) <= 1e-8);
-        }
-        float q[3], qd[3];
-        bool feasible = true, is64 = false;
-        if (hold) {
-            const bool z = sf & ROBOY_F_HELD_ZERO64;
-            is64 = z;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                q[k] = z ? 0.0f : p.held[(uint64_t)k * p.n + e];
-                qd[k] = z ? 0.0f : p.held[(uint64_t)(3 + k) * p.n + e];
-            }
-            feasible = z || !(sf & ROBOY_F_HELD_INFEASIBLE);
-            if (p.mode == 0) atomicAdd(p.stats + ROBOY_STAT_HOLDS, 1.0);
-        } else {
-            const Draw6 d = split6x21(philox_draw(gid, t, kStreamState, p.keys));
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                q[k] = uniform_in21(d.k[k], p.a_lo, p.a_span * 0x1p-21f);
-                qd[k] = uniform_in21(d.k[3 + k], p.a_lo, p.a_span * 0x1p-21f);
-            }
-        }
-        if (p.out_q) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                p.out_q[e * 3 + k] = q[k];
-                p.out_qd[e * 3 + k] = qd[k];
-            }
-            if (p.out_feasible) p.out_feasible[e] = (uint8_t)feasible | (is64 ? 2 : 0);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) counter_end(p.cc, t);
-}
-
-cudaError_t launch_sim(const SimParams &p, int sm_count, cudaStream_t stream) {
-    if (p.n == 0) return cudaSuccess;
-    const uint64_t want = (p.n + 255) / 256;
-    const int grid = (int)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
-    sim_kernel<<<grid, 256, 0, stream>>>(p);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_scatter(const ScatterParams &p, int sm_count, cudaStream_t stream) {
-    if (p.k == 0) return cudaSuccess;
-    const uint64_t want = (p.k + 255) / 256;
-    const int grid = (int)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
-    scatter_kernel<<<grid, 256, 0, stream>>>(p);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------
-// Env step / reset fed by an external simulator.  The wire values are float64 in the reference
-// (python floats -> np.array), so the float64 branches of compute_reward / _did_reach_goal apply.
-// One thread per env; this path is bound by the external simulator, not by this kernel.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) external_kernel(const __grid_constant__ ExternalParams p) {
-    const uint64_t t = counter_begin(p.cc);
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += stride) {
-        if (p.reset && p.mask && !p.mask[e]) continue;
-        const uint64_t gid = p.gid_base + e;
-        HeldState s;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            s.q[k] = (double)p.q[e * 3 + k];
-            s.qd[k] = (double)p.qd[e * 3 + k];
-        }
-        s.is64 = true;
-        s.feasible = p.feasible ? p.feasible[e] != 0 : true;
-        float g[3] = {p.goal[e], p.goal[p.n + e], p.goal[2 * p.n + e]};
-        uint32_t sf = p.step_flags[e];
-        bool new_goal = p.reset != 0;
-        if (!p.reset) {
-            double r;
-            bool reached, violation;
-            const float no_gqd[3] = {0.f, 0.f, 0.f};
-            reward_reached_general(s, g, false, no_gqd, p.penalty, p.bonus, p.c, r, reached, violation);
-            uint32_t step = sf & ROBOY_STEP_MASK;
-            step += step < ROBOY_STEP_MASK;                                   // roboy_env.py:60
-            const bool done = reached || (int32_t)step > p.max_len;           // :65-66
-            sf = step | (sf & ~ROBOY_STEP_MASK);
-            p.reward[e] = (float)r;
-            p.done[e] = (uint8_t)done;
-            new_goal = done;                                                  // :67-68
-            atomicAdd(p.stats + ROBOY_STAT_STEPS, 1.0);
-            atomicAdd(p.stats + ROBOY_STAT_SUM_REWARD, (double)(float)r);
-            if (done) {
-                atomicAdd(p.stats + ROBOY_STAT_EPISODES, 1.0);
-                atomicAdd(p.stats + (reached ? ROBOY_STAT_SUCCESSES : ROBOY_STAT_TIMEOUTS), 1.0);
-                atomicAdd(p.stats + ROBOY_STAT_SUM_EPLEN, (double)(step - 1));
-            }
-            if (violation) {
-                atomicOr(p.err_flags, ROBOY_ERR_REWARD_RANGE);
-                atomicMin(p.first_bad, (unsigned long long)gid);
-                atomicAdd(p.stats + ROBOY_STAT_VIOLATIONS, 1.0);
-            }
-        } else {
-            sf = 1u | (sf & ~ROBOY_STEP_MASK);                                // :85
-        }
-        float *o = p.obs + e * kObsDim;
-        if (!p.reset) {                                                       // :62 obs carries the goal in force
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { o[k] = (float)s.q[k]; o[3 + k] = (float)s.qd[k]; o[6 + k] = g[k]; }
-        }
-        if (new_goal) {
-            const uint4 rg = philox_draw(gid, t, kStreamGoal, p.keys);
-            g[0] = uniform_in24(rg.x, p.c.a_lo, p.a_span24);
-            g[1] = uniform_in24(rg.y, p.c.a_lo, p.a_span24);
-            g[2] = uniform_in24(rg.z, p.c.a_lo, p.a_span24);
-            p.goal[e] = g[0];
-            p.goal[p.n + e] = g[1];
-            p.goal[2 * p.n + e] = g[2];
-        }
-        if (p.reset) {                                                        // :86-87 obs carries the NEW goal
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { o[k] = (float)s.q[k]; o[3 + k] = (float)s.qd[k]; o[6 + k] = g[k]; }
-        }
-        p.step_flags[e] = sf;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) counter_end(p.cc, t);
-}
-
-cudaError_t launch_external(const ExternalParams &p, int sm_count, cudaStream_t stream) {
-    if (p.n == 0) return cudaSuccess;
-    const uint64_t want = (p.n + 255) / 256;
-    const int grid = (int)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
-    external_kernel<<<grid, 256, 0, stream>>>(p);
-    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -102,102 +102,6 @@ cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto
 cudaError_t launch_step_many(const StepParams &p, uint32_t T, bool penalty, bool bonus, bool auto_reset, bool fastdiv,
                              int sm_count, cudaStream_t stream);
 
-struct InitParams {
-    uint64_t n, gid_base;
-    CallCounter cc;
-    PhiloxKeys keys;
-    float a_lo, a_span;
-    float *goal;
-    uint32_t *step_flags;
-    float *held;             // nullptr for reset (held state becomes the zero state via the flag)
-    const uint8_t *mask;     // nullptr: all envs
-    float *obs;              // nullptr: do not write observations
-};
-// init (held != nullptr): RoboyEnv.__init__ / Stub.__init__;  reset (held == nullptr): RoboyEnv.reset
-cudaError_t launch_init_or_reset(const InitParams &p, int sm_count, cudaStream_t stream);
-
-struct RewardParams {
-    uint64_t k;
-    RobotConsts c;
-    bool penalty, bonus, check_range;
-    uint64_t gid_base;
-    const float *q, *qd, *goal_q, *goal_qd;  // [k][3]; goal_qd may be nullptr
-    const uint8_t *feasible;                 // [k] or nullptr
-    double *reward;                          // [k]
-    uint8_t *reached;                        // [k] or nullptr
-    double *stats;
-    uint32_t *err_flags;
-    unsigned long long *first_bad;
-};
-cudaError_t launch_compute_reward(const RewardParams &p, int sm_count, cudaStream_t stream);
-
-struct ScatterParams {
-    uint64_t k, n;
-    const int64_t *idx;
-    float a_lo, a_hi;
-    uint64_t gid_base;
-    // any of the following groups may be null
-    const float *goal_q;  // -> goal
-    const float *q, *qd;  // -> held (+ flags)
-    const uint8_t *feasible;
-    const int32_t *step;  // -> step_num
-    float *goal;
-    float *held;
-    uint32_t *step_flags;
-    uint32_t *err_flags;
-    unsigned long long *first_bad;
-    // gather (read_state): outputs
-    float *out_q, *out_qd;
-    uint8_t *out_feasible;
-};
-cudaError_t launch_scatter(const ScatterParams &p, int sm_count, cudaStream_t stream);
-
-// The un-fused plug-in calls of SimulationClient (simulation_client.py:11-23), batched:
-//   mode 0  forward_step_command(action in robot units)  -> state      (:36-40)
-//   mode 1  forward_reset_command()                      -> zero state (:42-44), masked
-//   mode 2  get_new_goal_joint_angles()                  -> goal draw  (:46-47), does not touch env state
-struct SimParams {
-    int mode;
-    uint64_t n, gid_base;
-    CallCounter cc;
-    uint32_t sub;
-    PhiloxKeys keys;
-    float a_lo, a_span;
-    const float *actions;  // mode 0: [n][8] robot units
-    const uint8_t *mask;   // mode 1
-    uint32_t *step_flags;
-    const float *held;
-    float *out_q, *out_qd;  // [n][3]; mode 2 writes the goal to out_q
-    uint8_t *out_feasible;  // [n] or nullptr
-    double *stats;
-};
-cudaError_t launch_sim(const SimParams &p, int sm_count, cudaStream_t stream);
-
-// RoboyEnv.step / reset when the states come from an EXTERNAL simulator (the role of
-// RosSimulationClient, ros_simulation_client.py:40-60: q, qdot, feasible arrive over the wire and
-// are held as float64 arrays) instead of the in-process Stub.
-struct ExternalParams {
-    int reset;                 // 0: step (roboy_env.py:51-70), 1: reset (roboy_env.py:82-87)
-    uint64_t n, gid_base;
-    CallCounter cc;
-    PhiloxKeys keys;
-    RobotConsts c;
-    float a_span24;
-    bool penalty, bonus;
-    int32_t max_len;
-    const float *q, *qd;       // [n][3]
-    const uint8_t *feasible;   // [n] or nullptr
-    const uint8_t *mask;       // reset only; nullptr = all
-    float *goal;               // [3][n]
-    uint32_t *step_flags;
-    float *obs, *reward;
-    uint8_t *done;
-    double *stats;
-    uint32_t *err_flags;
-    unsigned long long *first_bad;
-};
-cudaError_t launch_external(const ExternalParams &p, int sm_count, cudaStream_t stream);
-
 // Generalised advantage estimation over rollout buffers [T][n] that the step kernel filled in place
 // (the PPO2 runner of train_parallel.py:31-34 does this on the host; stable-baselines is external).
 struct GaeParams {

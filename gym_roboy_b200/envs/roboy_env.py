@@ -206,10 +206,11 @@ class RoboyEnv(_GoalEnvBase):
         if self._last_obs is None:
             return None
         o = self._last_obs
+        J = self._simulation_client.dim_joint
         if self._single:
             o = o[0].cpu().numpy()
-            return RobotState(o[0:3], o[3:6], True)
-        return RobotState(o[:, 0:3], o[:, 3:6], torch.ones(self.num_envs, dtype=torch.bool, device=o.device))
+            return RobotState(o[0:J], o[J:2 * J], True)
+        return RobotState(o[:, 0:J], o[:, J:2 * J], torch.ones(self.num_envs, dtype=torch.bool, device=o.device))
 
     # ------------------------------------------------------------------ batched extras
     def check_errors(self):

@@ -23,11 +23,28 @@ from ..robots import MsjRobot, RobotState, RoboyRobot
 from .simulation_client import SimulationClient
 
 
-def _scalar_bound(space_side, what):
-    v = np.unique(np.asarray(space_side))
-    if v.size != 1:
-        raise ValueError("per-component {} bounds are not supported by the CUDA path".format(what))
-    return float(v[0])
+def _fill_bounds(cfg, robot):
+    """The robot's three spaces (roboy_robot.py:23-33) into struct roboy_cfg: dims, and one bound per component when a
+    space is not uniform.  Returns (dim_joint, dim_action)."""
+    angles, vels, acts = robot.get_joint_angles_space(), robot.get_joint_vels_space(), robot.get_action_space()
+    if len(angles.shape) != 1 or angles.shape != vels.shape or len(acts.shape) != 1:
+        raise ValueError("joint angle / velocity spaces must be 1-D and of equal length, the action space 1-D")
+    J, A = int(angles.shape[0]), int(acts.shape[0])
+    if not (1 <= J <= _native.MAX_JOINT and 1 <= A <= _native.MAX_ACTION):
+        raise ValueError("the CUDA path takes robots with 1..{} joints and 1..{} tendons (numpy sums longer vectors in a "
+                         "CPU-dependent order, so parity with the reference is undefined beyond)".format(
+                             _native.MAX_JOINT, _native.MAX_ACTION))
+    sides = dict(angle_low=angles.low, angle_high=angles.high, vel_low=vels.low, vel_high=vels.high,
+                 act_low=acts.low, act_high=acts.high)
+    sides = {k: np.asarray(v, np.float32).reshape(-1) for k, v in sides.items()}
+    cfg.dim_joint, cfg.dim_action = J, A
+    cfg.per_component_bounds = int(any(np.unique(v).size != 1 for v in sides.values()))
+    for name, v in sides.items():
+        setattr(cfg, name, float(v[0]))
+        arr = getattr(cfg, name + "_v")
+        for k, x in enumerate(v):
+            arr[k] = float(x)
+    return J, A
 
 
 class CudaSimulationClient(SimulationClient):
@@ -35,9 +52,6 @@ class CudaSimulationClient(SimulationClient):
     def __init__(self, robot: RoboyRobot = None, num_envs: int = 1, device=None, seed: int = None,
                  env_id_base: int = 0):
         self.robot = robot if robot is not None else MsjRobot()
-        if self.robot.get_joint_angles_space().shape != (_native.DIM_JOINT,) or \
-                self.robot.get_action_space().shape != (_native.DIM_ACTION,):
-            raise ValueError("the CUDA path is built for 3 joint angles and 8 tendons (MSJ)")
         self.num_envs = int(num_envs)
         if self.num_envs < 1:
             raise ValueError("num_envs must be >= 1")
@@ -53,21 +67,18 @@ class CudaSimulationClient(SimulationClient):
         cfg = _native.RoboyCfg()
         _native.check(self._lib.roboy_cfg_msj(ctypes.byref(cfg)))
         cfg.n_envs, cfg.env_id_base, cfg.seed = self.num_envs, self.env_id_base, self.seed_value
-        angles, vels, acts = (self.robot.get_joint_angles_space(), self.robot.get_joint_vels_space(),
-                              self.robot.get_action_space())
-        cfg.angle_low, cfg.angle_high = _scalar_bound(angles.low, "angle"), _scalar_bound(angles.high, "angle")
-        cfg.vel_low, cfg.vel_high = _scalar_bound(vels.low, "velocity"), _scalar_bound(vels.high, "velocity")
-        cfg.act_low, cfg.act_high = _scalar_bound(acts.low, "action"), _scalar_bound(acts.high, "action")
+        self.dim_joint, self.dim_action = _fill_bounds(cfg, self.robot)
+        self.dim_obs = 3 * self.dim_joint
         self._cfg = cfg
         handle = ctypes.c_void_p()
         _native.check(self._lib.roboy_create(ctypes.byref(cfg), self.device.index or 0, ctypes.byref(handle)))
         self._h = handle
 
         # zero-copy torch views of the HBM buffers the handle owns (DLPack)
-        self.goal = self._view(_native.BUF_GOAL)                # float32 [3, N]
+        self.goal = self._view(_native.BUF_GOAL)                # float32 [J, N]
         self.step_flags = self._view(_native.BUF_STEP_FLAGS)    # int32   [N]
-        self.held = self._view(_native.BUF_HELD)                # float32 [6, N]
-        self.obs = self._view(_native.BUF_OBS)                  # float32 [N, 9]
+        self.held = self._view(_native.BUF_HELD)                # float32 [2J, N]
+        self.obs = self._view(_native.BUF_OBS)                  # float32 [N, 3J]
         self.reward = self._view(_native.BUF_REWARD)            # float32 [N]
         self.done_u8 = self._view(_native.BUF_DONE)             # uint8   [N]
         self.done = self.done_u8.view(torch.bool)
@@ -127,10 +138,17 @@ class CudaSimulationClient(SimulationClient):
         return RobotState(q, qd, (feasible & 1).view(torch.bool))
 
     # ------------------------------------------------------------------ SimulationClient API
+    @property
+    def msj_kernels(self):
+        """True when the tuned MSJ kernels run this robot's fused step (MSJ's dims, uniform bounds), else the generic ones."""
+        m = ctypes.c_int()
+        _native.check(self._lib.roboy_robot_dims(self._h, None, None, None, ctypes.byref(m)))
+        return bool(m.value)
+
     def read_state(self) -> RobotState:
         """simulation_client.py:33-34"""
         n = self.num_envs
-        q = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        q = torch.empty((n, self.dim_joint), dtype=torch.float32, device=self.device)
         qd = torch.empty_like(q)
         f = torch.empty(n, dtype=torch.uint8, device=self.device)
         _native.check(self._lib.roboy_read_state(self._h, n, self._p(self._idx(None)), self._p(q), self._p(qd),
@@ -141,9 +159,9 @@ class CudaSimulationClient(SimulationClient):
         """simulation_client.py:36-40.  `action`: 8 floats in robot units (or a `[N,8]` tensor)."""
         if not torch.is_tensor(action):
             assert self.robot.get_action_space().shape[0] == len(action)
-        a = self._dev(action, torch.float32, (self.num_envs, _native.DIM_ACTION))
+        a = self._dev(action, torch.float32, (self.num_envs, self.dim_action))
         n = self.num_envs
-        q = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        q = torch.empty((n, self.dim_joint), dtype=torch.float32, device=self.device)
         qd = torch.empty_like(q)
         f = torch.empty(n, dtype=torch.uint8, device=self.device)
         _native.check(self._lib.roboy_sim_step(self._h, self._p(a), self._p(q), self._p(qd), self._p(f), self._stream()))
@@ -157,7 +175,7 @@ class CudaSimulationClient(SimulationClient):
 
     def get_new_goal_joint_angles(self):
         """simulation_client.py:46-47: `(3,)` numpy array for one env, `[N,3]` tensor otherwise."""
-        g = torch.empty((self.num_envs, 3), dtype=torch.float32, device=self.device)
+        g = torch.empty((self.num_envs, self.dim_joint), dtype=torch.float32, device=self.device)
         _native.check(self._lib.roboy_new_goal(self._h, self._p(g), self._stream()))
         return g[0].cpu().numpy() if self.num_envs == 1 else g
 
@@ -179,7 +197,7 @@ class CudaSimulationClient(SimulationClient):
 
     def enable_terminal_obs(self, enable=True):
         if enable and self.terminal_obs is None:
-            self.terminal_obs = torch.zeros((self.num_envs, _native.DIM_OBS), dtype=torch.float32, device=self.device)
+            self.terminal_obs = torch.zeros((self.num_envs, self.dim_obs), dtype=torch.float32, device=self.device)
         if not enable:
             self.terminal_obs = None
         if self.info_sink is not None:   # RoboyEnv's info dict: carries the side buffer when enabled
@@ -192,8 +210,8 @@ class CudaSimulationClient(SimulationClient):
         """One launch: RoboyEnv.step for all envs.  `actions` float32 CUDA `[N,8]`, contiguous.
         Results land in the handle's obs/reward/done buffers unless output tensors are given."""
         if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous() \
-                or actions.numel() != self.num_envs * _native.DIM_ACTION:
-            raise ValueError("actions must be a contiguous float32 CUDA tensor of shape [N, 8]")
+                or actions.numel() != self.num_envs * self.dim_action:
+            raise ValueError("actions must be a contiguous float32 CUDA tensor of shape [N, {}]".format(self.dim_action))
         _native.check(self._lib.roboy_step(self._h, self._p(actions), self._p(obs), self._p(reward), self._p(done),
                                            self._stream()))
 
@@ -203,9 +221,9 @@ class CudaSimulationClient(SimulationClient):
         bit-identical to T `step_fused` calls."""
         T, n = actions.shape[0], self.num_envs
         if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous() \
-                or actions.numel() != T * n * _native.DIM_ACTION:
-            raise ValueError("actions must be a contiguous float32 CUDA tensor of shape [T, N, 8]")
-        obs = torch.empty((T, n, _native.DIM_OBS), dtype=torch.float32, device=self.device) if obs is None else obs
+                or actions.numel() != T * n * self.dim_action:
+            raise ValueError("actions must be a contiguous float32 CUDA tensor of shape [T, N, {}]".format(self.dim_action))
+        obs = torch.empty((T, n, self.dim_obs), dtype=torch.float32, device=self.device) if obs is None else obs
         reward = torch.empty((T, n), dtype=torch.float32, device=self.device) if reward is None else reward
         done = torch.empty((T, n), dtype=torch.uint8, device=self.device) if done is None else done
         _native.check(self._lib.roboy_step_many(self._h, T, self._p(actions), self._p(obs), self._p(reward),
@@ -219,14 +237,14 @@ class CudaSimulationClient(SimulationClient):
     def step_external(self, q, qd, feasible=None, obs=None, reward=None, done=None):
         """RoboyEnv.step on states produced by an external simulator (float32 CUDA `[N,3]`, uint8 `[N]`)."""
         n = self.num_envs
-        q, qd = self._dev(q, torch.float32, (n, 3)), self._dev(qd, torch.float32, (n, 3))
+        q, qd = self._dev(q, torch.float32, (n, self.dim_joint)), self._dev(qd, torch.float32, (n, self.dim_joint))
         f = None if feasible is None else self._dev(feasible, torch.uint8, (n,))
         _native.check(self._lib.roboy_step_external(self._h, self._p(q), self._p(qd), self._p(f), self._p(obs),
                                                     self._p(reward), self._p(done), self._stream()))
 
     def reset_external(self, q, qd, mask=None, obs=None):
         n = self.num_envs
-        q, qd = self._dev(q, torch.float32, (n, 3)), self._dev(qd, torch.float32, (n, 3))
+        q, qd = self._dev(q, torch.float32, (n, self.dim_joint)), self._dev(qd, torch.float32, (n, self.dim_joint))
         m = None if mask is None else self._dev(mask, torch.uint8, (n,))
         _native.check(self._lib.roboy_reset_external(self._h, self._p(m), self._p(q), self._p(qd), self._p(obs),
                                                      self._stream()))
@@ -254,8 +272,8 @@ class CudaSimulationClient(SimulationClient):
         """Page-locked, device-mapped numpy buffers `(actions [N,8], obs [N,9], reward [N], done [N])` for `step_host`
         (`roboy_host_alloc`); freed when the client closes."""
         n, out = self.num_envs, []
-        for shape, dt, wc in (((n, _native.DIM_ACTION), np.float32, write_combined_actions),
-                              ((n, _native.DIM_OBS), np.float32, False), ((n,), np.float32, False), ((n,), np.uint8, False)):
+        for shape, dt, wc in (((n, self.dim_action), np.float32, write_combined_actions),
+                              ((n, self.dim_obs), np.float32, False), ((n,), np.float32, False), ((n,), np.uint8, False)):
             nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
             ptr = ctypes.c_void_p()
             _native.check(self._lib.roboy_host_alloc(nbytes, int(wc), ctypes.byref(ptr)))
@@ -290,7 +308,7 @@ class CudaSimulationClient(SimulationClient):
         rows = None
         if with_terminal_obs:
             if self._done_rows is None or self._done_rows.shape[0] < cap:
-                self._done_rows = torch.empty((cap, _native.DIM_OBS), dtype=torch.float32, device=self.device)
+                self._done_rows = torch.empty((cap, self.dim_obs), dtype=torch.float32, device=self.device)
             rows = self._done_rows
         _native.check(self._lib.roboy_done_indices(self._h, self._p(self._done_idx), cap, self._p(self._done_count),
                                                    self._p(rows), self._stream()))
@@ -299,19 +317,21 @@ class CudaSimulationClient(SimulationClient):
 
     def step_host(self, actions, obs, reward, done):
         """The fused step through HOST numpy buffers (pinned for full speed); synchronous."""
-        for a, dt, k in ((actions, np.float32, 8), (obs, np.float32, 9), (reward, np.float32, 1), (done, np.uint8, 1)):
+        for a, dt, k in ((actions, np.float32, self.dim_action), (obs, np.float32, self.dim_obs), (reward, np.float32, 1),
+                         (done, np.uint8, 1)):
             if a.dtype != dt or not a.flags["C_CONTIGUOUS"] or a.size != self.num_envs * k:
-                raise ValueError("host buffers must be C-contiguous float32 [N,8], float32 [N,9], float32 [N], uint8 [N]")
+                raise ValueError("host buffers must be C-contiguous float32 [N,A], float32 [N,3J], float32 [N], uint8 [N]")
         _native.check(self._lib.roboy_step_host(self._h, actions.ctypes.data, obs.ctypes.data, reward.ctypes.data,
                                                 done.ctypes.data))
 
     def compute_reward(self, q, qd, feasible, goal_q, goal_qd=None, check_range=False):
         """Batched compute_reward + _did_reach_goal: returns (reward float64 [k], reached bool [k])."""
-        q = self._dev(q, torch.float32).reshape(-1, 3)
+        J = self.dim_joint
+        q = self._dev(q, torch.float32).reshape(-1, J)
         k = q.shape[0]
-        qd = self._dev(qd, torch.float32, (k, 3))
-        goal_q = self._dev(goal_q, torch.float32, (k, 3))
-        gqd = None if goal_qd is None else self._dev(goal_qd, torch.float32, (k, 3))
+        qd = self._dev(qd, torch.float32, (k, J))
+        goal_q = self._dev(goal_q, torch.float32, (k, J))
+        gqd = None if goal_qd is None else self._dev(goal_qd, torch.float32, (k, J))
         f = None if feasible is None else self._dev(feasible, torch.uint8, (k,))
         reward = torch.empty(k, dtype=torch.float64, device=self.device)
         reached = torch.empty(k, dtype=torch.uint8, device=self.device)
@@ -323,13 +343,13 @@ class CudaSimulationClient(SimulationClient):
     # ------------------------------------------------------------------ injection / introspection
     def set_goal(self, goal_q, idx=None):
         i = self._idx(idx)
-        g = self._dev(goal_q, torch.float32, (i.numel(), 3))
+        g = self._dev(goal_q, torch.float32, (i.numel(), self.dim_joint))
         _native.check(self._lib.roboy_set_goal(self._h, i.numel(), self._p(i), self._p(g), self._stream()))
 
     def set_state(self, q, qd, feasible=None, idx=None):
         i = self._idx(idx)
-        q = self._dev(q, torch.float32, (i.numel(), 3))
-        qd = self._dev(qd, torch.float32, (i.numel(), 3))
+        q = self._dev(q, torch.float32, (i.numel(), self.dim_joint))
+        qd = self._dev(qd, torch.float32, (i.numel(), self.dim_joint))
         f = None if feasible is None else self._dev(feasible, torch.uint8, (i.numel(),))
         _native.check(self._lib.roboy_set_state(self._h, i.numel(), self._p(i), self._p(q), self._p(qd), self._p(f),
                                                 self._stream()))

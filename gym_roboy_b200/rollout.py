@@ -153,8 +153,11 @@ class RolloutCollector:
         self.noise_seed, self.envs_per_thread = int(noise_seed), int(envs_per_thread)
         dev, T, N = self.client.device, self.T, self.N
         f32 = dict(dtype=torch.float32, device=dev)
-        self.obs = torch.zeros((T + 1, N, 9), **f32)
-        self.actions = torch.zeros((T, N, 8), **f32)
+        d_obs, d_act = self.client.dim_obs, self.client.dim_action
+        if self.fused and not self.client.msj_kernels:
+            raise ValueError("the fused policy rollouts are built for MSJ-shaped robots; use fused=False for this robot")
+        self.obs = torch.zeros((T + 1, N, d_obs), **f32)
+        self.actions = torch.zeros((T, N, d_act), **f32)
         self.logp = torch.zeros((T, N), **f32)
         self.values = torch.zeros((T + 1, N), **f32)
         self.rewards = torch.zeros((T, N), **f32)
@@ -162,7 +165,7 @@ class RolloutCollector:
         self.adv = torch.zeros((T, N), **f32)
         self.ret = torch.zeros((T, N), **f32)
         self._graph = None
-        self._clipped = torch.zeros((N, 8), **f32)
+        self._clipped = torch.zeros((N, d_act), **f32)
         self._image, self._image_key = None, None
         if self.fused == "fp32":
             self._image = torch.zeros(_native.POLICY_IMAGE_FLOATS, **f32)

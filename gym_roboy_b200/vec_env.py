@@ -24,8 +24,8 @@ _PER_ENV_ATTRS = ("step_num",)
 
 class RoboyVecEnv:
     def __init__(self, num_envs, seed=0, device=None, env_id_base=0, terminal_observation=True, clip_actions=False,
-                 **env_kwargs):
-        client = CudaSimulationClient(num_envs=num_envs, seed=seed, device=device, env_id_base=env_id_base)
+                 robot=None, **env_kwargs):
+        client = CudaSimulationClient(robot=robot, num_envs=num_envs, seed=seed, device=device, env_id_base=env_id_base)
         self.env = RoboyEnv(client, auto_reset=True, strict=False, **env_kwargs)
         if num_envs == 1:
             self.env._single = False   # a VecEnv is batched even with one env
@@ -45,10 +45,10 @@ class RoboyVecEnv:
         self.env.seed(seed)
 
     def reset(self):
-        return self.env.reset().cpu().numpy().reshape(self.num_envs, 9)
+        return self.env.reset().cpu().numpy().reshape(self.num_envs, self.client.dim_obs)
 
     def step_async(self, actions):
-        a = np.asarray(actions, np.float32).reshape(self.num_envs, 8)
+        a = np.asarray(actions, np.float32).reshape(self.num_envs, self.client.dim_action)
         if self._clip:
             np.clip(a, -1.0, 1.0, out=self._actions)
         else:

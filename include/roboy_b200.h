@@ -17,12 +17,13 @@
  *     offending global env id (roboy_errors) and counted in the statistics.
  *   - there is no CPU fallback: without a CUDA device roboy_create fails with ROBOY_E_CUDA.
  *
- * Memory layout in HBM (structure of arrays, n = n_envs of this shard):
- *   goal        float32 [3][n]   desired joint angles            (RoboyEnv._goal_state)
+ * Memory layout in HBM (structure of arrays, n = n_envs of this shard; J = dim_joint = 3 and A = dim_action = 8 for MSJ):
+ *   goal        float32 [J][n]   desired joint angles            (RoboyEnv._goal_state)
  *   step_flags  uint32  [n]      bits 0..23 step_num, bit 24 HELD_ZERO64, bit 25 HELD_INFEASIBLE
- *   held        float32 [6][n]   StubSimulationClient._state: q0..q2, qd0..qd2 (cold; read only
+ *   held        float32 [2J][n]  StubSimulationClient._state: q_0..q_{J-1}, qd_0..qd_{J-1} (cold; read only
  *                                on the hold branch when HELD_ZERO64 is clear)
- *   obs         float32 [n][9]   row-major, what the policy consumes (roboy_env.py:75-80)
+ *   obs         float32 [n][3J]  row-major [q, qd, goal], what the policy consumes (roboy_env.py:75-80)
+ *   actions     float32 [n][A]   caller's, in [-1, 1]
  *   reward      float32 [n]
  *   done        uint8   [n]
  *   stats       float64 [8]      ROBOY_STAT_*
@@ -38,9 +39,16 @@ extern "C" {
 
 #define ROBOY_B200_ABI_VERSION 2
 
-#define ROBOY_DIM_JOINT 3  /* msj_robot.py:8  */
+#define ROBOY_DIM_JOINT 3  /* msj_robot.py:8  (the MSJ robot; other robots: roboy_cfg.dim_joint) */
 #define ROBOY_DIM_ACTION 8 /* msj_robot.py:12 */
-#define ROBOY_DIM_OBS 9    /* roboy_env.py:32-36 */
+#define ROBOY_DIM_OBS 9    /* roboy_env.py:32-36: 3 * dim_joint */
+
+/* Robots other than MSJ (roboy_robot.py:21-33; README.md:6-7 "MSJ platform, Upper Body, etc."): up to 15 joints and
+ * 64 tendons, one bound per component.  15, because numpy's norm changes its summation order from 16 float64
+ * elements on (OpenBLAS kernels, CPU dependent): beyond that, bit-exact parity with the reference is not defined. */
+#define ROBOY_MAX_JOINT 15
+#define ROBOY_JOINT_PAD 16
+#define ROBOY_MAX_ACTION 64
 
 /* error codes */
 #define ROBOY_OK 0
@@ -95,6 +103,16 @@ typedef struct roboy_cfg {
     float penalty_boundary;      /* roboy_env.py:26 */
     float bonus_goal;            /* roboy_env.py:27 */
     double reward_lo, reward_hi; /* roboy_env.py:30,109; +-inf disables the check */
+    /* Other robots.  dim_joint / dim_action: RoboyRobot.get_joint_angles_space().shape[0] / get_action_space().shape[0]
+     * (0 = MSJ's 3 / 8).  per_component_bounds != 0: the arrays below hold one low / high per joint or tendon
+     * (spaces.Box built from arrays) and the six scalars above are ignored; == 0: the scalars apply to every component.
+     * A robot with MSJ's dims and uniform bounds runs the tuned MSJ kernels, any other the generic ones (same results). */
+    int32_t dim_joint, dim_action;
+    int32_t per_component_bounds;
+    int32_t reserved;
+    float angle_low_v[ROBOY_JOINT_PAD], angle_high_v[ROBOY_JOINT_PAD];
+    float vel_low_v[ROBOY_JOINT_PAD], vel_high_v[ROBOY_JOINT_PAD];
+    float act_low_v[ROBOY_MAX_ACTION], act_high_v[ROBOY_MAX_ACTION];
 } roboy_cfg;
 
 typedef struct roboy_env roboy_env; /* opaque */
@@ -109,8 +127,10 @@ int roboy_cfg_msj(roboy_cfg *cfg);
 /* Host-only helper (no GPU needed): the closed float32 interval [lo, hi] of action components
  * for which the Stub holds its state -- the pre-image of numpy's allclose(rescaled, 0)
  * (simulation_client.py:38) under the float32 rescale of roboy_env.py:157-158.  For MSJ this is
- * [-2^-24, 2^-25].  lo > hi means the interval is empty.  The step kernel compares against it. */
+ * [-2^-24, 2^-25].  lo > hi means the interval is empty.  The step kernel compares against it.
+ * roboy_hold_interval: tendon 0;  roboy_hold_intervals: all dim_action tendons (lo, hi: float[dim_action]). */
 int roboy_hold_interval(const roboy_cfg *cfg, float *lo, float *hi);
+int roboy_hold_intervals(const roboy_cfg *cfg, float *lo, float *hi);
 
 /* RoboyEnv.__init__ over StubSimulationClient.__init__ (roboy_env.py:12-38,
  * simulation_client.py:29-31) for n_envs envs on CUDA device `device`: allocates the SoA state
@@ -382,6 +402,9 @@ int roboy_policy_tc_geometry(roboy_env *env, int tiles_per_group, int exact, int
  * launch geometry the step kernel uses for this n_envs. */
 int roboy_launch_count(roboy_env *env, uint64_t *launches);
 int roboy_step_geometry(roboy_env *env, int *grid, int *block, int *smem_bytes);
+/* The robot this handle was built for: joints, tendons, floats per observation row (3 * joints), and whether the tuned
+ * MSJ kernels (1) or the generic ones (0) run its fused step.  Any pointer may be NULL. */
+int roboy_robot_dims(roboy_env *env, int *dim_joint, int *dim_action, int *dim_obs, int *msj_kernels);
 /* Measurement only: an EMPTY kernel launched exactly like roboy_step launches the step kernel (grid, block,
  * programmatic dependent launch) -- the launch-latency floor bench.py reports next to the launch-bound sizes.
  * Not counted by roboy_launch_count. */

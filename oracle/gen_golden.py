@@ -31,7 +31,19 @@ GOLDEN_DIR = os.path.join(_ROOT, "tests", "golden")
 EV_SET_GOAL, EV_SET_STATE, EV_SET_STEP = 0, 1, 2  # event kinds
 
 
-def make_actions(rng, T, N):
+def make_actions(rng, T, N, bounds=None):
+    if bounds is not None:   # another robot: hold rows sit at the per-tendon zero crossing of the rescale
+        _, A, _, _ = orc.robot_bounds(bounds)
+        zero, _ = orc.hold_action(bounds)
+        a = rng.uniform(-1, 1, (T, N, A)).astype(np.float32)
+        a[rng.random((T, N)) < 0.05] = zero
+        a[rng.random((T, N)) < 0.01] = np.nextafter(zero, np.float32(1))      # right next to the hold interval
+        a[rng.random((T, N)) < 0.01] = np.nextafter(zero, np.float32(-1))
+        one_off = zero.copy(); one_off[-1] = np.float32(0.5)
+        a[rng.random((T, N)) < 0.01] = one_off                                # one tendon off: no hold
+        a[3, 1] = np.float32(1.0)                                             # the ends of the action space
+        a[5, 2] = np.float32(-1.0)
+        return a, zero
     a = rng.uniform(-1, 1, (T, N, 8)).astype(np.float32)
     a[rng.random((T, N)) < 0.03] = 0.0                      # hold branch
     up, dn = np.float32(2.0 ** -25), np.float32(-(2.0 ** -24))
@@ -50,43 +62,53 @@ def make_actions(rng, T, N):
     return a
 
 
-def make_events(rng, T, N, seed, thr_a, thr_v):
-    """List of (before_step, env, kind, payload[7]) -- payload: q[3], qd[3], flag."""
+def make_events(rng, T, N, seed, thr_a, thr_v, J=3, lo=None, hi=None):
+    """List of (before_step, env, kind, payload[2J+1]) -- payload: q[J], qd[J], flag."""
     ev = []
-    zero_action_at = []  # (step, env) whose action row must be exactly zero
+    zero_action_at = []  # (step, env) whose action row must hold (exactly zero for MSJ)
+    lo = np.full(J, -3.0) if lo is None else np.asarray(lo, np.float64) * 0.95
+    hi = np.full(J, 3.0) if hi is None else np.asarray(hi, np.float64) * 0.95
+    rootJ = np.float32(np.sqrt(J))
+    zeros = (0.0,) * J
 
-    def add(t, e, kind, q=(0, 0, 0), qd=(0, 0, 0), flag=0.0):
+    def add(t, e, kind, q=zeros, qd=zeros, flag=0.0):
         ev.append((t, e, kind, list(q) + list(qd) + [flag]))
+
+    def first(d):       # (d, 0, 0, ...)
+        return (d,) + (0.0,) * (J - 1)
+
+    def alternating(d):  # (d, -d, d, ...)
+        return tuple(d if k % 2 == 0 else -d for k in range(J))
 
     # (a) goal := current (zero) state right after the initial reset -> reached on a zero action
     #     (test_roboy_env.py:60-68), exactly at / just inside / just outside the angle threshold.
     for k, scale in enumerate([0.0, 0.5, 1.0 - 3e-7, 1.0, 1.0 + 3e-7, 2.0]):
         e, t = k, 3 + k
         d = np.float32(thr_a) * np.float32(scale)
-        add(t, e, EV_SET_STATE, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), 1.0)      # float32 held state
-        add(t, e, EV_SET_GOAL, (d, 0.0, 0.0))
+        add(t, e, EV_SET_STATE, zeros, zeros, 1.0)                           # float32 held state
+        add(t, e, EV_SET_GOAL, first(d))
         zero_action_at.append((t, e))
     # (b) float32 held state at the goal but moving: velocity norm around its threshold
     #     (test_roboy_env.py:71-79)
     for k, scale in enumerate([0.5, 1.0 - 3e-7, 1.0, 1.0 + 3e-7, 3.0]):
         e, t = 8 + k, 10 + k
-        q = rng.uniform(-3, 3, 3).astype(np.float32)
-        v = np.float32(thr_v) * np.float32(scale) / np.float32(np.sqrt(3))
-        add(t, e, EV_SET_STATE, q, (v, v, v), 1.0)
+        q = rng.uniform(lo, hi).astype(np.float32)
+        v = np.float32(thr_v) * np.float32(scale) / rootJ
+        add(t, e, EV_SET_STATE, q, (v,) * J, 1.0)
         add(t, e, EV_SET_GOAL, q)
         zero_action_at.append((t, e))
     # (c) infeasible held state -> boundary penalty (roboy_env.py:102-103), near and far from goal
     for k in range(3):
         e, t = 14 + k, 20 + k
-        q = rng.uniform(-3, 3, 3).astype(np.float32)
-        add(t, e, EV_SET_STATE, q, rng.uniform(-0.2, 0.2, 3).astype(np.float32), 0.0)
-        add(t, e, EV_SET_GOAL, q if k == 0 else rng.uniform(-3, 3, 3).astype(np.float32))
+        q = rng.uniform(lo, hi).astype(np.float32)
+        add(t, e, EV_SET_STATE, q, rng.uniform(-0.2, 0.2, J).astype(np.float32), 0.0)
+        add(t, e, EV_SET_GOAL, q if k == 0 else rng.uniform(lo, hi).astype(np.float32))
         zero_action_at.append((t, e))
     # (d) float64 zero held state (after a reset) with the goal near zero -> reached in float64
     for k, scale in enumerate([0.3, 1.0 - 1e-7, 1.0 + 1e-7]):
         e, t = 18 + k, 30 + k
-        d = np.float32(thr_a) * np.float32(scale) / np.float32(np.sqrt(3))
-        add(t, e, EV_SET_GOAL, (d, -d, d))
+        d = np.float32(thr_a) * np.float32(scale) / rootJ
+        add(t, e, EV_SET_GOAL, alternating(d))
         zero_action_at.append((t, e))
     # (e) episode counter pokes (test_roboy_env.py:170-180): timeouts at scattered steps
     for k in range(8):
@@ -94,40 +116,53 @@ def make_events(rng, T, N, seed, thr_a, thr_v):
     return ev, zero_action_at
 
 
-def sampled_branch_goals(seed, N, T, thr_v, counter_of_step, taken):
+def sampled_branch_goals(seed, N, T, thr_v, counter_of_step, taken, low=orc.MSJ["angle_low"], high=orc.MSJ["angle_high"], J=3):
     """Events that make _did_reach_goal fire on freshly SAMPLED states: pick (env, step) whose
     Philox velocity draw is slow enough and put the goal next to the drawn angles just before."""
     ev = []
     for t in range(40, T):
         c = counter_of_step(t)
-        q_all, qd = orc.draw_state(seed, np.arange(N), c)
+        q_all, qd = orc.draw_state(seed, np.arange(N), c, low, high, J=J)
         qd = qd.astype(np.float64)
         slow = np.flatnonzero(np.sqrt((qd * qd).sum(1)) < 0.9 * float(thr_v))
         for e in slow:
             if (t, int(e)) in taken:
                 continue
             q = q_all[int(e)]
-            g = np.clip(q + np.float32(0.01), -orc.PI32, orc.PI32)
-            ev.append((t, int(e), EV_SET_GOAL, list(g) + [0, 0, 0, 0]))
+            g = np.clip(q + np.float32(0.01), np.asarray(low, np.float32), np.asarray(high, np.float32))
+            ev.append((t, int(e), EV_SET_GOAL, list(g) + [0] * (J + 1)))
     return ev
 
 
-def run_fixture(name, N, T, seed, joint_vel_penalty, bonus, auto_reset=True):
+def run_fixture(name, N, T, seed, joint_vel_penalty, bonus, auto_reset=True, bounds=None):
     rng = np.random.default_rng(seed)
-    cfg = orc.make_cfg(N, seed=seed)
-    thr_a, thr_v = orc.thresholds(cfg)
-    actions = make_actions(rng, T, N)
-    events, zero_rows = make_events(rng, T, N, seed, thr_a, thr_v)
-    for (t, e) in zero_rows:
-        actions[t, e] = 0.0
-    # call counter: 0 = construction, 1 = initial reset, step index t runs at counter t + 2
-    events += sampled_branch_goals(seed, N, T, thr_v, lambda t: t + 2, set(zero_rows))
+    J, A, D, extra = 3, 8, 9, {}
+    if bounds is None:
+        cfg = orc.make_cfg(N, seed=seed)
+        thr_a, thr_v = orc.thresholds(cfg)
+        actions = make_actions(rng, T, N)
+        events, zero_rows = make_events(rng, T, N, seed, thr_a, thr_v)
+        for (t, e) in zero_rows:
+            actions[t, e] = 0.0
+        # call counter: 0 = construction, 1 = initial reset, step index t runs at counter t + 2
+        events += sampled_branch_goals(seed, N, T, thr_v, lambda t: t + 2, set(zero_rows))
+    else:   # a robot with other dims / per-component bounds (a RoboyRobot subclass of the reference)
+        J, A, _, bb = orc.robot_bounds(bounds)
+        D = 3 * J
+        cfg = orc.make_cfg(N, seed=seed, **bounds)
+        thr_a, thr_v = orc.thresholds(cfg)
+        actions, zero = make_actions(rng, T, N, bounds)
+        events, zero_rows = make_events(rng, T, N, seed, thr_a, thr_v, J, bb["angle_low"], bb["angle_high"])
+        for (t, e) in zero_rows:
+            actions[t, e] = zero
+        events += sampled_branch_goals(seed, N, T, thr_v, lambda t: t + 2, set(zero_rows), bb["angle_low"], bb["angle_high"], J)
+        extra = {"robot_" + k: v for k, v in bb.items()}
     events.sort(key=lambda x: (x[0], x[1], x[2]))
 
-    ref = ReferenceVecEnv(N, seed=seed, joint_vel_penalty=joint_vel_penalty, bonus=bonus, auto_reset=auto_reset)
+    ref = ReferenceVecEnv(N, seed=seed, joint_vel_penalty=joint_vel_penalty, bonus=bonus, auto_reset=auto_reset, bounds=bounds)
     out = dict(
-        obs=np.zeros((T, N, 9), np.float32), reward=np.zeros((T, N), np.float64), done=np.zeros((T, N), bool),
-        terminal_obs=np.zeros((T, N, 9), np.float32), goal_after=np.zeros((T, N, 3), np.float32),
+        obs=np.zeros((T, N, D), np.float32), reward=np.zeros((T, N), np.float64), done=np.zeros((T, N), bool),
+        terminal_obs=np.zeros((T, N, D), np.float32), goal_after=np.zeros((T, N, J), np.float32),
         step_num_after=np.zeros((T, N), np.int32), valid=np.ones((T, N), bool),
     )
     init_goal = ref.goals()
@@ -140,11 +175,11 @@ def run_fixture(name, N, T, seed, joint_vel_penalty, bonus, auto_reset=True):
     for t in range(T):
         for (_, e, kind, p) in by_step.get(t, []):
             if kind == EV_SET_GOAL:
-                ref.set_goal(e, p[0:3])
+                ref.set_goal(e, p[0:J])
             elif kind == EV_SET_STATE:
-                ref.set_state(e, p[0:3], p[3:6], feasible=bool(p[6]))
+                ref.set_state(e, p[0:J], p[J:2 * J], feasible=bool(p[2 * J]))
             else:
-                ref.set_step_num(e, int(p[6]))
+                ref.set_step_num(e, int(p[2 * J]))
         o, r, d, term, raised = ref.step(actions[t])
         for i, msg in enumerate(raised):
             if msg and alive[i]:
@@ -156,7 +191,7 @@ def run_fixture(name, N, T, seed, joint_vel_penalty, bonus, auto_reset=True):
         if not auto_reset:  # plain gym loop: the caller resets finished envs
             if d.any():
                 ro = ref.reset(mask=d)
-                out.setdefault("reset_obs_after", np.zeros((T, N, 9), np.float32))[t] = ro.astype(np.float32)
+                out.setdefault("reset_obs_after", np.zeros((T, N, D), np.float32))[t] = ro.astype(np.float32)
         out["goal_after"][t] = ref.goals()
         out["step_num_after"][t] = ref.step_nums()
     ev_arr = np.array([[e[0], e[1], e[2]] + [float(x) for x in e[3]] for e in events], np.float64)
@@ -164,7 +199,8 @@ def run_fixture(name, N, T, seed, joint_vel_penalty, bonus, auto_reset=True):
     np.savez_compressed(
         path, actions=actions, events=ev_arr, init_goal=init_goal, reset_obs=reset_obs, raised_at=raised_at,
         reward_range=np.array(ref.reward_range, np.float64),
-        meta=np.array([N, T, seed, int(joint_vel_penalty), int(bonus), int(auto_reset)], np.int64), **out)
+        meta=np.array([N, T, seed, int(joint_vel_penalty), int(bonus), int(auto_reset)] + ([J, A] if bounds is not None else []),
+                      np.int64), **extra, **out)
     n_succ = int((out["done"] & (out["reward"] > 500) & out["valid"]).sum())
     print("{}: N={} T={} done={} bonus-rewards={} raised={} events={} -> {} ({} KiB)".format(
         name, N, T, int((out["done"] & out["valid"]).sum()), n_succ, int((raised_at >= 0).sum()), len(events),
@@ -179,7 +215,20 @@ FIXTURES = [
     ("rollout_manual_reset", 32, 420, 20240904, False, True, False),
 ]
 
+# robots other than MSJ: synthetic RoboyRobot subclasses of the reference
+ROBOT_FIXTURES = [
+    ("rollout_six_joints_14_tendons", 32, 300, 20241001, False, True, True,
+     dict(dim_joint=6, dim_action=14, angle_low=-2.5, angle_high=2.5, vel_low=-0.6, vel_high=0.6, act_low=-0.2, act_high=0.2)),
+    ("rollout_per_component_5_joints_11_tendons", 32, 300, 20241002, False, True, True,
+     dict(angle_low=[-3.1, -1.0, -2.0, -0.7, -1.3], angle_high=[3.1, 1.0, 2.5, 0.9, 1.3],
+          vel_low=[-0.5, -0.4, -0.3, -0.2, -0.1], vel_high=[0.5, 0.4, 0.6, 0.2, 0.3],
+          act_low=[-0.3, -0.1, -0.2, -0.3, -0.25, -0.4, -0.3, -0.25, -0.5, -0.125, -0.3],
+          act_high=[0.3, 0.4, 0.2, 0.1, 0.25, 0.4, 0.6, 0.25, 0.5, 0.375, 0.1])),
+]
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for fx in FIXTURES:
-        run_fixture(*fx)
+    which = sys.argv[1:]
+    for fx in FIXTURES + ROBOT_FIXTURES:
+        if not which or fx[0] in which:
+            run_fixture(*fx)

@@ -56,14 +56,17 @@ def _import_reference():
 
 
 def _custom_reference_robot(bounds):
-    """A robot plug-in written against the REFERENCE's RoboyRobot base (3 joints, 8 tendons, other spaces)."""
+    """A robot plug-in written against the REFERENCE's RoboyRobot base: any joint / tendon count, scalar or
+    per-component bounds (roboy_robot.py:21-33 -- what "Upper Body, etc." of README.md:6-7 would subclass)."""
     from gym import spaces
     from gym_roboy.envs.robots import RoboyRobot
+    from oracle import oracle as orc
+    J, A, _, b = orc.robot_bounds(bounds)
 
     class CustomRobot(RoboyRobot):
-        _A = spaces.Box(low=bounds["angle_low"], high=bounds["angle_high"], shape=(3,), dtype="float32")
-        _V = spaces.Box(low=bounds["vel_low"], high=bounds["vel_high"], shape=(3,), dtype="float32")
-        _T = spaces.Box(low=bounds["act_low"], high=bounds["act_high"], shape=(8,), dtype="float32")
+        _A = spaces.Box(low=b["angle_low"], high=b["angle_high"], dtype="float32")
+        _V = spaces.Box(low=b["vel_low"], high=b["vel_high"], dtype="float32")
+        _T = spaces.Box(low=b["act_low"], high=b["act_high"], dtype="float32")
 
         @classmethod
         def get_action_space(cls):
@@ -77,6 +80,7 @@ def _custom_reference_robot(bounds):
         def get_joint_vels_space(cls):
             return cls._V
 
+    assert CustomRobot._A.shape == (J,) and CustomRobot._T.shape == (A,)
     return CustomRobot
 
 
@@ -93,11 +97,10 @@ def _make_replay_robot(MsjRobot, RobotState, state_fn, goal_fn):
             gid, t = cls.ctx["gid"], cls.ctx["t"]
             if caller == "get_new_goal_joint_angles":
                 cls.log.append("goal")
-                if cls.ctx["goal_real"]:
-                    g = goal_fn(gid, t)
-                else:  # goal that the worker's reset() overwrites at once: never observable
-                    g = np.zeros(3, np.float32)
-                return RobotState(joint_angles=g, joint_vels=np.zeros(3, np.float32), is_feasible=True)
+                J = cls.get_joint_angles_space().shape[0]
+                else_goal = np.zeros(J, np.float32)   # goal that the worker's reset() overwrites at once: never observable
+                g = goal_fn(gid, t) if cls.ctx["goal_real"] else else_goal
+                return RobotState(joint_angles=g, joint_vels=np.zeros(J, np.float32), is_feasible=True)
             assert caller in ("forward_step_command", "__init__"), caller
             cls.log.append("state")
             q, qd = state_fn(gid, t)
@@ -114,10 +117,12 @@ class ReferenceVecEnv:
         from oracle import oracle as orc
 
         RoboyEnv, MsjRobot, RobotState, Stub = _import_reference()
-        low, high = orc.MSJ["angle_low"], orc.MSJ["angle_high"]
-        if bounds is not None:   # another robot: same dims, other spaces (a RoboyRobot subclass of the reference)
+        low, high, J = orc.MSJ["angle_low"], orc.MSJ["angle_high"], 3
+        if bounds is not None:   # another robot (a RoboyRobot subclass of the reference): other dims and / or spaces
             MsjRobot = _custom_reference_robot(bounds)
-            low, high = bounds["angle_low"], bounds["angle_high"]
+            J, _, _, b = orc.robot_bounds(bounds)
+            low, high = b["angle_low"], b["angle_high"]
+        self.J, self.obs_dim = J, 3 * J
         self.RobotState = RobotState
         self.n = n_envs
         self.seed = seed
@@ -126,11 +131,11 @@ class ReferenceVecEnv:
         self.envs, self.robots = [], []
 
         def state_fn(gid, t):
-            q, qd = orc.draw_state(seed, [gid], t, low, high)
+            q, qd = orc.draw_state(seed, [gid], t, low, high, J=J)
             return q[0], qd[0]
 
         def goal_fn(gid, t):
-            return orc.draw_goal(seed, [gid], t, low, high)[0]
+            return orc.draw_goal(seed, [gid], t, low, high, J=J)[0]
 
         with contextlib.redirect_stdout(io.StringIO()):
             for i in range(n_envs):
@@ -171,7 +176,7 @@ class ReferenceVecEnv:
 
     def reset(self, mask=None):
         self.t += 1
-        obs = np.zeros((self.n, 9), np.float64)
+        obs = np.zeros((self.n, self.obs_dim), np.float64)
         with contextlib.redirect_stdout(io.StringIO()):
             for i, env in enumerate(self.envs):
                 if mask is not None and not mask[i]:
@@ -186,8 +191,8 @@ class ReferenceVecEnv:
         terminal_obs f64 [n,9], raised [n] (AssertionError text or '')."""
         self.t += 1
         n = self.n
-        obs = np.zeros((n, 9), np.float64)
-        term = np.zeros((n, 9), np.float64)
+        obs = np.zeros((n, self.obs_dim), np.float64)
+        term = np.zeros((n, self.obs_dim), np.float64)
         rew = np.zeros(n, np.float64)
         done = np.zeros(n, bool)
         raised = [""] * n

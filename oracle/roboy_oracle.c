@@ -1,7 +1,8 @@
 /*
  * oracle/roboy_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * A plain-C, CPU restatement of gym-roboy's environment hot path for the MSJ robot, used
+ * A plain-C, CPU restatement of gym-roboy's environment hot path for any RoboyRobot plug-in (MsjRobot and robots with
+ * other joint / tendon counts and per-component bounds, roboy_robot.py:21-33), used
  * ONLY as the checker for the CUDA path (tests/, __graft_entry__.smoke(), and bench.py's
  * cpu_baseline / --impl reference legs).  Nothing under gym_roboy_b200/ may import, link or
  * call it.  Every function cites the reference lines it follows (paths relative to
@@ -14,8 +15,12 @@
  * that container (numpy 2.3.5 + scipy-openblas 0.3.30, x86-64):
  *   - np.linalg.norm(float32[3], ord=2) == sqrtf((float)(sum_k (double)(float)(x_k*x_k)))
  *     (OpenBLAS sdot: float products accumulated sequentially in a double, cast to float);
- *   - np.linalg.norm(float64[3]) == sqrt(((x0*x0)+(x1*x1))+(x2*x2))  for the float32-valued
- *     inputs this path produces (the products are then exact, so FMA use is unobservable);
+ *   - np.linalg.norm(float64[n]), n < 16 == sqrt(fma(x_{n-1}, x_{n-1}, ... fma(x1, x1, x0*x0)))  (OpenBLAS ddot's
+ *     scalar tail loop, compiled with FMA contraction: pinned on 1,500 random vectors per length, 0 mismatches for
+ *     n = 3..15, while the unfused sum mismatches ~12 % of them; with float32-valued inputs -- all the MSJ stub path
+ *     produces -- the products are exact and the two agree).  From n = 16 (float64) / n = 32 (float32) on OpenBLAS
+ *     switches to SIMD-blocked partial sums whose order depends on the host CPU's kernel: that is why the CUDA path
+ *     and this oracle cap a robot at ORC_MAX_JOINT = 15 joints;
  *   - np.exp(float32) is NOT correctly rounded (about 40 % of inputs differ from libm expf by
  *     one ulp), so rewards are compared with a relative tolerance (1e-6), never bit-exactly.
  *
@@ -35,11 +40,15 @@
 /* ------------------------------------------------------------------------------------------
  * Configuration and state (mirrors include/roboy_b200.h field by field, written independently)
  * ---------------------------------------------------------------------------------------- */
+#define ORC_MAX_JOINT 15   /* see the header: numpy's norm changes its summation order from 16 float64 elements on */
+#define ORC_JOINT_PAD 16
+#define ORC_MAX_ACTION 64
+
 typedef struct {
     uint64_t n_envs;
     uint64_t env_id_base;      /* global id of local env 0 (multi-GPU sharding) */
     uint64_t seed;
-    float angle_low, angle_high;   /* msj_robot.py:9   +-pi  as float32 */
+    float angle_low, angle_high;   /* msj_robot.py:9   +-pi  as float32 (scalar bounds: every component) */
     float vel_low, vel_high;       /* msj_robot.py:10  +-pi/6 as float32 */
     float act_low, act_high;       /* msj_robot.py:16  +-0.3 as float32 */
     int32_t max_episode_len;       /* roboy_env.py:28  400 */
@@ -49,7 +58,23 @@ typedef struct {
     float penalty_boundary;        /* roboy_env.py:26  1 */
     float bonus_goal;              /* roboy_env.py:27  1000 */
     double reward_lo, reward_hi;   /* roboy_env.py:30,109 (use -inf/+inf to disable) */
+    /* other robots (roboy_robot.py:21-33): dims (0 = MSJ's 3 / 8) and, if per_component_bounds, one bound per component */
+    int32_t dim_joint, dim_action;
+    int32_t per_component_bounds;
+    int32_t reserved;
+    float angle_low_v[ORC_JOINT_PAD], angle_high_v[ORC_JOINT_PAD];
+    float vel_low_v[ORC_JOINT_PAD], vel_high_v[ORC_JOINT_PAD];
+    float act_low_v[ORC_MAX_ACTION], act_high_v[ORC_MAX_ACTION];
 } orc_cfg;
+
+static int cfg_J(const orc_cfg *c) { return c->dim_joint > 0 ? c->dim_joint : 3; }
+static int cfg_A(const orc_cfg *c) { return c->dim_action > 0 ? c->dim_action : 8; }
+static float a_lo(const orc_cfg *c, int k) { return c->per_component_bounds ? c->angle_low_v[k] : c->angle_low; }
+static float a_hi(const orc_cfg *c, int k) { return c->per_component_bounds ? c->angle_high_v[k] : c->angle_high; }
+static float v_lo(const orc_cfg *c, int k) { return c->per_component_bounds ? c->vel_low_v[k] : c->vel_low; }
+static float v_hi(const orc_cfg *c, int k) { return c->per_component_bounds ? c->vel_high_v[k] : c->vel_high; }
+static float t_lo(const orc_cfg *c, int k) { return c->per_component_bounds ? c->act_low_v[k] : c->act_low; }
+static float t_hi(const orc_cfg *c, int k) { return c->per_component_bounds ? c->act_high_v[k] : c->act_high; }
 
 /* step_flags word: low 24 bits step_num, then flag bits */
 #define ORC_STEP_MASK 0x00ffffffu
@@ -89,16 +114,14 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 enum { STREAM_STATE = 0, STREAM_GOAL = 2 };
 
-/* counter = (env id lo, env id hi, call counter lo, stream<<28 | sub<<20 | call counter hi);
- * sub numbers repeated goal draws at one call counter (un-fused plug-in API); 0 in the step. */
-static void draw4s(const orc_cfg *cfg, uint64_t gid, uint64_t t, uint32_t stream, uint32_t sub, uint32_t out[4]) {
-    uint32_t ctr[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t,
+/* counter = (env id lo, env id hi | block << 24, call counter lo, stream<<28 | sub<<20 | call counter hi);
+ * sub numbers repeated goal draws at one call counter (un-fused plug-in API); 0 in the step.  block numbers the
+ * Philox blocks of one draw for robots with more than 3 joints (0 for MSJ; global env ids stay below 2^56). */
+static void draw4b(const orc_cfg *cfg, uint64_t gid, uint64_t t, uint32_t stream, uint32_t sub, uint32_t block, uint32_t out[4]) {
+    uint32_t ctr[4] = {(uint32_t)gid, (uint32_t)(gid >> 32) | (block << 24), (uint32_t)t,
                        (stream << 28) | ((sub & 0xffu) << 20) | ((uint32_t)(t >> 32) & 0x000fffffu)};
     uint32_t key[2] = {(uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32)};
     orc_philox4x32_10(ctr, key, out);
-}
-static void draw4(const orc_cfg *cfg, uint64_t gid, uint64_t t, uint32_t stream, uint32_t out[4]) {
-    draw4s(cfg, gid, t, stream, 0, out);
 }
 
 /* u = (x>>8)*2^-24 in [0,1); v = low + (high-low)*u, float32 mul then add (no FMA).
@@ -110,47 +133,53 @@ static float uniform_in(uint32_t x, float low, float high) {
     return low + m;
 }
 
-/* roboy_robot.py:35-39 new_random_state(): q ~ U[angle space]^3, and -- reference quirk --
+/* roboy_robot.py:35-39 new_random_state(): q ~ U[angle space]^J, and -- reference quirk --
  * the velocities are ALSO drawn from the ANGLE space (:38). is_feasible = True.
- * One Philox block per state: its 128 bits are cut into six 21-bit integers k0..k5 (bits 127..2),
- * v_i = low + (span * 2^-21) * (float)k_i  (float32 multiply then add). */
-void orc_draw_state(const orc_cfg *cfg, uint64_t gid, uint64_t t, float q[3], float qd[3]) {
-    uint32_t r[4], k[6];
-    draw4(cfg, gid, t, STREAM_STATE, r);
-    k[0] = r[0] >> 11;
-    k[1] = ((r[0] & 0x7ffu) << 10) | (r[1] >> 22);
-    k[2] = (r[1] >> 1) & 0x1fffffu;
-    k[3] = r[2] >> 11;
-    k[4] = ((r[2] & 0x7ffu) << 10) | (r[3] >> 22);
-    k[5] = (r[3] >> 1) & 0x1fffffu;
-    const float span21 = (cfg->angle_high - cfg->angle_low) * 0x1p-21f;
-    for (int i = 0; i < 3; ++i) {
-        float m = span21 * (float)k[i];
-        q[i] = cfg->angle_low + m;
-        m = span21 * (float)k[3 + i];
-        qd[i] = cfg->angle_low + m;
+ * The 2J values (q_0..q_{J-1}, qd_0..qd_{J-1}) are numbered c = 0..2J-1; value c comes from Philox block c / 6, whose
+ * 128 bits are cut into six 21-bit integers k0..k5 (bits 127..2): v = low + (span * 2^-21) * (float)k  (float32
+ * multiply then add), with low / span of the ANGLE component the value belongs to.  MSJ (J = 3): one block. */
+void orc_draw_state(const orc_cfg *cfg, uint64_t gid, uint64_t t, float *q, float *qd) {
+    const int J = cfg_J(cfg);
+    uint32_t r[4] = {0, 0, 0, 0}, k[6] = {0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < 2 * J; ++c) {
+        if (c % 6 == 0) {
+            draw4b(cfg, gid, t, STREAM_STATE, 0, (uint32_t)(c / 6), r);
+            k[0] = r[0] >> 11;
+            k[1] = ((r[0] & 0x7ffu) << 10) | (r[1] >> 22);
+            k[2] = (r[1] >> 1) & 0x1fffffu;
+            k[3] = r[2] >> 11;
+            k[4] = ((r[2] & 0x7ffu) << 10) | (r[3] >> 22);
+            k[5] = (r[3] >> 1) & 0x1fffffu;
+        }
+        const int j = c < J ? c : c - J;
+        const float span21 = (a_hi(cfg, j) - a_lo(cfg, j)) * 0x1p-21f;
+        float m = span21 * (float)k[c % 6];
+        float v = a_lo(cfg, j) + m;
+        if (c < J) q[j] = v; else qd[j] = v;
     }
 }
 
-/* simulation_client.py:46-47 get_new_goal_joint_angles(): new_random_state().joint_angles */
-void orc_draw_goal_sub(const orc_cfg *cfg, uint64_t gid, uint64_t t, uint32_t sub, float g[3]) {
-    uint32_t a[4];
-    draw4s(cfg, gid, t, STREAM_GOAL, sub, a);
-    for (int k = 0; k < 3; ++k) g[k] = uniform_in(a[k], cfg->angle_low, cfg->angle_high);
+/* simulation_client.py:46-47 get_new_goal_joint_angles(): new_random_state().joint_angles.  Goal component k comes from
+ * word k % 3 of Philox block k / 3 on the goal stream (24-bit draws). */
+void orc_draw_goal_sub(const orc_cfg *cfg, uint64_t gid, uint64_t t, uint32_t sub, float *g) {
+    const int J = cfg_J(cfg);
+    uint32_t a[4] = {0, 0, 0, 0};
+    for (int k = 0; k < J; ++k) {
+        if (k % 3 == 0) draw4b(cfg, gid, t, STREAM_GOAL, sub, (uint32_t)(k / 3), a);
+        g[k] = uniform_in(a[k % 3], a_lo(cfg, k), a_hi(cfg, k));
+    }
 }
-void orc_draw_goal(const orc_cfg *cfg, uint64_t gid, uint64_t t, float g[3]) {
-    uint32_t a[4];
-    draw4(cfg, gid, t, STREAM_GOAL, a);
-    for (int k = 0; k < 3; ++k) g[k] = uniform_in(a[k], cfg->angle_low, cfg->angle_high);
-}
+void orc_draw_goal(const orc_cfg *cfg, uint64_t gid, uint64_t t, float *g) { orc_draw_goal_sub(cfg, gid, t, 0, g); }
 
 /* ------------------------------------------------------------------------------------------
  * numpy arithmetic restated (see header for how each was pinned)
  * ---------------------------------------------------------------------------------------- */
+#define JP ORC_JOINT_PAD
+
 /* roboy_env.py:137-140 _l2_distance on float32 operands */
-static float l2_f32(const float a[3], const float b[3]) {
+static float l2_f32(int J, const float *a, const float *b) {
     double s = 0.0;
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < J; ++k) {
         float d = a[k] - b[k];      /* :138 np.subtract in float32 */
         if (isnan(d)) d = 0.0f;     /* :139 */
         float p = d * d;            /* OpenBLAS sdot: float product ... */
@@ -159,13 +188,13 @@ static float l2_f32(const float a[3], const float b[3]) {
     return sqrtf((float)s);         /* :140 np.linalg.norm -> sqrt(float32) */
 }
 
-/* roboy_env.py:137-140 _l2_distance once either operand is float64 */
-static double l2_f64(const double a[3], const double b[3]) {
+/* roboy_env.py:137-140 _l2_distance once either operand is float64 (OpenBLAS ddot tail: sequential FMA) */
+static double l2_f64(int J, const double *a, const double *b) {
     double s = 0.0;
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < J; ++k) {
         double d = a[k] - b[k];
         if (isnan(d)) d = 0.0;
-        s += d * d;
+        s = fma(d, d, s);
     }
     return sqrt(s);
 }
@@ -186,83 +215,85 @@ static double normalize_f64(double v, float hi, float lo) {
 
 /* One env's state as the reference holds it: values + the dtype numpy would carry. */
 typedef struct {
-    double q[3], qd[3]; /* float32-valued when is64 == 0 */
-    int is64;           /* 1: float64 zero state (roboy_robot.py:41-45), 0: float32 sample */
+    double q[JP], qd[JP]; /* float32-valued when is64 == 0 */
+    int is64;             /* 1: float64 arrays (zero state roboy_robot.py:41-45, wire values), 0: float32 sample */
     int feasible;
 } orc_state;
 
 /* roboy_env.py:125-134 _did_reach_goal.  goal_q is float32; goal velocities are either the
  * float64 zeros of roboy_env.py:23 (goal_qd == NULL) or float32 values (stand-alone call). */
-static int did_reach_goal(const orc_cfg *cfg, const orc_state *s, const float goal_q[3],
+static int did_reach_goal(const orc_cfg *cfg, const orc_state *s, const float *goal_q,
                           const float *goal_qd, float thr_angle, float thr_vel) {
+    const int J = cfg_J(cfg);
     int angles_close, vels_close;
     if (!s->is64) {
-        float q[3] = {(float)s->q[0], (float)s->q[1], (float)s->q[2]};
-        angles_close = l2_f32(q, goal_q) < thr_angle;              /* :126-127 float32 */
+        float q[JP];
+        for (int k = 0; k < J; ++k) q[k] = (float)s->q[k];
+        angles_close = l2_f32(J, q, goal_q) < thr_angle;           /* :126-127 float32 */
     } else {
-        double g[3] = {goal_q[0], goal_q[1], goal_q[2]};
-        angles_close = l2_f64(s->q, g) < (double)thr_angle;        /* float64 state promotes */
+        double g[JP];
+        for (int k = 0; k < J; ++k) g[k] = goal_q[k];
+        angles_close = l2_f64(J, s->q, g) < (double)thr_angle;     /* float64 state promotes */
     }
     if (!s->is64 && goal_qd) {
-        float v[3] = {(float)s->qd[0], (float)s->qd[1], (float)s->qd[2]};
-        vels_close = l2_f32(v, goal_qd) < thr_vel;
+        float v[JP];
+        for (int k = 0; k < J; ++k) v[k] = (float)s->qd[k];
+        vels_close = l2_f32(J, v, goal_qd) < thr_vel;
     } else {
-        double gv[3] = {0.0, 0.0, 0.0};
-        if (goal_qd) { gv[0] = goal_qd[0]; gv[1] = goal_qd[1]; gv[2] = goal_qd[2]; }
-        vels_close = l2_f64(s->qd, gv) < (double)thr_vel;          /* :129-130 float64 */
+        double gv[JP];
+        for (int k = 0; k < J; ++k) gv[k] = goal_qd ? (double)goal_qd[k] : 0.0;
+        vels_close = l2_f64(J, s->qd, gv) < (double)thr_vel;       /* :129-130 float64 */
     }
-    (void)cfg;
     return angles_close && vels_close;                             /* :134 */
 }
 
 /* roboy_env.py:92-112 compute_reward.  Returns the python float; *violation set when the
  * assert at :109 would fire.  `reached` is the value of the _did_reach_goal call at :105. */
-static double compute_reward(const orc_cfg *cfg, const orc_state *s, const float goal_q[3],
+static double compute_reward(const orc_cfg *cfg, const orc_state *s, const float *goal_q,
                              const float *goal_qd, int reached, int *violation) {
-    const float ahi = cfg->angle_high, alo = cfg->angle_low, vhi = cfg->vel_high, vlo = cfg->vel_low;
+    const int J = cfg_J(cfg);
     double reward; /* carries float32 values exactly while the reference is in float32 */
     int r64;       /* dtype numpy would carry */
     float r32 = 0.0f;
-    float ng[3];
-    for (int k = 0; k < 3; ++k) ng[k] = normalize_f32(goal_q[k], ahi, alo);           /* :95 */
+    float ng[JP];
+    for (int k = 0; k < J; ++k) ng[k] = normalize_f32(goal_q[k], a_hi(cfg, k), a_lo(cfg, k));           /* :95 */
     if (!s->is64) {
-        float nq[3];
-        for (int k = 0; k < 3; ++k) nq[k] = normalize_f32((float)s->q[k], ahi, alo);  /* :94 */
-        r32 = -expf(l2_f32(nq, ng));                                                  /* :96 */
+        float nq[JP];
+        for (int k = 0; k < J; ++k) nq[k] = normalize_f32((float)s->q[k], a_hi(cfg, k), a_lo(cfg, k));  /* :94 */
+        r32 = -expf(l2_f32(J, nq, ng));                                                                 /* :96 */
         r64 = 0;
         reward = r32;
     } else {
-        double nq[3], g64[3];
-        for (int k = 0; k < 3; ++k) { nq[k] = normalize_f64(s->q[k], ahi, alo); g64[k] = ng[k]; }
-        reward = -exp(l2_f64(nq, g64));
+        double nq[JP], g64[JP];
+        for (int k = 0; k < J; ++k) { nq[k] = normalize_f64(s->q[k], a_hi(cfg, k), a_lo(cfg, k)); g64[k] = ng[k]; }
+        reward = -exp(l2_f64(J, nq, g64));
         r64 = 1;
     }
     if (cfg->joint_vel_penalty) {                                                     /* :98-100 */
         if (!s->is64 && goal_qd) { /* all-float32 stand-alone call (roboy_env.py:40-49) */
-            float nv[3], ngv[3];
-            for (int k = 0; k < 3; ++k) {
-                nv[k] = normalize_f32((float)s->qd[k], vhi, vlo);
-                ngv[k] = normalize_f32(goal_qd[k], vhi, vlo);
+            float nv[JP], ngv[JP];
+            for (int k = 0; k < J; ++k) {
+                nv[k] = normalize_f32((float)s->qd[k], v_hi(cfg, k), v_lo(cfg, k));
+                ngv[k] = normalize_f32(goal_qd[k], v_hi(cfg, k), v_lo(cfg, k));
             }
-            float d[3] = {nv[0] - ngv[0], nv[1] - ngv[1], nv[2] - ngv[2]};
-            double acc = 0.0;
-            for (int k = 0; k < 3; ++k) { float p = d[k] * d[k]; acc += (double)p; }
+            double acc = 0.0;   /* np.linalg.norm(float32 difference): no NaN guard at :99 */
+            for (int k = 0; k < J; ++k) { float d = nv[k] - ngv[k]; float p = d * d; acc += (double)p; }
             float v = sqrtf((float)acc);
             float e = expf(r32);
             float diff = r32 - e;
             r32 = (v + 1.0f) * diff;
             reward = r32;
         } else {
-            double nv[3], ngv[3];
-            for (int k = 0; k < 3; ++k) {
-                nv[k] = s->is64 ? normalize_f64(s->qd[k], vhi, vlo)
-                                : (double)normalize_f32((float)s->qd[k], vhi, vlo);
-                ngv[k] = goal_qd ? (double)normalize_f32(goal_qd[k], vhi, vlo)
-                                 : normalize_f64(0.0, vhi, vlo);
-            }
             double acc = 0.0;
-            for (int k = 0; k < 3; ++k) { double d = nv[k] - ngv[k]; acc += d * d; }
-            double v = sqrt(acc);                       /* np.linalg.norm, float64 */
+            for (int k = 0; k < J; ++k) {
+                double nv = s->is64 ? normalize_f64(s->qd[k], v_hi(cfg, k), v_lo(cfg, k))
+                                    : (double)normalize_f32((float)s->qd[k], v_hi(cfg, k), v_lo(cfg, k));
+                double ngv = goal_qd ? (double)normalize_f32(goal_qd[k], v_hi(cfg, k), v_lo(cfg, k))
+                                     : normalize_f64(0.0, v_hi(cfg, k), v_lo(cfg, k));
+                double d = nv - ngv;
+                acc = fma(d, d, acc);                   /* np.linalg.norm, float64: sequential FMA */
+            }
+            double v = sqrt(acc);
             double diff = r64 ? (reward - exp(reward)) : (double)(r32 - expf(r32));
             reward = (v + 1.0) * diff;
             r64 = 1;
@@ -283,32 +314,33 @@ static double compute_reward(const orc_cfg *cfg, const orc_state *s, const float
 
 /* roboy_env.py:24-25 + :127,:130 thresholds:  _l2_distance(low, high)/200 and /5, float32 */
 void orc_thresholds(const orc_cfg *cfg, float *thr_angle, float *thr_vel) {
-    float lo[3] = {cfg->angle_low, cfg->angle_low, cfg->angle_low};
-    float hi[3] = {cfg->angle_high, cfg->angle_high, cfg->angle_high};
-    *thr_angle = l2_f32(lo, hi) / 200.0f;
-    float vlo[3] = {cfg->vel_low, cfg->vel_low, cfg->vel_low};
-    float vhi[3] = {cfg->vel_high, cfg->vel_high, cfg->vel_high};
-    *thr_vel = l2_f32(vlo, vhi) / 5.0f;
+    const int J = cfg_J(cfg);
+    float lo[JP], hi[JP];
+    for (int k = 0; k < J; ++k) { lo[k] = a_lo(cfg, k); hi[k] = a_hi(cfg, k); }
+    *thr_angle = l2_f32(J, lo, hi) / 200.0f;
+    for (int k = 0; k < J; ++k) { lo[k] = v_lo(cfg, k); hi[k] = v_hi(cfg, k); }
+    *thr_vel = l2_f32(J, lo, hi) / 5.0f;
 }
 
 /* Stand-alone GoalEnv.compute_reward(current_state, goal_state) over float32 arrays
  * (roboy_env.py:92-112 as called from :40-49 and by the reference's tests).
- * q,qd,goal_q,goal_qd: [n][3] row-major; feasible: [n] bytes.  goal_qd may be NULL (= the
+ * q,qd,goal_q,goal_qd: [n][J] row-major; feasible: [n] bytes.  goal_qd may be NULL (= the
  * float64 zeros of roboy_env.py:23).  Outputs reward (double) and reached (byte). */
 void orc_compute_reward(const orc_cfg *cfg, uint64_t n, const float *q, const float *qd,
                         const uint8_t *feasible, const float *goal_q, const float *goal_qd,
                         double *reward, uint8_t *reached, uint8_t *violation) {
+    const int J = cfg_J(cfg);
     float ta, tv;
     orc_thresholds(cfg, &ta, &tv);
     for (uint64_t i = 0; i < n; ++i) {
         orc_state s;
-        for (int k = 0; k < 3; ++k) { s.q[k] = q[3 * i + k]; s.qd[k] = qd[3 * i + k]; }
+        for (int k = 0; k < J; ++k) { s.q[k] = q[J * i + k]; s.qd[k] = qd[J * i + k]; }
         s.is64 = 0;
         s.feasible = feasible ? feasible[i] : 1;
-        const float *gv = goal_qd ? goal_qd + 3 * i : NULL;
-        int r = did_reach_goal(cfg, &s, goal_q + 3 * i, gv, ta, tv);
+        const float *gv = goal_qd ? goal_qd + J * i : NULL;
+        int r = did_reach_goal(cfg, &s, goal_q + J * i, gv, ta, tv);
         int viol = 0;
-        reward[i] = compute_reward(cfg, &s, goal_q + 3 * i, gv, r, &viol);
+        reward[i] = compute_reward(cfg, &s, goal_q + J * i, gv, r, &viol);
         if (reached) reached[i] = (uint8_t)r;
         if (violation) violation[i] = (uint8_t)viol;
     }
@@ -316,7 +348,7 @@ void orc_compute_reward(const orc_cfg *cfg, uint64_t n, const float *q, const fl
 
 /* ------------------------------------------------------------------------------------------
  * Batched env state.  Layout mirrors the CUDA path's structure-of-arrays:
- *   goal[3][n] f32, step_flags[n] u32, held[6][n] f32 (q0..q2, qd0..qd2).
+ *   goal[J][n] f32, step_flags[n] u32, held[2J][n] f32 (q_0..q_{J-1}, qd_0..qd_{J-1}).
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     orc_cfg cfg;
@@ -331,25 +363,27 @@ typedef struct {
 } orc_env;
 
 orc_env *orc_create(const orc_cfg *cfg) {
+    const int J = cfg_J(cfg);
+    if (J > ORC_MAX_JOINT || cfg_A(cfg) > ORC_MAX_ACTION) return NULL;
     orc_env *e = (orc_env *)calloc(1, sizeof(orc_env));
     e->cfg = *cfg;
     orc_thresholds(cfg, &e->thr_angle, &e->thr_vel);
     uint64_t n = cfg->n_envs;
-    e->goal = (float *)calloc(3 * n + 1, sizeof(float));
+    e->goal = (float *)calloc((size_t)J * n + 1, sizeof(float));
     e->step_flags = (uint32_t *)calloc(n + 1, sizeof(uint32_t));
-    e->held = (float *)calloc(6 * n + 1, sizeof(float));
+    e->held = (float *)calloc((size_t)2 * J * n + 1, sizeof(float));
     e->first_bad_env = UINT64_MAX;
     e->t = 0;
     /* RoboyEnv.__init__ (roboy_env.py:12-38) over StubSimulationClient.__init__
      * (simulation_client.py:29-31): held state := random sample, goal := random, step_num = 1 */
     for (uint64_t i = 0; i < n; ++i) {
         uint64_t gid = cfg->env_id_base + i;
-        float q[3], qd[3], g[3];
+        float q[JP], qd[JP], g[JP];
         orc_draw_state(cfg, gid, 0, q, qd);
         orc_draw_goal(cfg, gid, 0, g);
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < J; ++k) {
             e->held[(size_t)k * n + i] = q[k];
-            e->held[(size_t)(3 + k) * n + i] = qd[k];
+            e->held[(size_t)(J + k) * n + i] = qd[k];
             e->goal[(size_t)k * n + i] = g[k];
         }
         e->step_flags[i] = 1u;
@@ -378,40 +412,43 @@ static void note_error(orc_env *e, uint32_t bits, uint64_t gid) {
 }
 
 /* RoboyEnv.reset() (roboy_env.py:82-87) over the Stub (simulation_client.py:42-44,33-34),
- * for envs with mask[i] != 0 (mask == NULL: all).  obs [n][9] rows are written for reset envs
+ * for envs with mask[i] != 0 (mask == NULL: all).  obs [n][3J] rows are written for reset envs
  * only (obs may be NULL). */
 void orc_reset(orc_env *e, const uint8_t *mask, float *obs) {
     const uint64_t n = e->cfg.n_envs;
+    const int J = cfg_J(&e->cfg), D = 3 * J;
     e->t += 1;
     for (uint64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
-        float g[3];
+        float g[JP];
         orc_draw_goal(&e->cfg, e->cfg.env_id_base + i, e->t, g);       /* :86 */
-        for (int k = 0; k < 3; ++k) e->goal[(size_t)k * n + i] = g[k];
+        for (int k = 0; k < J; ++k) e->goal[(size_t)k * n + i] = g[k];
         e->step_flags[i] = 1u | ORC_F_HELD_ZERO64;                      /* :83-85 */
         if (obs) {
-            for (int k = 0; k < 6; ++k) obs[9 * i + k] = 0.0f;          /* :87 */
-            for (int k = 0; k < 3; ++k) obs[9 * i + 6 + k] = g[k];
+            for (int k = 0; k < 2 * J; ++k) obs[D * i + k] = 0.0f;      /* :87 */
+            for (int k = 0; k < J; ++k) obs[D * i + 2 * J + k] = g[k];
         }
     }
 }
 
 /* RoboyEnv.step (roboy_env.py:51-70) / reset (:82-87) on states handed in by an external simulator
  * (RosSimulationClient's role, ros_simulation_client.py:40-60; wire values are float64 arrays).
- * q, qd [n][3] float32 values; feasible [n] or NULL; reset != 0: masked reset, obs carries the NEW goal. */
+ * q, qd [n][J] float32 values; feasible [n] or NULL; reset != 0: masked reset, obs carries the NEW goal. */
 void orc_external(orc_env *e, int reset, const uint8_t *mask, const float *q, const float *qd,
                   const uint8_t *feasible, float *obs, float *reward, uint8_t *done) {
     const orc_cfg *cfg = &e->cfg;
     const uint64_t n = cfg->n_envs;
+    const int J = cfg_J(cfg), D = 3 * J;
     e->t += 1;
     for (uint64_t i = 0; i < n; ++i) {
         if (reset && mask && !mask[i]) continue;
         const uint64_t gid = cfg->env_id_base + i;
         orc_state s;
-        for (int k = 0; k < 3; ++k) { s.q[k] = q[3 * i + k]; s.qd[k] = qd[3 * i + k]; }
+        for (int k = 0; k < J; ++k) { s.q[k] = q[J * i + k]; s.qd[k] = qd[J * i + k]; }
         s.is64 = 1;
         s.feasible = feasible ? feasible[i] != 0 : 1;
-        float g[3] = {e->goal[i], e->goal[n + i], e->goal[2 * n + i]};
+        float g[JP];
+        for (int k = 0; k < J; ++k) g[k] = e->goal[(size_t)k * n + i];
         uint32_t sf = e->step_flags[i];
         int new_goal = reset;
         if (!reset) {
@@ -429,16 +466,16 @@ void orc_external(orc_env *e, int reset, const uint8_t *mask, const float *q, co
             e->stats[ST_SUM_REWARD] += (double)(float)r;
             if (dn) { e->stats[ST_EPISODES] += 1.0; e->stats[reached ? ST_SUCCESSES : ST_TIMEOUTS] += 1.0; e->stats[ST_SUM_EPLEN] += (double)step - 1.0; }
             if (viol) { e->stats[ST_VIOLATIONS] += 1.0; note_error(e, ORC_ERR_REWARD_RANGE, gid); }
-            for (int k = 0; k < 3; ++k) { obs[9 * i + k] = (float)s.q[k]; obs[9 * i + 3 + k] = (float)s.qd[k]; obs[9 * i + 6 + k] = g[k]; }
+            for (int k = 0; k < J; ++k) { obs[D * i + k] = (float)s.q[k]; obs[D * i + J + k] = (float)s.qd[k]; obs[D * i + 2 * J + k] = g[k]; }
         } else {
             sf = 1u | (sf & ~ORC_STEP_MASK);
         }
         if (new_goal) {
             orc_draw_goal(cfg, gid, e->t, g);
-            for (int k = 0; k < 3; ++k) e->goal[(size_t)k * n + i] = g[k];
+            for (int k = 0; k < J; ++k) e->goal[(size_t)k * n + i] = g[k];
         }
         if (reset)
-            for (int k = 0; k < 3; ++k) { obs[9 * i + k] = (float)s.q[k]; obs[9 * i + 3 + k] = (float)s.qd[k]; obs[9 * i + 6 + k] = g[k]; }
+            for (int k = 0; k < J; ++k) { obs[D * i + k] = (float)s.q[k]; obs[D * i + J + k] = (float)s.qd[k]; obs[D * i + 2 * J + k] = g[k]; }
         e->step_flags[i] = sf;
     }
 }
@@ -462,49 +499,52 @@ static void step_range(step_job *j) {
     const orc_cfg *cfg = &e->cfg;
     const uint64_t n = cfg->n_envs;
     const uint64_t t = e->t;
+    const int J = cfg_J(cfg), A = cfg_A(cfg), D = 3 * J;
     const float in_hi = 1.0f, in_lo = -1.0f;                    /* roboy_env.py:31 */
-    const float slope = (cfg->act_high - cfg->act_low) / (in_hi - in_lo); /* :157 float32 */
+    float slope[ORC_MAX_ACTION];
+    for (int k = 0; k < A; ++k) slope[k] = (t_hi(cfg, k) - t_lo(cfg, k)) / (in_hi - in_lo); /* :157 float32, per component */
     for (uint64_t i = j->lo; i < j->hi; ++i) {
         const uint64_t gid = cfg->env_id_base + i;
-        const float *a = j->actions + 8 * i;
+        const float *a = j->actions + (size_t)A * i;
         uint32_t err = 0;
         /* :52 assert action_space.contains(action) -- closed interval, NaN fails */
         int ok = 1, hold = 1;
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < A; ++k) {
             if (!(a[k] >= in_lo && a[k] <= in_hi)) ok = 0;
             float r = a[k] - in_hi;                             /* :158 float32, unfused */
-            r = slope * r;
-            r = r + cfg->act_high;
+            r = slope[k] * r;
+            r = r + t_hi(cfg, k);
             /* simulation_client.py:38 np.allclose(list_of_py_floats, 0): |x| <= 1e-8, NaN/inf fail */
             if (!(fabs((double)r) <= 1e-8)) hold = 0;
         }
         if (!ok) err |= ORC_ERR_ACTION;
 
         uint32_t sf = e->step_flags[i];
-        float g[3] = {e->goal[i], e->goal[n + i], e->goal[2 * n + i]};
+        float g[JP];
+        for (int k = 0; k < J; ++k) g[k] = e->goal[(size_t)k * n + i];
         orc_state s;
         if (hold) {                                             /* simulation_client.py:38-39 */
             if (sf & ORC_F_HELD_ZERO64) {
-                for (int k = 0; k < 3; ++k) { s.q[k] = 0.0; s.qd[k] = 0.0; }
+                for (int k = 0; k < J; ++k) { s.q[k] = 0.0; s.qd[k] = 0.0; }
                 s.is64 = 1; s.feasible = 1;
             } else {
-                for (int k = 0; k < 3; ++k) {
+                for (int k = 0; k < J; ++k) {
                     s.q[k] = e->held[(size_t)k * n + i];
-                    s.qd[k] = e->held[(size_t)(3 + k) * n + i];
+                    s.qd[k] = e->held[(size_t)(J + k) * n + i];
                 }
                 s.is64 = 0; s.feasible = !(sf & ORC_F_HELD_INFEASIBLE);
             }
         } else {                                                /* :40 fresh sample, not stored */
-            float q[3], qd[3];
+            float q[JP], qd[JP];
             orc_draw_state(cfg, gid, t, q, qd);
-            for (int k = 0; k < 3; ++k) { s.q[k] = q[k]; s.qd[k] = qd[k]; }
+            for (int k = 0; k < J; ++k) { s.q[k] = q[k]; s.qd[k] = qd[k]; }
             s.is64 = 0; s.feasible = 1;
         }
         uint32_t step = (sf & ORC_STEP_MASK);
         if (step < ORC_STEP_MASK) step += 1;                    /* roboy_env.py:60 (saturating) */
 
-        float o[9];                                             /* :62 -> :75-80 */
-        for (int k = 0; k < 3; ++k) { o[k] = (float)s.q[k]; o[3 + k] = (float)s.qd[k]; o[6 + k] = g[k]; }
+        float o[3 * JP];                                        /* :62 -> :75-80 */
+        for (int k = 0; k < J; ++k) { o[k] = (float)s.q[k]; o[J + k] = (float)s.qd[k]; o[2 * J + k] = g[k]; }
 
         int reached = did_reach_goal(cfg, &s, g, NULL, e->thr_angle, e->thr_vel); /* :65 / :105 */
         int viol = 0;
@@ -515,16 +555,16 @@ static void step_range(step_job *j) {
 
         uint32_t flags = sf & ~ORC_STEP_MASK;
         if (done) {
-            float ng[3];
+            float ng[JP];
             /* :67-68 _set_new_goal(); under auto-reset the worker's reset() (:82-87) draws
              * again and only that second goal is observable, so one draw is materialised. */
             orc_draw_goal(cfg, gid, t, ng);
-            for (int k = 0; k < 3; ++k) e->goal[(size_t)k * n + i] = ng[k];
+            for (int k = 0; k < J; ++k) e->goal[(size_t)k * n + i] = ng[k];
             j->stats[ST_SUM_EPLEN] += (double)step - 1.0;   /* steps taken since reset(): step_num starts at 1 */
             if (cfg->auto_reset) {
-                if (j->terminal_obs) memcpy(j->terminal_obs + 9 * i, o, sizeof(o));
-                for (int k = 0; k < 6; ++k) o[k] = 0.0f;
-                for (int k = 0; k < 3; ++k) o[6 + k] = ng[k];
+                if (j->terminal_obs) memcpy(j->terminal_obs + (size_t)D * i, o, sizeof(float) * D);
+                for (int k = 0; k < 2 * J; ++k) o[k] = 0.0f;
+                for (int k = 0; k < J; ++k) o[2 * J + k] = ng[k];
                 step = 1;
                 flags = ORC_F_HELD_ZERO64;
             }
@@ -533,7 +573,7 @@ static void step_range(step_job *j) {
             else j->stats[ST_TIMEOUTS] += 1.0;
         }
         e->step_flags[i] = step | flags;
-        memcpy(j->obs + 9 * i, o, sizeof(o));
+        memcpy(j->obs + (size_t)D * i, o, sizeof(float) * D);
         j->reward[i] = (float)rew;
         j->done[i] = (uint8_t)done;
         j->stats[ST_STEPS] += 1.0;
@@ -550,7 +590,7 @@ static void step_range(step_job *j) {
 static void *step_thread(void *p) { step_range((step_job *)p); return NULL; }
 
 /* One batched step over all envs with `threads` host threads (>=1).
- * actions [n][8] f32; obs [n][9] f32; reward [n] f32; done [n] u8; terminal_obs [n][9] or NULL */
+ * actions [n][A] f32; obs [n][3J] f32; reward [n] f32; done [n] u8; terminal_obs [n][3J] or NULL */
 void orc_step(orc_env *e, const float *actions, float *obs, float *reward, uint8_t *done,
               float *terminal_obs, int threads) {
     const uint64_t n = e->cfg.n_envs;

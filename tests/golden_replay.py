@@ -14,8 +14,12 @@ REWARD_RTOL = 1e-6   # north_star: within 1e-6 relative for fp32 observations an
 def load(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     fx = {k: z[k] for k in z.files}
-    N, T, seed, pen, bonus, auto = fx["meta"].tolist()
-    fx.update(N=N, T=T, seed=seed, joint_vel_penalty=bool(pen), bonus=bool(bonus), auto_reset=bool(auto))
+    meta = fx["meta"].tolist()
+    N, T, seed, pen, bonus, auto = meta[:6]
+    J, A = (meta[6], meta[7]) if len(meta) >= 8 else (3, 8)
+    fx.update(N=N, T=T, seed=seed, joint_vel_penalty=bool(pen), bonus=bool(bonus), auto_reset=bool(auto), J=J, A=A)
+    # robots other than MSJ carry their spaces (per component) in the fixture
+    fx["bounds"] = {k[len("robot_"):]: fx[k] for k in fx if isinstance(k, str) and k.startswith("robot_")} or None
     return fx
 
 
@@ -43,12 +47,13 @@ def replay(fx, impl: Adaptor):
     for t in range(T):
         for row in by_step.get(t, []):
             e, kind, p = int(row[1]), int(row[2]), row[3:].astype(np.float32)
+            J = fx["J"]
             if kind == EV_SET_GOAL:
-                impl.set_goal(e, p[0:3])
+                impl.set_goal(e, p[0:J])
             elif kind == EV_SET_STATE:
-                impl.set_state(e, p[0:3], p[3:6], bool(p[6]))
+                impl.set_state(e, p[0:J], p[J:2 * J], bool(p[2 * J]))
             else:
-                impl.set_step_num(e, int(p[6]))
+                impl.set_step_num(e, int(p[2 * J]))
         obs, reward, done, term = impl.step(fx["actions"][t])
         ok = fx["valid"][t]   # envs whose reference instance has not raised so far
         assert np.array_equal(done[ok], fx["done"][t][ok]), "done mask, step %d" % t

@@ -6,8 +6,10 @@ from oracle import oracle as orc
 
 class OracleAdaptor(Adaptor):
     def __init__(self, fx, **kw):
+        kw = dict(kw, **(fx.get("bounds") or {}))
         self.env = orc.OracleEnv(fx["N"], seed=fx["seed"], joint_vel_penalty=fx["joint_vel_penalty"],
                                  bonus=fx["bonus"], auto_reset=fx["auto_reset"], **kw)
+        self.J = self.env.J
 
     def goals(self):
         return self.env.goal.T.copy()
@@ -19,8 +21,8 @@ class OracleAdaptor(Adaptor):
         self.env.goal[:, e] = g
 
     def set_state(self, e, q, qd, feasible):
-        self.env.held[0:3, e] = q
-        self.env.held[3:6, e] = qd
+        self.env.held[0:self.J, e] = q
+        self.env.held[self.J:2 * self.J, e] = qd
         sf = int(self.env.step_flags[e]) & orc.STEP_MASK
         self.env.step_flags[e] = sf | (0 if feasible else orc.F_HELD_INFEASIBLE)
 

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_cfg_struct_and_msj_constants():
     lib = _native.load()
     cfg = _native.RoboyCfg()
-    assert ctypes.sizeof(cfg) == 88
+    assert ctypes.sizeof(cfg) == 88 + 16 + 4 * 4 * _native.JOINT_PAD + 2 * 4 * _native.MAX_ACTION
     _native.check(lib.roboy_cfg_msj(ctypes.byref(cfg)))
     # float32 bounds of msj_robot.py:9,10,16 (hex from SURVEY.md 8a a13)
     assert float(cfg.angle_high).hex() == "0x1.921fb60000000p+1" and cfg.angle_low == -cfg.angle_high
@@ -41,6 +41,30 @@ def test_cfg_struct_and_msj_constants():
     assert float(cfg.act_high).hex() == "0x1.3333340000000p-2" and cfg.act_low == -cfg.act_high
     assert (cfg.max_episode_len, cfg.joint_vel_penalty, cfg.bonus_for_goal, cfg.auto_reset) == (400, 0, 1, 1)
     assert (cfg.penalty_boundary, cfg.bonus_goal) == (1.0, 1000.0)
+    assert (cfg.dim_joint, cfg.dim_action, cfg.per_component_bounds) == (3, 8, 0)
+    assert list(cfg.angle_high_v)[:3] == [cfg.angle_high] * 3 and list(cfg.act_low_v)[:8] == [cfg.act_low] * 8
+
+
+def test_hold_intervals_per_tendon_and_robot_caps():
+    lib = _native.load()
+    cfg = _native.RoboyCfg()
+    lib.roboy_cfg_msj(ctypes.byref(cfg))
+    lo, hi = (ctypes.c_float * 64)(), (ctypes.c_float * 64)()
+    _native.check(lib.roboy_hold_intervals(ctypes.byref(cfg), lo, hi))
+    assert all(lo[k] == -(2.0 ** -24) and hi[k] == 2.0 ** -25 for k in range(8))     # SURVEY.md 8a a4 [probe]
+    cfg.per_component_bounds, cfg.dim_action = 1, 3
+    for k, (a, b) in enumerate(((-0.3, 0.3), (-0.1, 0.4), (-0.5, 0.25))):
+        cfg.act_low_v[k], cfg.act_high_v[k] = a, b
+    _native.check(lib.roboy_hold_intervals(ctypes.byref(cfg), lo, hi))
+    assert lo[0] == -(2.0 ** -24) and hi[0] == 2.0 ** -25
+    for k in (1, 2):   # asymmetric tendon ranges hold around the action that rescales to zero, if any float32 does
+        zero = 1 - 2 * cfg.act_high_v[k] / (cfg.act_high_v[k] - cfg.act_low_v[k])
+        assert lo[k] > hi[k] or (lo[k] <= hi[k] and abs(lo[k] - zero) < 1e-6 and abs(hi[k] - zero) < 1e-6)
+    cfg.dim_joint = 16
+    h = ctypes.c_void_p()
+    assert lib.roboy_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1 and b"dim_joint" in lib.roboy_last_error()
+    cfg.dim_joint, cfg.dim_action = 3, 65
+    assert lib.roboy_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1 and b"dim_action" in lib.roboy_last_error()
 
 
 def test_argument_errors_are_reported_not_crashed():

@@ -1,0 +1,241 @@
+"""robots with other joint / tendon counts and one bound per component (roboy_robot.py:21-33,
+README.md:6-7 "MSJ platform, Upper Body, etc.") on the generic kernels -- CUDA against the CPU oracle, which
+tests/test_oracle_vs_reference.py pins against the unmodified reference for the same robots."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cuda_adaptor import robot_from_bounds
+from oracle import oracle as orc
+from test_oracle_vs_reference import GENERIC_ROBOTS
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+def make_pair(b, n, seed, penalty=False, auto_reset=True, env_id_base=0):
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    client = CudaSimulationClient(robot=robot_from_bounds(b), num_envs=n, seed=seed, env_id_base=env_id_base, device="cuda:0")
+    env = RoboyEnv(client, joint_vel_penalty=penalty, auto_reset=auto_reset, strict=False)
+    env._single = False
+    ora = orc.OracleEnv(n, seed=seed, env_id_base=env_id_base, joint_vel_penalty=penalty, auto_reset=auto_reset, threads=8, **b)
+    return env, client, ora
+
+
+def set_phases(client, ora, steps):
+    client.set_step_num(steps)
+    ora.step_flags[:] = (ora.step_flags & ~np.uint32(orc.STEP_MASK)) | steps.astype(np.uint32)
+
+
+def compare_step(env, client, ora, a, t):
+    obs, rew, done, _ = env.step(torch.as_tensor(a, device="cuda:0"))
+    o_obs, o_rew, o_done = ora.step(a)
+    assert np.array_equal(done.cpu().numpy(), o_done), "done mask differs at step %d" % t
+    assert np.array_equal(obs.cpu().numpy(), o_obs), "obs differ at step %d" % t
+    rel = np.abs(rew.cpu().numpy().astype(np.float64) - o_rew) / np.maximum(np.abs(o_rew.astype(np.float64)), 1e-30)
+    assert rel.max() <= RTOL, "reward rel err %g at step %d" % (rel.max(), t)
+    return o_done
+
+
+@pytest.mark.parametrize("penalty", [False, True])
+@pytest.mark.parametrize("name", sorted(GENERIC_ROBOTS))
+def test_generic_robot_rollout_matches_oracle(name, penalty):
+    b = GENERIC_ROBOTS[name]
+    J, A, _, bb = orc.robot_bounds(b)
+    n, T, seed = 4096, 430, 6
+    env, client, ora = make_pair(b, n, seed, penalty)
+    assert not client.msj_kernels and (client.dim_joint, client.dim_action, client.dim_obs) == (J, A, 3 * J)
+    assert client.obs.shape == (n, 3 * J) and client.goal.shape == (J, n) and client.held.shape == (2 * J, n)
+    assert np.allclose(env.reward_range, ora.reward_range, rtol=RTOL, atol=0)
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal) and np.array_equal(client.held.cpu().numpy(), ora.held)
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset())
+    rng = np.random.default_rng(2)
+    zero_action, can_hold = orc.hold_action(b)
+    set_phases(client, ora, rng.integers(1, 400, n).astype(np.int32))
+    client.enable_done_index(True)
+    thr_a, _ = orc.thresholds(ora.cfg)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (n, A)).astype(np.float32)
+        hold = rng.random(n) < 0.03
+        a[hold] = zero_action
+        a[rng.random(n) < 0.01] = np.nextafter(zero_action, np.float32(1))   # right next to the hold interval
+        if t % 40 == 5:     # goals around the next state (sampled rows) / the held zero state (hold rows), both sides of the threshold
+            q, _ = orc.draw_state(seed, np.arange(n), ora.counter + 1, bb["angle_low"], bb["angle_high"], J=J)
+            d = rng.normal(size=(n, J)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+            r = float(thr_a) * (1 + rng.choice([-1e-7, 1e-7, -0.3, 0.2], n))
+            base = np.where(hold[:, None], 0.0, q.astype(np.float64))
+            g = np.clip(base + d * r[:, None], bb["angle_low"], bb["angle_high"]).astype(np.float32)
+            client.set_goal(g); ora.goal[:] = g.T
+        if t % 60 == 20:    # injected float32 held states, some infeasible
+            q = rng.uniform(bb["angle_low"], bb["angle_high"], (n, J)).astype(np.float32)
+            qd = (rng.uniform(bb["vel_low"], bb["vel_high"], (n, J)) * 0.2).astype(np.float32)
+            feas = rng.random(n) < 0.6
+            client.set_state(q, qd, feas.astype(np.uint8))
+            ora.held[0:J] = q.T; ora.held[J:2 * J] = qd.T
+            ora.step_flags[:] = (ora.step_flags & np.uint32(orc.STEP_MASK)) | np.where(feas, 0, orc.F_HELD_INFEASIBLE).astype(np.uint32)
+        od = compare_step(env, client, ora, a, t)
+        if t % 50 == 0:
+            assert np.array_equal(client.done_indices()[0].cpu().numpy(), np.flatnonzero(od).astype(np.int32))
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+    assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
+    s, so = client.stats(), ora.stats()
+    for k in ("steps", "episodes", "successes", "timeouts", "sum_episode_len", "holds", "violations"):
+        assert s[k] == so[k], (k, s[k], so[k])
+    assert abs(s["sum_reward"] - so["sum_reward"]) <= 1e-6 * abs(so["sum_reward"])
+    assert s["timeouts"] > n * 0.9 and (s["holds"] > 0) == can_hold
+    assert client.errors()[0] == ora.errors()[0]
+    if client.errors()[0]:
+        assert client.errors()[1] == ora.errors()[1]
+
+
+def test_which_robots_run_the_tuned_kernels():
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    msj_like = dict(angle_low=-2.0, angle_high=2.0, vel_low=-0.7, vel_high=0.7, act_low=-0.5, act_high=0.5)
+    assert CudaSimulationClient(num_envs=64, seed=1, device="cuda:0").msj_kernels
+    assert CudaSimulationClient(robot=robot_from_bounds(msj_like), num_envs=64, seed=1, device="cuda:0").msj_kernels
+    for name in GENERIC_ROBOTS:
+        assert not CudaSimulationClient(robot=robot_from_bounds(GENERIC_ROBOTS[name]), num_envs=64, seed=1, device="cuda:0").msj_kernels
+    with pytest.raises(ValueError, match="joints"):
+        CudaSimulationClient(robot=robot_from_bounds(dict(dim_joint=16, dim_action=8)), num_envs=4, device="cuda:0")
+
+
+@pytest.mark.parametrize("penalty", [False, True])
+def test_msj_through_the_generic_kernels_equals_the_tuned_kernels(penalty):
+    """The tuned MSJ kernels are an instantiation of the generic path: same seed, same actions -> the same bits
+    (rewards included: the 3-instruction division is proved identical to IEEE division)."""
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    n, T = 40_001, 30
+    tuned_c = CudaSimulationClient(num_envs=n, seed=3, device="cuda:0")
+    os.environ["ROBOY_B200_FORCE_GENERIC"] = "1"
+    try:
+        gen_c = CudaSimulationClient(num_envs=n, seed=3, device="cuda:0")
+    finally:
+        del os.environ["ROBOY_B200_FORCE_GENERIC"]
+    assert tuned_c.msj_kernels and not gen_c.msj_kernels
+    tuned, gen = RoboyEnv(tuned_c, joint_vel_penalty=penalty, strict=False), RoboyEnv(gen_c, joint_vel_penalty=penalty, strict=False)
+    assert torch.equal(tuned.reset(), gen.reset())
+    steps = (np.arange(n) % 400 + 1).astype(np.int32)
+    tuned_c.set_step_num(steps); gen_c.set_step_num(steps)
+    rng = np.random.default_rng(0)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        a[rng.random(n) < 0.05] = 0.0
+        a_dev = torch.as_tensor(a, device="cuda:0")
+        o1, r1, d1, _ = tuned.step(a_dev)
+        o2, r2, d2, _ = gen.step(a_dev)
+        assert torch.equal(o1, o2) and torch.equal(d1, d2) and torch.equal(r1, r2), t
+    assert torch.equal(tuned_c.goal, gen_c.goal) and torch.equal(tuned_c.step_flags, gen_c.step_flags)
+    s1, s2 = tuned_c.stats(), gen_c.stats()
+    for k in s1:
+        assert s1[k] == s2[k] if k != "sum_reward" else abs(s1[k] - s2[k]) <= 1e-9 * abs(s2[k]), k
+
+
+def test_generic_robot_host_path_step_many_unfused_calls_and_external_feed():
+    b = GENERIC_ROBOTS["five_joints_11_tendons_per_component"]
+    J, A, _, bb = orc.robot_bounds(b)
+    n, seed = 70_003, 11
+    env, client, ora = make_pair(b, n, seed)
+    env2, client2, _ = make_pair(b, n, seed)
+    env.reset(); env2.reset(); ora.reset()
+    steps = (np.arange(n) % 400 + 1).astype(np.int32)
+    set_phases(client, ora, steps); client2.set_step_num(steps)
+    rng = np.random.default_rng(4)
+    zero_action, _ = orc.hold_action(b)
+    # ---- host buffers (several stages, ragged) ----
+    client.set_host_pipeline(stage_envs=1 << 14, n_streams=2)
+    a_h, obs_h, rew_h, done_h = client.host_buffers()
+    for t in range(2):
+        a = rng.uniform(-1, 1, (n, A)).astype(np.float32); a[rng.random(n) < 0.05] = zero_action
+        a_h[...] = a
+        client.step_host(a_h, obs_h, rew_h, done_h)
+        o, r, d = ora.step(a)
+        assert np.array_equal(obs_h, o) and np.array_equal(done_h.astype(bool), d) and np.allclose(rew_h, r, rtol=RTOL, atol=0)
+        client2.step_fused(torch.as_tensor(a, device="cuda:0"))
+    # ---- T steps in one call (generic robots: T launches) ----
+    acts = rng.uniform(-1, 1, (3, n, A)).astype(np.float32)
+    obs, rew, done = client.step_many(torch.as_tensor(acts, device="cuda:0"))
+    for t in range(3):
+        o, r, d = ora.step(acts[t])
+        assert np.array_equal(obs[t].cpu().numpy(), o) and np.array_equal(done[t].cpu().numpy().astype(bool), d)
+    assert client.counter == ora.counter == 1 + 2 + 3
+    # ---- external feed ----
+    q = rng.uniform(bb["angle_low"], bb["angle_high"], (n, J)).astype(np.float32)
+    qd = (rng.uniform(bb["vel_low"], bb["vel_high"], (n, J)) * 0.3).astype(np.float32)
+    feas = (rng.random(n) < 0.8).astype(np.uint8)
+    client.set_goal(np.clip(q + np.float32(0.002), bb["angle_low"], bb["angle_high"]).astype(np.float32), idx=np.arange(0, n, 3))
+    ora.goal[:, ::3] = np.clip(q + np.float32(0.002), bb["angle_low"], bb["angle_high"]).astype(np.float32)[::3].T
+    client.step_external(q, qd, feas)
+    o, r, d = ora.step_external(q, qd, feas)
+    assert np.array_equal(client.obs.cpu().numpy(), o) and np.array_equal(client.done.cpu().numpy(), d)
+    assert np.allclose(client.reward.cpu().numpy(), r, rtol=RTOL, atol=0) and d.sum() > n // 10
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+    client.reset_external(q, qd, mask=d.astype(np.uint8))
+    assert np.array_equal(client.obs.cpu().numpy()[d], ora.reset_external(q, qd, d.astype(np.uint8))[d])
+
+
+def test_generic_robot_unfused_plugin_calls_reproduce_the_fused_env():
+    b = GENERIC_ROBOTS["six_joints_14_tendons"]
+    J, A, _, bb = orc.robot_bounds(b)
+    n, T, seed = 3000, 25, 77
+    fused_env, fused_client, _ = make_pair(b, n, seed, auto_reset=False)
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    plug = CudaSimulationClient(robot=fused_client.robot, num_envs=n, seed=seed, device="cuda:0")
+    hi, lo = bb["act_high"], bb["act_low"]
+    slope = ((hi - lo) / np.float32(2.0)).astype(np.float32)
+
+    def plug_reset(mask=None):
+        state = plug.forward_reset_command(mask)
+        goal = plug.get_new_goal_joint_angles()
+        idx = None if mask is None else torch.nonzero(torch.as_tensor(mask)).flatten()
+        plug.set_goal(goal if idx is None else goal[idx.to(goal.device)], idx=idx)
+        return state
+
+    assert torch.equal(fused_client.goal, plug.goal) and torch.equal(fused_client.held, plug.held)
+    assert torch.equal(plug.get_new_goal_joint_angles().t(), fused_client.goal)      # first goal asked = construction goal
+    fused_env.reset(); plug_reset()
+    assert torch.equal(fused_client.goal, plug.goal)
+    fused_client.set_step_num(np.full(n, 395, np.int32))
+    rng = np.random.default_rng(0)
+    zero_action, _ = orc.hold_action(b)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (n, A)).astype(np.float32)
+        a[rng.random(n) < 0.1] = zero_action
+        obs, _, done, _ = fused_env.step(torch.as_tensor(a, device="cuda:0"))
+        rescaled = (slope * (a - np.float32(1.0))).astype(np.float32) + hi            # roboy_env.py:54-57,157-158
+        state = plug.forward_step_command(torch.as_tensor(rescaled))
+        assert torch.equal(state.joint_angles, obs[:, 0:J]) and torch.equal(state.joint_vels, obs[:, J:2 * J])
+        assert torch.equal(obs[:, 2 * J:], plug.goal.t())
+        d = done.cpu().numpy()
+        if d.any():
+            idx = torch.nonzero(done).flatten()
+            plug.set_goal(plug.get_new_goal_joint_angles()[idx], idx=idx)
+            assert torch.equal(fused_client.goal, plug.goal)
+            fused_env.reset(mask=done.to(torch.uint8)); plug_reset(d.astype(np.uint8))
+            assert torch.equal(fused_client.goal, plug.goal)
+    assert fused_client.counter == plug.counter and fused_client.stats()["holds"] == plug.stats()["holds"] > 0
+
+
+def test_vec_env_adapter_with_another_robot():
+    from gym_roboy_b200.vec_env import RoboyVecEnv
+    b = GENERIC_ROBOTS["six_joints_14_tendons"]
+    n = 500
+    venv = RoboyVecEnv(n, seed=4, robot=robot_from_bounds(b))
+    ora = orc.OracleEnv(n, seed=4, **b)
+    obs = venv.reset()
+    assert obs.shape == (n, 18) and np.array_equal(obs, ora.reset())
+    assert venv.observation_space.shape == (18,) and venv.action_space.shape == (14,)
+    venv.client.set_step_num(np.full(n, 399, np.int32))
+    ora.step_flags[:] = (ora.step_flags & ~np.uint32(orc.STEP_MASK)) | np.uint32(399)
+    rng = np.random.default_rng(0)
+    for t in range(3):
+        a = rng.uniform(-1, 1, (n, 14)).astype(np.float32)
+        obs, rew, done, infos = venv.step(a)
+        o, r, d, term = ora.step(a, want_terminal_obs=True)
+        assert np.array_equal(obs, o) and np.array_equal(done, d) and np.allclose(rew, r, rtol=1e-6, atol=0)
+        for i in np.flatnonzero(d):
+            assert np.array_equal(infos[i]["terminal_observation"], term[i])
+    venv.close()

@@ -123,3 +123,82 @@ def test_other_robot_bounds_match_reference(name):
         assert np.allclose(orw[alive], rr[alive], rtol=1e-6, atol=0)
         assert np.array_equal(ref.goals()[alive], o.goal.T[alive])
     assert o.stats()["episodes"] >= N and o.stats()["holds"] > 0
+
+
+# Robots with other joint / tendon counts and per-component bounds (roboy_robot.py:21-33,
+# README.md:6-7 "Upper Body, etc."): synthetic RoboyRobot subclasses of the REFERENCE drive the unmodified RoboyEnv.
+GENERIC_ROBOTS = {
+    "six_joints_14_tendons": dict(dim_joint=6, dim_action=14, angle_low=-2.5, angle_high=2.5, vel_low=-0.6, vel_high=0.6,
+                                  act_low=-0.2, act_high=0.2),
+    "per_component_msj_dims": dict(angle_low=[-3.0, -1.5, -0.5], angle_high=[3.0, 2.0, 2.5],
+                                   vel_low=[-0.5, -0.25, -1.0], vel_high=[0.5, 0.75, 1.0],
+                                   act_low=[-0.3, -0.1, -0.2, -0.3, -0.05, -0.4, -0.3, -0.25],
+                                   act_high=[0.3, 0.4, 0.2, 0.1, 0.05, 0.4, 0.6, 0.25]),
+    "five_joints_11_tendons_per_component": dict(
+        angle_low=[-3.1, -1.0, -2.0, -0.7, -1.3], angle_high=[3.1, 1.0, 2.5, 0.9, 1.3],
+        vel_low=[-0.5, -0.4, -0.3, -0.2, -0.1], vel_high=[0.5, 0.4, 0.6, 0.2, 0.3],
+        act_low=-np.linspace(0.1, 0.6, 11), act_high=np.linspace(0.15, 0.5, 11)),
+    "fifteen_joints_64_tendons": dict(dim_joint=15, dim_action=64, angle_low=-np.linspace(1.0, 3.0, 15),
+                                      angle_high=np.linspace(0.5, 3.1, 15), vel_low=-0.5, vel_high=0.5,
+                                      act_low=-0.3, act_high=np.linspace(0.1, 0.9, 64)),
+}
+
+
+generic_zero_action = orc.hold_action
+
+
+@pytest.mark.parametrize("penalty", [False, True])
+@pytest.mark.parametrize("name", sorted(GENERIC_ROBOTS))
+def test_generic_robots_match_reference(name, penalty):
+    b = GENERIC_ROBOTS[name]
+    J, A, _, bb = orc.robot_bounds(b)
+    N, T = 6, 140
+    ref = rh.ReferenceVecEnv(N, seed=5, bounds=b, joint_vel_penalty=penalty)
+    o = orc.OracleEnv(N, seed=5, joint_vel_penalty=penalty, **b)
+    assert (o.J, o.A) == (J, A) and ref.obs_dim == 3 * J
+    assert np.allclose(ref.reward_range, o.reward_range, rtol=1e-6, atol=0)
+    assert np.array_equal(ref.goals().T, o.goal)
+    assert np.array_equal(ref.reset().astype(np.float32), o.reset())
+    for i in range(N):
+        ref.set_step_num(i, 300 + 17 * i)
+    o.step_flags[:] = (o.step_flags & ~np.uint32(orc.STEP_MASK)) | (300 + 17 * np.arange(N)).astype(np.uint32)
+    rng = np.random.default_rng(3)
+    alive = np.ones(N, bool)
+    zero_action, can_hold = generic_zero_action(b)
+    thr_a, thr_v = orc.thresholds(o.cfg)
+    reached = 0
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, A)).astype(np.float32)
+        hold = rng.random(N) < 0.25
+        a[hold] = zero_action
+        a[rng.random(N) < 0.05] = np.nextafter(zero_action, np.float32(1))     # right next to the hold interval
+        if t % 9 == 4:
+            # near-threshold goals: around the held float64 zero state (hold rows) and around the next sampled state
+            q, _ = orc.draw_state(5, np.arange(N), o.counter + 1, bb["angle_low"], bb["angle_high"], J=J)
+            d = rng.normal(size=(N, J)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+            r = float(thr_a) * (1 + rng.choice([-1e-7, 1e-7, -0.3, 0.2], N))
+            base = np.where(hold[:, None], 0.0, q.astype(np.float64))
+            g = np.clip(base + d * r[:, None], bb["angle_low"], bb["angle_high"]).astype(np.float32)
+            for i in range(N):
+                ref.set_goal(i, g[i])
+            o.goal[:] = g.T
+        if t % 20 == 7:   # an injected float32 held state, some infeasible
+            for i in range(N):
+                q = rng.uniform(bb["angle_low"], bb["angle_high"]).astype(np.float32)
+                qd = rng.uniform(bb["vel_low"], bb["vel_high"]).astype(np.float32) * np.float32(0.2)
+                feas = bool(rng.random() < 0.6)
+                ref.set_state(i, q, qd, feas)
+                o.held[0:J, i] = q; o.held[J:2 * J, i] = qd
+                o.step_flags[i] = (int(o.step_flags[i]) & orc.STEP_MASK) | (0 if feas else orc.F_HELD_INFEASIBLE)
+        ro, rr, rd, rt, raised = ref.step(a)
+        oo, orw, od, ot = o.step(a, want_terminal_obs=True)
+        alive &= np.array([m == "" for m in raised])
+        assert np.array_equal(ro.astype(np.float32)[alive], oo[alive]), t
+        assert np.array_equal(rd[alive], od[alive]), t
+        assert np.allclose(orw[alive], rr[alive], rtol=1e-6, atol=0), t
+        assert np.array_equal(rt.astype(np.float32)[alive & rd], ot[alive & rd]), t
+        assert np.array_equal(ref.goals()[alive], o.goal.T[alive])
+        assert np.array_equal(ref.step_nums()[alive], o.step_num[alive])
+        reached += int((rd & (rr > 500) & alive).sum())
+    assert o.stats()["episodes"] >= N and (o.stats()["holds"] > 0) == can_hold and alive.sum() >= (1 if penalty else N)
+    assert penalty or reached > 0 or not can_hold   # (a robot that can never hold reaches goals only by sampling)
