@@ -166,8 +166,9 @@ def test_generic_robot_host_path_step_many_unfused_calls_and_external_feed():
     q = rng.uniform(bb["angle_low"], bb["angle_high"], (n, J)).astype(np.float32)
     qd = (rng.uniform(bb["vel_low"], bb["vel_high"], (n, J)) * 0.3).astype(np.float32)
     feas = (rng.random(n) < 0.8).astype(np.uint8)
-    client.set_goal(np.clip(q + np.float32(0.002), bb["angle_low"], bb["angle_high"]).astype(np.float32), idx=np.arange(0, n, 3))
-    ora.goal[:, ::3] = np.clip(q + np.float32(0.002), bb["angle_low"], bb["angle_high"]).astype(np.float32)[::3].T
+    near = np.clip(q + np.float32(0.002), bb["angle_low"], bb["angle_high"]).astype(np.float32)
+    client.set_goal(near[::3], idx=np.arange(0, n, 3))
+    ora.goal[:, ::3] = near[::3].T
     client.step_external(q, qd, feas)
     o, r, d = ora.step_external(q, qd, feas)
     assert np.array_equal(client.obs.cpu().numpy(), o) and np.array_equal(client.done.cpu().numpy(), d)
