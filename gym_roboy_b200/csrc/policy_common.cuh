@@ -142,7 +142,7 @@ __device__ __forceinline__ void sample_and_step(const StepParams &p, const Polic
     row[0] = q0; row[1] = q1; row[2] = q2; row[3] = qd0; row[4] = qd1; row[5] = qd2;
     row[6] = g0; row[7] = g1; row[8] = g2;
     if (done && live) {
-        const uint32_t r = finish_episode(p, t, env, step, reached, AUTO_RESET, row, s_cnt);
+        const uint32_t r = finish_episode(episode_end(p, t, env, step, reached, AUTO_RESET, row, s_cnt));
         word = (r & 0x80000000u) ? word : (r | ROBOY_F_HELD_ZERO64);
         s.g0 = p.goal[env];   // the new goal was stored by finish_episode (same thread)
         s.g1 = p.goal1[env];

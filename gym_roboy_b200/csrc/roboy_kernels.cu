@@ -51,6 +51,9 @@ namespace roboy {
 #define ROBOY_DEFER_DONE 0  // 1: queue finished envs in shared memory and resample their goals at the end of the CTA (measured SLOWER:
                             // 0.2606 vs 0.2563 ms per 16,777,216-env step with 1/400 of the envs finishing -- the pass is a serial tail)
 #endif
+#ifndef ROBOY_FAST_ACTION_TEST
+#define ROBOY_FAST_ACTION_TEST 1  // one NaN-propagating max-abs per float4 + warp votes; per-env ballots only when needed
+#endif
 #ifndef ROBOY_LD_HINT
 #define ROBOY_LD_HINT 0  // streamed inputs:  0 default (measured best: +3% over .cs), 1 ld.global.cs, 2 ld.global.nc.L1::no_allocate
 #endif
@@ -82,9 +85,9 @@ __device__ __forceinline__ void st_stream(T *p, const T &v) {
 #endif
 }
 
-// One chunk's inputs: 32 envs = 1 KiB of actions (2 x float4 per lane), goal, step word.
+// One chunk's state inputs (32 envs): goal and step word.  The chunk's 1 KiB of actions travels separately (Actions2):
+// the actions are only ever reduced to two verdicts per env (in range? hold?).
 struct ChunkIn {
-    float4 a0, a1;
     float g0, g1, g2;
     uint32_t sf;
     float ng0, ng1, ng2;  // normalised goal; only maintained by the open-loop kernel (KEEP_STATE)
@@ -93,13 +96,10 @@ struct ChunkIn {
 // Local env indices are 32-bit (a shard holds < 2^32 envs: 4 Gi envs would need 400 GB of HBM);
 // only the Philox counter uses the 64-bit global id.
 template <bool TAIL>
-__device__ __forceinline__ ChunkIn load_chunk(const StepParams &p, uint32_t base, int lane) {
+__device__ __forceinline__ ChunkIn load_state(const StepParams &p, uint32_t base, int lane) {
     ChunkIn in;
-    const float4 *a4 = reinterpret_cast<const float4 *>(p.actions) + (size_t)base * 2;
     const uint32_t e = base + lane;
     if (!TAIL) {
-        in.a0 = ld_stream(a4 + lane);  // streamed once
-        in.a1 = ld_stream(a4 + 32 + lane);
 #ifdef ROBOY_EXPERIMENT_SKIP_GOAL
         in.g0 = in.g1 = in.g2 = 0.25f;
 #else
@@ -114,9 +114,6 @@ __device__ __forceinline__ ChunkIn load_chunk(const StepParams &p, uint32_t base
 #endif
     } else {  // ragged tail: out-of-range slots read as neutral values
         const uint32_t n_end = (uint32_t)p.e_end;
-        const float4 z = make_float4(0.5f, 0.5f, 0.5f, 0.5f);  // in range, not "close to zero"
-        in.a0 = (base * 2 + lane < n_end * 2) ? ld_stream(a4 + lane) : z;
-        in.a1 = (base * 2 + 32 + lane < n_end * 2) ? ld_stream(a4 + 32 + lane) : z;
         const bool live = e < n_end;
         in.g0 = live ? p.goal[e] : 0.f;
         in.g1 = live ? p.goal1[e] : 0.f;
@@ -137,7 +134,7 @@ __device__ __forceinline__ Actions2 load_actions(const float *actions, uint32_t 
         a.a0 = ld_stream(a4 + lane);
         a.a1 = ld_stream(a4 + 32 + lane);
     } else {
-        const float4 z = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+        const float4 z = make_float4(0.5f, 0.5f, 0.5f, 0.5f);  // ragged tail: in range, not "close to zero"
         a.a0 = (base * 2 + lane < n_end * 2) ? ld_stream(a4 + lane) : z;
         a.a1 = (base * 2 + 32 + lane < n_end * 2) ? ld_stream(a4 + 32 + lane) : z;
     }
@@ -167,6 +164,24 @@ struct L2Prefetch {
         ptr += inc;
     }
 };
+
+// max(|x|, |y|, |z|, |w|) that PROPAGATES NaN (fmaxf would drop it): one value answers both the range assert of
+// roboy_env.py:52 (m <= 1; false for NaN) and the pre-filter of the hold test (m <= hold_mag).  Two FMNMX in SASS.
+__device__ __forceinline__ float maxabs4_nan(const float4 &v) {
+    float m;
+    asm("{\n\t.reg .f32 ax, ay, az, aw, t;\n\t"
+        "abs.f32 ax, %1;\n\tabs.f32 ay, %2;\n\tabs.f32 az, %3;\n\tabs.f32 aw, %4;\n\t"
+        "max.NaN.f32 t, az, aw;\n\t"
+        "max.NaN.f32 %0, ax, ay, t;\n\t}"
+        : "=f"(m)
+        : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+    return m;
+}
+
+// simulation_client.py:38 on the rescaled action, exact: all four components inside [hold_lo, hold_hi]
+__device__ __forceinline__ bool action_hold4_exact(const float4 &v, float lo, float hi) {
+    return v.x >= lo && v.x <= hi && v.y >= lo && v.y <= hi && v.z >= lo && v.z <= hi && v.w >= lo && v.w <= hi;
+}
 
 // roboy_env.py:52: every component inside [-1, 1] (closed; NaN fails).
 __device__ __forceinline__ bool action_ok4(const float4 &v, float hi) {
@@ -207,6 +222,40 @@ struct OutPtrs {
 
 // One env-step for the 32 envs of a chunk.  KEEP_STATE: the caller keeps the step word (and goal) in
 // registers across several steps (open-loop rollout) instead of storing it per step.
+// roboy_env.py:52 assert + simulation_client.py:38 allclose for the 32 envs of a chunk.
+// Each lane tests the two float4 it loaded (float4 i belongs to env i / 2); env `lane` owns float4 2*lane and 2*lane+1
+// of the chunk's 64.  The common case -- every action in range, none near zero -- costs two NaN-propagating max-abs,
+// four compares and two votes for the whole warp; the per-env ballots run only when a vote says so.
+__device__ __forceinline__ void test_actions(const StepParams &p, const Actions2 &act, int lane, bool live, bool &act_ok_out,
+                                             bool &hold_out) {
+#if ROBOY_FAST_ACTION_TEST
+    const float m_a = maxabs4_nan(act.a0), m_b = maxabs4_nan(act.a1);
+    bool act_ok = true, hold = false;
+    if (!__all_sync(kFull, m_a <= p.act_in_hi && m_b <= p.act_in_hi)) {   // somebody out of range or NaN: who?
+        const uint32_t okm0 = __ballot_sync(kFull, m_a <= p.act_in_hi);
+        const uint32_t okm1 = __ballot_sync(kFull, m_b <= p.act_in_hi);
+        act_ok = (((lane < 16 ? okm0 : okm1) >> ((lane & 15) << 1)) & 3u) == 3u;
+    }
+    if (__any_sync(kFull, m_a <= p.hold_mag || m_b <= p.hold_mag)) {      // somebody near zero: exact interval test
+        const uint32_t hdm0 = __ballot_sync(kFull, m_a <= p.hold_mag && action_hold4_exact(act.a0, p.hold_lo, p.hold_hi));
+        const uint32_t hdm1 = __ballot_sync(kFull, m_b <= p.hold_mag && action_hold4_exact(act.a1, p.hold_lo, p.hold_hi));
+        hold = live && (((lane < 16 ? hdm0 : hdm1) >> ((lane & 15) << 1)) & 3u) == 3u;
+    }
+#else
+    const float hold_mag = p.hold_mag;
+    const bool ok_a = action_ok4(act.a0, p.act_in_hi), ok_b = action_ok4(act.a1, p.act_in_hi);
+    const uint32_t okm0 = __ballot_sync(kFull, ok_a);
+    const uint32_t okm1 = __ballot_sync(kFull, ok_b);
+    const uint32_t hdm0 = __ballot_sync(kFull, action_hold4(act.a0, p.hold_lo, p.hold_hi, hold_mag, ok_a));
+    const uint32_t hdm1 = __ballot_sync(kFull, action_hold4(act.a1, p.hold_lo, p.hold_hi, hold_mag, ok_b));
+    const uint32_t sh = (lane & 15) << 1;
+    const bool act_ok = (((lane < 16 ? okm0 : okm1) >> sh) & 3u) == 3u;
+    const bool hold = live && (((lane < 16 ? hdm0 : hdm1) >> sh) & 3u) == 3u;
+#endif
+    act_ok_out = act_ok;
+    hold_out = hold;
+}
+
 // EXPERIMENT (ROBOY_DEFER_DONE=1, not the product build): finished envs of one CTA, queued by the hot loop and worked off
 // by all threads of the CTA at its end.  An episode end costs a Philox block, three scattered goal stores and, under
 // auto-reset, a rewritten observation row: ~150 instructions that one lane of a warp executes alone, and with 1/400 of the
@@ -221,23 +270,11 @@ struct DoneQueue {
 };
 
 template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV, bool TAIL, bool KEEP_STATE, bool DEFER = false>
-__device__ __forceinline__ uint32_t process_chunk(const StepParams &p, uint64_t t, const ChunkIn &cur, uint32_t base,
-                                                  int lane, float *so, unsigned int *s_cnt, float &sum_reward,
+__device__ __forceinline__ uint32_t process_chunk(const StepParams &p, uint64_t t, const ChunkIn &cur, bool act_ok, bool hold,
+                                                  uint32_t base, int lane, float *so, unsigned int *s_cnt, float &sum_reward,
                                                   const OutPtrs &out, bool &done_out, DoneQueue *dq = nullptr) {
     const uint32_t e = base + lane;
     const bool live = TAIL ? (e < (uint32_t)p.e_end) : true;
-
-    // ---- roboy_env.py:52 assert + simulation_client.py:38 allclose, as warp ballots ----
-    // env `lane` owns float4 2*lane and 2*lane+1 of the chunk's 64
-    const float hold_mag = p.hold_mag;
-    const bool ok_a = action_ok4(cur.a0, p.act_in_hi), ok_b = action_ok4(cur.a1, p.act_in_hi);
-    const uint32_t okm0 = __ballot_sync(kFull, ok_a);
-    const uint32_t okm1 = __ballot_sync(kFull, ok_b);
-    const uint32_t hdm0 = __ballot_sync(kFull, action_hold4(cur.a0, p.hold_lo, p.hold_hi, hold_mag, ok_a));
-    const uint32_t hdm1 = __ballot_sync(kFull, action_hold4(cur.a1, p.hold_lo, p.hold_hi, hold_mag, ok_b));
-    const uint32_t sh = (lane & 15) << 1;
-    const bool act_ok = (((lane < 16 ? okm0 : okm1) >> sh) & 3u) == 3u;
-    const bool hold = live && (((lane < 16 ? hdm0 : hdm1) >> sh) & 3u) == 3u;
 
     const float g0 = cur.g0, g1 = cur.g1, g2 = cur.g2;
     const uint32_t sf = cur.sf;
@@ -245,7 +282,7 @@ __device__ __forceinline__ uint32_t process_chunk(const StepParams &p, uint64_t 
     bool reached, violation;
 #ifdef ROBOY_EXPERIMENT_MEMONLY  // traffic-pattern ceiling experiment: same loads/stores, no arithmetic
     if (!hold) {
-        q0 = cur.a0.x; q1 = cur.a0.y; q2 = cur.a0.z; qd0 = cur.a1.x; qd1 = cur.a1.y; qd2 = cur.a1.z;
+        q0 = g0; q1 = g1; q2 = g2; qd0 = g1; qd1 = g2; qd2 = g0;
         reward = g0 + g1; reached = false; violation = false;
     } else
 #endif
@@ -296,7 +333,9 @@ __device__ __forceinline__ uint32_t process_chunk(const StepParams &p, uint64_t 
             }
         }
         if (!queued) {
-            const uint32_t r = finish_episode(p, t, e, step, reached, AUTO_RESET, row, s_cnt);
+            // (tried: the whole warp rewriting its 128-byte goal lines instead of one lane's 4-byte partial-sector stores --
+            // 0.9404 against 0.9461 of peak in the steady state, not kept)
+            const uint32_t r = finish_episode(episode_end(p, t, e, step, reached, AUTO_RESET, row, s_cnt));
             word = (r & 0x80000000u) ? word : (r | ROBOY_F_HELD_ZERO64);
         }
     }
@@ -407,25 +446,25 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
     bool done_unused;
 
     uint32_t chunk = (uint32_t)(p.e_begin >> 5) + blockIdx.x * kWarpsPerBlock + warp;
-#if ROBOY_PREFETCH == 1
+    // Software prefetch into registers: the next chunk's loads are ISSUED FIRST, then this chunk is computed while they are
+    // in flight.  (Testing this chunk's actions before issuing the next loads would save the eight-register copy, but the
+    // warp then waits for its own data before it has the next request out: measured 1.5 % slower.)
+    Actions2 acts;
     ChunkIn in;
-    if (chunk < n_full) in = load_chunk<false>(p, chunk << 5, lane);
-#elif ROBOY_PREFETCH == 2
-    L2Prefetch pf;
-    pf.init(p, chunk, warp_stride, lane);
-#endif
+    if (chunk < n_full) {
+        acts = load_actions<false>(p.actions, chunk << 5, 0, lane);
+        in = load_state<false>(p, chunk << 5, lane);
+    }
     while (chunk < n_full) {
         const uint32_t next = chunk + warp_stride;
-#if ROBOY_PREFETCH == 1
-        // software prefetch into registers: the next chunk's loads are in flight during this compute
         const ChunkIn cur = in;
-        if (next < n_full) in = load_chunk<false>(p, next << 5, lane);
-#else
-        const ChunkIn cur = load_chunk<false>(p, chunk << 5, lane);
-#if ROBOY_PREFETCH == 2
-        pf.issue_and_advance(chunk + ROBOY_PREFETCH_DIST * warp_stride < n_full, lane);
-#endif
-#endif
+        const Actions2 cur_acts = acts;
+        if (next < n_full) {
+            acts = load_actions<false>(p.actions, next << 5, 0, lane);
+            in = load_state<false>(p, next << 5, lane);
+        }
+        bool act_ok, hold;
+        test_actions(p, cur_acts, lane, true, act_ok, hold);
 #if ROBOY_OBS_BULK_STORE
         // the bulk copy issued two chunks ago read this buffer: wait until at most one is still reading
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -433,8 +472,8 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
         so = s_obs[parity][warp];
         parity ^= 1;
 #endif
-        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false, false, kDefer>(p, t, cur, chunk << 5, lane, so, s_cnt,
-                                                                                 sum_reward, out, done_unused, dq);
+        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false, false, kDefer>(p, t, cur, act_ok, hold, chunk << 5, lane, so,
+                                                                                 s_cnt, sum_reward, out, done_unused, dq);
         chunk = next;
     }
 #if ROBOY_OBS_BULK_STORE
@@ -445,9 +484,12 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
     so = s_obs[0][warp];
 #endif
     if (chunk == n_full && (p.e_end & 31)) {  // the ragged last chunk belongs to exactly one warp
-        const ChunkIn cur = load_chunk<true>(p, chunk << 5, lane);
-        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true, false, kDefer>(p, t, cur, chunk << 5, lane, so, s_cnt,
-                                                                                sum_reward, out, done_unused, dq);
+        const Actions2 tail_acts = load_actions<true>(p.actions, chunk << 5, (uint32_t)p.e_end, lane);
+        const ChunkIn cur = load_state<true>(p, chunk << 5, lane);
+        bool act_ok, hold;
+        test_actions(p, tail_acts, lane, ((chunk << 5) + lane) < (uint32_t)p.e_end, act_ok, hold);
+        process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true, false, kDefer>(p, t, cur, act_ok, hold, chunk << 5, lane, so,
+                                                                                s_cnt, sum_reward, out, done_unused, dq);
     }
 #if ROBOY_DEFER_DONE
     // ---- queued episode ends: one pass of the whole CTA ----
@@ -504,11 +546,12 @@ __device__ __forceinline__ void rollout_chunk(const StepParams &p, uint32_t T, u
     cur.ng1 = normalize32_hot<FASTDIV>(cur.g1, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
     cur.ng2 = normalize32_hot<FASTDIV>(cur.g2, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
     const size_t n = (size_t)p.n;
-    Actions2 nxt = load_actions<TAIL>(p.actions, base, n_end, lane);
+    Actions2 acts = load_actions<TAIL>(p.actions, base, n_end, lane);
     for (uint32_t tt = 0; tt < T; ++tt) {
-        cur.a0 = nxt.a0;
-        cur.a1 = nxt.a1;
-        if (tt + 1 < T) nxt = load_actions<TAIL>(p.actions + (size_t)(tt + 1) * n * kActDim, base, n_end, lane);
+        const Actions2 cur_acts = acts;
+        if (tt + 1 < T) acts = load_actions<TAIL>(p.actions + (size_t)(tt + 1) * n * kActDim, base, n_end, lane);
+        bool act_ok, hold;
+        test_actions(p, cur_acts, lane, live, act_ok, hold);
         const OutPtrs out{p.obs + (size_t)tt * n * kObsDim, p.reward + (size_t)tt * n, p.done + (size_t)tt * n,
                           p.obs_aligned != 0};
 #if ROBOY_OBS_BULK_STORE
@@ -518,8 +561,8 @@ __device__ __forceinline__ void rollout_chunk(const StepParams &p, uint32_t T, u
         float *so = stage[parity][warp];
         parity ^= 1;
         bool done;
-        cur.sf = process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, TAIL, true>(p, t_first + tt, cur, base, lane, so, s_cnt,
-                                                                                sum_reward, out, done);
+        cur.sf = process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, TAIL, true>(p, t_first + tt, cur, act_ok, hold, base, lane, so,
+                                                                                s_cnt, sum_reward, out, done);
         if (done && live) {  // rare: the new goal was stored by finish_episode (same thread)
             cur.g0 = p.goal[e];
             cur.g1 = p.goal1[e];

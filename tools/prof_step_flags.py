@@ -6,6 +6,7 @@ from gym_roboy_b200.envs.simulations import CudaSimulationClient
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 24
 c = CudaSimulationClient(num_envs=n, seed=1234, device="cuda:0")
 e = RoboyEnv(c, joint_vel_penalty=True, strict=False); e.reset()
+c.set_step_num(((torch.arange(n, device="cuda:0") % 400) + 1).to(torch.int32))   # steady state: 1/400 of the envs finish per step
 g = torch.Generator(device="cuda:0"); g.manual_seed(0)
 a = [torch.rand((n, 8), device="cuda:0", generator=g) * 2 - 1 for _ in range(2)]
 for i in range(6): e.step(a[i & 1])
