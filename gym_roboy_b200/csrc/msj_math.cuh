@@ -89,6 +89,9 @@ struct FastConsts {
     float a_span21;          // a_span * 2^-21 (exact): state draws, v = low + a_span21 * float(k), k < 2^21
     float reward_lo_f, reward_hi_f;  // reward range rounded INWARD to float32: for a float32 reward
                                      // r,  lo <= r <= hi  <=>  reward_lo_f <= r <= reward_hi_f
+    double v_gz;             // the normalised float64 zero velocity of the goal (roboy_env.py:23,95):
+                             // ((2*0.0 - v_hi) - v_lo) / v_span in float64 -- a constant of the robot, derived on the host
+                             // (in the kernel it was a double-precision division per env-step)
 };
 
 template <bool FASTDIV>
@@ -135,10 +138,12 @@ __device__ __forceinline__ void reward_reached_sampled_ng(float q0, float q1, fl
     s = __dadd_rn(s, (double)__fmul_rn(d2, d2));
     float r32 = -expf(__fsqrt_rn((float)s));
     if (PENALTY) {  // :98-100, float64 because the goal velocities are
-        const double gz = normalize64(0.0, c.v_hi, c.v_lo, c.v_span);
-        const double v = l2_f64((double)normalize32_hot<FASTDIV>(qd0, c.v_hi, c.v_lo, c.v_span, f.v_rc),
-                                (double)normalize32_hot<FASTDIV>(qd1, c.v_hi, c.v_lo, c.v_span, f.v_rc),
-                                (double)normalize32_hot<FASTDIV>(qd2, c.v_hi, c.v_lo, c.v_span, f.v_rc), gz, gz, gz);
+        // (every operand is finite on this path, so the NaN -> 0 of _l2_distance cannot trigger -- and :99 has none anyway)
+        const double gz = f.v_gz;
+        const double e0 = __dsub_rn((double)normalize32_hot<FASTDIV>(qd0, c.v_hi, c.v_lo, c.v_span, f.v_rc), gz);
+        const double e1 = __dsub_rn((double)normalize32_hot<FASTDIV>(qd1, c.v_hi, c.v_lo, c.v_span, f.v_rc), gz);
+        const double e2 = __dsub_rn((double)normalize32_hot<FASTDIV>(qd2, c.v_hi, c.v_lo, c.v_span, f.v_rc), gz);
+        const double v = __dsqrt_rn(__fma_rn(e2, e2, __fma_rn(e1, e1, __dmul_rn(e0, e0))));
         double r64 = __dmul_rn(__dadd_rn(v, 1.0), (double)__fsub_rn(r32, expf(r32)));
         if (BONUS && reached) r64 = __dadd_rn(r64, (double)c.bonus_goal);  // :105-107
         reward_out = (float)r64;

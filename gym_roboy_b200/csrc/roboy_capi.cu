@@ -480,6 +480,12 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
     e->fast.a_span21 = c.a_span * 0x1p-21f;
     e->fast.reward_lo_f = -INFINITY;
     e->fast.reward_hi_f = INFINITY;
+    {   // roboy_robot.py:93-95 on the float64 zero velocity of the goal (roboy_env.py:23): (2*0 - max - min) / (max - min)
+        volatile double t = 2.0 * 0.0;
+        t = t - (double)c.v_hi;
+        t = t - (double)c.v_lo;
+        e->fast.v_gz = t / (double)c.v_span;
+    }
     e->fastdiv = e->msj_shaped && spans_are_proved(c.a_lo, c.a_hi, c.v_lo, c.v_hi);
 
     const uint64_t n = cfg->n_envs;
