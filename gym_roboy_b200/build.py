@@ -39,18 +39,36 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    """Compile libroboy_b200.so if missing or older than its sources; returns its path."""
+    """Compile libroboy_b200.so if missing or older than its sources; returns its path.  The translation units are
+    compiled in parallel (one nvcc per .cu) and linked into one shared library."""
     if not force and not is_stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(os.path.dirname(_PKG), "build", "obj")
+    os.makedirs(obj_dir, exist_ok=True)
     extra = os.environ.get("ROBOY_NVCC_EXTRA", "").split()   # experiments only, e.g. -DROBOY_STEP_MIN_BLOCKS=3
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [
-        os.path.join(CSRC, f) for f in SOURCES]
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + flags + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return obj, cmd, proc
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    for obj, cmd, proc in results:
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(proc.stdout)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed (exit {}): {}".format(proc.returncode, " ".join(cmd)))
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + [r[0] for r in results]
+    proc = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed (exit {}): {}".format(proc.returncode, " ".join(cmd)))
+        raise RuntimeError("link failed (exit {}): {}".format(proc.returncode, " ".join(link)))
     return LIB_PATH
 
 
