@@ -110,15 +110,16 @@ def robot_bounds(bounds):
     b.update(bounds)
     J = int(b.pop("dim_joint", 0)) or None
     A = int(b.pop("dim_action", 0)) or None
+    is_vec = {k: np.ndim(v) > 0 for k, v in b.items()}       # a sequence (even of length 1) gives the dimension
     arrs = {k: np.atleast_1d(np.asarray(v, np.float32)) for k, v in b.items()}
     for k in ("angle_low", "angle_high", "vel_low", "vel_high"):
-        if arrs[k].size > 1:
+        if is_vec[k]:
             J = J or arrs[k].size
     for k in ("act_low", "act_high"):
-        if arrs[k].size > 1:
+        if is_vec[k]:
             A = A or arrs[k].size
     J, A = J or 3, A or 8
-    per_component = any(a.size > 1 for a in arrs.values())
+    per_component = any(is_vec.values())
     out = {}
     for k, a in arrs.items():
         n = A if k.startswith("act") else J

@@ -240,3 +240,46 @@ def test_vec_env_adapter_with_another_robot():
         for i in np.flatnonzero(d):
             assert np.array_equal(infos[i]["terminal_observation"], term[i])
     venv.close()
+
+
+@pytest.mark.parametrize("J", list(range(1, 16)))
+def test_every_joint_count_instantiation_matches_oracle(J):
+    """generic_step_kernel<J> for J = 1..15, each on a random robot (per-component asymmetric bounds, random tendon
+    count), both penalty modes alternating, ragged size; the same robots are pinned against the reference on the CPU
+    (tests/test_oracle_vs_reference.py::test_every_joint_count_matches_reference)."""
+    from test_oracle_vs_reference import random_robot
+    rng = np.random.default_rng(1000 + J)
+    b = random_robot(rng, J)
+    _, A, _, bb = orc.robot_bounds(b)
+    n, T = 3001, 70
+    env, client, ora = make_pair(b, n, seed=J, penalty=bool(J % 2))
+    assert not client.msj_kernels or (J == 3 and A == 8)
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset())
+    set_phases(client, ora, rng.integers(340, 401, n).astype(np.int32))
+    zero_action, can_hold = orc.hold_action(b)
+    thr_a, _ = orc.thresholds(ora.cfg)
+    client.enable_terminal_obs(True)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (n, A)).astype(np.float32)
+        hold = rng.random(n) < 0.05
+        a[hold] = zero_action
+        a[rng.random(n) < 0.002] = np.float32(1.5)          # outside the action space: error word, first offending env
+        if t % 10 == 4:
+            q, _ = orc.draw_state(J, np.arange(n), ora.counter + 1, bb["angle_low"], bb["angle_high"], J=J)
+            d = rng.normal(size=(n, J)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+            base = np.where(hold[:, None], 0.0, q.astype(np.float64))
+            g = np.clip(base + d * float(thr_a) * (1 + rng.choice([-1e-7, 1e-7, -0.4, 0.3], n))[:, None],
+                        bb["angle_low"], bb["angle_high"]).astype(np.float32)
+            client.set_goal(g); ora.goal[:] = g.T
+        obs, rew, done, info = env.step(torch.as_tensor(a, device="cuda:0"))
+        o_obs, o_rew, o_done, o_term = ora.step(a, want_terminal_obs=True)
+        assert np.array_equal(done.cpu().numpy(), o_done) and np.array_equal(obs.cpu().numpy(), o_obs), t
+        rel = np.abs(rew.cpu().numpy().astype(np.float64) - o_rew) / np.maximum(np.abs(o_rew.astype(np.float64)), 1e-30)
+        assert rel.max() <= RTOL, (t, rel.max())
+        assert np.array_equal(client.terminal_obs.cpu().numpy()[o_done], o_term[o_done]), t
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+    assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
+    s, so = client.stats(), ora.stats()
+    for k in ("steps", "episodes", "successes", "timeouts", "sum_episode_len", "holds", "violations"):
+        assert s[k] == so[k], (k, s[k], so[k])
+    assert client.errors() == ora.errors() and client.errors()[0] & 1 and s["episodes"] > n // 2

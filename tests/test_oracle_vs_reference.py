@@ -202,3 +202,54 @@ def test_generic_robots_match_reference(name, penalty):
         reached += int((rd & (rr > 500) & alive).sum())
     assert o.stats()["episodes"] >= N and (o.stats()["holds"] > 0) == can_hold and alive.sum() >= (1 if penalty else N)
     assert penalty or reached > 0 or not can_hold   # (a robot that can never hold reaches goals only by sampling)
+
+
+def random_robot(rng, J, A=None):
+    """A random RoboyRobot: J joints, A tendons, one (asymmetric) bound per component."""
+    A = int(rng.integers(1, 65)) if A is None else A
+    a_hi = rng.uniform(0.3, 3.1, J); a_lo = -rng.uniform(0.3, 3.1, J)
+    v_hi = rng.uniform(0.1, 1.0, J); v_lo = -rng.uniform(0.1, 1.0, J)
+    t_hi = rng.uniform(0.05, 0.9, A); t_lo = -rng.uniform(0.05, 0.9, A)
+    if rng.random() < 0.5:   # some tendon ranges symmetric and dyadic: those robots CAN hold
+        t_hi = np.full(A, rng.choice([0.25, 0.5, 0.125])); t_lo = -t_hi
+    return dict(angle_low=a_lo, angle_high=a_hi, vel_low=v_lo, vel_high=v_hi, act_low=t_lo, act_high=t_hi)
+
+
+@pytest.mark.parametrize("J", list(range(1, 16)))
+def test_every_joint_count_matches_reference(J):
+    """One random robot per joint count 1..15 (every instantiation of the CUDA generic step kernel has an oracle that is
+    itself pinned against the unmodified reference)."""
+    rng = np.random.default_rng(1000 + J)
+    b = random_robot(rng, J)
+    _, A, _, bb = orc.robot_bounds(b)
+    N, T = 3, 45
+    penalty = bool(J % 2)
+    ref = rh.ReferenceVecEnv(N, seed=J, bounds=b, joint_vel_penalty=penalty)
+    o = orc.OracleEnv(N, seed=J, joint_vel_penalty=penalty, **b)
+    assert np.allclose(ref.reward_range, o.reward_range, rtol=1e-6, atol=0)
+    assert np.array_equal(ref.goals().T, o.goal)
+    assert np.array_equal(ref.reset().astype(np.float32), o.reset())
+    zero_action, can_hold = orc.hold_action(b)
+    thr_a, _ = orc.thresholds(o.cfg)
+    alive = np.ones(N, bool)
+    for i in range(N):
+        ref.set_step_num(i, 380 + 10 * i)
+    o.step_flags[:] = (o.step_flags & ~np.uint32(orc.STEP_MASK)) | (380 + 10 * np.arange(N)).astype(np.uint32)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, A)).astype(np.float32)
+        hold = rng.random(N) < 0.3
+        a[hold] = zero_action
+        if t % 6 == 2:
+            d = rng.normal(size=(N, J)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+            g = np.clip(d * float(thr_a) * (1 + rng.choice([-1e-7, 1e-7, -0.4], N))[:, None], bb["angle_low"], bb["angle_high"]).astype(np.float32)
+            for i in range(N):
+                ref.set_goal(i, g[i])
+            o.goal[:] = g.T
+        ro, rr, rd, rt, raised = ref.step(a)
+        oo, orw, od, ot = o.step(a, want_terminal_obs=True)
+        alive &= np.array([m == "" for m in raised])
+        assert np.array_equal(ro.astype(np.float32)[alive], oo[alive]), t
+        assert np.array_equal(rd[alive], od[alive]), t
+        assert np.allclose(orw[alive], rr[alive], rtol=1e-6, atol=0), t
+        assert np.array_equal(ref.goals()[alive], o.goal.T[alive])
+    assert o.stats()["episodes"] >= 1 and (o.stats()["holds"] > 0) == can_hold
