@@ -54,13 +54,6 @@ namespace roboy {
 #ifndef ROBOY_FAST_ACTION_TEST
 #define ROBOY_FAST_ACTION_TEST 1  // one NaN-propagating max-abs per float4 + warp votes; per-env ballots only when needed
 #endif
-#ifndef ROBOY_TMA_ACTIONS
-#define ROBOY_TMA_ACTIONS 0  // 1: the actions arrive through a per-warp ring of shared-memory stages filled by bulk copies
-                             //    (cp.async.bulk global -> shared, mbarrier completion) kInStages chunks ahead
-#endif
-#ifndef ROBOY_IN_STAGES
-#define ROBOY_IN_STAGES 4
-#endif
 #ifndef ROBOY_LD_HINT
 #define ROBOY_LD_HINT 0  // streamed inputs:  0 default (measured best: +3% over .cs), 1 ld.global.cs, 2 ld.global.nc.L1::no_allocate
 #endif
@@ -71,31 +64,6 @@ namespace roboy {
 namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kInStages = ROBOY_IN_STAGES;   // depth of the per-warp action ring (ROBOY_TMA_ACTIONS)
-
-// ---- per-warp input ring: bulk copies global -> shared with mbarrier completion (TMA without a tensor map) ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-// lane 0: arm the stage's barrier with the byte count and hand the chunk's 1 KiB of actions to the copy engine
-__device__ __forceinline__ void ring_request(uint32_t bar, uint32_t dst, const float *src, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "RING_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra RING_DONE;\n\t"
-        "bra RING_WAIT;\n\t"
-        "RING_DONE:\n\t}" ::"r"(bar),
-        "r"(phase)
-        : "memory");
-}
 
 __device__ __forceinline__ float4 ld_stream(const float4 *p) {
 #if ROBOY_LD_HINT == 1
@@ -442,15 +410,6 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
     // atomics where they happen instead of tying up registers in the hot loop
     __shared__ unsigned int s_cnt[5];  // done, success, hold, violation, sum of episode lengths
     if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
-#if ROBOY_TMA_ACTIONS
-    extern __shared__ __align__(128) float4 s_ring[];   // [kWarpsPerBlock][kInStages][64]: 1 KiB of actions per stage
-    __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock][kInStages];
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int st = 0; st < kInStages; ++st) mbar_init(smem_u32(&s_bar[threadIdx.x >> 5][st]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-#endif
 #if ROBOY_DEFER_DONE
     __shared__ DoneQueue s_dq;
     if (threadIdx.x == 0) s_dq.n = 0;
@@ -487,56 +446,6 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
     bool done_unused;
 
     uint32_t chunk = (uint32_t)(p.e_begin >> 5) + blockIdx.x * kWarpsPerBlock + warp;
-#if ROBOY_TMA_ACTIONS
-    // The actions (32 of the 48 bytes read per env) arrive through a per-warp ring of kInStages 1-KiB stages in shared
-    // memory: lane 0 hands each chunk to the copy engine kInStages chunks ahead (cp.async.bulk, completion on the stage's
-    // mbarrier), so the depth of the prefetch no longer costs registers.  Goal and step word (16 bytes per env) stay on a
-    // two-deep register prefetch.
-    {
-        float4 *ring = s_ring + warp * (kInStages * 64);
-        const uint32_t ring_a = smem_u32(ring), bar_a = smem_u32(&s_bar[warp][0]);
-        uint32_t req = chunk;   // next chunk to request
-        if (lane == 0) {
-#pragma unroll
-            for (int st = 0; st < kInStages; ++st) {
-                if (req < n_full) ring_request(bar_a + 8 * st, ring_a + 1024 * st, p.actions + (size_t)req * 256, 1024);
-                req += warp_stride;
-            }
-        }
-        ChunkIn in0, in1;
-        if (chunk < n_full) in0 = load_state<false>(p, chunk << 5, lane);
-        if (chunk + warp_stride < n_full) in1 = load_state<false>(p, (chunk + warp_stride) << 5, lane);
-        uint32_t stage = 0, phase = 0;
-        while (chunk < n_full) {
-            const uint32_t next = chunk + warp_stride;
-            const ChunkIn cur = in0;
-            in0 = in1;
-            if (next + warp_stride < n_full) in1 = load_state<false>(p, (next + warp_stride) << 5, lane);
-            mbar_wait(bar_a + 8 * stage, phase);
-            Actions2 cur_acts;
-            cur_acts.a0 = ring[stage * 64 + lane];
-            cur_acts.a1 = ring[stage * 64 + 32 + lane];
-            __syncwarp();   // every lane has its two float4: the stage can be refilled
-            if (lane == 0) {
-                if (req < n_full) ring_request(bar_a + 8 * stage, ring_a + 1024 * stage, p.actions + (size_t)req * 256, 1024);
-                req += warp_stride;
-            }
-            bool act_ok, hold;
-            test_actions(p, cur_acts, lane, true, act_ok, hold);
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
-            so = s_obs[parity][warp];
-            parity ^= 1;
-            process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false, false, kDefer>(p, t, cur, act_ok, hold, chunk << 5, lane, so,
-                                                                                     s_cnt, sum_reward, out, done_unused, dq);
-            if (++stage == kInStages) {
-                stage = 0;
-                phase ^= 1;
-            }
-            chunk = next;
-        }
-    }
-#else
     // Software prefetch into registers: the next chunk's loads are ISSUED FIRST, then this chunk is computed while they are
     // in flight.  (Testing this chunk's actions before issuing the next loads would save the eight-register copy, but the
     // warp then waits for its own data before it has the next request out: measured 1.5 % slower.)
@@ -567,7 +476,6 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
                                                                                  s_cnt, sum_reward, out, done_unused, dq);
         chunk = next;
     }
-#endif
 #if ROBOY_OBS_BULK_STORE
     // all bulk copies of this warp have completed (their global writes included: the queued episode ends below rewrite
     // observation rows they wrote)
@@ -622,60 +530,36 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
 // step word in registers across the T steps, so per env-step only the action is read and obs /
 // reward / done are written (73 B instead of 93).  Results are bit-identical to T step_kernel launches.
 // ---------------------------------------------------------------------------------------------
+// One chunk of 32 envs through T steps; the next step's actions are in flight while a step is computed.  A chunk switch used
+// to cost one exposed memory latency (0.73 us per switch: 72 / 80 / 84 % of peak at T = 4 / 16 / 64).  During the LAST step of
+// a chunk the action registers have no next step to hold, so the first actions of the warp's NEXT chunk (next_base, or
+// kNoChunk) are loaded into them, and the next chunk's goal / step-word lines are prefetched into L2 (no registers).
+// (Carrying the next chunk's state in registers as well spilled and lost 1.5 %.)
+constexpr uint32_t kNoChunk = 0xffffffffu;
+
 template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV, bool TAIL>
 __device__ __forceinline__ void rollout_chunk(const StepParams &p, uint32_t T, uint64_t t_first, uint32_t base, int lane,
                                               float (*stage)[kWarpsPerBlock][32 * kObsDim], int warp, uint32_t &parity,
-                                              unsigned int *s_cnt, float &sum_reward, float4 *ring, uint32_t bar_a,
-                                              uint32_t &in_stage, uint32_t &in_phase) {
+                                              unsigned int *s_cnt, float &sum_reward, Actions2 &acts, uint32_t next_base) {
     const uint32_t n_end = (uint32_t)p.e_end;
     const uint32_t e = base + lane;
     const bool live = TAIL ? e < n_end : true;
-    ChunkIn cur;
-    cur.g0 = live ? p.goal[e] : 0.f;
-    cur.g1 = live ? p.goal1[e] : 0.f;
-    cur.g2 = live ? p.goal2[e] : 0.f;
-    cur.sf = live ? p.step_flags[e] : 1u;
+    ChunkIn cur = load_state<TAIL>(p, base, lane);
     cur.ng0 = normalize32_hot<FASTDIV>(cur.g0, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
     cur.ng1 = normalize32_hot<FASTDIV>(cur.g1, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
     cur.ng2 = normalize32_hot<FASTDIV>(cur.g2, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
     const size_t n = (size_t)p.n;
-#if ROBOY_TMA_ACTIONS
-    // the actions of the next kInStages steps of this chunk are on their way into the warp's shared-memory ring
-    const bool use_ring = !TAIL;
-    const uint32_t ring_a = smem_u32(ring);
-    const float *chunk_actions = p.actions + (size_t)base * kActDim;
-    if (use_ring && lane == 0) {
-#pragma unroll
-        for (uint32_t st = 0; st < (uint32_t)kInStages; ++st) {
-            const uint32_t s2 = (in_stage + st) % kInStages;
-            if (st < T) ring_request(bar_a + 8 * s2, ring_a + 1024 * s2, chunk_actions + (size_t)st * n * kActDim, 1024);
-        }
-    }
-#else
-    (void)ring; (void)bar_a; (void)in_stage; (void)in_phase;
-    const bool use_ring = false;
-#endif
-    Actions2 acts;
-    if (!use_ring) acts = load_actions<TAIL>(p.actions, base, n_end, lane);
     for (uint32_t tt = 0; tt < T; ++tt) {
-        Actions2 cur_acts;
-#if ROBOY_TMA_ACTIONS
-        if (use_ring) {
-            mbar_wait(bar_a + 8 * in_stage, in_phase);
-            cur_acts.a0 = ring[in_stage * 64 + lane];
-            cur_acts.a1 = ring[in_stage * 64 + 32 + lane];
-            __syncwarp();   // every lane has its two float4: the stage can be refilled
-            if (lane == 0 && tt + kInStages < T)
-                ring_request(bar_a + 8 * in_stage, ring_a + 1024 * in_stage, chunk_actions + (size_t)(tt + kInStages) * n * kActDim, 1024);
-            if (++in_stage == (uint32_t)kInStages) {
-                in_stage = 0;
-                in_phase ^= 1;
+        const Actions2 cur_acts = acts;
+        if (tt + 1 < T) {
+            acts = load_actions<TAIL>(p.actions + (size_t)(tt + 1) * n * kActDim, base, n_end, lane);
+        } else if (!TAIL && next_base != kNoChunk) {   // hand-over to the warp's next chunk
+            acts = load_actions<false>(p.actions, next_base, n_end, lane);
+            if (lane < 4) {
+                const float *row = lane == 0 ? p.goal : lane == 1 ? p.goal1 : lane == 2 ? p.goal2
+                                                                         : reinterpret_cast<const float *>(p.step_flags);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + next_base));
             }
-        } else
-#endif
-        {
-            cur_acts = acts;
-            if (tt + 1 < T) acts = load_actions<TAIL>(p.actions + (size_t)(tt + 1) * n * kActDim, base, n_end, lane);
         }
         bool act_ok, hold;
         test_actions(p, cur_acts, lane, live, act_ok, hold);
@@ -709,21 +593,6 @@ __global__ void __launch_bounds__(kStepBlock, ROBOY_ROLLOUT_MIN_BLOCKS) rollout_
     __shared__ double s_red[kWarpsPerBlock];
     __shared__ unsigned int s_cnt[5];
     if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
-#if ROBOY_TMA_ACTIONS
-    extern __shared__ __align__(128) float4 s_ring[];   // [kWarpsPerBlock][kInStages][64]
-    __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock][kInStages];
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int st = 0; st < kInStages; ++st) mbar_init(smem_u32(&s_bar[threadIdx.x >> 5][st]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    float4 *ring = s_ring + (threadIdx.x >> 5) * (kInStages * 64);
-    const uint32_t bar_a = smem_u32(&s_bar[threadIdx.x >> 5][0]);
-#else
-    float4 *ring = nullptr;
-    const uint32_t bar_a = 0;
-#endif
-    uint32_t in_stage = 0, in_phase = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -733,12 +602,18 @@ __global__ void __launch_bounds__(kStepBlock, ROBOY_ROLLOUT_MIN_BLOCKS) rollout_
     float sum_reward = 0.0f;
     uint32_t parity = 0;
     uint32_t chunk = (uint32_t)(p.e_begin >> 5) + blockIdx.x * kWarpsPerBlock + warp;
-    for (; chunk < n_full; chunk += warp_stride)
+    Actions2 acts;
+    if (chunk < n_full) acts = load_actions<false>(p.actions, chunk << 5, (uint32_t)p.e_end, lane);
+    for (; chunk < n_full; chunk += warp_stride) {
+        const uint32_t next = chunk + warp_stride;
         rollout_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, false>(p, T, t_first, chunk << 5, lane, s_obs, warp, parity, s_cnt,
-                                                                  sum_reward, ring, bar_a, in_stage, in_phase);
-    if (chunk == n_full && (p.e_end & 31))
+                                                                  sum_reward, acts, next < n_full ? next << 5 : kNoChunk);
+    }
+    if (chunk == n_full && (p.e_end & 31)) {
+        acts = load_actions<true>(p.actions, chunk << 5, (uint32_t)p.e_end, lane);
         rollout_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true>(p, T, t_first, chunk << 5, lane, s_obs, warp, parity, s_cnt,
-                                                                 sum_reward, ring, bar_a, in_stage, in_phase);
+                                                                 sum_reward, acts, kNoChunk);
+    }
 #if ROBOY_OBS_BULK_STORE
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
@@ -790,19 +665,11 @@ int selector(bool penalty, bool bonus, bool auto_reset, bool fastdiv) {
     return (penalty ? 8 : 0) | (bonus ? 4 : 0) | (auto_reset ? 2 : 0) | (fastdiv ? 1 : 0);
 }
 
-#if ROBOY_TMA_ACTIONS
-constexpr size_t kStepDynSmem = (size_t)kWarpsPerBlock * kInStages * 1024;   // the per-warp action rings
-#else
-constexpr size_t kStepDynSmem = 0;
-#endif
-
 int blocks_per_sm(int sel) {
     static int cached[16] = {0};
     if (!cached[sel]) {
         int b = 0;
-        if (kStepDynSmem)   // static + dynamic shared memory exceeds the 48 KB a kernel gets without asking
-            cudaFuncSetAttribute(select_kernel(sel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStepDynSmem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, select_kernel(sel), kStepBlock, kStepDynSmem) != cudaSuccess || b < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, select_kernel(sel), kStepBlock, 0) != cudaSuccess || b < 1)
             b = 1;
         if (b > kStepMinBlocks) b = kStepMinBlocks;
         cached[sel] = b;
@@ -846,14 +713,12 @@ cudaError_t launch_step_many(const StepParams &p, uint32_t T, bool penalty, bool
     static int per_sm[16] = {0};
     if (!per_sm[sel]) {
         int b = 0;
-        if (kStepDynSmem)
-            cudaFuncSetAttribute(select_rollout(sel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStepDynSmem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, select_rollout(sel), kStepBlock, kStepDynSmem) != cudaSuccess || b < 1) b = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, select_rollout(sel), kStepBlock, 0) != cudaSuccess || b < 1) b = 1;
         if (b > ROBOY_ROLLOUT_MIN_BLOCKS) b = ROBOY_ROLLOUT_MIN_BLOCKS;
         per_sm[sel] = b;
     }
     const int grid = grid_for(p.e_end - p.e_begin, per_sm[sel], sm_count);
-    select_rollout(sel)<<<grid, kStepBlock, kStepDynSmem, stream>>>(p, T);
+    select_rollout(sel)<<<grid, kStepBlock, 0, stream>>>(p, T);
     return cudaGetLastError();
 }
 
@@ -874,13 +739,13 @@ cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto
         return !(v && v[0] == '0');
     }();
     if (!pdl) {
-        select_kernel(sel)<<<grid, kStepBlock, kStepDynSmem, stream>>>(p);
+        select_kernel(sel)<<<grid, kStepBlock, 0, stream>>>(p);
         return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kStepBlock);
-    cfg.dynamicSmemBytes = kStepDynSmem;
+    cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -889,7 +754,7 @@ cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, select_kernel(sel), p);
 #else
-    select_kernel(sel)<<<grid, kStepBlock, kStepDynSmem, stream>>>(p);
+    select_kernel(sel)<<<grid, kStepBlock, 0, stream>>>(p);
     return cudaGetLastError();
 #endif
 }
