@@ -153,6 +153,38 @@ void fill_robot_spec(const roboy_cfg &c, RobotSpec &r) {
     r.bonus_goal = c.bonus_goal;
     r.reward_lo = c.reward_lo;
     r.reward_hi = c.reward_hi;
+    // constants of the fused generic step, each the value the kernel would otherwise recompute per env-step
+    for (int k = 0; k < r.J; ++k) {
+        volatile float sa = r.a_hi[k] - r.a_lo[k], sv = r.v_hi[k] - r.v_lo[k];   // float32 - float32 (roboy_robot.py:95)
+        r.a_span[k] = sa;
+        r.v_span[k] = sv;
+        volatile float s21 = sa * 0x1p-21f;
+        r.a_span21[k] = s21;
+        volatile double t = 2.0 * 0.0;     // (2*0 - max - min) / (max - min) in float64, the goal's zero velocity (roboy_env.py:23)
+        t = t - (double)r.v_hi[k];
+        t = t - (double)r.v_lo[k];
+        r.v_gz[k] = t / (double)sv;
+    }
+    r.thr_angle_sq_hi = round_up_f32((double)r.thr_angle * (double)r.thr_angle * (1.0 + 1e-5));
+    {   // hull of the hold intervals: the whole-chunk pre-filter of the hold test
+        float lo = INFINITY, hi = -INFINITY;
+        bool possible = true;
+        for (int k = 0; k < r.A; ++k) {
+            if (!(r.hold_lo[k] <= r.hold_hi[k])) possible = false;
+            lo = fminf(lo, r.hold_lo[k]);
+            hi = fmaxf(hi, r.hold_hi[k]);
+        }
+        if (!possible) {
+            r.hold_c = 0.0f;
+            r.hold_h = -1.0f;
+            r.hold_pad = 0.0f;
+        } else {
+            const double c0 = 0.5 * ((double)lo + (double)hi), h0 = 0.5 * ((double)hi - (double)lo);
+            r.hold_c = (float)c0;
+            r.hold_h = round_up_f32(h0 * 1.001 + fabs(c0) * 1e-6 + 1e-30);   // covers the rounding of hold_c and of x - hold_c
+            r.hold_pad = c0 <= 0.0 ? 1.0f : -1.0f;   // farthest end of [-1, 1]: outside the hull unless the hull spans it
+        }
+    }
 }
 
 // MSJ's dims and the same bounds on every component: the tuned kernels apply

@@ -28,6 +28,13 @@ struct RobotSpec {
                                                      // (roboy_env.py:157-158) passes numpy's allclose(., 0)
                                                      // (simulation_client.py:38); lo > hi = empty
     float thr_angle, thr_vel;                 // roboy_env.py:24-25,127,130
+    // ---- derived on the host (fill_robot_spec), read by the fused step only ----
+    float a_span[kJointPad], v_span[kJointPad];      // fl32(max_k - min_k), the divisor of roboy_robot.py:95
+    float a_span21[kJointPad];                       // a_span * 2^-21 (exact): the grid step of a state draw
+    double v_gz[kJointPad];                          // roboy_robot.py:93-95 on the float64 zero velocity of the goal
+    float thr_angle_sq_hi;                           // thr_angle^2 * (1 + 1e-5), rounded up: pre-filter of _did_reach_goal
+    float hold_c, hold_h;                            // no action with |x - hold_c| > hold_h lies in any hold interval
+    float hold_pad;                                  // a value in [-1, 1] outside that hull (hold_h < 0: nobody can hold)
     float penalty_boundary, bonus_goal;       // roboy_env.py:26-27
     double reward_lo, reward_hi;              // roboy_env.py:30,109
 };
