@@ -687,7 +687,8 @@ def run_b200_arm(args):
         generic_robot = {"robot": "6 joints, 14 tendons (a RoboyRobot plug-in other than MsjRobot)", "envs": n, "ms_per_step": ms,
                          "env_steps_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_env_step": nbytes,
                          "GBps_algorithmic": nbytes * n / (ms * 1e-3) / 1e9, "frac_of_peak": nbytes * n / (ms * 1e-3) / 1e9 / peak,
-                         "kernel": "roboy::generic_step_kernel<6>", "msj_kernels": c.msj_kernels}
+                         "kernel": "roboy::generic_step_kernel<6, %s>" % ("true" if c.fast_division else "false"),
+                         "msj_kernels": c.msj_kernels, "fast_division_proved_at_create": c.fast_division}
         c.close()
         del e, c, acts
         torch.cuda.empty_cache()

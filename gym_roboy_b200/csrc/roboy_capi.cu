@@ -519,6 +519,16 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
         e->fast.v_gz = t / (double)c.v_span;
     }
     e->fastdiv = e->msj_shaped && spans_are_proved(c.a_lo, c.a_hi, c.v_lo, c.v_hi);
+    if (!e->msj_shaped) {   // the generic step's division by the per-joint spans: proved on this device, or IEEE
+        const char *off = getenv("ROBOY_B200_GENERIC_FASTDIV");
+        if (!(off && off[0] == '0')) {
+            const cudaError_t perr = prove_generic_fastdiv(e->spec, e->sm_count, nullptr);
+            if (perr != cudaSuccess) {
+                free_env(e);
+                return fail(ROBOY_E_CUDA, "fast-division proof: %s", cudaGetErrorString(perr));
+            }
+        }
+    }
 
     const uint64_t n = cfg->n_envs;
     cudaError_t err = cudaSuccess;
@@ -1442,6 +1452,13 @@ int roboy_robot_dims(roboy_env *env, int *dim_joint, int *dim_action, int *dim_o
     if (dim_action) *dim_action = env->A;
     if (dim_obs) *dim_obs = env->D;
     if (msj_kernels) *msj_kernels = env->msj_shaped ? 1 : 0;
+    return ROBOY_OK;
+}
+
+int roboy_fast_division(roboy_env *env, int *proved) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!proved) return fail(ROBOY_E_ARG, "NULL argument");
+    *proved = env->msj_shaped ? (env->fastdiv ? 1 : 0) : env->spec.fastdiv;
     return ROBOY_OK;
 }
 

@@ -35,6 +35,10 @@ struct RobotSpec {
     float thr_angle_sq_hi;                           // thr_angle^2 * (1 + 1e-5), rounded up: pre-filter of _did_reach_goal
     float hold_c, hold_h;                            // no action with |x - hold_c| > hold_h lies in any hold interval
     float hold_pad;                                  // a value in [-1, 1] outside that hull (hold_h < 0: nobody can hold)
+    // ---- derived on the DEVICE and proved there by exhaustion (prove_generic_fastdiv) ----
+    float a_rcp[kJointPad], v_rcp[kJointPad];        // the refined reciprocal the compiler's own division starts from
+    int32_t fastdiv;                                 // 1: t / span == fma(rcp, fma(-span, t * rcp, t), t * rcp) for every t in
+                                                     // [2^-60, 2^60] and each span of this robot, checked over all 2^32 floats
     float penalty_boundary, bonus_goal;       // roboy_env.py:26-27
     double reward_lo, reward_hi;              // roboy_env.py:30,109
 };
@@ -60,6 +64,13 @@ struct GStepParams {
     unsigned long long *first_bad;
 };
 cudaError_t launch_generic_step(const GStepParams &p, int sm_count, cudaStream_t stream);
+
+// Fills r.a_rcp / r.v_rcp / r.fastdiv.  The normalisation of roboy_robot.py:93-95 divides by a per-joint constant; IEEE
+// division costs ~11 instructions and a branch, its in-range core (reciprocal refined once, quotient corrected once) three
+// when the reciprocal is known.  Whether that core returns the correctly rounded quotient for EVERY float32 numerator in
+// [2^-60, 2^60] is checked on this device for each distinct span (all 2^32 bit patterns, ~3 ms per span, cached per
+// process); a span that fails, or one outside [2^-40, 2^40], leaves fastdiv = 0 and the kernel on IEEE division.
+cudaError_t prove_generic_fastdiv(RobotSpec &r, int sm_count, cudaStream_t stream);
 
 struct GInitParams {
     uint64_t n, gid_base;

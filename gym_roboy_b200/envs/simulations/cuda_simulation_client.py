@@ -145,6 +145,14 @@ class CudaSimulationClient(SimulationClient):
         _native.check(self._lib.roboy_robot_dims(self._h, None, None, None, ctypes.byref(m)))
         return bool(m.value)
 
+    @property
+    def fast_division(self):
+        """True when the fused step divides by the robot's spans with the proved three-instruction core (same results as
+        IEEE division: offline proof for MSJ, exhaustive check on this device at construction for any other robot)."""
+        m = ctypes.c_int()
+        _native.check(self._lib.roboy_fast_division(self._h, ctypes.byref(m)))
+        return bool(m.value)
+
     def read_state(self) -> RobotState:
         """simulation_client.py:33-34"""
         n = self.num_envs

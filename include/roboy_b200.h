@@ -405,6 +405,10 @@ int roboy_step_geometry(roboy_env *env, int *grid, int *block, int *smem_bytes);
 /* The robot this handle was built for: joints, tendons, floats per observation row (3 * joints), and whether the tuned
  * MSJ kernels (1) or the generic ones (0) run its fused step.  Any pointer may be NULL. */
 int roboy_robot_dims(roboy_env *env, int *dim_joint, int *dim_action, int *dim_obs, int *msj_kernels);
+/* How this handle's fused step divides by the spans of the robot's spaces (roboy_robot.py:95): 1 = the three-instruction
+ * core, proved equal to IEEE division for these spans (offline for MSJ, oracle/verify_fastdiv.c; by exhaustion over all
+ * float32 numerators on this device at roboy_create for any other robot); 0 = IEEE division.  Results are identical. */
+int roboy_fast_division(roboy_env *env, int *proved);
 /* Measurement only: an EMPTY kernel launched exactly like roboy_step launches the step kernel (grid, block,
  * programmatic dependent launch) -- the launch-latency floor bench.py reports next to the launch-bound sizes.
  * Not counted by roboy_launch_count. */

@@ -283,3 +283,43 @@ def test_every_joint_count_instantiation_matches_oracle(J):
     for k in ("steps", "episodes", "successes", "timeouts", "sum_episode_len", "holds", "violations"):
         assert s[k] == so[k], (k, s[k], so[k])
     assert client.errors() == ora.errors() and client.errors()[0] & 1 and s["episodes"] > n // 2
+
+
+@pytest.mark.parametrize("penalty", [False, True])
+@pytest.mark.parametrize("name", sorted(GENERIC_ROBOTS))
+def test_proved_fast_division_equals_ieee_division(name, penalty):
+    """The generic step divides by the robot's spans with a three-instruction core after checking it, at construction,
+    against IEEE division over all 2^32 numerators.  Same seed, same actions, same goals (some far outside the proved
+    numerator range, some making a numerator exactly zero) -> the same bits as a handle kept on IEEE division."""
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    b = GENERIC_ROBOTS[name]
+    J, A, _, bb = orc.robot_bounds(b)
+    n, T = 20_011, 24
+    fast_c = CudaSimulationClient(robot=robot_from_bounds(b), num_envs=n, seed=9, device="cuda:0")
+    os.environ["ROBOY_B200_GENERIC_FASTDIV"] = "0"
+    try:
+        ieee_c = CudaSimulationClient(robot=robot_from_bounds(b), num_envs=n, seed=9, device="cuda:0")
+    finally:
+        del os.environ["ROBOY_B200_GENERIC_FASTDIV"]
+    assert fast_c.fast_division and not ieee_c.fast_division
+    fast, ieee = (RoboyEnv(c, joint_vel_penalty=penalty, strict=False) for c in (fast_c, ieee_c))
+    assert torch.equal(fast.reset(), ieee.reset())
+    rng = np.random.default_rng(4)
+    lo, hi = np.broadcast_to(bb["angle_low"], (J,)).astype(np.float32), np.broadcast_to(bb["angle_high"], (J,)).astype(np.float32)
+    for t in range(T):
+        if t % 6 == 2:   # goals written straight into the state rows: the midpoint (numerator 0), denormals, huge values, inf
+            g = fast_c.goal.clone()
+            mid = torch.as_tensor((lo.astype(np.float64) + hi.astype(np.float64)) / 2, dtype=torch.float32, device="cuda:0")
+            g[:, 0::7] = mid[:, None]
+            g[:, 1::7] = 1e-42
+            g[:, 2::7] = 3e38
+            g[:, 3::7] = float("inf")
+            g[:, 4::7] = -1e25
+            fast_c.goal.copy_(g); ieee_c.goal.copy_(g)
+        a = torch.as_tensor(rng.uniform(-1, 1, (n, A)).astype(np.float32), device="cuda:0")
+        o1, r1, d1, _ = fast.step(a)
+        o2, r2, d2, _ = ieee.step(a)
+        assert torch.equal(o1, o2) and torch.equal(d1, d2), t
+        assert torch.equal(r1.view(torch.int32), r2.view(torch.int32)), t   # bit pattern: NaN-safe
+    assert torch.equal(fast_c.goal, ieee_c.goal) and torch.equal(fast_c.step_flags, ieee_c.step_flags)
