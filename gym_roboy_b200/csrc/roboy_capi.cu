@@ -1473,6 +1473,14 @@ int roboy_null_step(roboy_env *env, void *stream) {
 int roboy_step_geometry(roboy_env *env, int *grid, int *block, int *smem_bytes) {
     if (check_env(env)) return ROBOY_E_ARG;
     DeviceGuard g(env->device);
+    if (!env->msj_shaped) {
+        int gr, bl, sm;
+        generic_step_geometry(env->J, env->cfg.n_envs, env->sm_count, &gr, &bl, &sm);
+        if (grid) *grid = gr;
+        if (block) *block = bl;
+        if (smem_bytes) *smem_bytes = sm;
+        return ROBOY_OK;
+    }
     const LaunchGeom geo = step_geometry(env->cfg.n_envs, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal,
                                          env->cfg.auto_reset, env->fastdiv, env->sm_count);
     if (grid) *grid = geo.grid;

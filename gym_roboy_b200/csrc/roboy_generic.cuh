@@ -64,6 +64,7 @@ struct GStepParams {
     unsigned long long *first_bad;
 };
 cudaError_t launch_generic_step(const GStepParams &p, int sm_count, cudaStream_t stream);
+void generic_step_geometry(int J, uint64_t envs, int sm_count, int *grid, int *block, int *smem_bytes);
 
 // Fills r.a_rcp / r.v_rcp / r.fastdiv.  The normalisation of roboy_robot.py:93-95 divides by a per-joint constant; IEEE
 // division costs ~11 instructions and a branch, its in-range core (reciprocal refined once, quotient corrected once) three
