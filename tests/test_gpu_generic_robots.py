@@ -264,6 +264,8 @@ def test_every_joint_count_instantiation_matches_oracle(J):
         hold = rng.random(n) < 0.05
         a[hold] = zero_action
         a[rng.random(n) < 0.002] = np.float32(1.5)          # outside the action space: error word, first offending env
+        if t % 7 == 3:
+            a[rng.integers(0, n), rng.integers(0, A)] = np.nan   # one NaN component somewhere: fails the same assert
         if t % 10 == 4:
             q, _ = orc.draw_state(J, np.arange(n), ora.counter + 1, bb["angle_low"], bb["angle_high"], J=J)
             d = rng.normal(size=(n, J)); d /= np.linalg.norm(d, axis=1, keepdims=True)
@@ -323,3 +325,44 @@ def test_proved_fast_division_equals_ieee_division(name, penalty):
         assert torch.equal(o1, o2) and torch.equal(d1, d2), t
         assert torch.equal(r1.view(torch.int32), r2.view(torch.int32)), t   # bit pattern: NaN-safe
     assert torch.equal(fast_c.goal, ieee_c.goal) and torch.equal(fast_c.step_flags, ieee_c.step_flags)
+
+
+@pytest.mark.parametrize("name", ["six_joints_14_tendons", "fifteen_joints_64_tendons"])
+def test_quiet_chunks_and_unaligned_action_slices(name):
+    """The whole-chunk action test reads 32 rows as float4 when the slice is 16-byte aligned and falls back to one row per
+    lane otherwise.  A batch where most chunks contain no hold and no bad action (the quick path) and a few contain exactly
+    one of either, stepped one call at a time (aligned) and two steps per call (`step_many`: the second slice of an odd
+    population is only 4-byte aligned) -- both against the oracle."""
+    b = GENERIC_ROBOTS[name]
+    J, A, _, bb = orc.robot_bounds(b)
+    n, T = 50_003, 12
+    e1, c1, ora = make_pair(b, n, 11)
+    e2, c2, _ = make_pair(b, n, 11)
+    first = e1.reset()
+    assert torch.equal(first, e2.reset()) and np.array_equal(first.cpu().numpy(), ora.reset())
+    zero_action, can_hold = orc.hold_action(b)
+    rng = np.random.default_rng(5)
+    assert (n * A * 4) % 16 != 0 or A % 4 == 0   # 14 tendons: the second slice is only 8-byte aligned
+    for t in range(0, T, 2):
+        pair = []
+        for u in range(2):
+            a = rng.uniform(-1, 1, (n, A)).astype(np.float32)
+            for i in rng.integers(0, n, 40):
+                a[i] = zero_action                                   # 40 chunks of 1563 hold one env
+            for i in rng.integers(0, n, 20):
+                a[i, rng.integers(0, A)] = [np.nan, 1.0000001, -3.0][(t + u) % 3]
+            a[rng.integers(0, n, 20)] = np.nextafter(zero_action, np.float32(-1))   # next to the hold interval, not inside
+            pair.append(a)
+        both = torch.as_tensor(np.stack(pair), device="cuda:0")
+        obs_m, rew_m, done_m = c2.step_many(both)
+        for u in range(2):
+            o1, r1, d1, _ = e1.step(both[u].clone())
+            o_obs, o_rew, o_done = ora.step(pair[u])
+            assert np.array_equal(o1.cpu().numpy(), o_obs) and np.array_equal(d1.cpu().numpy(), o_done), (t, u)
+            assert torch.equal(obs_m[u], o1) and torch.equal(done_m[u].bool(), d1.bool()), (t, u)
+            assert torch.equal(rew_m[u].view(torch.int32), r1.view(torch.int32)), (t, u)
+    assert c1.errors() == c2.errors() == ora.errors() and c1.errors()[0] & 1
+    s1, s2, so = c1.stats(), c2.stats(), ora.stats()
+    for k in ("steps", "episodes", "successes", "timeouts", "holds", "violations"):
+        assert s1[k] == s2[k] == so[k], k
+    assert (s1["holds"] > 0) == can_hold
