@@ -925,7 +925,7 @@ int roboy_compute_reward(roboy_env *env, uint64_t k, const float *q_dev, const f
     p.r = env->spec;
     p.penalty = env->cfg.joint_vel_penalty != 0;
     p.bonus = env->cfg.bonus_for_goal != 0;
-    p.check_range = check_range != 0;
+    p.check_range = check_range;   // 0 no check, 1 check, 2 reward-range probe (no check, correctly rounded float32 exp)
     p.gid_base = env->cfg.env_id_base;
     p.q = q_dev;
     p.qd = qd_dev;

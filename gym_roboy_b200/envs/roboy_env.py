@@ -85,7 +85,7 @@ class RoboyEnv(_GoalEnvBase):
         q = np.stack([angles.high, angles.low])
         qd = np.stack([vels.high, vels.low])
         goal_q, goal_qd = np.stack([angles.high] * 2), np.stack([vels.high] * 2)
-        reward, _ = self._simulation_client.compute_reward(q, qd, [1, 0], goal_q, goal_qd, check_range=False)
+        reward, _ = self._simulation_client.compute_reward(q, qd, [1, 0], goal_q, goal_qd, check_range=_native.REWARD_RANGE_PROBE)
         max_reward, min_reward = reward.tolist()
         return min_reward, max_reward
 

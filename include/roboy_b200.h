@@ -234,7 +234,11 @@ int roboy_done_indices(roboy_env *env, int32_t *idx_dev, uint64_t capacity, uint
  * _did_reach_goal (:125-134) over float32 device arrays [k][3]; feasible_dev uint8 [k] or NULL
  * (all feasible); goal_qd_dev NULL = the float64 zero velocities of roboy_env.py:23.
  * reward_dev float64 [k] (the reference returns a python float), reached_dev uint8 [k] or NULL.
- * check_range != 0 applies the handle's reward range (violations go to the error word). */
+ * check_range: 0 = no range check; 1 = apply the handle's reward range (violations go to the error word);
+ * 2 (ROBOY_REWARD_RANGE_PROBE) = the two calls of _create_reward_range (roboy_env.py:40-49): no check, and the float32
+ * exponentials correctly rounded, so that the bounds the other rewards are checked against (:109) do not fall an ulp of the
+ * device's expf inside the range they are meant to enclose. */
+#define ROBOY_REWARD_RANGE_PROBE 2
 int roboy_compute_reward(roboy_env *env, uint64_t k, const float *q_dev, const float *qd_dev,
                          const uint8_t *feasible_dev, const float *goal_q_dev, const float *goal_qd_dev,
                          double *reward_dev, uint8_t *reached_dev, int check_range, void *stream);

@@ -366,3 +366,44 @@ def test_quiet_chunks_and_unaligned_action_slices(name):
     for k in ("steps", "episodes", "successes", "timeouts", "holds", "violations"):
         assert s1[k] == s2[k] == so[k], k
     assert (s1["holds"] > 0) == can_hold
+
+
+def test_generic_soak_slice():
+    """15 seconds of tools/soak_generic.py: random robots (1..15 joints, 1..64 tendons, asymmetric / one-sided / symmetric
+    spaces), random flags, goals around the reached threshold and at the midpoint of the angle space, bad actions."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from soak_generic import soak
+    summary = soak(15.0, master_seed=7)
+    assert not summary["mismatches"], summary["mismatches"][:3]
+    assert summary["configs"] >= 3 and summary["fast_division"] == summary["configs"]
+    assert summary["successes"] > 0 and summary["timeouts"] > 0 and summary["violations"] > 0
+
+
+@pytest.mark.parametrize("robot", ["msj", "six_joints_14_tendons"])
+def test_env_sitting_on_its_goal_is_inside_the_reward_range(robot):
+    """joint_vel_penalty on, bonus off: max_reward = fl32(-1 - e^-1) is an exact tie in float32 and must not come out below
+    the float64 reward of an env that holds the zero state with its goal planted exactly there (distance 0, velocity 0) --
+    the reference raises nothing for that env (roboy_env.py:109); found by tools/soak_generic.py."""
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    b = {} if robot == "msj" else GENERIC_ROBOTS[robot]
+    J, A, _, bb = orc.robot_bounds(b) if b else (3, 8, None, None)
+    n = 4099
+    client = CudaSimulationClient(robot=robot_from_bounds(b) if b else None, num_envs=n, seed=2, device="cuda:0")
+    env = RoboyEnv(client, joint_vel_penalty=True, is_agent_getting_bonus_for_reaching_goal=False, auto_reset=False, strict=False)
+    ora = orc.OracleEnv(n, seed=2, joint_vel_penalty=True, bonus=False, auto_reset=False, threads=4, **b)
+    assert env.reward_range == tuple(ora.reward_range), (env.reward_range, ora.reward_range)   # bit-equal: both exps correctly rounded
+    env.reset(); ora.reset()
+    zero_action, can_hold = orc.hold_action(b) if b else (np.zeros(8, np.float32), True)
+    assert can_hold
+    g = np.zeros((n, J), np.float32)
+    client.set_goal(g); ora.goal[:] = g.T
+    a = np.tile(zero_action, (n, 1)).astype(np.float32)
+    obs, rew, done, _ = env.step(torch.as_tensor(a, device="cuda:0"))
+    o_obs, o_rew, o_done = ora.step(a)
+    assert np.array_equal(obs.cpu().numpy(), o_obs) and np.array_equal(done.cpu().numpy(), o_done) and o_done.all()
+    assert np.allclose(rew.cpu().numpy(), o_rew, rtol=RTOL, atol=0)
+    assert np.all(rew.cpu().numpy() == np.float32(env.reward_range[1]))
+    assert client.errors()[0] == ora.errors()[0] == 0
+    assert client.stats()["violations"] == ora.stats()["violations"] == 0
