@@ -41,9 +41,16 @@ def soak(budget=120.0, master_seed=20261018):
                     d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
                     r = thr * (1.0 + rng.choice([1e-7, 1e-6, 1e-5, 1e-3, 0.1], n) * rng.choice([-1, 1], n))
                     g = np.clip((q.astype(np.float64) + d * r[:, None]), -orc.PI32, orc.PI32).astype(np.float32)
+                    pick = rng.random(n)
+                    g[pick < 0.05] = 0.0                                          # the zero state itself (held after a reset)
+                    g[(pick >= 0.05) & (pick < 0.07)] = -orc.PI32                 # on the bounds
+                    g[(pick >= 0.07) & (pick < 0.09)] = np.nextafter(orc.PI32, np.float32(0))
                     client.set_goal(g); ora.goal[:] = g.T
                 a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
                 a[rng.random(n) < 0.02] = 0.0
+                a[rng.random(n) < 0.003] = np.float32(1e-9)                       # next to the hold interval
+                if t % 5 == 1:
+                    a[rng.integers(0, n), rng.integers(0, 8)] = [np.nan, 1.5, -1.0000001][t % 3]
                 obs, rew, done, _ = env.step(torch.as_tensor(a, device="cuda:0"))
                 o_obs, o_rew, o_done = ora.step(a)
                 if not np.array_equal(done.cpu().numpy(), o_done): raise AssertionError("done mask, step %d" % t)
@@ -58,6 +65,8 @@ def soak(budget=120.0, master_seed=20261018):
             s, so = client.stats(), ora.stats()
             for k in ("steps", "episodes", "successes", "timeouts", "sum_episode_len", "holds", "violations"):
                 if s[k] != so[k]: raise AssertionError("stat %s: %r vs %r" % (k, s[k], so[k]))
+            if client.errors()[0] != ora.errors()[0] or (client.errors()[0] and client.errors()[1] != ora.errors()[1]):
+                raise AssertionError("error word / first offending env: %r vs %r" % (client.errors(), ora.errors()))
             if not np.array_equal(client.goal.cpu().numpy(), ora.goal): raise AssertionError("final goals")
             if not np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags): raise AssertionError("final step words")
             for k in ("successes", "timeouts", "holds", "violations"):
