@@ -290,3 +290,14 @@ def test_randomised_soak_slice():
     assert summary["mismatches"] == [], (master_seed, summary["mismatches"][:3])
     assert summary["configs"] >= 5 and summary["successes"] > 0 and summary["timeouts"] > 0 and summary["holds"] > 0
     assert summary["worst_reward_rel"] <= RTOL
+
+
+def test_host_path_soak_slice():
+    """12 seconds of tools/soak_host.py: `roboy_step_host` under random stage sizes, stream counts, ramp / pattern / mode,
+    autotune, done-index lists and terminal rows, MSJ and other robots, device steps in between -- against the oracle."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from soak_host import soak
+    summary = soak(12.0, master_seed=11)
+    assert not summary["mismatches"], summary["mismatches"][:3]
+    assert summary["configs"] >= 3
