@@ -407,3 +407,35 @@ def test_env_sitting_on_its_goal_is_inside_the_reward_range(robot):
     assert np.all(rew.cpu().numpy() == np.float32(env.reward_range[1]))
     assert client.errors()[0] == ora.errors()[0] == 0
     assert client.stats()["violations"] == ora.stats()["violations"] == 0
+
+
+def test_large_population_of_a_64_tendon_robot_addresses_beyond_4_gib():
+    """17,000,005 envs of the 15-joint / 64-tendon robot: the action array is 4.35 GB and the observations 3.06 GB, so
+    every row offset of the second half needs more than 32 bits.  Two steps against the oracle, bit-exact."""
+    b = GENERIC_ROBOTS["fifteen_joints_64_tendons"]
+    J, A, _, bb = orc.robot_bounds(b)
+    n = 17_000_005
+    env, client, ora = make_pair(b, n, seed=21)
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset())
+    rng = np.random.default_rng(8)
+    steps = rng.integers(399, 401, n).astype(np.int32)     # half the population times out on the first step
+    set_phases(client, ora, steps)
+    zero_action, _ = orc.hold_action(b)
+    for t in range(2):
+        a = rng.random((n, A), dtype=np.float32) * 2 - 1
+        a[::1001] = zero_action
+        a[n - 3, A - 1] = 1.5                                  # the last rows matter: out of range at the far end
+        obs, rew, done, _ = env.step(torch.as_tensor(a, device="cuda:0"))
+        o_obs, o_rew, o_done = ora.step(a)
+        assert np.array_equal(done.cpu().numpy(), o_done), t
+        assert np.array_equal(obs.cpu().numpy(), o_obs), t
+        r = rew.cpu().numpy().astype(np.float64)
+        assert (np.abs(r - o_rew) <= RTOL * np.abs(o_rew)).all(), t
+        del a, obs, rew, done, o_obs, o_rew, r
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+    assert np.array_equal(client.step_flags.cpu().numpy().astype(np.uint32), ora.step_flags)
+    assert client.errors() == ora.errors() and client.errors()[1] == n - 3
+    s, so = client.stats(), ora.stats()
+    for k in ("steps", "episodes", "successes", "timeouts", "holds", "violations"):
+        assert s[k] == so[k], k
+    assert s["episodes"] > n // 3
