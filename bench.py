@@ -654,44 +654,49 @@ def run_b200_arm(args):
         torch.cuda.empty_cache()
 
     # ---- a robot that is not MSJ: 6 joints / 14 tendons on the generic step kernel ----
-    generic_robot = None
+    generic_robot = generic_robot_15 = None
     if world == 1 and not args.no_sweep:
         from gym_roboy_b200.envs.robots import RoboyRobot
         from gym_roboy_b200.spaces import Box
-        J, A, n = 6, 14, 1 << 22
 
-        class SixJointRobot(RoboyRobot):
-            _A, _V, _T = Box(-2.5, 2.5, (J,), "float32"), Box(-0.6, 0.6, (J,), "float32"), Box(-0.2, 0.2, (A,), "float32")
-            get_action_space = classmethod(lambda cls: cls._T)
-            get_joint_angles_space = classmethod(lambda cls: cls._A)
-            get_joint_vels_space = classmethod(lambda cls: cls._V)
+        def time_generic(J, A, n, a_lo, a_hi, what):
+            class OtherRobot(RoboyRobot):
+                _A, _V, _T = Box(a_lo, a_hi, (J,), "float32"), Box(-0.6, 0.6, (J,), "float32"), Box(-0.2, 0.2, (A,), "float32")
+                get_action_space = classmethod(lambda cls: cls._T)
+                get_joint_angles_space = classmethod(lambda cls: cls._A)
+                get_joint_vels_space = classmethod(lambda cls: cls._V)
 
-        c = CudaSimulationClient(robot=SixJointRobot(), num_envs=n, seed=SEED, device=dev)
-        e = RoboyEnv(c, strict=False)
-        e.reset()
-        c.set_step_num(torch.as_tensor(episode_phases(0, n), device=dev))
-        gen = torch.Generator(device=dev); gen.manual_seed(2)
-        acts = [torch.rand((n, A), device=dev, generator=gen) * 2 - 1 for _ in range(2)]
-        for i in range(5):
-            c.step_fused(acts[i & 1])
-        torch.cuda.synchronize()
-        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k = 30
-        s_.record()
-        for i in range(k):
-            c.step_fused(acts[i & 1])
-        e_.record()
-        torch.cuda.synchronize()
-        ms = s_.elapsed_time(e_) / k
-        nbytes = 4 * A + 16 * J + 13    # read: action 4A, goal 4J, step word 4; written: obs 12J, reward 4, done 1, step word 4
-        generic_robot = {"robot": "6 joints, 14 tendons (a RoboyRobot plug-in other than MsjRobot)", "envs": n, "ms_per_step": ms,
-                         "env_steps_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_env_step": nbytes,
-                         "GBps_algorithmic": nbytes * n / (ms * 1e-3) / 1e9, "frac_of_peak": nbytes * n / (ms * 1e-3) / 1e9 / peak,
-                         "kernel": "roboy::generic_step_kernel<6, %s>" % ("true" if c.fast_division else "false"),
-                         "msj_kernels": c.msj_kernels, "fast_division_proved_at_create": c.fast_division}
-        c.close()
-        del e, c, acts
-        torch.cuda.empty_cache()
+            c = CudaSimulationClient(robot=OtherRobot(), num_envs=n, seed=SEED, device=dev)
+            e = RoboyEnv(c, strict=False)
+            e.reset()
+            c.set_step_num(torch.as_tensor(episode_phases(0, n), device=dev))
+            gen = torch.Generator(device=dev); gen.manual_seed(2)
+            acts = [torch.rand((n, A), device=dev, generator=gen) * 2 - 1 for _ in range(2)]
+            for i in range(5):
+                c.step_fused(acts[i & 1])
+            torch.cuda.synchronize()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k = 30
+            s_.record()
+            for i in range(k):
+                c.step_fused(acts[i & 1])
+            e_.record()
+            torch.cuda.synchronize()
+            ms = s_.elapsed_time(e_) / k
+            nbytes = 4 * A + 16 * J + 13    # read: action 4A, goal 4J, step word 4; written: obs 12J, reward 4, done 1, step word 4
+            row = {"robot": what, "envs": n, "ms_per_step": ms,
+                   "env_steps_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_env_step": nbytes,
+                   "GBps_algorithmic": nbytes * n / (ms * 1e-3) / 1e9, "frac_of_peak": nbytes * n / (ms * 1e-3) / 1e9 / peak,
+                   "kernel": "roboy::generic_step_kernel<%d, %s>" % (J, "true" if c.fast_division else "false"),
+                   "msj_kernels": c.msj_kernels, "fast_division_proved_at_create": c.fast_division}
+            c.close()
+            del e, c, acts
+            torch.cuda.empty_cache()
+            return row
+
+        generic_robot = time_generic(6, 14, 1 << 22, -2.5, 2.5, "6 joints, 14 tendons (a RoboyRobot plug-in other than MsjRobot)")
+        generic_robot_15 = time_generic(15, 64, 1 << 22, -np.linspace(1.0, 3.0, 15), np.linspace(0.5, 3.1, 15),
+                                        "15 joints, 64 tendons, one bound per joint (the largest robot the kernels take)")
 
     # ---- closed-loop policy rollouts (BASELINE configs[1] size and configs[4] shape), every N ----
     rollout = None
@@ -792,7 +797,7 @@ def run_b200_arm(args):
             "dtype": "f32", "data": "synthetic", "config": cfg, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
             "parity_gate": gate, "parity_checksum": checksum, "collectives_in_timed_region": collectives,
-            "episode_stats": stats, "sweep": sweep, "open_loop": open_loop, "generic_robot": generic_robot, "rollout": rollout,
+            "episode_stats": stats, "sweep": sweep, "open_loop": open_loop, "generic_robot": generic_robot, "generic_robot_15_joints": generic_robot_15, "rollout": rollout,
             "impl": "b200",
         }
         print(json.dumps(line), flush=True)

@@ -75,8 +75,11 @@ __device__ __forceinline__ double l2_f64(double a0, double a1, double a2, double
 // Three exactness-preserving shortcuts keep this path short (it is issue-bound otherwise):
 //  * FASTDIV: x / c as  q0 = x*rc; r = fma(-q0, c, x); q = fma(r, rc, q0)  -- bit-identical to the
 //    IEEE division for every numerator this path can produce with the MSJ constants (proved by
-//    exhaustion: oracle/verify_fastdiv.c, tests/test_fastdiv_proof.py); other robots take
-//    __fdiv_rn.
+//    exhaustion: oracle/verify_fastdiv.c, tests/test_fastdiv_proof.py): kDivProved.  An MSJ-shaped
+//    robot with OTHER limits gets the same three instructions with the reciprocal derived and the
+//    identity checked on the device when the handle is created (prove_generic_fastdiv: all 2^32
+//    numerators, valid for 2^-60 <= |x| <= 2^60), plus a range test of the numerators that sends
+//    the rare env outside it (x == 0) through __fdiv_rn: kDivChecked.  Spans that fail: kDivIeee.
 //  * the done test's angle distance is first bounded with a 3-instruction float32 estimate
 //    against a threshold widened by 1e-5 (the estimate is within 4e-7 of the exact sum); the
 //    exact numpy-order evaluation runs only when that cannot exclude "close".
@@ -94,9 +97,12 @@ struct FastConsts {
                              // (in the kernel it was a double-precision division per env-step)
 };
 
-template <bool FASTDIV>
+constexpr int kDivIeee = 0, kDivProved = 1, kDivChecked = 2;
+constexpr float kDivCheckedLo = 0x1p-60f, kDivCheckedHi = 0x1p60f;
+
+template <int FASTDIV>
 __device__ __forceinline__ float div_span(float t, float span, float rc) {
-    if (FASTDIV) {
+    if (FASTDIV != kDivIeee) {
         const float q0 = __fmul_rn(t, rc);
         const float r = fmaf(-q0, span, t);
         return fmaf(r, rc, q0);
@@ -104,12 +110,38 @@ __device__ __forceinline__ float div_span(float t, float span, float rc) {
     return __fdiv_rn(t, span);
 }
 
-template <bool FASTDIV>
+// one value (the rare callers: a goal normalised when it is drawn or loaded)
+template <int FASTDIV>
 __device__ __forceinline__ float normalize32_hot(float v, float hi, float lo, float span, float rc) {
-    return div_span<FASTDIV>(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, v), hi), lo), span, rc);
+    const float t = __fsub_rn(__fsub_rn(__fmul_rn(2.0f, v), hi), lo);
+    if (FASTDIV == kDivChecked) {
+        const float at = fabsf(t);
+        if (!(at >= kDivCheckedLo && at <= kDivCheckedHi)) return __fdiv_rn(t, span);
+    }
+    return div_span<FASTDIV>(t, span, rc);
 }
 
-template <bool PENALTY, bool BONUS, bool FASTDIV>
+// three values of one space (the hot callers): under kDivChecked the three numerators are range-tested together
+template <int FASTDIV>
+__device__ __forceinline__ void normalize32_hot3(float v0, float v1, float v2, float hi, float lo, float span, float rc,
+                                                 float &n0, float &n1, float &n2) {
+    const float t0 = __fsub_rn(__fsub_rn(__fmul_rn(2.0f, v0), hi), lo);
+    const float t1 = __fsub_rn(__fsub_rn(__fmul_rn(2.0f, v1), hi), lo);
+    const float t2 = __fsub_rn(__fsub_rn(__fmul_rn(2.0f, v2), hi), lo);
+    n0 = div_span<FASTDIV>(t0, span, rc);
+    n1 = div_span<FASTDIV>(t1, span, rc);
+    n2 = div_span<FASTDIV>(t2, span, rc);
+    if (FASTDIV == kDivChecked) {
+        const float mn = fminf(fminf(fabsf(t0), fabsf(t1)), fabsf(t2)), mx = fmaxf(fmaxf(fabsf(t0), fabsf(t1)), fabsf(t2));
+        if (!(mn >= kDivCheckedLo && mx <= kDivCheckedHi)) {
+            n0 = __fdiv_rn(t0, span);
+            n1 = __fdiv_rn(t1, span);
+            n2 = __fdiv_rn(t2, span);
+        }
+    }
+}
+
+template <bool PENALTY, bool BONUS, int FASTDIV>
 __device__ __forceinline__ void reward_reached_sampled_ng(float q0, float q1, float q2, float qd0, float qd1, float qd2,
                                                           float g0, float g1, float g2, float ng0, float ng1,
                                                           float ng2, const RobotConsts &c, const FastConsts &f,
@@ -130,9 +162,9 @@ __device__ __forceinline__ void reward_reached_sampled_ng(float q0, float q1, fl
         }
     }
     // compute_reward :94-96
-    const float d0 = __fsub_rn(normalize32_hot<FASTDIV>(q0, c.a_hi, c.a_lo, c.a_span, f.a_rc), ng0);
-    const float d1 = __fsub_rn(normalize32_hot<FASTDIV>(q1, c.a_hi, c.a_lo, c.a_span, f.a_rc), ng1);
-    const float d2 = __fsub_rn(normalize32_hot<FASTDIV>(q2, c.a_hi, c.a_lo, c.a_span, f.a_rc), ng2);
+    float nq0, nq1, nq2;
+    normalize32_hot3<FASTDIV>(q0, q1, q2, c.a_hi, c.a_lo, c.a_span, f.a_rc, nq0, nq1, nq2);
+    const float d0 = __fsub_rn(nq0, ng0), d1 = __fsub_rn(nq1, ng1), d2 = __fsub_rn(nq2, ng2);
     double s = (double)__fmul_rn(d0, d0);                    // OpenBLAS sdot: float products, double sum
     s = __dadd_rn(s, (double)__fmul_rn(d1, d1));
     s = __dadd_rn(s, (double)__fmul_rn(d2, d2));
@@ -140,9 +172,9 @@ __device__ __forceinline__ void reward_reached_sampled_ng(float q0, float q1, fl
     if (PENALTY) {  // :98-100, float64 because the goal velocities are
         // (every operand is finite on this path, so the NaN -> 0 of _l2_distance cannot trigger -- and :99 has none anyway)
         const double gz = f.v_gz;
-        const double e0 = __dsub_rn((double)normalize32_hot<FASTDIV>(qd0, c.v_hi, c.v_lo, c.v_span, f.v_rc), gz);
-        const double e1 = __dsub_rn((double)normalize32_hot<FASTDIV>(qd1, c.v_hi, c.v_lo, c.v_span, f.v_rc), gz);
-        const double e2 = __dsub_rn((double)normalize32_hot<FASTDIV>(qd2, c.v_hi, c.v_lo, c.v_span, f.v_rc), gz);
+        float nv0, nv1, nv2;
+        normalize32_hot3<FASTDIV>(qd0, qd1, qd2, c.v_hi, c.v_lo, c.v_span, f.v_rc, nv0, nv1, nv2);
+        const double e0 = __dsub_rn((double)nv0, gz), e1 = __dsub_rn((double)nv1, gz), e2 = __dsub_rn((double)nv2, gz);
         const double v = __dsqrt_rn(__fma_rn(e2, e2, __fma_rn(e1, e1, __dmul_rn(e0, e0))));
         double r64 = __dmul_rn(__dadd_rn(v, 1.0), (double)__fsub_rn(r32, expf(r32)));
         if (BONUS && reached) r64 = __dadd_rn(r64, (double)c.bonus_goal);  // :105-107
@@ -155,7 +187,7 @@ __device__ __forceinline__ void reward_reached_sampled_ng(float q0, float q1, fl
     }
 }
 
-template <bool PENALTY, bool BONUS, bool FASTDIV>
+template <bool PENALTY, bool BONUS, int FASTDIV>
 __device__ __forceinline__ void reward_reached_sampled(float q0, float q1, float q2, float qd0, float qd1, float qd2,
                                                        float g0, float g1, float g2, const RobotConsts &c,
                                                        const FastConsts &f, float &reward_out, bool &reached,

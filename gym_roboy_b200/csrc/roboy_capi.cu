@@ -235,7 +235,7 @@ struct roboy_env {
     FastConsts fast;
     float act_slope = 0.f, act_hi = 0.f;
     float hold_lo = 1.f, hold_hi = -1.f;
-    bool fastdiv = false;
+    int fastdiv = kDivIeee;      // division mode of the tuned MSJ-shaped kernels (msj_math.cuh): IEEE / proved offline / proved at create
     // HBM
     float *goal = nullptr;
     uint32_t *step_flags = nullptr;
@@ -324,6 +324,8 @@ void fill_step_params(roboy_env *e, StepParams &p, const float *actions, float *
     p.hold_lo = e->hold_lo;
     p.hold_hi = e->hold_hi;
     p.hold_mag = fmaxf(fabsf(e->hold_lo), fabsf(e->hold_hi));
+    p.hold_c = e->spec.hold_c;
+    p.hold_h = e->spec.hold_h;
     p.act_in_hi = 1.0f;   // roboy_env.py:31
     p.act_in_lo = -1.0f;
     p.act_hi = e->act_hi;
@@ -518,14 +520,22 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
         t = t - (double)c.v_lo;
         e->fast.v_gz = t / (double)c.v_span;
     }
-    e->fastdiv = e->msj_shaped && spans_are_proved(c.a_lo, c.a_hi, c.v_lo, c.v_hi);
-    if (!e->msj_shaped) {   // the generic step's division by the per-joint spans: proved on this device, or IEEE
+    e->fastdiv = (e->msj_shaped && spans_are_proved(c.a_lo, c.a_hi, c.v_lo, c.v_hi)) ? kDivProved : kDivIeee;
+    if (e->fastdiv == kDivIeee) {
+        // Any other robot: the division by its spans is checked against IEEE division on this device, over all 2^32
+        // numerators (roboy_generic.cuh).  The generic step uses the per-joint reciprocals; an MSJ-shaped robot with other
+        // limits runs the tuned kernels in their range-checked instantiation (kDivChecked) with the reciprocal of joint 0.
         const char *off = getenv("ROBOY_B200_GENERIC_FASTDIV");
         if (!(off && off[0] == '0')) {
             const cudaError_t perr = prove_generic_fastdiv(e->spec, e->sm_count, nullptr);
             if (perr != cudaSuccess) {
                 free_env(e);
                 return fail(ROBOY_E_CUDA, "fast-division proof: %s", cudaGetErrorString(perr));
+            }
+            if (e->msj_shaped && e->spec.fastdiv) {
+                e->fastdiv = kDivChecked;
+                e->fast.a_rc = e->spec.a_rcp[0];
+                e->fast.v_rc = e->spec.v_rcp[0];
             }
         }
     }
@@ -1345,10 +1355,10 @@ static int policy_rollout_common(roboy_env *env, bool tensor_cores, bool exact, 
     q.noise_keys = make_philox_keys(noise_seed);
     if (tensor_cores)
         CUDA_TRY(launch_policy_rollout_tc(p, q, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
-                                          env->fastdiv, env->sm_count, envs_per_thread, exact, (cudaStream_t)stream));
+                                          env->fastdiv == kDivProved, env->sm_count, envs_per_thread, exact, (cudaStream_t)stream));
     else
         CUDA_TRY(launch_policy_rollout(p, q, env->cfg.joint_vel_penalty, env->cfg.bonus_for_goal, env->cfg.auto_reset,
-                                       env->fastdiv, env->sm_count, envs_per_thread, (cudaStream_t)stream));
+                                       env->fastdiv == kDivProved, env->sm_count, envs_per_thread, (cudaStream_t)stream));
     env->launches++;
     return ROBOY_OK;
 }
@@ -1458,7 +1468,7 @@ int roboy_robot_dims(roboy_env *env, int *dim_joint, int *dim_action, int *dim_o
 int roboy_fast_division(roboy_env *env, int *proved) {
     if (check_env(env)) return ROBOY_E_ARG;
     if (!proved) return fail(ROBOY_E_ARG, "NULL argument");
-    *proved = env->msj_shaped ? (env->fastdiv ? 1 : 0) : env->spec.fastdiv;
+    *proved = env->msj_shaped ? (env->fastdiv != kDivIeee ? 1 : 0) : env->spec.fastdiv;
     return ROBOY_OK;
 }
 

@@ -226,11 +226,31 @@ struct OutPtrs {
 // Each lane tests the two float4 it loaded (float4 i belongs to env i / 2); env `lane` owns float4 2*lane and 2*lane+1
 // of the chunk's 64.  The common case -- every action in range, none near zero -- costs two NaN-propagating max-abs,
 // four compares and two votes for the whole warp; the per-env ballots run only when a vote says so.
+// CENTRED: the hold interval lies around 0 (MSJ: rescaled = 0.05 * (a + 1) - 0.05 ... any tendon range symmetric about 0), so
+// the max-abs doubles as its pre-filter.  Otherwise (a one-sided tendon range holds at a = -1) the pre-filter is the
+// distance of each float4's first component from the centre of the interval.
+template <bool CENTRED = true>
 __device__ __forceinline__ void test_actions(const StepParams &p, const Actions2 &act, int lane, bool live, bool &act_ok_out,
                                              bool &hold_out) {
 #if ROBOY_FAST_ACTION_TEST
     const float m_a = maxabs4_nan(act.a0), m_b = maxabs4_nan(act.a1);
     bool act_ok = true, hold = false;
+    if (!CENTRED) {
+        if (!__all_sync(kFull, m_a <= p.act_in_hi && m_b <= p.act_in_hi)) {
+            const uint32_t okm0 = __ballot_sync(kFull, m_a <= p.act_in_hi);
+            const uint32_t okm1 = __ballot_sync(kFull, m_b <= p.act_in_hi);
+            act_ok = (((lane < 16 ? okm0 : okm1) >> ((lane & 15) << 1)) & 3u) == 3u;
+        }
+        const bool near_a = fabsf(__fsub_rn(act.a0.x, p.hold_c)) <= p.hold_h, near_b = fabsf(__fsub_rn(act.a1.x, p.hold_c)) <= p.hold_h;
+        if (__any_sync(kFull, near_a || near_b)) {
+            const uint32_t hdm0 = __ballot_sync(kFull, near_a && action_hold4_exact(act.a0, p.hold_lo, p.hold_hi));
+            const uint32_t hdm1 = __ballot_sync(kFull, near_b && action_hold4_exact(act.a1, p.hold_lo, p.hold_hi));
+            hold = live && (((lane < 16 ? hdm0 : hdm1) >> ((lane & 15) << 1)) & 3u) == 3u;
+        }
+        act_ok_out = act_ok;
+        hold_out = hold;
+        return;
+    }
     if (!__all_sync(kFull, m_a <= p.act_in_hi && m_b <= p.act_in_hi)) {   // somebody out of range or NaN: who?
         const uint32_t okm0 = __ballot_sync(kFull, m_a <= p.act_in_hi);
         const uint32_t okm1 = __ballot_sync(kFull, m_b <= p.act_in_hi);
@@ -269,7 +289,7 @@ struct DoneQueue {
     uint32_t step[kDoneQueueCap];  // step_num at the episode end
 };
 
-template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV, bool TAIL, bool KEEP_STATE, bool DEFER = false>
+template <bool PENALTY, bool BONUS, bool AUTO_RESET, int FASTDIV, bool TAIL, bool KEEP_STATE, bool DEFER = false>
 __device__ __forceinline__ uint32_t process_chunk(const StepParams &p, uint64_t t, const ChunkIn &cur, bool act_ok, bool hold,
                                                   uint32_t base, int lane, float *so, unsigned int *s_cnt, float &sum_reward,
                                                   const OutPtrs &out, bool &done_out, DoneQueue *dq = nullptr) {
@@ -398,7 +418,7 @@ __device__ __forceinline__ uint32_t process_chunk(const StepParams &p, uint64_t 
 
 }  // namespace
 
-template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV>
+template <bool PENALTY, bool BONUS, bool AUTO_RESET, int FASTDIV>
 __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const __grid_constant__ StepParams p) {
 #if ROBOY_OBS_BULK_STORE
     __shared__ __align__(128) float s_obs[2][kWarpsPerBlock][32 * kObsDim];
@@ -464,7 +484,7 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
             in = load_state<false>(p, next << 5, lane);
         }
         bool act_ok, hold;
-        test_actions(p, cur_acts, lane, true, act_ok, hold);
+        test_actions<FASTDIV != kDivChecked>(p, cur_acts, lane, true, act_ok, hold);
 #if ROBOY_OBS_BULK_STORE
         // the bulk copy issued two chunks ago read this buffer: wait until at most one is still reading
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -487,7 +507,7 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
         const Actions2 tail_acts = load_actions<true>(p.actions, chunk << 5, (uint32_t)p.e_end, lane);
         const ChunkIn cur = load_state<true>(p, chunk << 5, lane);
         bool act_ok, hold;
-        test_actions(p, tail_acts, lane, ((chunk << 5) + lane) < (uint32_t)p.e_end, act_ok, hold);
+        test_actions<FASTDIV != kDivChecked>(p, tail_acts, lane, ((chunk << 5) + lane) < (uint32_t)p.e_end, act_ok, hold);
         process_chunk<PENALTY, BONUS, AUTO_RESET, FASTDIV, true, false, kDefer>(p, t, cur, act_ok, hold, chunk << 5, lane, so,
                                                                                 s_cnt, sum_reward, out, done_unused, dq);
     }
@@ -537,7 +557,7 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
 // (Carrying the next chunk's state in registers as well spilled and lost 1.5 %.)
 constexpr uint32_t kNoChunk = 0xffffffffu;
 
-template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV, bool TAIL>
+template <bool PENALTY, bool BONUS, bool AUTO_RESET, int FASTDIV, bool TAIL>
 __device__ __forceinline__ void rollout_chunk(const StepParams &p, uint32_t T, uint64_t t_first, uint32_t base, int lane,
                                               float (*stage)[kWarpsPerBlock][32 * kObsDim], int warp, uint32_t &parity,
                                               unsigned int *s_cnt, float &sum_reward, Actions2 &acts, uint32_t next_base) {
@@ -562,7 +582,7 @@ __device__ __forceinline__ void rollout_chunk(const StepParams &p, uint32_t T, u
             }
         }
         bool act_ok, hold;
-        test_actions(p, cur_acts, lane, live, act_ok, hold);
+        test_actions<FASTDIV != kDivChecked>(p, cur_acts, lane, live, act_ok, hold);
         const OutPtrs out{p.obs + (size_t)tt * n * kObsDim, p.reward + (size_t)tt * n, p.done + (size_t)tt * n,
                           p.obs_aligned != 0};
 #if ROBOY_OBS_BULK_STORE
@@ -586,7 +606,7 @@ __device__ __forceinline__ void rollout_chunk(const StepParams &p, uint32_t T, u
     if (live) p.step_flags[e] = cur.sf;
 }
 
-template <bool PENALTY, bool BONUS, bool AUTO_RESET, bool FASTDIV>
+template <bool PENALTY, bool BONUS, bool AUTO_RESET, int FASTDIV>
 __global__ void __launch_bounds__(kStepBlock, ROBOY_ROLLOUT_MIN_BLOCKS) rollout_kernel(const __grid_constant__ StepParams p,
                                                                             const uint32_t T) {
     __shared__ __align__(128) float s_obs[2][kWarpsPerBlock][32 * kObsDim];
@@ -645,28 +665,35 @@ using StepKernelFn = void (*)(const StepParams);
 
 template <int SEL>
 StepKernelFn kernel_for() {
-    return step_kernel<(SEL & 8) != 0, (SEL & 4) != 0, (SEL & 2) != 0, (SEL & 1) != 0>;
+    return step_kernel<(SEL & 4) != 0, (SEL & 2) != 0, (SEL & 1) != 0, (SEL >> 3)>;
 }
 
 StepKernelFn select_kernel(int sel) {
-    switch (sel & 15) {
-        case 0: return kernel_for<0>();   case 1: return kernel_for<1>();
-        case 2: return kernel_for<2>();   case 3: return kernel_for<3>();
-        case 4: return kernel_for<4>();   case 5: return kernel_for<5>();
-        case 6: return kernel_for<6>();   case 7: return kernel_for<7>();
-        case 8: return kernel_for<8>();   case 9: return kernel_for<9>();
+    switch (sel) {
+        case 0: return kernel_for<0>(); case 1: return kernel_for<1>();
+        case 2: return kernel_for<2>(); case 3: return kernel_for<3>();
+        case 4: return kernel_for<4>(); case 5: return kernel_for<5>();
+        case 6: return kernel_for<6>(); case 7: return kernel_for<7>();
+        case 8: return kernel_for<8>(); case 9: return kernel_for<9>();
         case 10: return kernel_for<10>(); case 11: return kernel_for<11>();
         case 12: return kernel_for<12>(); case 13: return kernel_for<13>();
-        case 14: return kernel_for<14>(); default: return kernel_for<15>();
+        case 14: return kernel_for<14>(); case 15: return kernel_for<15>();
+        case 16: return kernel_for<16>(); case 17: return kernel_for<17>();
+        case 18: return kernel_for<18>(); case 19: return kernel_for<19>();
+        case 20: return kernel_for<20>(); case 21: return kernel_for<21>();
+        case 22: return kernel_for<22>(); case 23: return kernel_for<23>();
+       
+        default: return nullptr;
     }
 }
 
-int selector(bool penalty, bool bonus, bool auto_reset, bool fastdiv) {
-    return (penalty ? 8 : 0) | (bonus ? 4 : 0) | (auto_reset ? 2 : 0) | (fastdiv ? 1 : 0);
+// 24 instantiations: penalty x bonus x auto-reset x division mode (kDivIeee / kDivProved / kDivChecked)
+int selector(bool penalty, bool bonus, bool auto_reset, int div_mode) {
+    return (div_mode << 3) | (penalty ? 4 : 0) | (bonus ? 2 : 0) | (auto_reset ? 1 : 0);
 }
 
 int blocks_per_sm(int sel) {
-    static int cached[16] = {0};
+    static int cached[24] = {0};
     if (!cached[sel]) {
         int b = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, select_kernel(sel), kStepBlock, 0) != cudaSuccess || b < 1)
@@ -688,29 +715,35 @@ using RolloutKernelFn = void (*)(const StepParams, const uint32_t);
 
 template <int SEL>
 RolloutKernelFn rollout_for() {
-    return rollout_kernel<(SEL & 8) != 0, (SEL & 4) != 0, (SEL & 2) != 0, (SEL & 1) != 0>;
+    return rollout_kernel<(SEL & 4) != 0, (SEL & 2) != 0, (SEL & 1) != 0, (SEL >> 3)>;
 }
 
 RolloutKernelFn select_rollout(int sel) {
-    switch (sel & 15) {
-        case 0: return rollout_for<0>();   case 1: return rollout_for<1>();
-        case 2: return rollout_for<2>();   case 3: return rollout_for<3>();
-        case 4: return rollout_for<4>();   case 5: return rollout_for<5>();
-        case 6: return rollout_for<6>();   case 7: return rollout_for<7>();
-        case 8: return rollout_for<8>();   case 9: return rollout_for<9>();
+    switch (sel) {
+        case 0: return rollout_for<0>(); case 1: return rollout_for<1>();
+        case 2: return rollout_for<2>(); case 3: return rollout_for<3>();
+        case 4: return rollout_for<4>(); case 5: return rollout_for<5>();
+        case 6: return rollout_for<6>(); case 7: return rollout_for<7>();
+        case 8: return rollout_for<8>(); case 9: return rollout_for<9>();
         case 10: return rollout_for<10>(); case 11: return rollout_for<11>();
         case 12: return rollout_for<12>(); case 13: return rollout_for<13>();
-        case 14: return rollout_for<14>(); default: return rollout_for<15>();
+        case 14: return rollout_for<14>(); case 15: return rollout_for<15>();
+        case 16: return rollout_for<16>(); case 17: return rollout_for<17>();
+        case 18: return rollout_for<18>(); case 19: return rollout_for<19>();
+        case 20: return rollout_for<20>(); case 21: return rollout_for<21>();
+        case 22: return rollout_for<22>(); case 23: return rollout_for<23>();
+       
+        default: return nullptr;
     }
 }
 
 }  // namespace
 
-cudaError_t launch_step_many(const StepParams &p, uint32_t T, bool penalty, bool bonus, bool auto_reset, bool fastdiv,
+cudaError_t launch_step_many(const StepParams &p, uint32_t T, bool penalty, bool bonus, bool auto_reset, int fastdiv,
                              int sm_count, cudaStream_t stream) {
     if (p.e_end <= p.e_begin || T == 0) return cudaSuccess;
     const int sel = selector(penalty, bonus, auto_reset, fastdiv);
-    static int per_sm[16] = {0};
+    static int per_sm[24] = {0};
     if (!per_sm[sel]) {
         int b = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, select_rollout(sel), kStepBlock, 0) != cudaSuccess || b < 1) b = 1;
@@ -722,13 +755,13 @@ cudaError_t launch_step_many(const StepParams &p, uint32_t T, bool penalty, bool
     return cudaGetLastError();
 }
 
-LaunchGeom step_geometry(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count) {
+LaunchGeom step_geometry(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, int fastdiv, int sm_count) {
     const int sel = selector(penalty, bonus, auto_reset, fastdiv);
     return LaunchGeom{grid_for(n_range, blocks_per_sm(sel), sm_count), kStepBlock,
                       (int)(sizeof(float) * kWarpsPerBlock * 32 * kObsDim + sizeof(double) * kWarpsPerBlock * ROBOY_STAT_COUNT)};
 }
 
-cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count,
+cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto_reset, int fastdiv, int sm_count,
                         cudaStream_t stream) {
     if (p.e_end <= p.e_begin) return cudaSuccess;
     const int sel = selector(penalty, bonus, auto_reset, fastdiv);
@@ -775,7 +808,7 @@ __global__ void __launch_bounds__(kStepBlock) null_step_kernel() {
 #endif
 }
 
-cudaError_t launch_null_step(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count,
+cudaError_t launch_null_step(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, int fastdiv, int sm_count,
                              cudaStream_t stream) {
     const int sel = selector(penalty, bonus, auto_reset, fastdiv);
     const int grid = grid_for(n_range, blocks_per_sm(sel), sm_count);

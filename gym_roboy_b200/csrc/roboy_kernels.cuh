@@ -62,6 +62,8 @@ struct StepParams {
     RobotConsts c;
     FastConsts f;
     float hold_mag;              // max(|hold_lo|, |hold_hi|): cheap pre-filter for the hold test
+    float hold_c, hold_h;        // centre and (padded) half width of the hold interval: the pre-filter of robots whose
+                                 // interval does not lie around 0 (kDivChecked instantiations)
     float hold_lo, hold_hi;      // the float32 interval of action components a for which
                                  // |fl(fl(slope*fl(a - in_hi)) + act_hi)| <= 1e-8, i.e. numpy's
                                  // allclose(rescaled, 0) (roboy_env.py:157-158, simulation_client.py:38)
@@ -86,7 +88,7 @@ struct StepParams {
     unsigned long long *__restrict__ first_bad;
 };
 
-cudaError_t launch_null_step(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count,
+cudaError_t launch_null_step(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, int fastdiv, int sm_count,
                              cudaStream_t stream);
 cudaError_t launch_counter_bump(unsigned long long *t_dev, unsigned int advance, cudaStream_t stream);
 
@@ -94,12 +96,12 @@ struct LaunchGeom {
     int grid, block, smem;
 };
 
-LaunchGeom step_geometry(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count);
-cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto_reset, bool fastdiv, int sm_count,
+LaunchGeom step_geometry(uint64_t n_range, bool penalty, bool bonus, bool auto_reset, int fastdiv, int sm_count);
+cudaError_t launch_step(const StepParams &p, bool penalty, bool bonus, bool auto_reset, int fastdiv, int sm_count,
                         cudaStream_t stream);
 // T consecutive steps on pre-recorded actions [T][n][8] -> obs [T][n][9], reward / done [T][n], with the
 // env state held in registers across the T steps (open loop: 73 B per env-step instead of 93).
-cudaError_t launch_step_many(const StepParams &p, uint32_t T, bool penalty, bool bonus, bool auto_reset, bool fastdiv,
+cudaError_t launch_step_many(const StepParams &p, uint32_t T, bool penalty, bool bonus, bool auto_reset, int fastdiv,
                              int sm_count, cudaStream_t stream);
 
 // Generalised advantage estimation over rollout buffers [T][n] that the step kernel filled in place

@@ -439,3 +439,82 @@ def test_large_population_of_a_64_tendon_robot_addresses_beyond_4_gib():
     for k in ("steps", "episodes", "successes", "timeouts", "holds", "violations"):
         assert s[k] == so[k], k
     assert s["episodes"] > n // 3
+
+
+MSJ_SHAPED_OTHER_LIMITS = {
+    "symmetric": dict(angle_low=-2.0, angle_high=2.0, vel_low=-0.7, vel_high=0.7, act_low=-0.5, act_high=0.5),
+    "one_sided": dict(angle_low=0.0, angle_high=2.5, vel_low=-0.3, vel_high=0.9, act_low=0.0, act_high=0.4),
+    "asymmetric": dict(angle_low=-1.1, angle_high=2.9, vel_low=-0.45, vel_high=0.2, act_low=-0.3, act_high=0.1),
+}
+
+
+@pytest.mark.parametrize("penalty", [False, True])
+@pytest.mark.parametrize("name", sorted(MSJ_SHAPED_OTHER_LIMITS))
+def test_msj_shaped_robot_with_other_limits_runs_the_tuned_kernels_with_the_checked_division(name, penalty):
+    """3 joints / 8 tendons / uniform bounds that are not MSJ's: the tuned kernels in their range-checked instantiation (the
+    division proved on this device at construction, numerators outside the proved range -- exactly zero here -- through
+    IEEE division; hold pre-filter around the centre of the hold interval, which a one-sided tendon range puts at -1).
+    Against the oracle, and bit for bit (rewards included) against a handle kept on IEEE division; closed loop, open loop
+    (`step_many`) and the host-buffer path."""
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    b = MSJ_SHAPED_OTHER_LIMITS[name]
+    J, A, _, bb = orc.robot_bounds(b)
+    n, T, seed = 20_011, 120, 17
+    env, client, ora = make_pair(b, n, seed, penalty)
+    os.environ["ROBOY_B200_GENERIC_FASTDIV"] = "0"
+    try:
+        ieee_c = CudaSimulationClient(robot=robot_from_bounds(b), num_envs=n, seed=seed, device="cuda:0")
+    finally:
+        del os.environ["ROBOY_B200_GENERIC_FASTDIV"]
+    ieee = RoboyEnv(ieee_c, joint_vel_penalty=penalty, auto_reset=True, strict=False)
+    ieee._single = False
+    assert client.msj_kernels and ieee_c.msj_kernels and client.fast_division and not ieee_c.fast_division
+    first = env.reset()
+    assert torch.equal(first, ieee.reset()) and np.array_equal(first.cpu().numpy(), ora.reset())
+    rng = np.random.default_rng(3)
+    steps = rng.integers(1, 400, n).astype(np.int32)
+    set_phases(client, ora, steps); ieee_c.set_step_num(steps)
+    zero_action, can_hold = orc.hold_action(b)
+    thr_a, _ = orc.thresholds(ora.cfg)
+    lo, hi = np.float32(bb["angle_low"]), np.float32(bb["angle_high"])
+    mid = np.float32((np.float64(lo) + np.float64(hi)) / 2)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (n, A)).astype(np.float32)
+        a[rng.random(n) < 0.03] = zero_action
+        a[rng.random(n) < 0.01] = np.nextafter(zero_action, np.float32(1))
+        if t % 9 == 4:
+            q, _ = orc.draw_state(seed, np.arange(n), ora.counter + 1, bb["angle_low"], bb["angle_high"], J=J)
+            d = rng.normal(size=(n, J)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+            g = np.clip(q.astype(np.float64) + d * float(thr_a) * (1 + rng.choice([-1e-7, 1e-7, -0.3, 0.2], n))[:, None], lo, hi).astype(np.float32)
+            pick = rng.random(n)
+            g[pick < 0.1] = mid          # zero numerators: outside the proved range
+            g[(pick >= 0.1) & (pick < 0.15)] = lo
+            client.set_goal(g); ieee_c.set_goal(g); ora.goal[:] = g.T
+        a_dev = torch.as_tensor(a, device="cuda:0")
+        o1, r1, d1, _ = env.step(a_dev)
+        o2, r2, d2, _ = ieee.step(a_dev)
+        assert torch.equal(o1, o2) and torch.equal(d1, d2) and torch.equal(r1.view(torch.int32), r2.view(torch.int32)), t
+        o_obs, o_rew, o_done = ora.step(a)
+        assert np.array_equal(d1.cpu().numpy(), o_done) and np.array_equal(o1.cpu().numpy(), o_obs), t
+        rel = np.abs(r1.cpu().numpy().astype(np.float64) - o_rew) / np.maximum(np.abs(o_rew.astype(np.float64)), 1e-30)
+        assert rel.max() <= RTOL, (t, rel.max())
+    # open loop and host buffers on the same handles
+    acts = rng.uniform(-1, 1, (3, n, A)).astype(np.float32); acts[:, ::17] = zero_action
+    obs_m, rew_m, done_m = client.step_many(torch.as_tensor(acts, device="cuda:0"))
+    obs_i, rew_i, done_i = ieee_c.step_many(torch.as_tensor(acts, device="cuda:0"))
+    assert torch.equal(obs_m, obs_i) and torch.equal(done_m, done_i) and torch.equal(rew_m.view(torch.int32), rew_i.view(torch.int32))
+    for t in range(3):
+        o_obs, o_rew, o_done = ora.step(acts[t])
+        assert np.array_equal(obs_m[t].cpu().numpy(), o_obs) and np.array_equal(done_m[t].cpu().numpy().astype(bool), o_done), t
+    a_h, obs_h, rew_h, done_h = client.host_buffers()
+    a_h[...] = rng.uniform(-1, 1, (n, A)).astype(np.float32); a_h[::13] = zero_action
+    client.set_host_pipeline(stage_envs=4096, n_streams=2)
+    client.step_host(a_h, obs_h, rew_h, done_h)
+    o_obs, o_rew, o_done = ora.step(np.array(a_h))
+    assert np.array_equal(obs_h, o_obs) and np.array_equal(done_h.astype(bool), o_done) and np.allclose(rew_h, o_rew, rtol=RTOL, atol=0)
+    s, so = client.stats(), ora.stats()
+    for k in ("steps", "episodes", "successes", "timeouts", "sum_episode_len", "holds", "violations"):
+        assert s[k] == so[k], (k, s[k], so[k])
+    assert (s["holds"] > 0) == can_hold and s["successes"] > 0
+    assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
