@@ -2,6 +2,7 @@
 // the reference lines each entry point replaces).  Host side only: handle, HBM allocation,
 // launch bookkeeping, the pinned/pipelined host-buffer path and DLPack export.
 #include <cuda_runtime.h>
+#include <float.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -83,15 +84,18 @@ float rescale_f32(float a, float in_hi, float slope, float act_hi) {
     return r;
 }
 
-// The set of action components a in [in_lo, in_hi] whose rescaled value passes numpy's
-// allclose(., 0) (|x| <= 1e-8, simulation_client.py:38).  rescale is monotone non-decreasing in a,
-// so the set is an interval of floats; both ends by bisection.  Empty -> lo > hi.
-void hold_interval(float in_lo, float in_hi, float slope, float act_hi, float *lo, float *hi) {
+// The set of action components a whose rescaled value passes numpy's allclose(., 0) (|x| <= 1e-8,
+// simulation_client.py:38).  rescale is monotone non-decreasing in a, so the set is an interval of floats; both ends by
+// bisection over EVERY finite float32, not just [-1, 1]: an action outside the action space fails the assert of
+// roboy_env.py:52 (error word), but the batch goes on, and what the Stub then does with that env is what numpy would do
+// under `python -O` -- a one-sided tendon range [0, hi] holds at a = -1, and a = -1.0000001 rescales to within 1e-8 of
+// zero as well (tools/soak_parity.py found the oracle holding there and the kernels not).  Empty -> lo > hi.
+void hold_interval(float in_hi, float slope, float act_hi, float *lo, float *hi) {
     const double tol = 1e-8;
-    uint32_t a = fkey(in_lo), b = fkey(in_hi);
+    const uint32_t a = fkey(-FLT_MAX), b = fkey(FLT_MAX);
     // smallest a with rescale(a) >= -tol
     uint32_t l = a, r = b;
-    if ((double)rescale_f32(in_hi, in_hi, slope, act_hi) < -tol) { *lo = 1.f; *hi = -1.f; return; }
+    if (!((double)rescale_f32(FLT_MAX, in_hi, slope, act_hi) >= -tol)) { *lo = 1.f; *hi = -1.f; return; }
     while (l < r) {
         const uint32_t m = l + (r - l) / 2;
         if ((double)rescale_f32(fkey_inv(m), in_hi, slope, act_hi) >= -tol) r = m; else l = m + 1;
@@ -99,7 +103,7 @@ void hold_interval(float in_lo, float in_hi, float slope, float act_hi, float *l
     const float first = fkey_inv(l);
     // largest a with rescale(a) <= tol
     l = a; r = b;
-    if ((double)rescale_f32(in_lo, in_hi, slope, act_hi) > tol) { *lo = 1.f; *hi = -1.f; return; }
+    if (!((double)rescale_f32(-FLT_MAX, in_hi, slope, act_hi) <= tol)) { *lo = 1.f; *hi = -1.f; return; }
     while (l < r) {
         const uint32_t m = l + (r - l + 1) / 2;
         if ((double)rescale_f32(fkey_inv(m), in_hi, slope, act_hi) <= tol) l = m; else r = m - 1;
@@ -145,7 +149,7 @@ void fill_robot_spec(const roboy_cfg &c, RobotSpec &r) {
         const float lo = c.per_component_bounds ? c.act_low_v[k] : c.act_low;
         const float hi = c.per_component_bounds ? c.act_high_v[k] : c.act_high;
         const float slope = (hi - lo) / (1.0f - (-1.0f));  // roboy_env.py:157, float32, per component
-        hold_interval(-1.0f, 1.0f, slope, hi, &r.hold_lo[k], &r.hold_hi[k]);
+        hold_interval(1.0f, slope, hi, &r.hold_lo[k], &r.hold_hi[k]);
     }
     r.thr_angle = box_diagonal_f32(r.a_lo, r.a_hi, r.J) / 200.0f;  // roboy_env.py:127
     r.thr_vel = box_diagonal_f32(r.v_lo, r.v_hi, r.J) / 5.0f;      // roboy_env.py:130

@@ -127,7 +127,9 @@ int roboy_cfg_msj(roboy_cfg *cfg);
 /* Host-only helper (no GPU needed): the closed float32 interval [lo, hi] of action components
  * for which the Stub holds its state -- the pre-image of numpy's allclose(rescaled, 0)
  * (simulation_client.py:38) under the float32 rescale of roboy_env.py:157-158.  For MSJ this is
- * [-2^-24, 2^-25].  lo > hi means the interval is empty.  The step kernel compares against it.
+ * [-2^-24, 2^-25].  lo > hi means the interval is empty.  The step kernel compares against it.  The interval is taken over
+ * every finite float32, not only [-1, 1]: a one-sided tendon range [0, hi] holds at a = -1 and just below it, and an
+ * action outside the action space (error word, roboy_env.py:52) still meets the Stub the way numpy would treat it.
  * roboy_hold_interval: tendon 0;  roboy_hold_intervals: all dim_action tendons (lo, hi: float[dim_action]). */
 int roboy_hold_interval(const roboy_cfg *cfg, float *lo, float *hi);
 int roboy_hold_intervals(const roboy_cfg *cfg, float *lo, float *hi);

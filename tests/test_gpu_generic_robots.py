@@ -518,3 +518,31 @@ def test_msj_shaped_robot_with_other_limits_runs_the_tuned_kernels_with_the_chec
         assert s[k] == so[k], (k, s[k], so[k])
     assert (s["holds"] > 0) == can_hold and s["successes"] > 0
     assert np.array_equal(client.goal.cpu().numpy(), ora.goal)
+
+
+@pytest.mark.parametrize("shape", ["msj_shaped", "generic"])
+def test_one_sided_tendon_range_holds_at_the_edge_of_the_action_space_and_just_outside(shape):
+    """Tendon range [0, hi]: the rescaled action is 0 at a = -1, and a = -1.0000001 -- outside the action space, so the
+    error word is set -- still rescales to within 1e-8 of zero: numpy's allclose (simulation_client.py:38) holds there, and
+    so must the kernels (the hold interval is searched over every float32, not only [-1, 1]).  Found by tools/soak_parity.py."""
+    b = dict(angle_low=-1.5, angle_high=2.0, vel_low=-0.5, vel_high=0.5, act_low=0.0, act_high=0.3)
+    if shape == "generic":
+        b = dict(b, dim_joint=4, dim_action=5)
+    J, A, _, bb = orc.robot_bounds(b)
+    n = 1000
+    env, client, ora = make_pair(b, n, seed=5, auto_reset=False)
+    assert client.msj_kernels == (shape == "msj_shaped")
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset())
+    rng = np.random.default_rng(0)
+    below = np.nextafter(np.float32(-1), np.float32(-2))
+    for t in range(4):
+        a = rng.uniform(-1, 1, (n, A)).astype(np.float32)
+        a[0::5] = -1.0                      # holds
+        a[1::5] = below                     # holds too, and is an action error
+        a[2::5, 0] = below                  # one component outside, the others random: no hold, action error
+        obs, rew, done, _ = env.step(torch.as_tensor(a, device="cuda:0"))
+        o_obs, o_rew, o_done = ora.step(a)
+        assert np.array_equal(obs.cpu().numpy(), o_obs) and np.array_equal(done.cpu().numpy(), o_done), t
+    s, so = client.stats(), ora.stats()
+    assert s["holds"] == so["holds"] == 4 * (len(range(0, n, 5)) + len(range(1, n, 5)))
+    assert s["violations"] == so["violations"] and client.errors() == ora.errors() and client.errors() == (1, 1)

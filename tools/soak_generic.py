@@ -24,8 +24,10 @@ def random_robot(rng, J):
         t_hi = np.full(A, rng.choice([0.25, 0.5, 0.125])); t_lo = -t_hi
     elif kind == 1:   # symmetric angle space: 2*v - max - min is exactly 2*v, the midpoint exactly 0
         a_lo = -a_hi
-    elif kind == 2:   # one-sided spaces
+    elif kind == 2:   # one-sided spaces (a one-sided tendon range holds at a = -1, the edge of the action space)
         a_lo = np.zeros(J); v_lo = np.zeros(J)
+        if rng.integers(0, 2):
+            t_lo = np.zeros(A)
     return dict(angle_low=a_lo, angle_high=a_hi, vel_low=v_lo, vel_high=v_hi, act_low=t_lo, act_high=t_hi)
 
 
