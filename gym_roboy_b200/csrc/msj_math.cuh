@@ -43,11 +43,14 @@ __device__ __forceinline__ double normalize64(double v, float hi, float lo, floa
 __device__ __forceinline__ float nan_to_zero(float d) { return (d != d) ? 0.0f : d; }
 __device__ __forceinline__ double nan_to_zero(double d) { return (d != d) ? 0.0 : d; }
 
-// ||a - b||_2 for float32 operands, exactly as numpy/OpenBLAS evaluate it.
+// ||a - b||_2 for float32 operands, exactly as numpy/OpenBLAS evaluate it.  GUARD: the NaN -> 0 of _l2_distance
+// (roboy_env.py:139); the penalty term (:99) calls np.linalg.norm on the difference directly and has none -- a NaN velocity
+// makes that reward NaN (tools/soak_api.py found the guarded form returning a finite one for injected NaN velocities).
+template <bool GUARD = true>
 __device__ __forceinline__ float l2_f32(float a0, float a1, float a2, float b0, float b1, float b2) {
-    const float d0 = nan_to_zero(__fsub_rn(a0, b0));
-    const float d1 = nan_to_zero(__fsub_rn(a1, b1));
-    const float d2 = nan_to_zero(__fsub_rn(a2, b2));
+    const float d0 = GUARD ? nan_to_zero(__fsub_rn(a0, b0)) : __fsub_rn(a0, b0);
+    const float d1 = GUARD ? nan_to_zero(__fsub_rn(a1, b1)) : __fsub_rn(a1, b1);
+    const float d2 = GUARD ? nan_to_zero(__fsub_rn(a2, b2)) : __fsub_rn(a2, b2);
     double s = (double)__fmul_rn(d0, d0);
     s = __dadd_rn(s, (double)__fmul_rn(d1, d1));
     s = __dadd_rn(s, (double)__fmul_rn(d2, d2));
@@ -55,10 +58,11 @@ __device__ __forceinline__ float l2_f32(float a0, float a1, float a2, float b0, 
 }
 
 // ||a - b||_2 once numpy has promoted to float64.
+template <bool GUARD = true>
 __device__ __forceinline__ double l2_f64(double a0, double a1, double a2, double b0, double b1, double b2) {
-    const double d0 = nan_to_zero(__dsub_rn(a0, b0));
-    const double d1 = nan_to_zero(__dsub_rn(a1, b1));
-    const double d2 = nan_to_zero(__dsub_rn(a2, b2));
+    const double d0 = GUARD ? nan_to_zero(__dsub_rn(a0, b0)) : __dsub_rn(a0, b0);
+    const double d1 = GUARD ? nan_to_zero(__dsub_rn(a1, b1)) : __dsub_rn(a1, b1);
+    const double d2 = GUARD ? nan_to_zero(__dsub_rn(a2, b2)) : __dsub_rn(a2, b2);
     // OpenBLAS ddot's scalar tail (n < 16) is compiled with FMA contraction: s = fma(d, d, s), sequentially -- pinned
     // against numpy in oracle/roboy_oracle.c's header.  (With float32-valued operands the products are exact and the
     // unfused sum gives the same bits; with the float64 normalised zero of an asymmetric velocity space it does not.)
@@ -250,7 +254,7 @@ static __device__ __noinline__ void reward_reached_general(const HeldState &s, c
     }
     if (penalty) {
         if (!s.is64 && has_goal_qd) {  // everything float32 (roboy_env.py:40-49 path)
-            const float v = l2_f32(normalize32((float)s.qd[0], c.v_hi, c.v_lo, c.v_span),
+            const float v = l2_f32<false>(normalize32((float)s.qd[0], c.v_hi, c.v_lo, c.v_span),
                                    normalize32((float)s.qd[1], c.v_hi, c.v_lo, c.v_span),
                                    normalize32((float)s.qd[2], c.v_hi, c.v_lo, c.v_span),
                                    normalize32(gqd[0], c.v_hi, c.v_lo, c.v_span),
@@ -267,7 +271,7 @@ static __device__ __noinline__ void reward_reached_general(const HeldState &s, c
                 ngv[k] = has_goal_qd ? (double)normalize32(gqd[k], c.v_hi, c.v_lo, c.v_span)
                                      : normalize64(0.0, c.v_hi, c.v_lo, c.v_span);
             }
-            const double v = l2_f64(nv[0], nv[1], nv[2], ngv[0], ngv[1], ngv[2]);
+            const double v = l2_f64<false>(nv[0], nv[1], nv[2], ngv[0], ngv[1], ngv[2]);   // :99: no NaN guard
             const double diff = r_is64 ? __dsub_rn(r, exp(r)) : (double)__fsub_rn(r32, expf(r32));
             r = __dmul_rn(__dadd_rn(v, 1.0), diff);
             r_is64 = true;

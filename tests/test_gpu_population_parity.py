@@ -301,3 +301,44 @@ def test_host_path_soak_slice():
     summary = soak(12.0, master_seed=11)
     assert not summary["mismatches"], summary["mismatches"][:3]
     assert summary["configs"] >= 3
+
+
+def test_api_soak_slice():
+    """12 seconds of tools/soak_api.py: stand-alone compute_reward, the external-simulator feed and state / goal / step
+    injection on values salted with NaN, infinities, the bounds, 3e38 and denormals, for MSJ, MSJ-shaped robots with other
+    limits and other robots -- against the oracle (NaN payloads included)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from soak_api import soak
+    summary = soak(12.0, master_seed=5)
+    assert not summary["mismatches"], [{k: v for k, v in m.items() if k != "bounds"} for m in summary["mismatches"][:3]]
+    assert summary["configs"] >= 3 and summary["rewards_checked"] > 0 and summary["injected_steps"] > 0
+
+
+def test_nan_velocity_in_a_held_state_makes_the_penalty_reward_nan():
+    """roboy_env.py:99 takes np.linalg.norm of the velocity difference directly -- no NaN -> 0 as in _l2_distance (:139): an
+    env holding a state whose velocity has a NaN component gets a NaN reward with joint_vel_penalty on (and a finite one
+    without).  The tuned kernels' hold path used the guarded norm there; found by tools/soak_api.py."""
+    import numpy as np, torch
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    from oracle import oracle as orc
+    for penalty in (True, False):
+        n = 64
+        client = CudaSimulationClient(num_envs=n, seed=3, device="cuda:0")
+        env = RoboyEnv(client, joint_vel_penalty=penalty, auto_reset=False, strict=False)
+        ora = orc.OracleEnv(n, seed=3, joint_vel_penalty=penalty, auto_reset=False)
+        env.reset(); ora.reset()
+        q = np.full((n, 3), 0.25, np.float32); qd = np.full((n, 3), 0.1, np.float32)
+        qd[::2, 1] = np.nan
+        client.set_state(q, qd, np.ones(n, np.uint8))
+        ora.held[0:3] = q.T; ora.held[3:6] = qd.T
+        ora.step_flags[:] = ora.step_flags & np.uint32(orc.STEP_MASK)
+        a = np.zeros((n, 8), np.float32)                       # hold: the injected state is the env's state
+        obs, rew, done, _ = env.step(torch.as_tensor(a, device="cuda:0"))
+        o_obs, o_rew, o_done = ora.step(a)
+        r = rew.cpu().numpy()
+        assert np.array_equal(np.isnan(r), np.isnan(o_rew)) and np.isnan(r[::2]).all() == penalty and not np.isnan(r[1::2]).any()
+        assert np.allclose(r[1::2], o_rew[1::2], rtol=1e-6, atol=0)
+        assert np.array_equal(obs.cpu().numpy().view(np.uint32), o_obs.view(np.uint32)) and np.array_equal(done.cpu().numpy(), o_done)
+        assert client.stats()["violations"] == ora.stats()["violations"] == (n // 2 if penalty else 0)
