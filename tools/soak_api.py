@@ -130,7 +130,23 @@ def soak(budget=60.0, master_seed=20261018):
                 a = rng.uniform(-1, 1, (n, A)).astype(np.float32)
                 a[rng.random(n) < 0.6] = zero_action
                 ora_held_before, goal_before, flags_before = ora.held.copy(), ora.goal.copy(), ora.step_flags.copy()
+                twin = None
+                if t == 3:   # checkpoint -> a fresh handle -> the same step: every output and the whole state, bit for bit
+                    sd = dict(client.state_dict(), err_flags=0)
+                    twin = CudaSimulationClient(robot=robot_from_bounds(b) if b else None, num_envs=n, seed=0, device="cuda:0")
+                    twin_env = RoboyEnv(twin, joint_vel_penalty=flags["penalty"], is_agent_getting_bonus_for_reaching_goal=flags["bonus"],
+                                        auto_reset=False, strict=False)
+                    twin_env._single = False
+                    twin.load_state_dict(sd)
                 obs, rew, done, _ = env.step(torch.as_tensor(a, device="cuda:0"))
+                if twin is not None:
+                    o2, r2, d2, _ = twin_env.step(torch.as_tensor(a, device="cuda:0"))
+                    same = (torch.equal(obs.view(torch.int32), o2.view(torch.int32)) and torch.equal(rew.view(torch.int32), r2.view(torch.int32))
+                            and torch.equal(done, d2) and torch.equal(client.goal.view(torch.int32), twin.goal.view(torch.int32))
+                            and torch.equal(client.step_flags, twin.step_flags) and twin.counter == client.counter)
+                    twin.close()
+                    summary["checkpoints"] = summary.get("checkpoints", 0) + 1
+                    if not same: raise AssertionError("resumed handle diverges from the original")
                 o_obs, o_rew, o_done = ora.step(a)
                 if not same_bits(obs.cpu().numpy(), o_obs): raise AssertionError("injected obs, step %d" % t)
                 if not np.array_equal(done.cpu().numpy().astype(bool), o_done.astype(bool)): raise AssertionError("injected done, step %d" % t)
