@@ -163,6 +163,56 @@ def soak(budget=60.0, master_seed=20261018):
                 if m.any():
                     env.reset(mask=torch.as_tensor(m)); ora.reset(m)
                 summary["injected_steps"] += n
+            # ---- the un-fused plug-in calls, composed the way the reference's RoboyEnv composes them (level 1 of
+            # INTEGRATION.md): forward_step_command / compute_reward / get_new_goal_joint_angles / forward_reset_command on a
+            # second handle reproduce the fused env's states, goals, done flags and rewards ----
+            plug = CudaSimulationClient(robot=robot_from_bounds(b) if b else None, num_envs=n, seed=seed, device="cuda:0")
+            fused = CudaSimulationClient(robot=robot_from_bounds(b) if b else None, num_envs=n, seed=seed, device="cuda:0")
+            fenv = RoboyEnv(fused, joint_vel_penalty=flags["penalty"], is_agent_getting_bonus_for_reaching_goal=flags["bonus"],
+                            auto_reset=False, strict=False)
+            fenv._single = False
+            plug.configure_env(flags["penalty"], flags["bonus"], False)
+            plug.set_reward_range(*fenv.reward_range)
+            t_hi, t_lo = np.broadcast_to(bb["act_high"], (A,)).astype(np.float32), np.broadcast_to(bb["act_low"], (A,)).astype(np.float32)
+            slope = ((t_hi - t_lo) / np.float32(2.0)).astype(np.float32)
+
+            def plug_reset(mask=None):
+                plug.forward_reset_command(mask)
+                goal = plug.get_new_goal_joint_angles()
+                idx = None if mask is None else torch.nonzero(torch.as_tensor(mask)).flatten()
+                plug.set_goal(goal if idx is None else goal[idx.to(goal.device)], idx=idx)
+
+            fenv.reset(); plug_reset()
+            stp = np.full(n, 396, np.int32)
+            fused.set_step_num(stp)
+            plug_steps = stp.copy()
+            for t in range(8):
+                a = rng.uniform(-1, 1, (n, A)).astype(np.float32)
+                a[rng.random(n) < 0.1] = zero_action
+                obs, rew, done, _ = fenv.step(torch.as_tensor(a, device="cuda:0"))
+                rescaled = (slope * (a - np.float32(1.0))).astype(np.float32) + t_hi               # roboy_env.py:54-57,157-158
+                goal_before_step = plug.goal.t().contiguous()
+                state = plug.forward_step_command(torch.as_tensor(rescaled))
+                if not (same_bits(state.joint_angles.cpu().numpy(), obs[:, 0:J].cpu().numpy()) and same_bits(state.joint_vels.cpu().numpy(), obs[:, J:2 * J].cpu().numpy())):
+                    raise AssertionError("un-fused state, step %d" % t)
+                if not same_bits(obs[:, 2 * J:].cpu().numpy(), goal_before_step.cpu().numpy()): raise AssertionError("un-fused goal, step %d" % t)
+                r_p, reached_p = plug.compute_reward(state.joint_angles.to(torch.float32), state.joint_vels.to(torch.float32),
+                                                      state.is_feasible.to(torch.uint8), goal_before_step, None)
+                plug_steps += 1
+                d_p = reached_p.cpu().numpy() | (plug_steps > 400)
+                if not np.array_equal(d_p, done.cpu().numpy().astype(bool)): raise AssertionError("un-fused done, step %d" % t)
+                why = reward_mismatch(r_p.cpu().numpy(), rew.cpu().numpy().astype(np.float64))
+                if why: raise AssertionError("un-fused reward (%s), step %d" % (why, t))
+                if d_p.any():
+                    m = d_p.astype(np.uint8)
+                    idx = torch.nonzero(torch.as_tensor(d_p)).flatten().to(plug.goal.device)
+                    plug.set_goal(plug.get_new_goal_joint_angles()[idx], idx=idx)                   # roboy_env.py:67-68
+                    fenv.reset(mask=torch.as_tensor(m)); plug_reset(m)
+                    plug_steps[d_p] = 1
+                    if not same_bits(fused.goal.cpu().numpy(), plug.goal.cpu().numpy()): raise AssertionError("un-fused goals after reset, step %d" % t)
+                summary["unfused_steps"] = summary.get("unfused_steps", 0) + n
+            if fused.counter != plug.counter: raise AssertionError("un-fused call counter %r vs %r" % (plug.counter, fused.counter))
+            plug.close(); fused.close()
             s, so = client.stats(), ora.stats()
             for key in ("steps", "episodes", "successes", "timeouts", "sum_episode_len", "holds", "violations"):
                 if s[key] != so[key]: raise AssertionError("stat %s: %r vs %r" % (key, s[key], so[key]))
