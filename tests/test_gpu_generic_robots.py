@@ -546,3 +546,60 @@ def test_one_sided_tendon_range_holds_at_the_edge_of_the_action_space_and_just_o
     s, so = client.stats(), ora.stats()
     assert s["holds"] == so["holds"] == 4 * (len(range(0, n, 5)) + len(range(1, n, 5)))
     assert s["violations"] == so["violations"] and client.errors() == ora.errors() and client.errors() == (1, 1)
+
+
+CANARY_ROBOTS = {
+    "six_joints_14_tendons": GENERIC_ROBOTS["six_joints_14_tendons"],
+    "fifteen_joints_64_tendons": GENERIC_ROBOTS["fifteen_joints_64_tendons"],
+    "one_joint_3_tendons_one_sided": dict(dim_joint=1, dim_action=3, angle_low=0.0, angle_high=2.0, vel_low=0.0, vel_high=0.5, act_low=0.0, act_high=0.4),
+    "eleven_joints_17_tendons": dict(dim_joint=11, dim_action=17, angle_low=-1.0, angle_high=2.0, vel_low=-0.5, vel_high=0.25, act_low=-0.125, act_high=0.125),
+    "msj_shaped_other_limits": MSJ_SHAPED_OTHER_LIMITS["one_sided"],
+}
+
+
+@pytest.mark.parametrize("name", sorted(CANARY_ROBOTS))
+def test_caller_buffers_are_written_inside_their_bounds_only(name):
+    """(compute-sanitizer is not available on the GPU pool.)  Every output the fused step and the open-loop step write
+    into CALLER buffers lands between two guard bands that stay untouched, for ragged populations
+    (1 short of / 1 past a warp, a CTA, ...), and equals what a twin handle leaves in its own buffers."""
+    b = CANARY_ROBOTS[name]
+    J, A, _, bb = orc.robot_bounds(b)
+    D, G = 3 * J, 2048
+    zero_action, _ = orc.hold_action(b)
+    rng = np.random.default_rng(1)
+    for n in (2, 31, 33, 255, 257, 1000, 4097):
+        for penalty in (False, True):
+            e1, c1, _ = make_pair(b, n, seed=n, penalty=penalty)
+            e2, c2, _ = make_pair(b, n, seed=n, penalty=penalty)
+            e1.reset(); e2.reset()
+            steps = rng.integers(396, 401, n).astype(np.int32)
+            c1.set_step_num(steps); c2.set_step_num(steps)
+            T = 3
+            fbuf = torch.full((G + T * n * D + G,), float("nan"), device="cuda:0"); fbuf.view(torch.int32).fill_(0x7FC0DEAD)
+            rbuf = torch.empty((G + T * n + G,), device="cuda:0"); rbuf.view(torch.int32).fill_(0x7FC0DEAD)
+            dbuf = torch.full((G + T * n + G,), 0xAB, dtype=torch.uint8, device="cuda:0")
+            obs, rew, done = fbuf[G:G + n * D].view(n, D), rbuf[G:G + n], dbuf[G:G + n]
+
+            def guards_intact():
+                ok = bool((fbuf[:G].view(torch.int32) == 0x7FC0DEAD).all()) and bool((fbuf[G + T * n * D:].view(torch.int32) == 0x7FC0DEAD).all())
+                ok = ok and bool((rbuf[:G].view(torch.int32) == 0x7FC0DEAD).all()) and bool((rbuf[G + T * n:].view(torch.int32) == 0x7FC0DEAD).all())
+                return ok and bool((dbuf[:G] == 0xAB).all()) and bool((dbuf[G + T * n:] == 0xAB).all())
+
+            for t in range(2):
+                a = rng.uniform(-1, 1, (n, A)).astype(np.float32); a[::3] = zero_action; a[1::11, A - 1] = np.nan
+                a_dev = torch.as_tensor(a, device="cuda:0")
+                c1.step_fused(a_dev, obs, rew, done)
+                c2.step_fused(a_dev)
+                torch.cuda.synchronize()
+                assert guards_intact(), (n, penalty, t)
+                assert torch.equal(obs.view(torch.int32), c2.obs.view(torch.int32)) and torch.equal(rew.view(torch.int32), c2.reward.view(torch.int32))
+                assert torch.equal(done, c2.done)
+                # unused tail of the three-step buffers stays untouched too
+                assert bool((fbuf[G + n * D:G + T * n * D].view(torch.int32) == 0x7FC0DEAD).all()) and bool((dbuf[G + n:G + T * n] == 0xAB).all())
+            acts = torch.as_tensor(rng.uniform(-1, 1, (T, n, A)).astype(np.float32), device="cuda:0")
+            o3, r3, d3 = c1.step_many(acts, fbuf[G:G + T * n * D].view(T, n, D), rbuf[G:G + T * n].view(T, n), dbuf[G:G + T * n].view(T, n))
+            o3b, r3b, d3b = c2.step_many(acts)
+            torch.cuda.synchronize()
+            assert guards_intact(), (n, penalty, "step_many")
+            assert torch.equal(o3.view(torch.int32), o3b.view(torch.int32)) and torch.equal(d3, d3b) and torch.equal(r3.view(torch.int32), r3b.view(torch.int32))
+            c1.close(); c2.close()
