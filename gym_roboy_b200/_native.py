@@ -62,6 +62,7 @@ SIGNATURES = {
     "roboy_hold_intervals": (_int, [_cfgp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "roboy_robot_dims": (_int, [_vp, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     "roboy_fast_division": (_int, [_vp, ctypes.POINTER(_int)]),
+    "roboy_penalty_float32": (_int, [_vp, ctypes.POINTER(_int)]),
     "roboy_create": (_int, [_cfgp, _int, ctypes.POINTER(_vp)]),
     "roboy_destroy": (_int, [_vp]),
     "roboy_set_reward_range": (_int, [_vp, ctypes.c_double, ctypes.c_double]),

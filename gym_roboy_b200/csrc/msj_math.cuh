@@ -89,6 +89,21 @@ __device__ __forceinline__ double l2_f64(double a0, double a1, double a2, double
 //    exact numpy-order evaluation runs only when that cannot exclude "close".
 //  * NaN -> 0 of _l2_distance (roboy_env.py:139) cannot trigger: all operands are finite.
 // ---------------------------------------------------------------------------------------------
+// float32 evaluation of the velocity penalty (roboy_env.py:98-100) on the sampled-state path.  The reference evaluates
+//   (||nv - gz||_2 + 1) * (r - exp(r))   in float64 (gz, the goal's normalised zero velocity, is float64) and returns a
+// float; only two things are observable: the reward to 1e-6 relative (north_star) and whether it lies inside reward_range
+// (:109, exact).  The float32 chain  e = nv - gz_f, s = fma(e, e, ...), (sqrt_rn(s) + 1) * (r - exp(r))  differs from the
+// rounded float64 result by at most (J/2 + 3) roundings of 2^-24 (2.7e-7 at 3 joints; allowed up to 8 joints), so it
+// decides the range test everywhere except within 1e-5 (relative) of a bound -- there, and for an env that reached its
+// goal, the float64 expression runs as before.  Enabled on the host only when gz is a float32 value (symmetric velocity
+// spaces: gz = 0) and no normalised velocity can exceed 1e9 (float32 sum of squares stays finite).
+struct PenaltyF32 {
+    int32_t on;
+    float lo_in;    // reward_lo + 1e-5 |reward_lo|, rounded up:   r > lo_in  => reward_lo <= exact
+    float lo_out;   // reward_lo - 1e-5 |reward_lo|, rounded down: r < lo_out => exact < reward_lo
+    float hi_in;    // reward_hi - 1e-5 |reward_hi|, rounded down: r < hi_in  => exact <= reward_hi
+};
+
 struct FastConsts {
     float a_rc, v_rc;        // RN(1 / a_span), RN(1 / v_span)
     float thr_angle_sq_hi;   // (thr_angle^2) * (1 + 1e-5), rounded up
@@ -99,6 +114,8 @@ struct FastConsts {
     double v_gz;             // the normalised float64 zero velocity of the goal (roboy_env.py:23,95):
                              // ((2*0.0 - v_hi) - v_lo) / v_span in float64 -- a constant of the robot, derived on the host
                              // (in the kernel it was a double-precision division per env-step)
+    float v_gz_f;            // (float)v_gz, used when pen.on (then exact)
+    PenaltyF32 pen;
 };
 
 constexpr int kDivIeee = 0, kDivProved = 1, kDivChecked = 2;
@@ -175,15 +192,29 @@ __device__ __forceinline__ void reward_reached_sampled_ng(float q0, float q1, fl
     float r32 = -expf(__fsqrt_rn((float)s));
     if (PENALTY) {  // :98-100, float64 because the goal velocities are
         // (every operand is finite on this path, so the NaN -> 0 of _l2_distance cannot trigger -- and :99 has none anyway)
-        const double gz = f.v_gz;
         float nv0, nv1, nv2;
         normalize32_hot3<FASTDIV>(qd0, qd1, qd2, c.v_hi, c.v_lo, c.v_span, f.v_rc, nv0, nv1, nv2);
-        const double e0 = __dsub_rn((double)nv0, gz), e1 = __dsub_rn((double)nv1, gz), e2 = __dsub_rn((double)nv2, gz);
-        const double v = __dsqrt_rn(__fma_rn(e2, e2, __fma_rn(e1, e1, __dmul_rn(e0, e0))));
-        double r64 = __dmul_rn(__dadd_rn(v, 1.0), (double)__fsub_rn(r32, expf(r32)));
-        if (BONUS && reached) r64 = __dadd_rn(r64, (double)c.bonus_goal);  // :105-107
-        reward_out = (float)r64;
-        violation = !(c.reward_lo <= r64 && r64 <= c.reward_hi);  // :109
+        const float diff = __fsub_rn(r32, expf(r32));
+        bool exact = true;
+        if (f.pen.on) {   // float32 chain + band test (PenaltyF32)
+            const float e0 = __fsub_rn(nv0, f.v_gz_f), e1 = __fsub_rn(nv1, f.v_gz_f), e2 = __fsub_rn(nv2, f.v_gz_f);
+            const float r = __fmul_rn(__fadd_rn(__fsqrt_rn(fmaf(e2, e2, fmaf(e1, e1, __fmul_rn(e0, e0)))), 1.0f), diff);
+            const bool below = r < f.pen.lo_out;
+            if (!reached && (below || (r > f.pen.lo_in && r < f.pen.hi_in))) {
+                reward_out = r;
+                violation = below;  // :109
+                exact = false;
+            }
+        }
+        if (exact) {
+            const double gz = f.v_gz;
+            const double e0 = __dsub_rn((double)nv0, gz), e1 = __dsub_rn((double)nv1, gz), e2 = __dsub_rn((double)nv2, gz);
+            const double v = __dsqrt_rn(__fma_rn(e2, e2, __fma_rn(e1, e1, __dmul_rn(e0, e0))));
+            double r64 = __dmul_rn(__dadd_rn(v, 1.0), (double)diff);
+            if (BONUS && reached) r64 = __dadd_rn(r64, (double)c.bonus_goal);  // :105-107
+            reward_out = (float)r64;
+            violation = !(c.reward_lo <= r64 && r64 <= c.reward_hi);  // :109
+        }
     } else {
         if (BONUS && reached) r32 = __fadd_rn(r32, c.bonus_goal);
         reward_out = r32;

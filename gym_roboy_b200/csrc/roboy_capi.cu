@@ -304,6 +304,36 @@ void unref(roboy_env *e) {
     if (e->refs.fetch_sub(1) == 1) free_env(e);
 }
 
+// PenaltyF32 (msj_math.cuh): whether the float32 evaluation of roboy_env.py:98-100 applies is a property of the robot;
+// its fall-back band follows the current reward_range (roboy_create, roboy_set_reward_range).
+// ROBOY_B200_PENALTY_F64=1 keeps every handle on the float64 expression (A/B runs, the bit-equality test).
+void set_penalty_f32(roboy_env *e) {
+    const RobotSpec &r = e->spec;
+    PenaltyF32 pen{};
+    const char *off = getenv("ROBOY_B200_PENALTY_F64");
+    bool ok = r.J <= 8 && !(off && off[0] == '1');
+    for (int k = 0; k < r.J && ok; ++k) {
+        ok = ok && (double)(float)r.v_gz[k] == r.v_gz[k];
+        // the Stub draws velocities from the ANGLE space (roboy_robot.py:38): bound of the normalised velocity
+        const double span = (double)r.v_span[k], hi = (double)r.v_hi[k], lo = (double)r.v_lo[k];
+        const double n_lo = (2.0 * (double)r.a_lo[k] - hi - lo) / span, n_hi = (2.0 * (double)r.a_hi[k] - hi - lo) / span;
+        ok = ok && fabs(n_lo) < 1e9 && fabs(n_hi) < 1e9 && fabs(r.v_gz[k]) < 1e9;
+    }
+    const double lo = r.reward_lo, hi = r.reward_hi;
+    ok = ok && !(lo != lo) && !(hi != hi);
+    if (ok) {
+        const double band_lo = fabs(lo) <= DBL_MAX ? 1e-5 * fabs(lo) : 0.0, band_hi = fabs(hi) <= DBL_MAX ? 1e-5 * fabs(hi) : 0.0;
+        pen.on = 1;
+        pen.lo_in = round_up_f32(lo + band_lo);
+        pen.lo_out = round_down_f32(lo - band_lo);
+        pen.hi_in = round_down_f32(hi - band_hi);
+    }
+    e->spec.pen = pen;
+    e->fast.pen = pen;
+    e->fast.v_gz_f = (float)e->fast.v_gz;
+    for (int k = 0; k < r.J; ++k) e->spec.v_gz_f[k] = (float)r.v_gz[k];
+}
+
 CallCounter counter(roboy_env *e, CallCounter::Mode mode, unsigned long long t_fixed = 0) {
     CallCounter c;
     c.t_dev = e->t_dev;
@@ -544,6 +574,8 @@ int roboy_create(const roboy_cfg *cfg, int device, roboy_env **out) {
         }
     }
 
+    set_penalty_f32(e);
+
     const uint64_t n = cfg->n_envs;
     cudaError_t err = cudaSuccess;
     auto alloc = [&](void **p, size_t bytes) {
@@ -611,6 +643,7 @@ int roboy_set_reward_range(roboy_env *env, double lo, double hi) {
     if (check_env(env)) return ROBOY_E_ARG;
     env->cfg.reward_lo = env->consts.reward_lo = env->spec.reward_lo = lo;
     env->cfg.reward_hi = env->consts.reward_hi = env->spec.reward_hi = hi;
+    set_penalty_f32(env);
     return ROBOY_OK;
 }
 
@@ -1473,6 +1506,13 @@ int roboy_fast_division(roboy_env *env, int *proved) {
     if (check_env(env)) return ROBOY_E_ARG;
     if (!proved) return fail(ROBOY_E_ARG, "NULL argument");
     *proved = env->msj_shaped ? (env->fastdiv != kDivIeee ? 1 : 0) : env->spec.fastdiv;
+    return ROBOY_OK;
+}
+
+int roboy_penalty_float32(roboy_env *env, int *on) {
+    if (check_env(env)) return ROBOY_E_ARG;
+    if (!on) return fail(ROBOY_E_ARG, "NULL argument");
+    *on = env->spec.pen.on;
     return ROBOY_OK;
 }
 

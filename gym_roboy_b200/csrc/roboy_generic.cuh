@@ -32,6 +32,8 @@ struct RobotSpec {
     float a_span[kJointPad], v_span[kJointPad];      // fl32(max_k - min_k), the divisor of roboy_robot.py:95
     float a_span21[kJointPad];                       // a_span * 2^-21 (exact): the grid step of a state draw
     double v_gz[kJointPad];                          // roboy_robot.py:93-95 on the float64 zero velocity of the goal
+    float v_gz_f[kJointPad];                         // (float)v_gz[k]; exact whenever pen.on
+    PenaltyF32 pen;                                  // float32 evaluation of the velocity penalty (msj_math.cuh), J <= 8
     float thr_angle_sq_hi;                           // thr_angle^2 * (1 + 1e-5), rounded up: pre-filter of _did_reach_goal
     float hold_c, hold_h;                            // no action with |x - hold_c| > hold_h lies in any hold interval
     float hold_pad;                                  // a value in [-1, 1] outside that hull (hold_h < 0: nobody can hold)

@@ -153,6 +153,14 @@ class CudaSimulationClient(SimulationClient):
         _native.check(self._lib.roboy_fast_division(self._h, ctypes.byref(m)))
         return bool(m.value)
 
+    @property
+    def penalty_float32(self):
+        """True when the fused step evaluates the velocity penalty (roboy_env.py:98-100) of sampled states in float32 with
+        a float64 re-run next to the bounds of reward_range (same error word, rewards within 1e-6 of the reference)."""
+        m = ctypes.c_int()
+        _native.check(self._lib.roboy_penalty_float32(self._h, ctypes.byref(m)))
+        return bool(m.value)
+
     def read_state(self) -> RobotState:
         """simulation_client.py:33-34"""
         n = self.num_envs

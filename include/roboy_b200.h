@@ -415,6 +415,12 @@ int roboy_robot_dims(roboy_env *env, int *dim_joint, int *dim_action, int *dim_o
  * core, proved equal to IEEE division for these spans (offline for MSJ, oracle/verify_fastdiv.c; by exhaustion over all
  * float32 numerators on this device at roboy_create for any other robot); 0 = IEEE division.  Results are identical. */
 int roboy_fast_division(roboy_env *env, int *proved);
+/* How this handle's fused step evaluates the velocity penalty of roboy_env.py:98-100 for a freshly sampled state:
+ * 1 = in float32, with the reference's float64 expression re-run wherever the float32 result lies within 1e-5
+ * (relative) of a bound of reward_range or the env reached its goal -- the reward_range assert (:109) stays exact and
+ * the reward stays within 1e-6 of the reference's; 0 = the float64 expression always (more than 8 joints, an asymmetric
+ * velocity space, or ROBOY_B200_PENALTY_F64=1 in the environment). */
+int roboy_penalty_float32(roboy_env *env, int *on);
 /* Measurement only: an EMPTY kernel launched exactly like roboy_step launches the step kernel (grid, block,
  * programmatic dependent launch) -- the launch-latency floor bench.py reports next to the launch-bound sizes.
  * Not counted by roboy_launch_count. */
