@@ -99,10 +99,26 @@ __device__ __forceinline__ double l2_f64(double a0, double a1, double a2, double
 // spaces: gz = 0) and no normalised velocity can exceed 1e9 (float32 sum of squares stays finite).
 struct PenaltyF32 {
     int32_t on;
-    float lo_in;    // reward_lo + 1e-5 |reward_lo|, rounded up:   r > lo_in  => reward_lo <= exact
-    float lo_out;   // reward_lo - 1e-5 |reward_lo|, rounded down: r < lo_out => exact < reward_lo
-    float hi_in;    // reward_hi - 1e-5 |reward_hi|, rounded down: r < hi_in  => exact <= reward_hi
+    float lo_c;     // (float)reward_lo
+    float band;     // 1e-5 |reward_lo|, rounded up:  |r - lo_c| > band  =>  r and the float64 result lie on the same side of
+                    // reward_lo (r differs from it by < 1e-6 relative, lo_c from reward_lo by 6e-8)
+    float hi_in;    // reward_hi - 1e-5 |reward_hi|, rounded down:  r < hi_in  =>  float64 result <= reward_hi
 };
+
+// sqrt of the float32 penalty sum.  ROBOY_PENALTY_SQRT_APPROX=1 (experiment) uses MUFU.SQRT directly (2^-23 relative
+// error instead of the correctly rounded 2^-24: one more rounding in the bound above, ~7 instructions fewer).
+#ifndef ROBOY_PENALTY_SQRT_APPROX
+#define ROBOY_PENALTY_SQRT_APPROX 0
+#endif
+__device__ __forceinline__ float penalty_sqrt(float s) {
+#if ROBOY_PENALTY_SQRT_APPROX
+    float v;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(s));
+    return v;
+#else
+    return __fsqrt_rn(s);
+#endif
+}
 
 struct FastConsts {
     float a_rc, v_rc;        // RN(1 / a_span), RN(1 / v_span)
@@ -198,11 +214,11 @@ __device__ __forceinline__ void reward_reached_sampled_ng(float q0, float q1, fl
         bool exact = true;
         if (f.pen.on) {   // float32 chain + band test (PenaltyF32)
             const float e0 = __fsub_rn(nv0, f.v_gz_f), e1 = __fsub_rn(nv1, f.v_gz_f), e2 = __fsub_rn(nv2, f.v_gz_f);
-            const float r = __fmul_rn(__fadd_rn(__fsqrt_rn(fmaf(e2, e2, fmaf(e1, e1, __fmul_rn(e0, e0)))), 1.0f), diff);
-            const bool below = r < f.pen.lo_out;
-            if (!reached && (below || (r > f.pen.lo_in && r < f.pen.hi_in))) {
+            const float r = __fmul_rn(__fadd_rn(penalty_sqrt(fmaf(e2, e2, fmaf(e1, e1, __fmul_rn(e0, e0)))), 1.0f), diff);
+            const float t = __fsub_rn(r, f.pen.lo_c);
+            if (!reached && fabsf(t) > f.pen.band && r < f.pen.hi_in) {   // (a NaN fails both comparisons)
                 reward_out = r;
-                violation = below;  // :109
+                violation = t < 0.0f;  // :109
                 exact = false;
             }
         }

@@ -324,8 +324,8 @@ void set_penalty_f32(roboy_env *e) {
     if (ok) {
         const double band_lo = fabs(lo) <= DBL_MAX ? 1e-5 * fabs(lo) : 0.0, band_hi = fabs(hi) <= DBL_MAX ? 1e-5 * fabs(hi) : 0.0;
         pen.on = 1;
-        pen.lo_in = round_up_f32(lo + band_lo);
-        pen.lo_out = round_down_f32(lo - band_lo);
+        pen.lo_c = (float)lo;
+        pen.band = round_up_f32(band_lo);
         pen.hi_in = round_down_f32(hi - band_hi);
     }
     e->spec.pen = pen;

@@ -556,6 +556,9 @@ __global__ void __launch_bounds__(kStepBlock, kStepMinBlocks) step_kernel(const 
 // kNoChunk) are loaded into them, and the next chunk's goal / step-word lines are prefetched into L2 (no registers).
 // (Carrying the next chunk's state in registers as well spilled and lost 1.5 %.)
 constexpr uint32_t kNoChunk = 0xffffffffu;
+#ifndef ROBOY_ROLLOUT_L2_AHEAD
+#define ROBOY_ROLLOUT_L2_AHEAD 0   // steps of actions prefetched into L2 ahead of the register prefetch (0 / 1: off; at most 4)
+#endif
 
 template <bool PENALTY, bool BONUS, bool AUTO_RESET, int FASTDIV, bool TAIL>
 __device__ __forceinline__ void rollout_chunk(const StepParams &p, uint32_t T, uint64_t t_first, uint32_t base, int lane,
@@ -569,8 +572,18 @@ __device__ __forceinline__ void rollout_chunk(const StepParams &p, uint32_t T, u
     cur.ng1 = normalize32_hot<FASTDIV>(cur.g1, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
     cur.ng2 = normalize32_hot<FASTDIV>(cur.g2, p.c.a_hi, p.c.a_lo, p.c.a_span, p.f.a_rc);
     const size_t n = (size_t)p.n;
+#if ROBOY_ROLLOUT_L2_AHEAD > 1
+    // lanes 0..7 each own one of the eight 128-byte lines of a step's 32 action rows
+    const float *pf_line = p.actions + (size_t)base * kActDim + (size_t)(lane & 7) * 32;
+#endif
     for (uint32_t tt = 0; tt < T; ++tt) {
         const Actions2 cur_acts = acts;
+#if ROBOY_ROLLOUT_L2_AHEAD > 1
+        // The register prefetch below is one step deep: one memory latency per step and warp bounds the loop.  The lines
+        // of step tt + AHEAD go to L2 now (no registers), so the register load that follows AHEAD - 1 steps later is an L2 hit.
+        if (!TAIL && tt + ROBOY_ROLLOUT_L2_AHEAD < T && lane < 8)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_line + (size_t)(tt + ROBOY_ROLLOUT_L2_AHEAD) * n * kActDim));
+#endif
         if (tt + 1 < T) {
             acts = load_actions<TAIL>(p.actions + (size_t)(tt + 1) * n * kActDim, base, n_end, lane);
         } else if (!TAIL && next_base != kNoChunk) {   // hand-over to the warp's next chunk
@@ -580,6 +593,12 @@ __device__ __forceinline__ void rollout_chunk(const StepParams &p, uint32_t T, u
                                                                          : reinterpret_cast<const float *>(p.step_flags);
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(row + next_base));
             }
+#if ROBOY_ROLLOUT_L2_AHEAD > 1
+            // ... and the next chunk's steps 1 .. AHEAD - 1 (its step 0 just went into registers)
+            if (lane >= 8 && lane < 8 * ROBOY_ROLLOUT_L2_AHEAD && (uint32_t)(lane >> 3) < T)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + (size_t)next_base * kActDim + (size_t)(lane & 7) * 32 +
+                                                                (size_t)(lane >> 3) * n * kActDim));
+#endif
         }
         bool act_ok, hold;
         test_actions<FASTDIV != kDivChecked>(p, cur_acts, lane, live, act_ok, hold);
