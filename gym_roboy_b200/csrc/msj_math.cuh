@@ -93,7 +93,7 @@ __device__ __forceinline__ double l2_f64(double a0, double a1, double a2, double
 //   (||nv - gz||_2 + 1) * (r - exp(r))   in float64 (gz, the goal's normalised zero velocity, is float64) and returns a
 // float; only two things are observable: the reward to 1e-6 relative (north_star) and whether it lies inside reward_range
 // (:109, exact).  The float32 chain  e = nv - gz_f, s = fma(e, e, ...), (sqrt_rn(s) + 1) * (r - exp(r))  differs from the
-// rounded float64 result by at most (J/2 + 3) roundings of 2^-24 (2.7e-7 at 3 joints; allowed up to 8 joints), so it
+// rounded float64 result by at most (J/2 + 4) roundings of 2^-24 (3.3e-7 at 3 joints; allowed up to 8 joints), so it
 // decides the range test everywhere except within 1e-5 (relative) of a bound -- there, and for an env that reached its
 // goal, the float64 expression runs as before.  Enabled on the host only when gz is a float32 value (symmetric velocity
 // spaces: gz = 0) and no normalised velocity can exceed 1e9 (float32 sum of squares stays finite).
@@ -105,10 +105,11 @@ struct PenaltyF32 {
     float hi_in;    // reward_hi - 1e-5 |reward_hi|, rounded down:  r < hi_in  =>  float64 result <= reward_hi
 };
 
-// sqrt of the float32 penalty sum.  ROBOY_PENALTY_SQRT_APPROX=1 (experiment) uses MUFU.SQRT directly (2^-23 relative
-// error instead of the correctly rounded 2^-24: one more rounding in the bound above, ~7 instructions fewer).
+// sqrt of the float32 penalty sum: MUFU.SQRT directly (sqrt.approx.ftz: 2^-23 relative error, one rounding more than the
+// correctly rounded __fsqrt_rn and ~7 instructions fewer -- the penalty kernels are issue-bound: 0.909 -> 0.918 of HBM peak).
+// ROBOY_PENALTY_SQRT_APPROX=0 restores __fsqrt_rn.
 #ifndef ROBOY_PENALTY_SQRT_APPROX
-#define ROBOY_PENALTY_SQRT_APPROX 0
+#define ROBOY_PENALTY_SQRT_APPROX 1
 #endif
 __device__ __forceinline__ float penalty_sqrt(float s) {
 #if ROBOY_PENALTY_SQRT_APPROX

@@ -14,7 +14,7 @@ from oracle import oracle as orc
 from test_oracle_vs_reference import GENERIC_ROBOTS
 
 pytestmark = pytest.mark.gpu
-REL = 4e-7   # (J/2 + 3) roundings of 2^-24 at J <= 8: below 4.2e-7; measured ~2.2e-7 at 3 joints
+REL = 5e-7   # (J/2 + 4) roundings of 2^-24 at J <= 8 (msj_math.cuh): at most 4.8e-7
 ROBOTS = {   # symmetric velocity spaces, at most 8 joints: where the float32 evaluation applies
     "msj": {},
     "six_joints_14_tendons": GENERIC_ROBOTS["six_joints_14_tendons"],                  # generic kernels
@@ -74,6 +74,7 @@ def test_float32_penalty_keeps_every_exact_output(robot, bonus):
         worst = max(worst, rel_err(r1, r2))
         differing += int((r1 != r2).sum().item())
     assert worst <= REL, worst
+    print("worst relative difference between the float32 and the float64 penalty: %.3g (%s)" % (worst, robot))
     assert differing > n, "the float32 path never ran"   # about half of all rewards round differently
     assert torch.equal(c32.goal, c64.goal) and torch.equal(c32.step_flags, c64.step_flags)
     assert c32.errors() == c64.errors()
