@@ -24,6 +24,8 @@ def random_robot(rng, J):
         t_hi = np.full(A, rng.choice([0.25, 0.5, 0.125])); t_lo = -t_hi
     elif kind == 1:   # symmetric angle space: 2*v - max - min is exactly 2*v, the midpoint exactly 0
         a_lo = -a_hi
+        if rng.integers(0, 2):   # ... and symmetric velocity space: the float32 penalty path (PenaltyF32) up to 8 joints
+            v_lo = -v_hi
     elif kind == 2:   # one-sided spaces (a one-sided tendon range holds at a = -1, the edge of the action space)
         a_lo = np.zeros(J); v_lo = np.zeros(J)
         if rng.integers(0, 2):
@@ -67,6 +69,7 @@ def soak(budget=120.0, master_seed=20261018):
         tag["bounds"] = {k: np.asarray(v, np.float64).tolist() for k, v in b.items()}
         viol = [0, 0]
         summary["fast_division"] += int(client.fast_division)
+        summary["penalty_float32"] = summary.get("penalty_float32", 0) + int(client.penalty_float32 and flags["penalty"])
         try:
             for t in range(T):
                 if t % 7 == 3:

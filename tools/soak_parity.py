@@ -38,6 +38,7 @@ def soak(budget=120.0, master_seed=20261018):
         client = CudaSimulationClient(robot=robot_from_bounds(b) if b else None, num_envs=max(n, 2) if n == 1 else n, seed=seed,
                                       env_id_base=base, device="cuda:0")
         n = client.num_envs
+        summary["penalty_float32"] = summary.get("penalty_float32", 0) + int(client.penalty_float32 and flags["penalty"])
         env = RoboyEnv(client, joint_vel_penalty=flags["penalty"], is_agent_getting_bonus_for_reaching_goal=flags["bonus"],
                        auto_reset=flags["auto_reset"], strict=False)
         ora = orc.OracleEnv(n, seed=seed, env_id_base=base, joint_vel_penalty=flags["penalty"], bonus=flags["bonus"],
