@@ -653,6 +653,37 @@ def run_b200_arm(args):
         del e, c, a, obs, rew, dn
         torch.cuda.empty_cache()
 
+    # ---- the flag variant of the same step kernel: joint_vel_penalty=True (roboy_env.py:98-100), steady state ----
+    penalty_variant = None
+    if world == 1 and not args.no_sweep:
+        n = 1 << 24
+        c = CudaSimulationClient(num_envs=n, seed=SEED, device=dev)
+        e = RoboyEnv(c, joint_vel_penalty=True, strict=False)
+        e.reset()
+        c.set_step_num(torch.as_tensor(episode_phases(0, n), device=dev))
+        gen = torch.Generator(device=dev); gen.manual_seed(2)
+        a = [torch.rand((n, 8), device=dev, generator=gen) * 2 - 1 for _ in range(2)]
+        for i in range(5):
+            c.step_fused(a[i & 1])
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 30
+        s_.record()
+        for i in range(reps):
+            c.step_fused(a[i & 1])
+        e_.record()
+        torch.cuda.synchronize()
+        ms = s_.elapsed_time(e_) / reps
+        penalty_variant = {"envs": n, "ms_per_step": ms, "env_steps_per_s": n / (ms * 1e-3),
+                           "GBps_algorithmic": BYTES_PER_ENV_STEP * n / (ms * 1e-3) / 1e9,
+                           "frac_of_peak": BYTES_PER_ENV_STEP * n / (ms * 1e-3) / 1e9 / peak,
+                           "penalty_float32": c.penalty_float32,
+                           "note": "velocity penalty of sampled states in float32, the reference's float64 expression re-run "
+                                   "within 1e-5 of reward_range's bounds (DESIGN.md 5); reward_range violations counted: %d"
+                                   % int(c.stats()["violations"])}
+        del e, c, a
+        torch.cuda.empty_cache()
+
     # ---- a robot that is not MSJ: 6 joints / 14 tendons on the generic step kernel ----
     generic_robot = generic_robot_15 = None
     if world == 1 and not args.no_sweep:
@@ -797,7 +828,7 @@ def run_b200_arm(args):
             "dtype": "f32", "data": "synthetic", "config": cfg, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
             "parity_gate": gate, "parity_checksum": checksum, "collectives_in_timed_region": collectives,
-            "episode_stats": stats, "sweep": sweep, "open_loop": open_loop, "generic_robot": generic_robot, "generic_robot_15_joints": generic_robot_15, "rollout": rollout,
+            "episode_stats": stats, "sweep": sweep, "open_loop": open_loop, "joint_vel_penalty": penalty_variant, "generic_robot": generic_robot, "generic_robot_15_joints": generic_robot_15, "rollout": rollout,
             "impl": "b200",
         }
         print(json.dumps(line), flush=True)
