@@ -19,6 +19,8 @@ import numpy as np
 import torch
 
 from ... import _native
+
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)   # (device index) -> cudaStream_t as int
 from ..robots import MsjRobot, RobotState, RoboyRobot
 from .simulation_client import SimulationClient
 
@@ -61,6 +63,8 @@ class CudaSimulationClient(SimulationClient):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _native.RoboyNativeError("CudaSimulationClient needs a CUDA device; there is no CPU fallback")
+        self._device_index = self.device.index if self.device.index is not None else (
+            torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self.seed_value = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & (2 ** 64 - 1)
         self.env_id_base = int(env_id_base)
 
@@ -110,7 +114,11 @@ class CudaSimulationClient(SimulationClient):
             pass
 
     def _stream(self):
-        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # torch's current stream on this device as a raw handle.  The private accessor skips building a Stream object
+        # (1.5 us of a 9 us eager step at launch-bound sizes); the public one is the fall-back.
+        if _RAW_STREAM is not None:
+            return _RAW_STREAM(self._device_index)
+        return torch.cuda.current_stream(self.device).cuda_stream
 
     def _dev(self, x, dtype, shape=None):
         t = torch.as_tensor(x, dtype=dtype, device=self.device).contiguous()
@@ -127,7 +135,7 @@ class CudaSimulationClient(SimulationClient):
 
     @staticmethod
     def _p(t):
-        return None if t is None else ctypes.c_void_p(t.data_ptr())
+        return None if t is None else t.data_ptr()   # argtypes are c_void_p: ctypes converts the int
 
     def _state_out(self, q, qd, feasible):
         # feasible byte: bit 0 is_feasible, bit 1 "this is the float64 zero state" (roboy_robot.py:41-45)

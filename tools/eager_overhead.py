@@ -19,3 +19,7 @@ print('raw ctypes call     %.2f us' % timeit(lambda: L.roboy_step(h, pa, None, N
 print('stream lookup       %.2f us' % timeit(lambda: torch.cuda.current_stream(c.device).cuda_stream, 100000))
 print('data_ptr + c_void_p %.2f us' % timeit(lambda: ctypes.c_void_p(a.data_ptr()), 100000))
 print('a.to(...).reshape.contiguous %.2f us' % timeit(lambda: a.to(device=c.device, dtype=torch.float32).reshape(n, -1).contiguous(), 100000))
+raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+if raw is not None:
+    print('raw stream lookup   %.2f us' % timeit(lambda: raw(0), 100000))
+print('null_step           %.2f us' % timeit(lambda: c.null_step()))
