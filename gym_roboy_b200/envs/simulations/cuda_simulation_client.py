@@ -77,6 +77,7 @@ class CudaSimulationClient(SimulationClient):
         handle = ctypes.c_void_p()
         _native.check(self._lib.roboy_create(ctypes.byref(cfg), self.device.index or 0, ctypes.byref(handle)))
         self._h = handle
+        self._roboy_step = self._lib.roboy_step   # bound once: the eager hot path
 
         # zero-copy torch views of the HBM buffers the handle owns (DLPack)
         self.goal = self._view(_native.BUF_GOAL)                # float32 [J, N]
@@ -236,8 +237,9 @@ class CudaSimulationClient(SimulationClient):
         if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous() \
                 or actions.numel() != self.num_envs * self.dim_action:
             raise ValueError("actions must be a contiguous float32 CUDA tensor of shape [N, {}]".format(self.dim_action))
-        _native.check(self._lib.roboy_step(self._h, self._p(actions), self._p(obs), self._p(reward), self._p(done),
-                                           self._stream()))
+        code = self._roboy_step(self._h, actions.data_ptr(), self._p(obs), self._p(reward), self._p(done), self._stream())
+        if code:
+            _native.check(code)
 
     def step_many(self, actions, obs=None, reward=None, done=None):
         """Open-loop: T fused steps on pre-recorded `actions` float32 CUDA `[T,N,8]` in ONE launch (the env
