@@ -214,10 +214,15 @@ __device__ __forceinline__ void reward_reached_sampled_ng(float q0, float q1, fl
         const float diff = __fsub_rn(r32, expf(r32));
         bool exact = true;
         if (f.pen.on) {   // float32 chain + band test (PenaltyF32)
-            const float e0 = __fsub_rn(nv0, f.v_gz_f), e1 = __fsub_rn(nv1, f.v_gz_f), e2 = __fsub_rn(nv2, f.v_gz_f);
+            // kDivProved is MSJ's instantiation: its velocity space is symmetric, gz = +0 and nv - gz = nv
+            const bool gz0 = FASTDIV == kDivProved;
+            const float e0 = gz0 ? nv0 : __fsub_rn(nv0, f.v_gz_f), e1 = gz0 ? nv1 : __fsub_rn(nv1, f.v_gz_f),
+                        e2 = gz0 ? nv2 : __fsub_rn(nv2, f.v_gz_f);
             const float r = __fmul_rn(__fadd_rn(penalty_sqrt(fmaf(e2, e2, fmaf(e1, e1, __fmul_rn(e0, e0)))), 1.0f), diff);
-            const float t = __fsub_rn(r, f.pen.lo_c);
-            if (!reached && fabsf(t) > f.pen.band && r < f.pen.hi_in) {   // (a NaN fails both comparisons)
+            // an env that reached its goal takes the float64 expression: a NaN fails both comparisons below
+            const float rt = reached ? __int_as_float(0x7fc00000) : r;
+            const float t = __fsub_rn(rt, f.pen.lo_c);
+            if (fabsf(t) > f.pen.band && rt < f.pen.hi_in) {
                 reward_out = r;
                 violation = t < 0.0f;  // :109
                 exact = false;
