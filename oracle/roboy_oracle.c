@@ -11,7 +11,9 @@
  * Parity status: PINNED.  The restatement is checked (tests/test_oracle_vs_reference.py,
  * oracle/gen_golden.py) against the unmodified reference run in the build container through
  * a test-only gym shim and a replay robot, and against golden vectors generated that way
- * (tests/golden/).  Third-party arithmetic the reference leans on was pinned empirically in
+ * (tests/golden/); its stand-alone compute_reward / _did_reach_goal additionally on SALTED inputs -- NaN, +-inf,
+ * 3e38, denormals, in the state, the goal and the goal velocities, 3 robots x 4 flag combinations, reward / reached /
+ * the :109 assert all compared (tests/test_oracle_salted_vs_reference.py).  Third-party arithmetic the reference leans on was pinned empirically in
  * that container (numpy 2.3.5 + scipy-openblas 0.3.30, x86-64):
  *   - np.linalg.norm(float32[3], ord=2) == sqrtf((float)(sum_k (double)(float)(x_k*x_k)))
  *     (OpenBLAS sdot: float products accumulated sequentially in a double, cast to float);
