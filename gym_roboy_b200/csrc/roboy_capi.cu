@@ -210,6 +210,10 @@ const char *check_robot(const roboy_cfg &c) {
         const float al = c.per_component_bounds ? c.angle_low_v[k] : c.angle_low, ah = c.per_component_bounds ? c.angle_high_v[k] : c.angle_high;
         const float vl = c.per_component_bounds ? c.vel_low_v[k] : c.vel_low, vh = c.per_component_bounds ? c.vel_high_v[k] : c.vel_high;
         if (!(ah > al) || !(vh > vl)) return "empty robot space";
+        // ptxas evaluates fl(fl(2*v) - max) of the normalisation (roboy_robot.py:95) as fma(2, v, -max) -- the same bits for
+        // every float32 v as long as |max| < 2^103 (oracle/verify_fused_numerator.c); bounds that large are not joint limits
+        if (!(fabsf(al) < 0x1p100f && fabsf(ah) < 0x1p100f && fabsf(vl) < 0x1p100f && fabsf(vh) < 0x1p100f))
+            return "robot space bounds must be below 2^100 in magnitude";
     }
     for (int k = 0; k < A; ++k) {
         const float tl = c.per_component_bounds ? c.act_low_v[k] : c.act_low, th = c.per_component_bounds ? c.act_high_v[k] : c.act_high;

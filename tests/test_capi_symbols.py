@@ -65,6 +65,10 @@ def test_hold_intervals_per_tendon_and_robot_caps():
     assert lib.roboy_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1 and b"dim_joint" in lib.roboy_last_error()
     cfg.dim_joint, cfg.dim_action = 3, 65
     assert lib.roboy_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1 and b"dim_action" in lib.roboy_last_error()
+    # joint limits of 2^100 and beyond: outside what the normalisation's fused numerator is proved for (test_fastdiv_proof)
+    lib.roboy_cfg_msj(ctypes.byref(cfg))
+    cfg.n_envs, cfg.angle_high = 8, 2.0 ** 100
+    assert lib.roboy_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1 and b"2^100" in lib.roboy_last_error()
 
 
 def test_argument_errors_are_reported_not_crashed():

@@ -23,6 +23,21 @@ def test_fast_division_is_exact_for_the_msj_spans(tmp_path):
         assert out.returncode == 0 and " 0 mismatches" in out.stdout, out.stdout + out.stderr
 
 
+def test_fused_numerator_is_exact(tmp_path):
+    """fma(2, v, -max) == fl(fl(2*v) - max) for EVERY float32 v (all 2^32 bit patterns): the FFMA ptxas emits for the
+    numerator of roboy_robot.py:95 (a value-preserving contraction it performs even under -fmad=false) is the reference's
+    multiply-then-subtract.  MSJ's two `max` values, a negative and a large one; and the check is sensitive -- it fails
+    for |max| >= 2^103, bounds roboy_create refuses."""
+    exe = str(tmp_path / "verify_fused_numerator")
+    subprocess.check_call(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-fopenmp", "-o", exe,
+                           os.path.join(ROOT, "oracle", "verify_fused_numerator.c"), "-lm"])
+    for mx in (np.float32(np.pi), np.float32(np.pi / 6), np.float32(-2.5), np.float32(1e30)):
+        out = subprocess.run([exe, "%08x" % mx.view(np.uint32)], capture_output=True, text=True)
+        assert out.returncode == 0 and " 0 mismatches" in out.stdout, out.stdout + out.stderr
+    out = subprocess.run([exe, "7f000000"], capture_output=True, text=True)   # max = 2^127
+    assert out.returncode == 1 and " 0 mismatches" not in out.stdout
+
+
 def test_numerators_are_zero_or_not_tiny():
     """The premise of the proof's range: t = (2v - max) - min is 0 or >= 2^-25 in magnitude."""
     rng = np.random.default_rng(0)
