@@ -49,7 +49,8 @@ def val(name):
 
 
 traffic = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
-STEP_KERNEL = "step_kernel" in kname   # traffic.json feeds bench.py's roofline of the env step kernel only
+# traffic.json feeds bench.py's roofline of the DEFAULT env step kernel only (not the penalty instantiation, not the generic step)
+STEP_KERNEL = ("::step_kernel<0" in kname or "::step_kernel<false" in kname) and "generic" not in kname
 if STEP_KERNEL:
   json.dump({"envs": envs, "dram_bytes_per_launch": traffic, "dram_bytes_read": val("dram__bytes_read.sum"),
            "dram_bytes_write": val("dram__bytes_write.sum"), "algorithmic_bytes_per_launch": 93 * envs,
