@@ -31,9 +31,6 @@ namespace roboy {
 #ifndef ROBOY_PREFETCH
 #define ROBOY_PREFETCH 1  // 0: none, 1: next chunk into registers (measured best), 2: next chunk into L2
 #endif
-#ifndef ROBOY_PREFETCH_DIST
-#define ROBOY_PREFETCH_DIST 1  // how many of this warp's chunks ahead the L2 prefetch runs
-#endif
 
 #ifndef ROBOY_OBS_BULK_STORE
 #define ROBOY_OBS_BULK_STORE 1  // 1 (measured +1%): drain the staged observations with cp.async.bulk (TMA bulk copy smem -> global)
@@ -141,30 +138,6 @@ __device__ __forceinline__ Actions2 load_actions(const float *actions, uint32_t 
     return a;
 }
 
-// Next-chunk prefetch into L2 (no registers held across the compute phase): lanes 0..7 touch the
-// chunk's eight 128 B action lines, lanes 8..10 its three goal lines, lane 11 the step-word line.
-// The per-lane pointer and its per-iteration increment are set up once, outside the loop.
-struct L2Prefetch {
-    const char *ptr;   // address this lane touches for the warp's NEXT chunk (lanes >= 12: unused)
-    uint32_t inc;      // bytes per loop iteration
-    __device__ __forceinline__ void init(const StepParams &p, uint32_t first_chunk, uint32_t warp_stride, int lane) {
-        const size_t base = (size_t)(first_chunk + ROBOY_PREFETCH_DIST * warp_stride) << 5;
-        if (lane < 8) {
-            ptr = reinterpret_cast<const char *>(p.actions) + base * 32 + lane * 128;
-            inc = warp_stride * 32u * 32u;
-        } else {
-            const float *row = lane == 8 ? p.goal : lane == 9 ? p.goal1 : lane == 10 ? p.goal2
-                                                                     : reinterpret_cast<const float *>(p.step_flags);
-            ptr = reinterpret_cast<const char *>(row + base);
-            inc = warp_stride * 32u * 4u;
-        }
-    }
-    __device__ __forceinline__ void issue_and_advance(bool valid, int lane) {
-        if (valid && lane < 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-        ptr += inc;
-    }
-};
-
 // max(|x|, |y|, |z|, |w|) that PROPAGATES NaN (fmaxf would drop it): one value answers both the range assert of
 // roboy_env.py:52 (m <= 1; false for NaN) and the pre-filter of the hold test (m <= hold_mag).  Two FMNMX in SASS.
 __device__ __forceinline__ float maxabs4_nan(const float4 &v) {
@@ -183,6 +156,7 @@ __device__ __forceinline__ bool action_hold4_exact(const float4 &v, float lo, fl
     return v.x >= lo && v.x <= hi && v.y >= lo && v.y <= hi && v.z >= lo && v.z <= hi && v.w >= lo && v.w <= hi;
 }
 
+#if !ROBOY_FAST_ACTION_TEST   // helpers of the pre-v8 action test (kept for A/B builds)
 // roboy_env.py:52: every component inside [-1, 1] (closed; NaN fails).
 __device__ __forceinline__ bool action_ok4(const float4 &v, float hi) {
     return fabsf(v.x) <= hi && fabsf(v.y) <= hi && fabsf(v.z) <= hi && fabsf(v.w) <= hi;
@@ -206,6 +180,7 @@ __device__ __forceinline__ bool action_hold4(const float4 &v, float lo, float hi
     return v.x >= lo && v.x <= hi && v.y >= lo && v.y <= hi && v.z >= lo && v.z <= hi && v.w >= lo && v.w <= hi;
 }
 #endif
+#endif  // !ROBOY_FAST_ACTION_TEST
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -159,6 +159,7 @@ __device__ __forceinline__ float tanh_approx(float x) {
 #ifndef ROBOY_TC_FMA_TANH_EVERY
 #define ROBOY_TC_FMA_TANH_EVERY 0
 #endif
+#if ROBOY_TC_FMA_TANH_EVERY > 0
 __device__ __forceinline__ float tanh_fma(float x) {
     const float xc = fminf(fmaxf(x, -4.97f), 4.97f);
     const float t = xc * xc;
@@ -169,6 +170,7 @@ __device__ __forceinline__ float tanh_fma(float x) {
     r = r * fmaf(-den, r, 2.0f);
     return num * r;
 }
+#endif
 // activation j of a 16-wide chunk: which unit evaluates it
 __device__ __forceinline__ float tanh_fast_mixed(float x, int j) {
 #if ROBOY_TC_FMA_TANH_EVERY > 0
