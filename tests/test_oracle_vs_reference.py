@@ -253,3 +253,17 @@ def test_every_joint_count_matches_reference(J):
         assert np.allclose(orw[alive], rr[alive], rtol=1e-6, atol=0), t
         assert np.array_equal(ref.goals()[alive], o.goal.T[alive])
     assert o.stats()["episodes"] >= 1 and (o.stats()["holds"] > 0) == can_hold
+
+
+def test_oracle_vs_reference_soak_slice():
+    """An 8-second slice of tools/soak_oracle_vs_reference.py (random robots, flags, seeds; a fresh master seed every run;
+    the 15-minute record is profiles/r2_soak_oracle_vs_reference.json)."""
+    import importlib.util
+    import time
+    spec = importlib.util.spec_from_file_location("soak_ovr", os.path.join(ROOT, "tools", "soak_oracle_vs_reference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    seed = int(time.time())
+    s = mod.soak(8.0, master_seed=seed)
+    assert not s["mismatches"], (seed, s["mismatches"][:2])
+    assert s["configs"] >= 3 and s["env_steps"] > 500
