@@ -15,7 +15,7 @@ MAX_JOINT, JOINT_PAD, MAX_ACTION = 15, 16, 64    # ROBOY_MAX_JOINT, ROBOY_JOINT_
 STEP_MASK = 0x00FFFFFF
 F_HELD_ZERO64 = 1 << 24
 F_HELD_INFEASIBLE = 1 << 25
-ERR_ACTION, ERR_REWARD_RANGE, ERR_GOAL_BOUNDS = 1, 2, 4
+ERR_ACTION, ERR_REWARD_RANGE, ERR_GOAL_BOUNDS, ERR_STATE_BOUNDS = 1, 2, 4, 8
 REWARD_RANGE_PROBE = 2   # roboy_compute_reward(check_range=ROBOY_REWARD_RANGE_PROBE)
 STAT_NAMES = ("steps", "episodes", "successes", "timeouts", "sum_reward", "sum_episode_len", "holds", "violations")
 # layout of the packed policy image of roboy_policy_rollout (ROBOY_POLICY_* in include/roboy_b200.h), in floats

@@ -219,7 +219,8 @@ class RoboyEnv(_GoalEnvBase):
         if flags:
             what = [name for bit, name in ((_native.ERR_ACTION, "action outside action_space (roboy_env.py:52)"),
                                            (_native.ERR_REWARD_RANGE, "reward outside reward_range (roboy_env.py:109)"),
-                                           (_native.ERR_GOAL_BOUNDS, "goal outside the joint angle space (roboy_robot.py:76)"))
+                                           (_native.ERR_GOAL_BOUNDS, "goal outside the joint angle space (roboy_robot.py:76)"),
+                                           (_native.ERR_STATE_BOUNDS, "external state outside the joint angle space (roboy_robot.py:76)"))
                     if flags & bit]
             self._simulation_client.clear_errors()
             raise AssertionError("{}; first offending env id {}".format("; ".join(what), first))

@@ -65,6 +65,9 @@ extern "C" {
 #define ROBOY_ERR_ACTION 1u       /* roboy_env.py:52   action outside [-1,1]^8 or NaN */
 #define ROBOY_ERR_REWARD_RANGE 2u /* roboy_env.py:109  reward outside reward_range */
 #define ROBOY_ERR_GOAL_BOUNDS 4u  /* roboy_robot.py:76 injected goal outside the angle space */
+#define ROBOY_ERR_STATE_BOUNDS 8u /* roboy_robot.py:76 joint angles handed in by an external simulator outside the angle
+                                   * space or NaN (roboy_step_external / roboy_reset_external): where the reference's client
+                                   * builds the state with robot.new_state(), ros_simulation_client.py:40-46 */
 
 /* indices into the statistics vector */
 enum {

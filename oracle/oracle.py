@@ -17,7 +17,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 STEP_MASK = 0x00FFFFFF
 F_HELD_ZERO64 = 1 << 24
 F_HELD_INFEASIBLE = 1 << 25
-ERR_ACTION, ERR_REWARD_RANGE, ERR_GOAL_BOUNDS = 1, 2, 4
+ERR_ACTION, ERR_REWARD_RANGE, ERR_GOAL_BOUNDS, ERR_STATE_BOUNDS = 1, 2, 4, 8
 STAT_NAMES = ("steps", "episodes", "successes", "timeouts", "sum_reward", "sum_episode_len", "holds", "violations")
 STREAM_STATE, STREAM_GOAL = 0, 2
 

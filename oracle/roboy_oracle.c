@@ -87,6 +87,7 @@ static float t_hi(const orc_cfg *c, int k) { return c->per_component_bounds ? c-
 #define ORC_ERR_ACTION 1u       /* roboy_env.py:52 */
 #define ORC_ERR_REWARD_RANGE 2u /* roboy_env.py:109 */
 #define ORC_ERR_GOAL_BOUNDS 4u  /* roboy_robot.py:76 */
+#define ORC_ERR_STATE_BOUNDS 8u /* roboy_robot.py:76 through ros_simulation_client.py:40-46: an external state's angles */
 
 enum { ST_STEPS = 0, ST_EPISODES, ST_SUCCESSES, ST_TIMEOUTS, ST_SUM_REWARD, ST_SUM_EPLEN, ST_HOLDS, ST_VIOLATIONS, ST_N };
 
@@ -449,6 +450,13 @@ void orc_external(orc_env *e, int reset, const uint8_t *mask, const float *q, co
         for (int k = 0; k < J; ++k) { s.q[k] = q[J * i + k]; s.qd[k] = qd[J * i + k]; }
         s.is64 = 1;
         s.feasible = feasible ? feasible[i] != 0 : 1;
+        /* robot.new_state() in the client (ros_simulation_client.py:40-46) asserts the angles inside the angle space
+         * (roboy_robot.py:76: Box.contains, closed interval, NaN fails; the velocity assert is commented out, :77) */
+        int bad_state = 0;
+        for (int k = 0; k < J; ++k) {
+            if (!(q[J * i + k] >= a_lo(cfg, k) && q[J * i + k] <= a_hi(cfg, k))) bad_state = 1;
+        }
+        if (bad_state && reset) note_error(e, ORC_ERR_STATE_BOUNDS, gid);
         float g[JP];
         for (int k = 0; k < J; ++k) g[k] = e->goal[(size_t)k * n + i];
         uint32_t sf = e->step_flags[i];
@@ -467,7 +475,10 @@ void orc_external(orc_env *e, int reset, const uint8_t *mask, const float *q, co
             e->stats[ST_STEPS] += 1.0;
             e->stats[ST_SUM_REWARD] += (double)(float)r;
             if (dn) { e->stats[ST_EPISODES] += 1.0; e->stats[reached ? ST_SUCCESSES : ST_TIMEOUTS] += 1.0; e->stats[ST_SUM_EPLEN] += (double)step - 1.0; }
-            if (viol) { e->stats[ST_VIOLATIONS] += 1.0; note_error(e, ORC_ERR_REWARD_RANGE, gid); }
+            if (viol || bad_state) {
+                e->stats[ST_VIOLATIONS] += 1.0;
+                note_error(e, (viol ? ORC_ERR_REWARD_RANGE : 0u) | (bad_state ? ORC_ERR_STATE_BOUNDS : 0u), gid);
+            }
             for (int k = 0; k < J; ++k) { obs[D * i + k] = (float)s.q[k]; obs[D * i + J + k] = (float)s.qd[k]; obs[D * i + 2 * J + k] = g[k]; }
         } else {
             sf = 1u | (sf & ~ORC_STEP_MASK);

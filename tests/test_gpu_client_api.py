@@ -146,3 +146,52 @@ def test_unfused_plugin_protocol_reproduces_the_fused_env():
             assert torch.equal(fused_client.goal, plug.goal)
     assert fused_client.counter == plug.counter
     assert fused_client.stats()["holds"] == plug.stats()["holds"] > 0
+
+
+@pytest.mark.parametrize("robot", ["msj", "five_joints_11_tendons_per_component"])
+def test_external_state_outside_the_angle_space_sets_its_error_bit(robot):
+    """The reference's client builds every state it receives with robot.new_state() (ros_simulation_client.py:40-46),
+    whose assert (roboy_robot.py:76) rejects joint angles outside the angle space and NaN; velocities are not checked
+    (:77).  roboy_step_external / roboy_reset_external report that as ROBOY_ERR_STATE_BOUNDS + the first offending env and
+    carry on with the batch -- same word, same env, same violation count as the oracle (pinned against the reference's
+    new_state in tests/test_oracle_vs_reference.py)."""
+    from cuda_adaptor import robot_from_bounds
+    from gym_roboy_b200 import _native
+    from gym_roboy_b200.envs import RoboyEnv
+    from gym_roboy_b200.envs.simulations import CudaSimulationClient
+    from test_oracle_vs_reference import GENERIC_ROBOTS
+    b = {} if robot == "msj" else GENERIC_ROBOTS[robot]
+    J, _, _, bb = orc.robot_bounds(b)
+    n = 5000
+    rng = np.random.default_rng(12)
+    lo, hi = bb["angle_low"], bb["angle_high"]
+
+    def states(first_bad):
+        q = rng.uniform(lo, hi, (n, J)).astype(np.float32)
+        qd = (rng.uniform(bb["vel_low"], bb["vel_high"], (n, J)) * 3).astype(np.float32)     # velocities may leave their space
+        q[first_bad + 3, 0] = np.nextafter(hi[0], np.float32(10))
+        q[first_bad, J - 1] = np.nextafter(lo[J - 1], np.float32(-10))
+        q[first_bad + 40, J // 2] = np.nan
+        q[first_bad + 41, 0] = np.inf
+        q[first_bad + 50] = hi                                                               # on the bounds: inside
+        q[first_bad + 51] = lo
+        return q, qd
+
+    client = CudaSimulationClient(robot=robot_from_bounds(b) if b else None, num_envs=n, seed=3, env_id_base=1000, device="cuda:0")
+    env = RoboyEnv(client, auto_reset=False, strict=False)
+    o = orc.OracleEnv(n, seed=3, env_id_base=1000, auto_reset=False, **b)
+    q, qd = states(700)
+    obs = env.reset_from_states(q, qd).cpu().numpy()
+    assert np.array_equal(obs.view(np.uint32), o.reset_external(q, qd).view(np.uint32))
+    assert client.errors() == (_native.ERR_STATE_BOUNDS, 1700) and o.errors() == (orc.ERR_STATE_BOUNDS, 1700)
+    client.clear_errors()
+    q, qd = states(200)
+    obs, rew, done, _ = env.step_from_states(q, qd)
+    oo, orw, od = o.step_external(q, qd)
+    assert np.array_equal(obs.cpu().numpy().view(np.uint32), oo.view(np.uint32)) and np.array_equal(done.cpu().numpy(), od)
+    # (the env handed an infinite angle also gets an infinite reward: both bits, in the kernel and in the oracle)
+    both = _native.ERR_STATE_BOUNDS | _native.ERR_REWARD_RANGE
+    assert client.errors() == (both, 1200) and o.errors() == (both, 1200), (client.errors(), o.errors())
+    assert client.stats()["violations"] == o.stats()["violations"] == 4
+    with pytest.raises(AssertionError, match="roboy_robot.py:76"):
+        env.check_errors()

@@ -267,3 +267,55 @@ def test_oracle_vs_reference_soak_slice():
     s = mod.soak(8.0, master_seed=seed)
     assert not s["mismatches"], (seed, s["mismatches"][:2])
     assert s["configs"] >= 3 and s["env_steps"] > 500
+
+
+@pytest.mark.parametrize("name", ["msj", "five_joints_11_tendons_per_component"])
+def test_external_state_bounds_match_the_reference_new_state(name):
+    """roboy_robot.py:76 through the reference's client (ros_simulation_client.py:40-46 builds every received state with
+    robot.new_state(python floats)): the envs whose new_state() raises are exactly the envs the oracle's external step
+    flags with ERR_STATE_BOUNDS -- bounds themselves inside, one ulp outside out, NaN and inf out, velocities unchecked."""
+    b = {} if name == "msj" else GENERIC_ROBOTS[name]
+    J, _, _, bb = orc.robot_bounds(b)
+    _, MsjRobot, _, _ = rh._import_reference()
+    robot = (rh._custom_reference_robot(b) if b else MsjRobot)()
+    n = 400
+    rng = np.random.default_rng(21)
+    lo, hi = bb["angle_low"], bb["angle_high"]
+    q = rng.uniform(lo, hi, (n, J)).astype(np.float32)
+    qd = (rng.uniform(bb["vel_low"], bb["vel_high"], (n, J)) * 5).astype(np.float32)
+    pick = rng.random((n, J))
+    q = np.where(pick < 0.03, np.nextafter(hi, np.float32(10)), q)
+    q = np.where((pick >= 0.03) & (pick < 0.06), np.nextafter(lo, np.float32(-10)), q)
+    q = np.where((pick >= 0.06) & (pick < 0.09), hi, q)
+    q = np.where((pick >= 0.09) & (pick < 0.12), lo, q)
+    q = np.where((pick >= 0.12) & (pick < 0.13), np.float32(np.nan), q)
+    q = np.where((pick >= 0.13) & (pick < 0.14), np.float32(np.inf), q).astype(np.float32)
+    raised = np.zeros(n, bool)
+    for i in range(n):
+        try:   # exactly RosSimulationClient._make_robot_state: lists of python floats
+            robot.new_state(joint_angle=[float(x) for x in q[i]], joint_vel=[float(x) for x in qd[i]], is_feasible=True)
+        except AssertionError:
+            raised[i] = True
+    assert 20 < raised.sum() < n - 20
+    for reset in (True, False):
+        o = orc.OracleEnv(n, seed=1, env_id_base=50, auto_reset=False, **b)
+        if reset:
+            o.reset_external(q, qd)
+        else:
+            o.step_external(q, qd)
+        flags, first = o.errors()
+        assert flags & orc.ERR_STATE_BOUNDS and first == 50 + int(np.flatnonzero(raised)[0])
+        # without the offenders nothing is flagged
+        ok = ~raised
+        o2 = orc.OracleEnv(int(ok.sum()), seed=1, auto_reset=False, **b)
+        if reset:
+            o2.reset_external(q[ok], qd[ok])
+        else:
+            o2.step_external(q[ok], qd[ok])
+        assert not (o2.errors()[0] & orc.ERR_STATE_BOUNDS)
+        # and every single offender is flagged on its own
+        bad = np.flatnonzero(raised)
+        o3 = orc.OracleEnv(int(bad.size), seed=1, auto_reset=False, **b)
+        if not reset:
+            o3.step_external(q[bad], qd[bad])
+            assert o3.stats()["violations"] == bad.size
