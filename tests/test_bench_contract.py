@@ -55,3 +55,13 @@ def test_shared_inputs_are_deterministic_and_match_the_oracle_population():
     assert r1 > 0 and r2 > 0
     for k in ("done_count", "obs_xor32", "obs_sum64", "goal_xor32", "step_word_xor32"):
         assert c1[k] == c2[k], k                                                     # thread count does not change results
+
+
+def test_traffic_json_is_the_default_step_kernel():
+    """roofline.traffic comes from profiles/traffic.json: it must describe the kernel the headline times (the default
+    instantiation of the step kernel at the benchmarked size), not another capture that happened to be summarised last."""
+    import json
+    tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    assert "step_kernel<0" in tj["kernel"] and "generic" not in tj["kernel"]
+    assert tj["envs"] == 16777216 and tj["algorithmic_bytes_per_launch"] == 93 * 16777216
+    assert 0.9 < tj["dram_bytes_per_launch"] / tj["algorithmic_bytes_per_launch"] < 1.1
