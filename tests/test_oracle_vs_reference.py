@@ -256,14 +256,13 @@ def test_every_joint_count_matches_reference(J):
 
 
 def test_oracle_vs_reference_soak_slice():
-    """An 8-second slice of tools/soak_oracle_vs_reference.py (random robots, flags, seeds; a fresh master seed every run;
-    the 15-minute record is profiles/r2_soak_oracle_vs_reference.json)."""
+    """An 8-second slice of tools/soak_oracle_vs_reference.py (random robots, flags, seeds; a master seed of its own; the
+    long records are in profiles/r2_soak_oracle_vs_reference.json)."""
     import importlib.util
-    import time
     spec = importlib.util.spec_from_file_location("soak_ovr", os.path.join(ROOT, "tools", "soak_oracle_vs_reference.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    seed = int(time.time())
+    seed = 424242
     s = mod.soak(8.0, master_seed=seed)
     assert not s["mismatches"], (seed, s["mismatches"][:2])
     assert s["configs"] >= 3 and s["env_steps"] > 500
